@@ -1,0 +1,428 @@
+// br_lz77.h -- LZ77 backward-reference search for one input block, one warp per block.
+//
+// What it replaces: BrotliCreateBackwardReferences (c/enc/backward_references_inc.h:10) with
+// the bucket-ring hashers H5/H6/H58/H68 (c/enc/hash_longest_match*_inc.h), plus
+// ExtendLastCommand (c/enc/encode.c:905).
+//
+// Why it looks nothing like the reference: the reference keeps ONE mutable hash table per
+// stream, so every block depends on the complete history of the parse before it.  Here the
+// table is replaced by two immutable, position-ordered structures built by sorting kernels:
+//
+//   S[]     all positions sorted by (bucket key, position)   -> "the bucket ring at time p"
+//           is the run of STORED positions just before rank[p] in S;
+//   bits[]  one "was this position ever inserted" bit per position, produced by the parse
+//           itself (every FindLongestMatch / StoreRange / Stitch call site sets bits).
+//
+// A block's walker only needs (a) the small serial state at its start (distance cache,
+// pending literals, dictionary counters: BrBlockIn) and (b) the stored-bits of earlier
+// positions.  All blocks of a stream therefore run CONCURRENTLY from speculated inputs, and a
+// serial-but-tiny chain kernel (br_chain below) re-derives the true inputs from the outputs;
+// blocks whose inputs changed are re-run until a fixpoint.  By induction over blocks a
+// fixpoint equals the sequential parse, so the commands are bit-identical to the reference.
+#pragma once
+#include "br_cmd.h"
+
+struct BrSR { u32 len, distance, score; int delta; };
+
+#define BR_SCORE_BASE 1920u  /* hash.h:102: 30 * 8 * sizeof(size_t) */
+#define BR_MIN_SCORE (BR_SCORE_BASE + 100u)
+
+BR_DEV u32 br_match_len(const u8* d, u32 a, u32 b, u32 limit) {
+  u32 len = 0;
+  while (len + 8 <= limit) {
+    u64 x = br_ld64u(d, a + len) ^ br_ld64u(d, b + len);
+    if (x) return len + (u32)(br_ctz64(x) >> 3);
+    len += 8;
+  }
+  while (len < limit && br_ldg(d + a + len) == br_ldg(d + b + len)) ++len;
+  return len;
+}
+
+// hash_longest_match64_inc.h:23 / hash_longest_match_inc.h:23 HashBytes
+BR_DEV u32 br_hash_key(const BrParams& P, const u8* d, u32 pos) {
+  if (P.hash64) {
+    u64 v = br_ld64u(d, pos);
+    return (u32)((v * (0x1FE35A7BD3579BD3ull << 24)) >> (64 - 15));
+  }
+  return (br_ld32u(d, pos) * 0x1E35A7BDu) >> (32 - P.bucket_bits);
+}
+
+struct BrWalk {
+  const BrStream* s;
+  const u8* d;
+  u32 p0, pend;
+  u32* own;        // stored bits of this block's own positions (shared memory)
+  u32 own_w0;
+  int dc[16];
+  u64 dict_l, dict_m;
+  u32 dl, dm, gate_checks, gate_fail;
+  u32 min_wrap;
+  u32 stale;       // the byte the reference finds just past the block end (see oracle)
+};
+
+BR_DEV int br_own_get(const BrWalk& w, u32 q) {
+  return (w.own[(q >> 5) - w.own_w0] >> (q & 31)) & 1;
+}
+BR_DEV void br_own_set(BrWalk& w, u32 q) {
+  if (br_lane() == 0) w.own[(q >> 5) - w.own_w0] |= 1u << (q & 31);
+  br_syncwarp();
+}
+BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
+  if (a >= b) return;
+  u32 wa = a >> 5, wb = (b - 1) >> 5;
+  for (u32 x = wa + (u32)br_lane(); x <= wb; x += BR_WARP) {
+    u32 m = 0xffffffffu;
+    if (x == wa) m &= 0xffffffffu << (a & 31);
+    if (x == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+    w.own[x - w.own_w0] |= m;
+  }
+  br_syncwarp();
+}
+BR_DEV int br_is_stored(const BrWalk& w, u32 q) {
+  if (q >= w.p0) return br_own_get(w, q);
+  return (br_ldg(w.s->bits_latest + (q >> 5)) >> (q & 31)) & 1;
+}
+
+// Number of stored positions (latest snapshot) among S[a .. b).
+BR_DEV u32 br_countS_upto(const BrStream& s, u32 x) {
+  u32 base = br_ldg(s.prefS + (x >> 10));
+  u32 w0 = (x >> 10) << 5, w1 = x >> 5, acc = 0;
+  for (u32 wi = w0 + (u32)br_lane(); wi < w1; wi += BR_WARP) acc += (u32)br_popc(br_ldg(s.storedS + wi));
+  acc = br_warp_sum(acc);
+  if (x & 31) acc += (u32)br_popc(br_ldg(s.storedS + w1) & ((1u << (x & 31)) - 1u));
+  return base + acc;
+}
+
+// hash.h:140 TestStaticDictionaryItem
+BR_DEV int br_test_dict_item(const BrWalk& w, u32 len, u32 word_idx, u32 cur, u32 max_length,
+                             u32 max_backward, BrSR& out) {
+  const BrStream& s = *w.s;
+  if (len > max_length) return 0;
+  u32 offset = br_ldg(s.dict_offsets + len) + len * word_idx;
+  u32 matchlen = 0;
+  while (matchlen < len && br_ldg(w.d + cur + matchlen) == br_ldg(s.dict + offset + matchlen)) ++matchlen;
+  if (matchlen + 10 <= len || matchlen == 0) return 0;
+  u32 cut = len - matchlen;
+  u32 transform_id = (cut << 2) + (u32)((0x071B520ADA2D3200ull >> (cut * 6)) & 0x3F);
+  u32 backward = max_backward + 1 + word_idx + (transform_id << br_ldg(s.dict_size_bits + len));
+  if (backward > 0x3FFFFFCu) return 0;
+  u32 score = BR_SCORE_BASE + 135u * matchlen - 30u * br_log2floor(backward);
+  if (score < out.score) return 0;
+  out.len = matchlen;
+  out.delta = (int)len - (int)matchlen;
+  out.distance = backward;
+  out.score = score;
+  return 1;
+}
+// hash.h:179 SearchInStaticDictionary (warp-uniform)
+BR_DEV void br_search_static_dict(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, BrSR& out) {
+  const BrStream& s = *w.s;
+  ++w.gate_checks;
+  if (w.dict_m < (w.dict_l >> 7)) { ++w.gate_fail; return; }
+  u32 key = ((br_ld32u(w.d, cur) * 0x1E35A7BDu) >> (32 - 14)) << 1;
+  for (int i = 0; i < 2; ++i, ++key) {
+    ++w.dict_l; ++w.dl;
+    u32 len = br_ldg(s.dict_hash_lengths + key);
+    if (len != 0) {
+      if (br_test_dict_item(w, len, br_ldg(s.dict_hash_words + key), cur, max_length, max_backward, out)) {
+        ++w.dict_m; ++w.dm;
+      }
+    }
+  }
+}
+
+// FindLongestMatch (hash_longest_match64_inc.h:157, hash_longest_match_inc.h:156), lane-parallel:
+// every candidate's full match length is computed by its own lane, then the reference's
+// sequential "better than the best so far" rule is replayed with ballots.  The reference's
+// quick reject (4 bytes ending at best_len) passes exactly when the candidate is longer than
+// best_len, or -- only when best_len already equals max_length -- when the byte just past the
+// block end compares equal (w.stale).  Candidates that pass it by coincidence with a shorter
+// length can never beat the running score, so they are dropped here without side effects.
+BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_backward,
+                                  u32 dict_distance, BrSR& out) {
+  const BrStream& s = *w.s;
+  const BrParams& P = s.P;
+  const u8* d = w.d;
+  const int lane = br_lane();
+  const u32 rmask = P.rmask;
+  const u32 cur_m = cur & rmask;
+  const u32 min_score = out.score;
+  u32 best_score = out.score, best_len = out.len;
+  out.len = 0; out.delta = 0;
+  bool brk = false;
+  // ---- distance cache probes
+  for (int base = 0; base < P.ndist && !brk; base += BR_WARP) {
+    int k = base + lane;
+    int back_i = (k < P.ndist) ? w.dc[k] : 0;
+    bool valid = (k < P.ndist) && back_i > 0 && (u32)back_i <= max_backward;
+    u32 back = (u32)back_i, len = 0; int eqmax = 0;
+    if (valid) {
+      len = br_match_len(d, cur - back, cur, max_length);
+      if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + (cur - back) + max_length));
+    }
+    int cnt = P.ndist - base < BR_WARP ? P.ndist - base : BR_WARP;
+    for (int t = 0; t < cnt; ++t) {
+      if (!br_shfl((int)valid, t)) continue;
+      u32 l = br_shfl(len, t), bk = br_shfl(back, t);
+      int em = br_shfl(eqmax, t);
+      u32 pm = (cur - bk) & rmask;
+      if (cur_m + best_len > rmask) { brk = true; break; }
+      if (pm + best_len > rmask) continue;
+      if (!(l > best_len || (l == best_len && best_len == max_length && em))) continue;
+      int kk = base + t;
+      if (l >= 3 || (l == 2 && kk < 2)) {
+        u32 score = 135u * l + BR_SCORE_BASE + 15u;
+        if (best_score < score) {
+          if (kk != 0) score -= 39u + ((0x1CA10u >> (kk & 0xE)) & 0xEu);
+          if (best_score < score) {
+            best_score = score; best_len = l;
+            out.len = l; out.distance = bk; out.score = score;
+          }
+        }
+      }
+    }
+  }
+  if (best_len < 3) best_len = 3;
+  // ---- bucket ring
+  {
+    const u32 key = br_hash_key(P, d, cur);
+    const u32 lo = br_ldg(s.seg + key), hi = br_ldg(s.seg + key + 1);
+    const u32 j = br_ldg(s.rank + cur);
+    const u32 block_size = 1u << P.block_bits;
+    u32 V = block_size;
+    if (hi - lo >= 65536u) {
+      // The reference's per-bucket counter is a uint16 (hash_longest_match64_inc.h:52): after
+      // 65536 insertions it wraps and the ring looks empty again.  c = insertions so far.
+      u32 own_cnt = 0, jj = j, n_own = 0;
+      while (jj > lo) {
+        u32 idx = jj - 1 - (u32)lane;
+        bool has = (jj >= lo + 1 + (u32)lane);
+        u32 q = has ? br_ldg(s.S + idx) : 0;
+        bool mine = has && q >= w.p0;
+        u32 mm = br_ballot(mine);
+        own_cnt += (u32)br_popc(br_ballot(mine && br_own_get(w, q)));
+        n_own += (u32)br_popc(mm);
+        if (mm != (BR_WARP == 32 ? 0xffffffffu : 1u)) break;
+        jj -= BR_WARP;
+      }
+      u32 jb = j - n_own;
+      u32 prev_cnt = br_countS_upto(s, jb) - br_countS_upto(s, lo);
+      u32 c = (prev_cnt + own_cnt) & 0xFFFFu;
+      if (c < block_size) { V = c; w.min_wrap = 0; }
+      else {
+        u32 sd = c - block_size, su = 65535u - c;
+        u32 m = sd < su ? sd : su;
+        if (m < w.min_wrap) w.min_wrap = m;
+      }
+    }
+    const u32 first4 = br_ld32u(d, cur);
+    u32 collected = 0, jj = j;
+    bool done = false;
+    while (!done && collected < V && jj > lo) {
+      u32 idx = jj - 1 - (u32)lane;
+      bool has = (jj >= lo + 1 + (u32)lane);
+      u32 q = has ? br_ldg(s.S + idx) : 0;
+      u32 backward = cur - q;
+      bool inwin = has && backward <= max_backward;
+      bool st = inwin && br_is_stored(w, q);
+      u32 m = br_ballot(st);
+      u32 rnk = (u32)br_popc(m & br_lanemask_lt());
+      bool take = st && (collected + rnk < V);
+      if (br_ballot(has && !inwin) != 0 || br_ballot(!has) != 0) done = true;
+      collected += (u32)br_popc(m);
+      // full match length of every taken candidate
+      u32 len = 0; int eqmax = 0;
+      if (take) {
+        if (P.hash64) {
+          if (br_ld32u(d, q) == first4) len = 4 + br_match_len(d, q + 4, cur + 4, max_length - 4);
+        } else {
+          len = br_match_len(d, q, cur, max_length);
+          if (len < 4) len = 0;
+        }
+        if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + q + max_length));
+      }
+      u32 score = len ? BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward) : 0;
+      u32 pm = q & rmask;
+      int last = -1;
+      for (;;) {
+        if (cur_m + best_len > rmask) { done = true; break; }
+        bool ok = take && len != 0 && lane > last && !(pm + best_len > rmask) &&
+                  (len > best_len || (len == best_len && best_len == max_length && eqmax)) &&
+                  score > best_score;
+        u32 mm = br_ballot(ok);
+        if (!mm) break;
+        int f = br_ffs(mm) - 1;
+        best_len = br_shfl(len, f);
+        best_score = br_shfl(score, f);
+        out.len = best_len; out.distance = br_shfl(backward, f); out.score = best_score;
+        last = f;
+      }
+      jj = jj > BR_WARP ? jj - BR_WARP : 0;
+    }
+    br_own_set(w, cur);  // the insertion at hash_longest_match64_inc.h:268
+  }
+  if (min_score == out.score) br_search_static_dict(w, cur, max_length, dict_distance, out);
+}
+
+// hash.h:80 PrepareDistanceCache
+BR_DEV void br_prepare_dist_cache(int* dc, int nd) {
+  if (nd > 4) {
+    int l = dc[0];
+    dc[4] = l - 1; dc[5] = l + 1; dc[6] = l - 2; dc[7] = l + 2; dc[8] = l - 3; dc[9] = l + 3;
+    if (nd > 10) {
+      int n = dc[1];
+      dc[10] = n - 1; dc[11] = n + 1; dc[12] = n - 2; dc[13] = n + 2; dc[14] = n - 3; dc[15] = n + 3;
+    }
+  }
+}
+// backward_references.c:87 ComputeDistanceCode
+BR_DEV u32 br_compute_distance_code(u32 distance, u32 max_distance, const int* dc) {
+  if (distance <= max_distance) {
+    u32 d3 = distance + 3;
+    u32 o0 = d3 - (u32)dc[0], o1 = d3 - (u32)dc[1];
+    if (distance == (u32)dc[0]) return 0;
+    if (distance == (u32)dc[1]) return 1;
+    if (o0 < 7) return (0x9750468u >> (4 * o0)) & 0xF;
+    if (o1 < 7) return (0xFDB1ACEu >> (4 * o1)) & 0xF;
+    if (distance == (u32)dc[2]) return 2;
+    if (distance == (u32)dc[3]) return 3;
+  }
+  return distance + 15;
+}
+
+// One input block.  `own` must hold ((end-1)>>5) - (pos>>5) + 1 words.
+BR_DEV void br_walk_block(const BrStream& s, u32 b, u32* own) {
+  const BrParams& P = s.P;
+  const BrBlockIn in = s.bin[b];
+  const int lane = br_lane();
+  BrWalk w;
+  w.s = &s; w.d = s.data; w.p0 = in.pos; w.pend = in.end;
+  w.own = own; w.own_w0 = in.pos >> 5;
+  w.dict_l = ((u64)in.dict_l_hi << 32) | in.dict_l_lo;
+  w.dict_m = ((u64)in.dict_m_hi << 32) | in.dict_m_lo;
+  w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
+  w.min_wrap = 0xffffffffu;
+  w.stale = in.end <= P.rmask ? 0u : (u32)s.data[in.end - (P.rmask + 1)];
+  for (int i = 0; i < 4; ++i) w.dc[i] = in.dc[i];
+  for (int i = 4; i < 16; ++i) w.dc[i] = 0;
+  {
+    u32 nw = ((in.end - 1) >> 5) - w.own_w0 + 1;
+    for (u32 x = (u32)lane; x < nw; x += BR_WARP) own[x] = 0;
+    br_syncwarp();
+  }
+  u32 position = in.pos, bytes = in.end - in.pos;
+  // ---- ExtendLastCommand (encode.c:941): grow the previous block's final copy.
+  u32 ext = 0;
+  if (in.ext_dist) {
+    while (bytes) {
+      u32 chunk = bytes < BR_WARP ? bytes : BR_WARP;
+      bool eq = (u32)lane < chunk &&
+                s.data[position + lane] == s.data[position + lane - in.ext_dist];
+      u32 m = br_ballot(eq);
+      u32 run = (u32)br_ffs(~m) - 1u;  // leading equal lanes
+      if (BR_WARP == 1) run = m ? 1 : 0;
+      if (run > chunk) run = chunk;
+      ext += run; position += run; bytes -= run;
+      if (run < chunk) break;
+    }
+  }
+  // ---- CreateBackwardReferences (backward_references_inc.h:10)
+  const u32 pos_end = in.end;
+  const u32 store_end = bytes >= P.htl ? position + bytes - P.htl + 1 : position;
+  const u32 window = P.spree;
+  u32 apply_random_heuristics = position + window;
+  u32 insert_length = in.last_insert_len;
+  u32 ncmd = 0, nlit = 0;
+  BrCmd* cmds = s.cmd_blocks + (size_t)b * s.cmd_stride;
+  br_prepare_dist_cache(w.dc, P.ndist);
+  while (position + P.htl < pos_end) {
+    u32 max_length = pos_end - position;
+    u32 max_distance = br_min(position, P.max_backward);
+    BrSR sr; sr.len = 0; sr.delta = 0; sr.distance = 0; sr.score = BR_MIN_SCORE;
+    br_find_longest_match(w, position, max_length, max_distance, max_distance, sr);
+    if (sr.score > BR_MIN_SCORE) {
+      int delayed = 0;
+      --max_length;
+      for (;; --max_length) {
+        BrSR sr2; sr2.len = 0; sr2.delta = 0; sr2.distance = 0; sr2.score = BR_MIN_SCORE;
+        max_distance = br_min(position + 1, P.max_backward);
+        br_find_longest_match(w, position + 1, max_length, max_distance, max_distance, sr2);
+        if (sr2.score >= sr.score + 175u) {
+          ++position; ++insert_length; sr = sr2;
+          if (++delayed < 4 && position + P.htl < pos_end) continue;
+        }
+        break;
+      }
+      apply_random_heuristics = position + 2 * sr.len + window;
+      u32 dictionary_start = br_min(position, P.max_backward);
+      u32 dcode = br_compute_distance_code(sr.distance, dictionary_start, w.dc);
+      if (sr.distance <= dictionary_start && dcode > 0) {
+        w.dc[3] = w.dc[2]; w.dc[2] = w.dc[1]; w.dc[1] = w.dc[0]; w.dc[0] = (int)sr.distance;
+        br_prepare_dist_cache(w.dc, P.ndist);
+      }
+      if (lane == 0) cmds[ncmd] = br_init_cmd(insert_length, sr.len, sr.delta, dcode);
+      ++ncmd;
+      nlit += insert_length;
+      insert_length = 0;
+      {
+        u32 range_start = position + 2;
+        u32 range_end = br_min(position + sr.len, store_end);
+        if (sr.distance < (sr.len >> 2)) {
+          u32 t = position + sr.len - (sr.distance << 2);
+          range_start = br_min(range_end, br_max(range_start, t));
+        }
+        br_own_set_range(w, range_start, range_end);
+      }
+      position += sr.len;
+    } else {
+      ++insert_length;
+      ++position;
+      if (position > apply_random_heuristics) {
+        u32 step, reach, margin;
+        if (position > apply_random_heuristics + 4 * window) {
+          step = 4; reach = 16; margin = br_max(P.htl - 1, 4);
+        } else {
+          step = 2; reach = 8; margin = br_max(P.htl - 1, 2);
+        }
+        u32 pos_jump = br_min(position + reach, pos_end - margin);
+        for (; position < pos_jump; position += step) {
+          br_own_set(w, position);
+          insert_length += step;
+        }
+      }
+    }
+  }
+  insert_length += pos_end - position;
+  // ---- StitchToPreviousBlock of the FOLLOWING blocks (hash_longest_match64_inc.h:127) stores
+  // the last three positions of this block; the set is static, so this block owns the bits.
+  for (u32 nb = b + 1; nb < P.nblocks; ++nb) {
+    u32 np = s.bin[nb].pos, ne = s.bin[nb].end;
+    if (np >= pos_end + 3) break;
+    if (ne - np >= P.htl - 1 && np >= 3) {
+      for (u32 q = np - 3; q < np; ++q)
+        if (q >= in.pos && q < pos_end) br_own_set(w, q);
+    }
+  }
+  // ---- publish
+  {
+    u32 w0 = in.pos >> 5, w1 = (pos_end - 1) >> 5;
+    for (u32 x = w0 + (u32)lane; x <= w1; x += BR_WARP) {
+      u32 m = 0xffffffffu;
+      if (x == w0) m &= 0xffffffffu << (in.pos & 31);
+      if (x == w1) m &= 0xffffffffu >> (31 - ((pos_end - 1) & 31));
+      u32 v = own[x - w0] & m;
+      if (m == 0xffffffffu) s.bits_cur[x] = v;
+      else { br_atomic_and(s.bits_cur + x, ~m); br_atomic_or(s.bits_cur + x, v); }
+    }
+  }
+  if (lane == 0) {
+    BrBlockOut o;
+    o.ncmd = ncmd; o.nlit = nlit; o.last_insert_len = insert_length;
+    for (int i = 0; i < 4; ++i) o.dc[i] = w.dc[i];
+    o.ext_len = ext; o.dl = w.dl; o.dm = w.dm;
+    o.gate_checks = w.gate_checks; o.gate_fail = w.gate_fail;
+    o.min_wrap_dist = w.min_wrap; o.valid = 1; o.epoch = s.epoch;
+    s.bout[b] = o;
+    s.bin_used[b] = in;
+  }
+}

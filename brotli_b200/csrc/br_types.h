@@ -1,0 +1,108 @@
+// br_types.h -- plain-old-data shared by host driver, CUDA kernels and the test sim.
+#pragma once
+#include "br_port.h"
+
+// One Brotli command, same 16-byte layout as the reference's Command (c/enc/command.h:108).
+struct BrCmd {
+  u32 insert_len;
+  u32 copy_len;    // low 25 bits: copy length; high 7 bits: copy_len_code - copy_len
+  u32 dist_extra;
+  u16 cmd_prefix;
+  u16 dist_prefix; // low 10 bits: distance symbol; high 6: number of extra bits
+};
+
+// Encoder parameters after the reference's sanitising (c/enc/quality.h, c/enc/encode.c:642).
+struct BrParams {
+  int quality, lgwin, lgblock;
+  int hash64;       // 1: 5-byte hash H6/H68 (quality.h:182), 0: 4-byte hash H5/H58
+  int bucket_bits;  // 14 or 15
+  int block_bits;   // quality - 1: bucket ring holds 1 << block_bits positions
+  int ndist;        // 4, 10 or 16 distance-cache probes
+  u32 htl;          // HashTypeLength == StoreLookahead: 8 (hash64) or 4
+  u32 rmask;        // ring buffer mask of the reference: (1 << (1 + max(lgwin, lgblock))) - 1
+  u32 max_backward; // (1 << lgwin) - 16
+  u32 spree;        // LiteralSpreeLengthForSparseSearch: 64 (q < 9) or 512
+  u32 max_mb;       // MaxMetablockSize
+  u32 size_hint;
+  u32 n;            // input bytes
+  u32 nblocks;      // input blocks (EncodeData calls)
+  u32 nbuckets;     // 1 << bucket_bits (+1 overflow bucket for the unhashable tail positions)
+};
+
+// Per input block: what the serial chain hands to the block's walker.
+struct BrBlockIn {
+  u32 pos, end;          // [pos, end) of this input block
+  u32 last_insert_len;
+  int dc[4];             // distance cache at block start
+  u32 ext_dist;          // != 0: ExtendLastCommand applies with this distance (encode.c:905)
+  u32 dict_l_lo, dict_l_hi, dict_m_lo, dict_m_hi;  // dict_num_lookups / dict_num_matches (hash.h:49)
+  u32 is_last;
+  u32 force_flush;       // BROTLI_OPERATION_FLUSH ended the input here (encode.c:1700)
+};
+// What the walker reports back.
+struct BrBlockOut {
+  u32 ncmd, nlit;        // commands emitted, literals covered by them
+  u32 last_insert_len;   // pending literals at block end
+  int dc[4];
+  u32 ext_len;           // bytes swallowed by ExtendLastCommand
+  u32 dl, dm;            // static-dictionary counter deltas
+  u32 gate_checks, gate_fail;
+  u32 min_wrap_dist;     // see br_lz77.h (bucket counter wrap sensitivity)
+  u32 valid;
+  u32 epoch;             // walker launch that produced this record
+};
+
+// Per metablock record produced by the chain kernel.
+struct BrMetaBlock {
+  u32 start, end;        // input range
+  u32 first_block, last_block;
+  u32 cmd_off, ncmd;     // commands in the compacted array (incl. trailing insert-only command)
+  u32 nlit;
+  u32 is_last;
+  u32 compress;          // 0: stored uncompressed (ShouldCompress said no or late fallback)
+  u8 prev_byte, prev_byte2, pad0, pad1;
+  u32 tail_insert;       // insert-only command appended at flush (0 if none)
+  u32 out_bits;          // bits produced by the compressed encoder (relative, from bit 0)
+  u32 scratch_off;
+};
+
+#define BR_MAX_EPOCHS 1024
+
+// Device-resident view of one stream (all pointers are device pointers).
+struct BrStream {
+  BrParams P;
+  const u8* data;        // n bytes + >= 16 zero bytes
+  const u32* S;          // positions sorted by (bucket key, position)
+  const u32* rank;       // rank[S[j]] = j
+  const u32* seg;        // seg[key] = first index of bucket key in S; nbuckets + 2 entries
+  u32* bits_latest;      // stored-position bitmap, latest run of every block
+  u32* bits_cur;         // written by the walkers of this iteration
+  const u32* storedS;    // bits_latest permuted into S order ...
+  const u32* prefS;      // ... with exclusive popcount prefix every 1024 bits
+  BrBlockIn* bin;        // [nblocks]   chain state handed to walkers
+  BrBlockIn* bin_used;   // [nblocks]   state the latest run of each block consumed
+  BrBlockOut* bout;      // [nblocks]
+  BrCmd* cmd_blocks;     // per block command buffers, stride cmd_stride
+  u32 cmd_stride;
+  u32* dirty;            // [nblocks] run this block in the next walker launch
+  u32* changed_bits;     // [nblocks] popcount of bitmap changes of the latest run
+  int* changed_epoch;    // [nblocks] last walker launch whose commit changed this block's bits (-1: never)
+  u32* epoch_changed;    // [BR_MAX_EPOCHS] total changed bits committed per walker launch
+  u32* epoch_suffix;     // [BR_MAX_EPOCHS + 1] suffix sums of the above (chain scratch)
+  u32 epoch;             // current walker launch number (1-based)
+  u32* ext_total;        // [nblocks] bytes added to the block's last command by ExtendLastCommand
+  u32* cmd_off;          // [nblocks] offset of the block's commands in the compacted array
+  BrMetaBlock* mbs;      // [max_mbs]
+  u32* force_unc;        // [max_mbs] late fallback: store this metablock uncompressed
+  u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags
+  u32* hist_scratch;     // [256]
+  // tables
+  const u8* dict;        // RFC 7932 dictionary
+  const u32* dict_offsets;  // [32]
+  const u8* dict_size_bits; // [32]
+  const u16* dict_hash_words;   // [32768]
+  const u8* dict_hash_lengths;  // [32768]
+  const u8* ctx_lut;     // [2048]
+  const double* log2tab; // [log2tab_n]
+  u32 log2tab_n;
+};

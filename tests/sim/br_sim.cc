@@ -1,0 +1,230 @@
+// tests/sim/br_sim.cc -- TEST INFRASTRUCTURE.  Compiles the product's warp-task device code
+// (brotli_b200/csrc/br_lz77.h, br_chain.h, br_entropy.h) for the CPU with a one-lane "warp"
+// (BR_SIM) so that the bit-exact logic can be debugged against the oracle in a container
+// without a GPU.  The data-parallel kernels (hash, sort, scans, packing) have trivial
+// sequential stand-ins here; their CUDA versions are checked on the GPU (tests -m gpu).
+#define BR_SIM 1
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <vector>
+#include "../../brotli_b200/csrc/br_params.h"
+#include "../../brotli_b200/csrc/br_lz77.h"
+#include "../../brotli_b200/csrc/br_chain.h"
+#ifdef BR_SIM_ENTROPY
+#include "../../brotli_b200/csrc/br_entropy.h"
+#endif
+
+struct SimTables {
+  std::vector<u8> blob;
+  std::vector<double> log2tab;
+};
+static SimTables g_t;
+
+extern "C" int sim_init(const u8* blob, size_t len, u32 log2n) {
+  g_t.blob.assign(blob, blob + len);
+  g_t.log2tab.resize(log2n);
+  g_t.log2tab[0] = 0;
+  for (u32 i = 1; i < log2n; ++i)
+    g_t.log2tab[i] = i < 256 ? (double)(float)log2((double)i) : log2((double)i);
+  return 1;
+}
+
+struct SimStream {
+  BrStream s;
+  std::vector<u8> data;
+  std::vector<u32> S, rank, seg, bits_latest, bits_cur, storedS, prefS, dirty, changed_bits,
+      epoch_changed, epoch_suffix, ext_total, cmd_off, force_unc, counters, hist, block_mb;
+  std::vector<int> changed_epoch;
+  std::vector<BrBlockIn> bin, bin_used;
+  std::vector<BrBlockOut> bout;
+  std::vector<BrCmd> cmd_blocks, cmds_all;
+  std::vector<BrMetaBlock> mbs;
+  int iterations = 0;
+  u64 block_runs = 0;
+};
+
+static void sim_build_sorted(SimStream& m) {
+  BrStream& s = m.s; const BrParams& P = s.P; u32 n = P.n;
+  std::vector<u32> key(n);
+  u32 hashable = n >= P.htl ? n - P.htl + 1 : 0;  // positions with a full hash load
+  for (u32 p = 0; p < n; ++p) key[p] = p < hashable ? br_hash_key(P, s.data, p) : P.nbuckets;
+  m.seg.assign(P.nbuckets + 2, 0);
+  for (u32 p = 0; p < n; ++p) m.seg[key[p] + 1]++;
+  for (u32 k = 0; k <= P.nbuckets; ++k) m.seg[k + 1] += m.seg[k];
+  std::vector<u32> cur(m.seg.begin(), m.seg.end() - 1);
+  m.S.resize(n); m.rank.resize(n);
+  for (u32 p = 0; p < n; ++p) { u32 j = cur[key[p]]++; m.S[j] = p; m.rank[p] = j; }
+  s.S = m.S.data(); s.rank = m.rank.data(); s.seg = m.seg.data();
+}
+static void sim_build_storedS(SimStream& m) {
+  u32 n = m.s.P.n;
+  std::fill(m.storedS.begin(), m.storedS.end(), 0);
+  for (u32 j = 0; j < n; ++j) {
+    u32 q = m.S[j];
+    if ((m.bits_latest[q >> 5] >> (q & 31)) & 1) m.storedS[j >> 5] |= 1u << (j & 31);
+  }
+  u32 acc = 0;
+  for (u32 b = 0; b * 1024 < n + 1024; ++b) {
+    m.prefS[b] = acc;
+    for (u32 w = b * 32; w < b * 32 + 32 && w < m.storedS.size(); ++w) acc += __builtin_popcount(m.storedS[w]);
+  }
+}
+
+static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
+  SimStream* m = new SimStream();
+  BrStream& s = m->s;
+  memset(&s, 0, sizeof(s));
+  if (!br_derive_params(q, lgwin, n, n, &s.P)) { delete m; return nullptr; }
+  BrParams& P = s.P;
+  u32 bs = 1u << P.lgblock;
+  P.nblocks = (n + bs - 1) / bs;
+  m->data.assign(in, in + n); m->data.resize(n + 64, 0);
+  s.data = m->data.data();
+  u32 nb = P.nblocks, words = (n + 31) / 32 + 2;
+  m->bin.resize(nb); m->bin_used.resize(nb); m->bout.resize(nb);
+  memset(m->bin.data(), 0, nb * sizeof(BrBlockIn));
+  memset(m->bout.data(), 0, nb * sizeof(BrBlockOut));
+  for (u32 k = 0; k < nb; ++k) {
+    m->bin[k].pos = k * bs; m->bin[k].end = std::min(n, (k + 1) * bs);
+    m->bin[k].is_last = (k + 1 == nb);
+  }
+  m->bits_latest.assign(words, 0); m->bits_cur.assign(words, 0);
+  // initial guess: everything stored except the unsearchable tail of each block
+  for (u32 k = 0; k < nb; ++k)
+    for (u32 p = m->bin[k].pos; p + P.htl <= m->bin[k].end; ++p) m->bits_latest[p >> 5] |= 1u << (p & 31);
+  m->storedS.assign(words + 32, 0); m->prefS.assign(n / 1024 + 4, 0);
+  m->dirty.assign(nb, 0); m->changed_bits.assign(nb, 0); m->changed_epoch.assign(nb, -1);
+  m->epoch_changed.assign(BR_MAX_EPOCHS, 0); m->epoch_suffix.assign(BR_MAX_EPOCHS + 1, 0);
+  m->ext_total.assign(nb, 0); m->cmd_off.assign(nb, 0); m->force_unc.assign(nb + 1, 0);
+  m->counters.assign(8, 0); m->hist.assign(256, 0); m->mbs.resize(nb + 1);
+  s.cmd_stride = bs / 2 + 2;
+  m->cmd_blocks.resize((size_t)nb * s.cmd_stride);
+  s.bits_latest = m->bits_latest.data(); s.bits_cur = m->bits_cur.data();
+  s.storedS = m->storedS.data(); s.prefS = m->prefS.data();
+  s.bin = m->bin.data(); s.bin_used = m->bin_used.data(); s.bout = m->bout.data();
+  s.cmd_blocks = m->cmd_blocks.data(); s.dirty = m->dirty.data();
+  s.changed_bits = m->changed_bits.data(); s.changed_epoch = m->changed_epoch.data();
+  s.epoch_changed = m->epoch_changed.data(); s.epoch_suffix = m->epoch_suffix.data();
+  s.ext_total = m->ext_total.data(); s.cmd_off = m->cmd_off.data();
+  s.mbs = m->mbs.data(); s.force_unc = m->force_unc.data(); s.counters = m->counters.data();
+  s.hist_scratch = m->hist.data();
+  const u8* p = g_t.blob.data() + 8;
+  s.dict_size_bits = p; p += 32;
+  s.dict_offsets = (const u32*)p; p += 128;
+  s.dict = p; p += 122784;
+  s.dict_hash_words = (const u16*)p; p += 65536;
+  s.dict_hash_lengths = p; p += 32768;
+  s.ctx_lut = p;
+  s.log2tab = g_t.log2tab.data(); s.log2tab_n = (u32)g_t.log2tab.size();
+  sim_build_sorted(*m);
+  return m;
+}
+
+static void sim_lz77_fixpoint(SimStream& m) {
+  BrStream& s = m.s; u32 nb = s.P.nblocks;
+  std::vector<u32> own((1u << s.P.lgblock) / 32 + 2);
+  s.epoch = 0;
+  for (;;) {
+    br_chain(s);
+    if (getenv("BR_SIM_TRACE")) { u32 h[6] = {0}; u32 first = nb; for (u32 k = 0; k < nb; ++k) { h[s.dirty[k]]++; if (s.dirty[k] && first == nb) first = k; }
+      fprintf(stderr, "epoch %u dirty %u first %u: never %u state %u dict %u window %u wrap %u\n", s.epoch, s.counters[0], first, h[1], h[2], h[3], h[4], h[5]); }
+    if (s.counters[0] == 0) break;
+    ++s.epoch; ++m.iterations;
+    sim_build_storedS(m);
+    std::vector<u32> ran;
+    for (u32 k = 0; k < nb; ++k) if (s.dirty[k]) { br_walk_block(s, k, own.data()); ran.push_back(k); }
+    m.block_runs += ran.size();
+    for (u32 k : ran) br_commit_bits(s, k);
+    if (s.epoch >= BR_MAX_EPOCHS - 1) { fprintf(stderr, "sim: no fixpoint\n"); break; }
+  }
+  u32 nm = s.counters[1];
+  m.block_mb.assign(nb, 0);
+  for (u32 i = 0; i < nm; ++i)
+    for (u32 k = s.mbs[i].first_block; k <= s.mbs[i].last_block; ++k) m.block_mb[k] = i;
+  m.cmds_all.resize(s.counters[2] + 1);
+  for (u32 k = 0; k < nb; ++k) br_compact_block(s, k, m.cmds_all.data(), m.block_mb.data());
+}
+
+// Runs the LZ77 stage; returns the commands of every metablock back to back.
+extern "C" long sim_lz77(int q, int lgwin, const u8* in, u32 n, BrCmd* cmds_out, u32 cmds_cap,
+                         u32* mb_info /* [5*i]: start,end,ncmd,compress,cmd_off */, u32 mb_cap, u32* stats) {
+  SimStream* m = sim_setup(q, lgwin, in, n);
+  if (!m) return -1;
+  sim_lz77_fixpoint(*m);
+  u32 nm = m->s.counters[1], total = m->s.counters[2];
+  if (total > cmds_cap || nm > mb_cap) { delete m; return -2; }
+  memcpy(cmds_out, m->cmds_all.data(), (size_t)total * sizeof(BrCmd));
+  for (u32 i = 0; i < nm; ++i) {
+    const BrMetaBlock& b = m->s.mbs[i];
+    mb_info[5 * i] = b.start; mb_info[5 * i + 1] = b.end; mb_info[5 * i + 2] = b.ncmd;
+    mb_info[5 * i + 3] = b.compress; mb_info[5 * i + 4] = b.cmd_off;
+  }
+  stats[0] = (u32)m->iterations; stats[1] = (u32)m->block_runs; stats[2] = m->s.P.nblocks;
+  delete m;
+  return nm;
+}
+
+#ifdef BR_SIM_ENTROPY
+static void put_bits_host(std::vector<u8>& o, u64& bit, u32 n, u64 v) {
+  for (u32 i = 0; i < n; ++i, ++bit) {
+    if ((bit >> 3) >= o.size()) o.resize((bit >> 3) + 1, 0);
+    if ((v >> i) & 1) o[bit >> 3] |= (u8)(1u << (bit & 7));
+  }
+}
+// Full pipeline; returns compressed size or negative error.
+extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, size_t out_cap, u32* stats) {
+  if (n == 0) { if (out_cap < 1) return -3; out[0] = 6; return 1; }
+  SimStream* m = sim_setup(q, lgwin, in, n);
+  if (!m) return -1;
+  BrStream& s = m->s;
+  std::vector<u8> res;
+  std::vector<u32> smem(4096);
+  int rounds = 0;
+  for (;;) {
+    ++rounds;
+    sim_lz77_fixpoint(*m);
+    u32 nm = s.counters[1];
+    res.clear();
+    u64 bit = 0;
+    if (lgwin == 17) put_bits_host(res, bit, 7, 1); else put_bits_host(res, bit, 4, ((lgwin - 17) << 1) | 1);
+    bool redo = false;
+    for (u32 i = 0; i < nm && !redo; ++i) {
+      BrMetaBlock mb = s.mbs[i];
+      u32 bytes = mb.end - mb.start;
+      bool compressed = mb.compress != 0;
+      if (compressed) {
+        std::vector<u8> scratch(br_mb_scratch_bytes(mb.nlit, mb.ncmd) + 64);
+        std::vector<u32> obuf((2 * (size_t)bytes + 503) / 4 + 8, 0);
+        u32 bits = br_encode_metablock(s, mb, m->cmds_all.data(), scratch.data(), obuf.data(), smem.data());
+        u64 storage_ix = (bit & 7) + bits;
+        if (mb.is_last) storage_ix = (storage_ix + 7) & ~7ull;
+        if ((u64)bytes + 4 < (storage_ix >> 3)) {
+          s.force_unc[i] = 1; redo = true; break;   // encode.c:604 late fallback
+        }
+        for (u32 b = 0; b < bits; ++b) put_bits_host(res, bit, 1, (obuf[b >> 5] >> (b & 31)) & 1);
+        if (mb.is_last) bit = (bit + 7) & ~7ull;
+      } else {
+        put_bits_host(res, bit, 1, 0);
+        u32 lg = bytes == 1 ? 1 : (32 - __builtin_clz(bytes - 1));
+        u32 mn = (lg < 16 ? 16 : lg + 3) / 4;
+        put_bits_host(res, bit, 2, mn - 4); put_bits_host(res, bit, mn * 4, bytes - 1);
+        put_bits_host(res, bit, 1, 1);
+        bit = (bit + 7) & ~7ull;
+        res.resize(bit >> 3, 0);
+        res.insert(res.end(), in + mb.start, in + mb.end);
+        bit += (u64)bytes * 8;
+        if (mb.is_last) { put_bits_host(res, bit, 2, 3); bit = (bit + 7) & ~7ull; }
+      }
+    }
+    if (!redo) { res.resize((bit + 7) >> 3, 0); break; }
+    if (rounds > 64) { delete m; return -4; }
+  }
+  stats[0] = (u32)m->iterations; stats[1] = (u32)m->block_runs; stats[2] = s.P.nblocks; stats[3] = (u32)rounds;
+  delete m;
+  if (res.size() > out_cap) return -3;
+  memcpy(out, res.data(), res.size());
+  return (long)res.size();
+}
+#endif
