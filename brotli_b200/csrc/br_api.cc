@@ -1,0 +1,327 @@
+// br_api.cc -- the BrotliEncoder* C ABI (include/brotli_b200.h) on top of the GPU pipeline.
+// Host-side mirror of the reference's stream driver, c/enc/encode.c: parameter handling
+// (:60 BrotliEncoderSetParameter, quality.h:59 SanitizeParams), the one-shot wrapper
+// (:1296 BrotliEncoderCompress with its :1264 MakeUncompressedStream fallback), and the
+// streaming state machine (:1634).  No compression happens on the host.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <thread>
+#include <vector>
+#include "../../include/brotli_b200.h"
+#include "br_pipeline.h"
+
+namespace {
+
+struct TlsJob {
+  BrJob* job = nullptr;
+  uint8_t* d_in = nullptr; size_t d_in_cap = 0;
+  double last[10] = {0};
+  ~TlsJob() { if (d_in) cudaFree(d_in); if (job) br_job_destroy(job); }
+};
+thread_local TlsJob tls;
+
+bool ensure_job() {
+  if (tls.job) return true;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    static bool warned = false;
+    if (!warned) { warned = true; fprintf(stderr, "brotli_b200: no CUDA device; this library has no CPU path\n"); }
+    return false;
+  }
+  tls.job = br_job_create();
+  return tls.job != nullptr;
+}
+
+void record_stats() {
+  const BrJobStats* s = br_job_stats(tls.job);
+  tls.last[0] = s->ms_total; tls.last[1] = s->ms_index; tls.last[2] = s->ms_lz77; tls.last[3] = s->ms_entropy;
+  tls.last[4] = s->ms_assemble; tls.last[5] = s->lz77_iterations; tls.last[6] = (double)s->block_runs;
+  tls.last[7] = s->nblocks; tls.last[8] = s->n_metablocks; tls.last[9] = s->launches;
+}
+
+struct Params {
+  int mode = BROTLI_MODE_GENERIC, quality = 11, lgwin = 22, lgblock = 0;
+  uint32_t size_hint = 0, disable_ctx = 0, large_window = 0, npostfix = 0, ndirect = 0, stream_offset = 0,
+           base64 = 0;
+};
+// What the pipeline implements; everything else must fail rather than emit different bytes.
+bool supported(Params p) {
+  if (p.quality > 11) p.quality = 11;          // quality.h:60 SanitizeParams
+  if (p.quality < 0) p.quality = 0;
+  if (p.lgwin < 10) p.lgwin = 10;
+  if (p.lgwin > 24 && !p.large_window) p.lgwin = 24;
+  if (p.quality < 5 || p.quality > 9) return false;
+  if (p.lgwin < 17 || p.lgwin > 24) return false;
+  if (p.large_window || p.npostfix || p.ndirect || p.stream_offset || p.base64 || p.disable_ctx) return false;
+  if (p.lgblock != 0) return false;
+  if (p.mode == BROTLI_MODE_FONT) return false;
+  return true;
+}
+
+// c/enc/encode.c:1264 MakeUncompressedStream
+size_t make_uncompressed_stream(const uint8_t* input, size_t input_size, uint8_t* output) {
+  size_t size = input_size, result = 0, offset = 0;
+  if (input_size == 0) { output[0] = 6; return 1; }
+  output[result++] = 0x21;
+  output[result++] = 0x03;
+  while (size > 0) {
+    uint32_t nibbles = 0, chunk, bits;
+    chunk = size > (1u << 24) ? (1u << 24) : (uint32_t)size;
+    if (chunk > (1u << 16)) nibbles = chunk > (1u << 20) ? 2 : 1;
+    bits = (nibbles << 1) | ((chunk - 1) << 3) | (1u << (19 + 4 * nibbles));
+    output[result++] = (uint8_t)bits;
+    output[result++] = (uint8_t)(bits >> 8);
+    output[result++] = (uint8_t)(bits >> 16);
+    if (nibbles == 2) output[result++] = (uint8_t)(bits >> 24);
+    memcpy(&output[result], &input[offset], chunk);
+    result += chunk; offset += chunk; size -= chunk;
+  }
+  output[result++] = 3;
+  return result;
+}
+
+// host buffer -> device -> pipeline -> host vector / buffer.  Returns 0 on failure.
+int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap,
+                  size_t* out_n, std::vector<uint8_t>* out_vec) {
+  if (!supported(p) || n == 0 || n > (1u << 30)) return 0;
+  if (!ensure_job()) return 0;
+  if (tls.d_in_cap < n) {
+    if (tls.d_in) cudaFree(tls.d_in);
+    tls.d_in = nullptr; tls.d_in_cap = 0;
+    if (cudaMalloc(&tls.d_in, n + 64) != cudaSuccess) { cudaGetLastError(); return 0; }
+    tls.d_in_cap = n;
+  }
+  cudaStream_t st = (cudaStream_t)br_job_stream(tls.job);
+  if (cudaMemcpyAsync(tls.d_in, in, n, cudaMemcpyHostToDevice, st) != cudaSuccess) return 0;
+  const uint8_t* d_out = nullptr; size_t sz = 0;
+  int q = p.quality, w = p.lgwin > 24 ? 24 : p.lgwin;
+  if (!br_job_compress_device(tls.job, q, w, size_hint, tls.d_in, (uint32_t)n, &d_out, &sz)) return 0;
+  record_stats();
+  if (out_vec) { out_vec->resize(sz); out = out_vec->data(); out_cap = sz; }
+  if (sz > out_cap) return 0;
+  if (cudaMemcpyAsync(out, d_out, sz, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 0;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return 0;
+  *out_n = sz;
+  return 1;
+}
+
+}  // namespace
+
+struct BrotliEncoderStateStruct {
+  brotli_alloc_func alloc_func; brotli_free_func free_func; void* opaque;
+  Params params;
+  bool initialized = false, finished = false, compressed = false, hint_fixed = false;
+  std::vector<uint8_t> input, output;
+  size_t out_pos = 0;
+  uint64_t total_out = 0;
+};
+
+extern "C" {
+
+uint32_t BrotliEncoderVersion(void) { return 0x1002000; }  /* c/common/version.h:18: 1.2.0 */
+
+int BrotliB200Available(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n > 0;
+}
+
+void BrotliB200LastStats(double out[10]) { memcpy(out, tls.last, sizeof(tls.last)); }
+
+size_t BrotliEncoderMaxCompressedSize(size_t input_size) {  /* encode.c:1251 */
+  size_t num_large_blocks = input_size >> 14;
+  size_t overhead = 2 + (4 * num_large_blocks) + 3 + 1;
+  size_t result = input_size + overhead;
+  if (input_size == 0) return 2;
+  return (result < input_size) ? 0 : result;
+}
+
+BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode, size_t input_size,
+    const uint8_t* input_buffer, size_t* encoded_size, uint8_t* encoded_buffer) {
+  size_t out_size = *encoded_size;
+  size_t max_out_size = BrotliEncoderMaxCompressedSize(input_size);
+  if (out_size == 0) return BROTLI_FALSE;
+  if (input_size == 0) { *encoded_size = 1; *encoded_buffer = 6; return BROTLI_TRUE; }
+  Params p; p.quality = quality; p.lgwin = lgwin; p.mode = mode;
+  p.size_hint = (uint32_t)input_size;
+  if (lgwin > 24) p.large_window = 1;
+  if (!supported(p)) { *encoded_size = 0; return BROTLI_FALSE; }
+  size_t got = 0;
+  int ok = compress_host(p, (uint32_t)input_size, input_buffer, input_size, encoded_buffer, out_size, &got, nullptr);
+  if (ok && !(max_out_size && got > max_out_size)) { *encoded_size = got; return BROTLI_TRUE; }
+  /* encode.c:1345 fallback */
+  *encoded_size = 0;
+  if (!ok && !BrotliB200Available()) return BROTLI_FALSE;
+  if (!max_out_size) return BROTLI_FALSE;
+  if (out_size >= max_out_size) {
+    *encoded_size = make_uncompressed_stream(input_buffer, input_size, encoded_buffer);
+    return BROTLI_TRUE;
+  }
+  return BROTLI_FALSE;
+}
+
+BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, size_t input_size, const void* d_input,
+                                     size_t* encoded_size, void* d_encoded) {
+  Params p; p.quality = quality; p.lgwin = lgwin;
+  if (!supported(p) || input_size == 0 || input_size > (1u << 30) || !ensure_job()) return BROTLI_FALSE;
+  const uint8_t* d_out = nullptr; size_t sz = 0;
+  if (!br_job_compress_device(tls.job, quality, lgwin, (uint32_t)input_size, (const uint8_t*)d_input,
+                              (uint32_t)input_size, &d_out, &sz)) return BROTLI_FALSE;
+  record_stats();
+  if (sz > *encoded_size) return BROTLI_FALSE;
+  cudaStream_t st = (cudaStream_t)br_job_stream(tls.job);
+  if (cudaMemcpyAsync(d_encoded, d_out, sz, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return BROTLI_FALSE;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return BROTLI_FALSE;
+  *encoded_size = sz;
+  return BROTLI_TRUE;
+}
+
+size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8_t* const* inputs,
+    const size_t* input_sizes, uint8_t* const* outputs, size_t* encoded_sizes, int threads) {
+  if (threads < 1) threads = 1;
+  if ((size_t)threads > count) threads = (int)count;
+  std::vector<size_t> okc((size_t)threads, 0);
+  int dev = 0; cudaGetDevice(&dev);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t)
+    th.emplace_back([&, t] {
+      cudaSetDevice(dev);
+      for (size_t i = (size_t)t; i < count; i += (size_t)threads) {
+        size_t sz = encoded_sizes[i];
+        if (BrotliEncoderCompress(quality, lgwin, BROTLI_MODE_GENERIC, input_sizes[i], inputs[i], &sz, outputs[i])) {
+          encoded_sizes[i] = sz; ++okc[(size_t)t];
+        } else encoded_sizes[i] = 0;
+      }
+    });
+  size_t ok = 0;
+  for (int t = 0; t < threads; ++t) { th[(size_t)t].join(); ok += okc[(size_t)t]; }
+  return ok;
+}
+
+BrotliEncoderState* BrotliEncoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque) {
+  if ((alloc_func == nullptr) != (free_func == nullptr)) return nullptr;   /* encode.h:295 */
+  BrotliEncoderState* s = new (std::nothrow) BrotliEncoderState();
+  if (!s) return nullptr;
+  s->alloc_func = alloc_func; s->free_func = free_func; s->opaque = opaque;
+  return s;
+}
+void BrotliEncoderDestroyInstance(BrotliEncoderState* state) { delete state; }
+
+BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* s, BrotliEncoderParameter p, uint32_t value) {
+  if (s->initialized) return BROTLI_FALSE;   /* encode.c:63 */
+  switch (p) {
+    case BROTLI_PARAM_MODE: s->params.mode = (int)value; return BROTLI_TRUE;
+    case BROTLI_PARAM_QUALITY: s->params.quality = (int)value; return BROTLI_TRUE;
+    case BROTLI_PARAM_LGWIN: s->params.lgwin = (int)value; return BROTLI_TRUE;
+    case BROTLI_PARAM_LGBLOCK: s->params.lgblock = (int)value; return BROTLI_TRUE;
+    case BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING:
+      if (value != 0 && value != 1) return BROTLI_FALSE;
+      s->params.disable_ctx = value; return BROTLI_TRUE;
+    case BROTLI_PARAM_SIZE_HINT: s->params.size_hint = value; return BROTLI_TRUE;
+    case BROTLI_PARAM_LARGE_WINDOW: s->params.large_window = !!value; return BROTLI_TRUE;
+    case BROTLI_PARAM_NPOSTFIX: s->params.npostfix = value; return BROTLI_TRUE;
+    case BROTLI_PARAM_NDIRECT: s->params.ndirect = value; return BROTLI_TRUE;
+    case BROTLI_PARAM_STREAM_OFFSET:
+      if (value > (1u << 30)) return BROTLI_FALSE;
+      s->params.stream_offset = value; return BROTLI_TRUE;
+    case BROTLI_PARAM_BASE64_MODE: s->params.base64 = value & 1; return BROTLI_TRUE;
+    case BROTLI_PARAM_MAX_BASE64_REGIONS: return BROTLI_TRUE;
+    case BROTLI_PARAM_SIMD_HASHER: return value > 2 ? BROTLI_FALSE : BROTLI_TRUE;  /* output-equivalent */
+    default: return BROTLI_FALSE;
+  }
+}
+
+BrotliEncoderPreparedDictionary* BrotliEncoderPrepareDictionary(int, size_t, const uint8_t*, int,
+    brotli_alloc_func, brotli_free_func, void*) { return nullptr; }
+void BrotliEncoderDestroyPreparedDictionary(BrotliEncoderPreparedDictionary*) {}
+BROTLI_BOOL BrotliEncoderAttachPreparedDictionary(BrotliEncoderState*, const BrotliEncoderPreparedDictionary*) {
+  return BROTLI_FALSE;
+}
+
+static void push_output(BrotliEncoderState* s, size_t* available_out, uint8_t** next_out, size_t* total_out) {
+  size_t avail = s->output.size() - s->out_pos;
+  if (avail && *available_out && next_out && *next_out) {
+    size_t c = avail < *available_out ? avail : *available_out;
+    memcpy(*next_out, s->output.data() + s->out_pos, c);
+    *next_out += c; *available_out -= c; s->out_pos += c; s->total_out += c;
+  }
+  if (total_out) *total_out = (size_t)s->total_out;
+}
+
+/* encode.c:1634.  Input is accumulated on the host until FINISH, then the whole stream goes
+   through the GPU pipeline in one piece -- the bytes equal the reference's for the same call
+   sequence (the size hint is frozen when the reference would have
+   frozen it, at its first EncodeData call).  FLUSH and EMIT_METADATA are not implemented yet:
+   they fail instead of silently behaving differently. */
+BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOperation op, size_t* available_in,
+    const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out) {
+  s->initialized = true;
+  if (op == BROTLI_OPERATION_EMIT_METADATA) return BROTLI_FALSE;
+  if (op == BROTLI_OPERATION_FLUSH) {
+    if (*available_in == 0 && s->input.empty()) { push_output(s, available_out, next_out, total_out); return BROTLI_TRUE; }
+    return BROTLI_FALSE;
+  }
+  if (s->compressed && *available_in != 0) return BROTLI_FALSE;   /* input after finish */
+  if (!supported(s->params)) return BROTLI_FALSE;
+  if (*available_in) {
+    s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
+    *next_in += *available_in; *available_in = 0;
+  }
+  if (!s->hint_fixed) {
+    /* encode.c:1619 UpdateSizeHint runs at the first EncodeData: when the first input block
+       (1 << lgblock) is full or the operation is not PROCESS. */
+    size_t lgblock = (s->params.quality >= 9 && s->params.lgwin > 16) ? (s->params.lgwin < 18 ? s->params.lgwin : 18) : 16;
+    if (op != BROTLI_OPERATION_PROCESS || s->input.size() >= ((size_t)1 << lgblock)) {
+      if (s->params.size_hint == 0) {
+        size_t t = s->input.size();
+        s->params.size_hint = t >= (1u << 30) ? (1u << 30) : (uint32_t)t;
+      }
+      s->hint_fixed = true;
+    }
+  }
+  if (op == BROTLI_OPERATION_FINISH && !s->compressed) {
+    if (s->input.empty()) {
+      /* encode.c:1006: empty stream = window bits + ISLAST + ISEMPTY */
+      int lgwin = s->params.lgwin > 24 ? 24 : s->params.lgwin;
+      uint32_t bits = lgwin == 17 ? 1u : (uint32_t)(((lgwin - 17) << 1) | 1), nb = lgwin == 17 ? 7 : 4;
+      bits |= 3u << nb; nb += 2;
+      s->output.assign((nb + 7) / 8, 0);
+      for (uint32_t i = 0; i < (nb + 7) / 8; ++i) s->output[i] = (uint8_t)(bits >> (8 * i));
+    } else {
+      size_t got = 0;
+      if (!compress_host(s->params, s->params.size_hint, s->input.data(), s->input.size(), nullptr, 0, &got, &s->output))
+        return BROTLI_FALSE;
+    }
+    s->compressed = true;
+    std::vector<uint8_t>().swap(s->input);
+  }
+  push_output(s, available_out, next_out, total_out);
+  if (s->compressed && s->out_pos == s->output.size()) s->finished = true;
+  return BROTLI_TRUE;
+}
+
+BROTLI_BOOL BrotliEncoderIsFinished(BrotliEncoderState* s) {
+  return (s->compressed && s->out_pos == s->output.size()) ? BROTLI_TRUE : BROTLI_FALSE;
+}
+BROTLI_BOOL BrotliEncoderHasMoreOutput(BrotliEncoderState* s) {
+  return s->out_pos < s->output.size() ? BROTLI_TRUE : BROTLI_FALSE;
+}
+const uint8_t* BrotliEncoderTakeOutput(BrotliEncoderState* s, size_t* size) {   /* encode.c:1742 */
+  size_t avail = s->output.size() - s->out_pos;
+  size_t consumed = avail;
+  const uint8_t* result = nullptr;
+  if (*size) consumed = *size < avail ? *size : avail;
+  if (consumed) {
+    result = s->output.data() + s->out_pos;
+    s->out_pos += consumed; s->total_out += consumed;
+    *size = consumed;
+  } else {
+    *size = 0;
+  }
+  return result;
+}
+
+}  // extern "C"

@@ -562,8 +562,8 @@ struct BrMbMem {
   u32 cmap[256 * 64];
 };
 // variable part follows: literal split (types, lengths), command split, distance split
-BR_DEV u32 br_align8(u32 x) { return (x + 7u) & ~7u; }
-BR_DEV u32 br_mb_scratch_bytes(u32 nlit, u32 ncmd) {
+BR_HD u32 br_align8(u32 x) { return (x + 7u) & ~7u; }
+BR_HD u32 br_mb_scratch_bytes(u32 nlit, u32 ncmd) {
   u32 lb = nlit / 512 + 2, cb = ncmd / 1024 + 2, db = ncmd / 512 + 2;
   return br_align8((u32)sizeof(BrMbMem)) + br_align8(lb) + lb * 4 + br_align8(cb) + cb * 4 + br_align8(db) + db * 4;
 }

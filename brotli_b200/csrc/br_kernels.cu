@@ -1,0 +1,563 @@
+// br_kernels.cu -- CUDA kernels (sm_100a) and the per-stream pipeline that drives them.
+//
+// Stage map (reference function -> kernel):
+//   hash keys / bucket rings (hash_longest_match64_inc.h Store*)  -> k_hash_keys, k_radix_*, k_rank, k_seg
+//   CreateBackwardReferences + FindLongestMatch                   -> k_walk      (one warp per input block)
+//   EncodeData glue (encode.c:985)                                -> k_chain     (one warp per stream)
+//   BrotliBuildMetaBlockGreedy + BrotliStoreMetaBlock             -> k_encode_mb (one warp per metablock)
+//   metablock concatenation / uncompressed fallback               -> k_assemble_scan, k_assemble_copy
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "br_params.h"
+#include "br_lz77.h"
+#include "br_chain.h"
+#include "br_entropy.h"
+#include "br_pipeline.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "brotli_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  return 0; } } while (0)
+
+// ---------------------------------------------------------------------------- hashing + sort
+__global__ void k_hash_keys(BrParams P, const u8* __restrict__ data, u16* __restrict__ keys) {
+  u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.n) return;
+  u32 hashable = P.n >= P.htl ? P.n - P.htl + 1 : 0;
+  keys[p] = (u16)(p < hashable ? br_hash_key(P, data, p) : P.nbuckets);
+}
+
+#define RADIX_TILE 4096
+// digit histogram of one tile -> hist[d * ntiles + tile]
+template <int SHIFT>
+__global__ void __launch_bounds__(256) k_radix_count(const u16* __restrict__ keys, u32 n, u32* __restrict__ hist, u32 ntiles) {
+  __shared__ u32 cnt[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  u32 base = blockIdx.x * RADIX_TILE;
+  for (u32 i = threadIdx.x; i < RADIX_TILE; i += 256) {
+    u32 j = base + i;
+    if (j < n) atomicAdd(&cnt[(keys[j] >> SHIFT) & 0xFF], 1u);
+  }
+  __syncthreads();
+  hist[threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
+}
+// stable scatter: warp w of the CTA owns elements [w*512, w*512+512) of the tile, row by row
+template <int SHIFT, bool HAS_VALS>
+__global__ void __launch_bounds__(256) k_radix_scatter(const u16* __restrict__ keys, const u32* __restrict__ vals, u32 n,
+    const u32* __restrict__ hist_scanned, u32 ntiles, u16* __restrict__ out_keys, u32* __restrict__ out_vals) {
+  __shared__ u32 wcnt[8][256];
+  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (u32 i = threadIdx.x; i < 8 * 256; i += 256) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const u32 wbase = blockIdx.x * RADIX_TILE + warp * 512;
+  for (u32 r = 0; r < 16; ++r) {
+    u32 j = wbase + r * 32 + lane;
+    u32 d = j < n ? ((keys[j] >> SHIFT) & 0xFFu) : 0xFFFFFFFFu;
+    u32 m = __match_any_sync(0xffffffffu, d);
+    if (d != 0xFFFFFFFFu && (m & ((1u << lane) - 1)) == 0) wcnt[warp][d] += __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    u32 d = threadIdx.x;
+    u32 running = hist_scanned[d * ntiles + blockIdx.x];
+    for (u32 w = 0; w < 8; ++w) { u32 t = wcnt[w][d]; wcnt[w][d] = running; running += t; }
+  }
+  __syncthreads();
+  for (u32 r = 0; r < 16; ++r) {
+    u32 j = wbase + r * 32 + lane;
+    u32 k = j < n ? keys[j] : 0;
+    u32 d = j < n ? ((k >> SHIFT) & 0xFFu) : 0xFFFFFFFFu;
+    u32 m = __match_any_sync(0xffffffffu, d);
+    u32 rank = __popc(m & ((1u << lane) - 1));
+    if (j < n) {
+      u32 dst = wcnt[warp][d] + rank;
+      out_keys[dst] = (u16)k;
+      out_vals[dst] = HAS_VALS ? vals[j] : j;
+    }
+    __syncwarp();
+    if (d != 0xFFFFFFFFu && rank == 0) wcnt[warp][d] += __popc(m);
+    __syncwarp();
+  }
+}
+__global__ void k_rank(const u32* __restrict__ S, u32 n, u32* __restrict__ rank) {
+  u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) rank[S[j]] = j;
+}
+// seg[k] = first index in S whose key is >= k, for k in [0, nbuckets + 1]
+__global__ void k_seg(const u16* __restrict__ sorted_keys, u32 n, u32 nbuckets, u32* __restrict__ seg) {
+  u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n) return;
+  int k0 = j == 0 ? -1 : (int)sorted_keys[j - 1];
+  int k1 = j == n ? (int)nbuckets + 1 : (int)sorted_keys[j];
+  for (int k = k0 + 1; k <= k1; ++k) seg[k] = j;
+}
+
+// ---------------------------------------------------------------------------- exclusive scan
+#define SCAN_CHUNK 2048
+__global__ void __launch_bounds__(256) k_scan_chunks(u32* __restrict__ a, u32 n, u32* __restrict__ sums) {
+  __shared__ u32 part[256];
+  u32 base = blockIdx.x * SCAN_CHUNK + threadIdx.x * 8;
+  u32 v[8], acc = 0;
+  for (int i = 0; i < 8; ++i) { v[i] = base + i < n ? a[base + i] : 0; acc += v[i]; }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    u32 t = threadIdx.x >= (u32)o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += t;
+    __syncthreads();
+  }
+  u32 run = part[threadIdx.x] - acc;
+  for (int i = 0; i < 8; ++i) { if (base + i < n) a[base + i] = run; run += v[i]; }
+  if (threadIdx.x == 255) sums[blockIdx.x] = part[255];
+}
+__global__ void k_scan_add(u32* __restrict__ a, u32 n, const u32* __restrict__ sums) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += sums[i / SCAN_CHUNK];
+}
+// in-place exclusive scan of a[0..n); tmp must hold >= n/SCAN_CHUNK + n/SCAN_CHUNK^2 + 8 words
+static void scan_exclusive(u32* a, u32 n, u32* tmp, cudaStream_t st) {
+  if (n == 0) return;
+  u32 chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  k_scan_chunks<<<chunks, 256, 0, st>>>(a, n, tmp);
+  if (chunks > 1) {
+    scan_exclusive(tmp, chunks, tmp + chunks, st);
+    k_scan_add<<<(n + 255) / 256, 256, 0, st>>>(a, n, tmp);
+  }
+}
+
+// ---------------------------------------------------------------------------- stored bits
+// Initial speculation: every hashable position of a block is stored (true for > 99.8 % of
+// text positions).
+__global__ void k_init_bits(BrStream s) {
+  u32 wi = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 nwords = (s.P.n + 31) / 32;
+  if (wi >= nwords) return;
+  u32 bs = 1u << s.P.lgblock, v = 0;
+  for (u32 b = 0; b < 32; ++b) {
+    u32 p = wi * 32 + b;
+    if (p >= s.P.n) break;
+    u32 blk_end = (p / bs + 1) * bs; if (blk_end > s.P.n) blk_end = s.P.n;   // uniform blocks (one-shot)
+    if (p + s.P.htl <= blk_end) v |= 1u << b;
+  }
+  s.bits_latest[wi] = v;
+}
+// bits_latest permuted into S order + per-1024 popcounts
+__global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restrict__ storedS, u32* __restrict__ blockcnt) {
+  __shared__ u32 wsum[32];
+  u32 j = blockIdx.x * 1024 + threadIdx.x;
+  int bit = 0;
+  if (j < s.P.n) { u32 q = s.S[j]; bit = (s.bits_latest[q >> 5] >> (q & 31)) & 1; }
+  u32 m = __ballot_sync(0xffffffffu, bit);
+  if ((threadIdx.x & 31) == 0) { storedS[j >> 5] = m; wsum[threadIdx.x >> 5] = __popc(m); }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u32 v = wsum[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------- warp-task kernels
+__global__ void k_walk(BrStream s, const u32* __restrict__ list, u32 count, u32 words_per_warp) {
+  extern __shared__ u32 sm[];
+  u32 warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  u32 t = blockIdx.x * wpb + warp;
+  if (t >= count) return;
+  br_walk_block(s, list[t], sm + warp * words_per_warp);
+}
+__global__ void k_commit(BrStream s, const u32* __restrict__ list, u32 count) {
+  u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= count) return;
+  br_commit_bits(s, list[t]);
+}
+__global__ void k_chain(BrStream s, u32* dirty_list, u32* block_mb) {
+  br_chain(s);
+  __threadfence_block();
+  __syncwarp();
+  // compact the dirty flags into a work list; map blocks to metablocks
+  u32 lane = threadIdx.x, cnt = 0;
+  for (u32 base = 0; base < s.P.nblocks; base += 32) {
+    u32 k = base + lane;
+    bool d = k < s.P.nblocks && s.dirty[k] != 0;
+    u32 m = __ballot_sync(0xffffffffu, d);
+    if (d) dirty_list[cnt + __popc(m & ((1u << lane) - 1))] = k;
+    cnt += __popc(m);
+  }
+  __syncwarp();
+  u32 nm = s.counters[1];
+  for (u32 i = 0; i < nm; ++i)
+    for (u32 k = s.mbs[i].first_block + lane; k <= s.mbs[i].last_block; k += 32) block_mb[k] = i;
+}
+__global__ void k_compact(BrStream s, BrCmd* cmds_all, const u32* __restrict__ block_mb) {
+  u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= s.P.nblocks) return;
+  br_compact_block(s, t, cmds_all, block_mb);
+}
+__global__ void __launch_bounds__(32) k_encode_mb(BrStream s, const BrCmd* __restrict__ cmds_all, u8* scratch,
+    const u64* __restrict__ scratch_off, u32* outbits, const u64* __restrict__ out_off /* in u32 words */) {
+  __shared__ u32 sm[4096];
+  u32 i = blockIdx.x;
+  BrMetaBlock mb = s.mbs[i];
+  if (!mb.compress) return;
+  u32 bits = br_encode_metablock(s, mb, cmds_all, scratch + scratch_off[i], outbits + out_off[i], sm);
+  if (threadIdx.x == 0) s.mbs[i].out_bits = bits;
+}
+
+// ---------------------------------------------------------------------------- stream assembly
+struct BrCopyDesc { u64 dst_bit; u64 src_off; u32 nbits; u32 kind; };  // kind 0: bit copy from outbits, 1: raw bytes from input
+// res[0..1]: total bytes (u64), res[2]: first metablock that needs the late fallback (+1), 0 if none
+__global__ void k_assemble_scan(BrStream s, const u64* __restrict__ out_off, u32* out, BrCopyDesc* desc, u32* res) {
+  if (threadIdx.x != 0) return;
+  u64 bit = 0;
+  const int lgwin = s.P.lgwin;
+  if (lgwin == 17) { br_put_bits_at(out, 0, 7, 1); bit = 7; }
+  else { br_put_bits_at(out, 0, 4, (u64)(((lgwin - 17) << 1) | 1)); bit = 4; }
+  u32 nm = s.counters[1], fallback = 0;
+  for (u32 i = 0; i < nm; ++i) {
+    BrMetaBlock mb = s.mbs[i];
+    u32 bytes = mb.end - mb.start;
+    BrCopyDesc d;
+    if (mb.compress) {
+      u64 storage_ix = (bit & 7) + mb.out_bits;
+      if (mb.is_last) storage_ix = (storage_ix + 7) & ~7ull;
+      if ((u64)bytes + 4 < (storage_ix >> 3)) { if (!fallback) fallback = i + 1; }   // encode.c:604
+      d.dst_bit = bit; d.src_off = out_off[i]; d.nbits = mb.out_bits; d.kind = 0;
+      bit += mb.out_bits;
+      if (mb.is_last) bit = (bit + 7) & ~7ull;
+    } else {
+      // brotli_bit_stream.c:1321 BrotliStoreUncompressedMetaBlock
+      u32* w32 = out + (bit >> 5); u32 sh = (u32)(bit & 31);   // write relative to a word base to keep ix in 32 bits
+      u32 ix = sh;
+      br_put_bits_at(w32, ix, 1, 0); ix += 1;
+      { u32 lg = bytes == 1 ? 1 : br_log2floor(bytes - 1) + 1; u32 mn = (lg < 16 ? 16 : (lg + 3)) / 4;
+        br_put_bits_at(w32, ix, 2, mn - 4); ix += 2; br_put_bits_at(w32, ix, mn * 4, bytes - 1); ix += mn * 4; }
+      br_put_bits_at(w32, ix, 1, 1); ix += 1;
+      bit += ix - sh;
+      bit = (bit + 7) & ~7ull;
+      d.dst_bit = bit; d.src_off = mb.start; d.nbits = bytes; d.kind = 1;
+      bit += (u64)bytes * 8;
+      if (mb.is_last) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 2, 3); bit += 2; bit = (bit + 7) & ~7ull; }
+    }
+    desc[i] = d;
+  }
+  u64 total = (bit + 7) >> 3;
+  res[0] = (u32)total; res[1] = (u32)(total >> 32); res[2] = fallback;
+}
+// grid.y = metablock, grid.x strides over its words / bytes
+__global__ void k_assemble_copy(BrStream s, const BrCopyDesc* __restrict__ desc, const u32* __restrict__ outbits, u32* out) {
+  const BrCopyDesc d = desc[blockIdx.y];
+  if (d.kind == 0) {
+    u32 nwords = (d.nbits + 31) / 32;
+    const u32* src = outbits + d.src_off;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) {
+      u32 nb = (i + 1) * 32 <= d.nbits ? 32 : d.nbits - i * 32;
+      u32 v = src[i];
+      if (nb < 32) v &= (1u << nb) - 1;
+      u64 db = d.dst_bit + (u64)i * 32;
+      br_put_bits_at(out + (db >> 5), (u32)(db & 31), nb, v);
+    }
+  } else {
+    // raw bytes: destination is byte aligned; go through 32-bit words of the destination
+    u64 dst_byte = d.dst_bit >> 3;
+    u32 nbytes = d.nbits;
+    u64 first_word = dst_byte >> 2, last_word = (dst_byte + nbytes - 1) >> 2;
+    u32 nw = (u32)(last_word - first_word + 1);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) {
+      u64 wbyte = (first_word + i) << 2;
+      u32 v = 0;
+      for (u32 b = 0; b < 4; ++b) {
+        u64 ob = wbyte + b;
+        if (ob >= dst_byte && ob < dst_byte + nbytes) v |= (u32)s.data[d.src_off + (ob - dst_byte)] << (8 * b);
+      }
+      if (v) atomicOr(out + first_word + i, v);
+    }
+  }
+}
+
+// ============================================================================ host pipeline
+struct BrDeviceTables {
+  int device = -1;
+  u8* blob = nullptr;       // brotli_tables.bin on the device
+  double* log2tab = nullptr;
+  u32 log2tab_n = 0;
+};
+static BrDeviceTables g_tables[16];
+
+extern "C" const unsigned char br_tables_blob[];
+extern "C" const unsigned int br_tables_blob_len;
+extern "C" const double* br_host_log2_table(u32* n);   // br_host.cc
+
+static BrDeviceTables* get_tables() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  BrDeviceTables& t = g_tables[dev];
+  if (t.device == dev) return &t;
+  if (cudaMalloc(&t.blob, br_tables_blob_len) != cudaSuccess) return nullptr;
+  cudaMemcpy(t.blob, br_tables_blob, br_tables_blob_len, cudaMemcpyHostToDevice);
+  u32 n = 0; const double* h = br_host_log2_table(&n);
+  if (cudaMalloc(&t.log2tab, (size_t)n * 8) != cudaSuccess) return nullptr;
+  cudaMemcpy(t.log2tab, h, (size_t)n * 8, cudaMemcpyHostToDevice);
+  t.log2tab_n = n;
+  t.device = dev;
+  return &t;
+}
+
+// Grow-only device arena owned by a job; all per-stream arrays are carved out of it.
+struct BrArena {
+  u8* base = nullptr; size_t cap = 0, used = 0;
+  bool reserve(size_t bytes) {
+    if (bytes <= cap) { used = 0; return true; }
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0;
+    if (cudaMalloc(&base, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = bytes; used = 0; return true;
+  }
+  template <class T> T* take(size_t count) {
+    size_t off = (used + 255) & ~(size_t)255;
+    used = off + count * sizeof(T);
+    if (used > cap) return nullptr;
+    return (T*)(base + off);
+  }
+  void release() { if (base) cudaFree(base); base = nullptr; cap = 0; }
+};
+
+struct BrJob {
+  cudaStream_t st = nullptr;
+  BrArena arena, arena2;     // arena2: metablock scratch / bit buffers / output (sized after LZ77)
+  u32* h_pinned = nullptr;    // small pinned readback area
+  BrJobStats stats;
+};
+
+extern "C" BrJob* br_job_create(void) {
+  BrJob* j = new BrJob();
+  if (cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking) != cudaSuccess) { delete j; return nullptr; }
+  if (cudaMallocHost(&j->h_pinned, 4096) != cudaSuccess) { cudaStreamDestroy(j->st); delete j; return nullptr; }
+  return j;
+}
+extern "C" void br_job_destroy(BrJob* j) {
+  if (!j) return;
+  j->arena.release(); j->arena2.release();
+  if (j->h_pinned) cudaFreeHost(j->h_pinned);
+  if (j->st) cudaStreamDestroy(j->st);
+  delete j;
+}
+extern "C" const BrJobStats* br_job_stats(const BrJob* j) { return &j->stats; }
+extern "C" void* br_job_stream(BrJob* j) { return (void*)j->st; }
+
+static size_t scan_tmp_words(size_t n) { return n / SCAN_CHUNK + n / SCAN_CHUNK / SCAN_CHUNK + 64; }
+
+// Compress one stream whose input already sits in device memory (d_in, n bytes).  The
+// compressed bytes are left in device memory (*d_out, *out_size; valid until the next call on
+// this job).  Returns 1 on success, 0 on failure (unsupported parameters, CUDA error).
+extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 size_hint,
+                                      const u8* d_in, u32 n, const u8** d_out, size_t* out_size) {
+  BrDeviceTables* T = get_tables();
+  if (!T || n == 0) return 0;
+  BrStream s; memset(&s, 0, sizeof(s));
+  if (!br_derive_params(quality, lgwin, size_hint, n, &s.P)) return 0;
+  BrParams& P = s.P;
+  const u32 bs = 1u << P.lgblock, nb = (n + bs - 1) / bs;
+  P.nblocks = nb;
+  cudaStream_t st = job->st;
+  memset(&job->stats, 0, sizeof(job->stats));
+  cudaEvent_t ev[6];
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], st);
+
+  const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
+  const size_t nwords = (size_t)(n + 31) / 32 + 2;
+  const u32 cmd_stride = bs / 2 + 2;
+  size_t need = 0;
+  auto add = [&](size_t bytes) { need += (bytes + 255) & ~(size_t)255; };
+  add((size_t)n + 64); add(2ull * n + 4); add(2ull * n + 4); add(4ull * n); add(2ull * n + 4); add(4ull * n); add(4ull * n);
+  add(256ull * ntiles * 4); add(scan_tmp_words(256ull * ntiles) * 4);
+  add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
+  add(scan_tmp_words((size_t)n / 1024 + 8) * 4);
+  add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
+  for (int i = 0; i < 8; ++i) add(nb * 4ull + 64);
+  add(BR_MAX_EPOCHS * 8 + 64); add((nb + 1) * sizeof(BrMetaBlock)); add(4096);
+  need += 1 << 20;
+  if (!job->arena.reserve(need)) return 0;
+  BrArena& A = job->arena;
+  u8* data = A.take<u8>((size_t)n + 64);
+  u16* keys = A.take<u16>((size_t)n + 2); u16* K1 = A.take<u16>((size_t)n + 2); u32* V1 = A.take<u32>(n);
+  u16* K2 = A.take<u16>((size_t)n + 2); u32* S = A.take<u32>(n); u32* rank = A.take<u32>(n);
+  u32* hist = A.take<u32>(256ull * ntiles); u32* scan_tmp = A.take<u32>(scan_tmp_words(256ull * ntiles));
+  u32* seg = A.take<u32>(P.nbuckets + 4);
+  u32* bits_latest = A.take<u32>(nwords); u32* bits_cur = A.take<u32>(nwords);
+  u32* storedS = A.take<u32>(nwords + 64); u32* prefS = A.take<u32>((size_t)n / 1024 + 8);
+  u32* scan_tmp2 = A.take<u32>(scan_tmp_words((size_t)n / 1024 + 8));
+  BrBlockIn* bin = A.take<BrBlockIn>(nb); BrBlockIn* bin_used = A.take<BrBlockIn>(nb);
+  BrBlockOut* bout = A.take<BrBlockOut>(nb);
+  BrCmd* cmd_blocks = A.take<BrCmd>((size_t)nb * cmd_stride);
+  u32* dirty = A.take<u32>(nb + 16); u32* changed_bits = A.take<u32>(nb + 16);
+  int* changed_epoch = A.take<int>(nb + 16); u32* ext_total = A.take<u32>(nb + 16);
+  u32* cmd_off = A.take<u32>(nb + 16); u32* force_unc = A.take<u32>(nb + 16);
+  u32* dirty_list = A.take<u32>(nb + 16); u32* block_mb = A.take<u32>(nb + 16);
+  u32* epoch_changed = A.take<u32>(BR_MAX_EPOCHS); u32* epoch_suffix = A.take<u32>(BR_MAX_EPOCHS + 1);
+  BrMetaBlock* mbs = A.take<BrMetaBlock>(nb + 1);
+  u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256);
+  if (!hist_scratch) return 0;
+
+  CK(cudaMemcpyAsync(data, d_in, n, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(data + n, 0, 64, st));
+  s.data = data; s.S = S; s.rank = rank; s.seg = seg; s.bits_latest = bits_latest; s.bits_cur = bits_cur;
+  s.storedS = storedS; s.prefS = prefS; s.bin = bin; s.bin_used = bin_used; s.bout = bout;
+  s.cmd_blocks = cmd_blocks; s.cmd_stride = cmd_stride; s.dirty = dirty; s.changed_bits = changed_bits;
+  s.changed_epoch = changed_epoch; s.epoch_changed = epoch_changed; s.epoch_suffix = epoch_suffix;
+  s.ext_total = ext_total; s.cmd_off = cmd_off; s.mbs = mbs; s.force_unc = force_unc;
+  s.counters = counters; s.hist_scratch = hist_scratch;
+  { const u8* p = T->blob + 8;
+    s.dict_size_bits = p; p += 32; s.dict_offsets = (const u32*)p; p += 128; s.dict = p; p += 122784;
+    s.dict_hash_words = (const u16*)p; p += 65536; s.dict_hash_lengths = p; p += 32768; s.ctx_lut = p; }
+  s.log2tab = T->log2tab; s.log2tab_n = T->log2tab_n;
+
+  // block table (one-shot: uniform blocks) + zeroed state
+  {
+    std::vector<BrBlockIn> hb(nb);
+    memset(hb.data(), 0, nb * sizeof(BrBlockIn));
+    for (u32 k = 0; k < nb; ++k) {
+      hb[k].pos = k * bs; hb[k].end = (u64)(k + 1) * bs < n ? (k + 1) * bs : n;
+      hb[k].is_last = (k + 1 == nb);
+    }
+    CK(cudaMemcpyAsync(bin, hb.data(), nb * sizeof(BrBlockIn), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  CK(cudaMemsetAsync(bout, 0, nb * sizeof(BrBlockOut), st));
+  CK(cudaMemsetAsync(bin_used, 0, nb * sizeof(BrBlockIn), st));
+  CK(cudaMemsetAsync(changed_bits, 0, (nb + 16) * 4, st));
+  CK(cudaMemsetAsync(changed_epoch, 0xFF, (nb + 16) * 4, st));
+  CK(cudaMemsetAsync(force_unc, 0, (nb + 16) * 4, st));
+  CK(cudaMemsetAsync(epoch_changed, 0, BR_MAX_EPOCHS * 4, st));
+  CK(cudaMemsetAsync(counters, 0, 256, st));
+  CK(cudaMemsetAsync(bits_cur, 0, nwords * 4, st));
+
+  // ---- position index: S, rank, seg
+  k_hash_keys<<<(n + 255) / 256, 256, 0, st>>>(P, data, keys);
+  k_radix_count<0><<<ntiles, 256, 0, st>>>(keys, n, hist, ntiles);
+  scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
+  k_radix_scatter<0, false><<<ntiles, 256, 0, st>>>(keys, nullptr, n, hist, ntiles, K1, V1);
+  k_radix_count<8><<<ntiles, 256, 0, st>>>(K1, n, hist, ntiles);
+  scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
+  k_radix_scatter<8, true><<<ntiles, 256, 0, st>>>(K1, V1, n, hist, ntiles, K2, S);
+  k_rank<<<(n + 255) / 256, 256, 0, st>>>(S, n, rank);
+  k_seg<<<(n + 1 + 255) / 256, 256, 0, st>>>(K2, n, P.nbuckets, seg);
+  k_init_bits<<<(u32)((nwords + 255) / 256), 256, 0, st>>>(s);
+  cudaEventRecord(ev[1], st);
+
+  // ---- LZ77 fixpoint
+  const u32 own_words = bs / 32 + 2;
+  const u32 wpb = P.lgblock <= 16 ? 4 : 2;
+  const size_t walk_smem = (size_t)wpb * own_words * 4;
+  CK(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+  u32* hp = job->h_pinned;
+  u32 n_mbs = 0, total_cmds = 0;
+  int rounds = 0;
+  const u8* final_out = nullptr; size_t final_size = 0;
+  for (;;) {   // rounds: repeated only when a metablock needs the late uncompressed fallback
+    ++rounds;
+    for (;;) {
+      k_chain<<<1, 32, 0, st>>>(s, dirty_list, block_mb);
+      CK(cudaMemcpyAsync(hp, counters, 32, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      u32 n_dirty = hp[0]; n_mbs = hp[1]; total_cmds = hp[2];
+      if (n_dirty == 0) break;
+      if (s.epoch + 2 >= BR_MAX_EPOCHS) { fprintf(stderr, "brotli_b200: LZ77 fixpoint did not converge\n"); return 0; }
+      ++s.epoch; ++job->stats.lz77_iterations; job->stats.block_runs += n_dirty;
+      k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
+      scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
+      k_walk<<<(n_dirty + wpb - 1) / wpb, wpb * 32, walk_smem, st>>>(s, dirty_list, n_dirty, own_words);
+      k_commit<<<(n_dirty * 32 + 127) / 128, 128, 0, st>>>(s, dirty_list, n_dirty);
+    }
+    cudaEventRecord(ev[2], st);
+    // ---- entropy stage
+    std::vector<BrMetaBlock> hm(n_mbs);
+    CK(cudaMemcpyAsync(hm.data(), mbs, n_mbs * sizeof(BrMetaBlock), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<u64> h_soff(n_mbs), h_ooff(n_mbs);
+    size_t scratch_total = 0, outw_total = 0;
+    for (u32 i = 0; i < n_mbs; ++i) {
+      h_soff[i] = scratch_total; h_ooff[i] = outw_total;
+      if (hm[i].compress) {
+        scratch_total += ((size_t)br_mb_scratch_bytes(hm[i].nlit, hm[i].ncmd) + 255) & ~(size_t)255;
+        outw_total += (2 * (size_t)(hm[i].end - hm[i].start) + 503) / 4 + 16;
+      }
+    }
+    size_t out_cap = (size_t)n + ((size_t)n >> 3) + 4096 + 8ull * n_mbs;
+    size_t need2 = scratch_total + outw_total * 4 + out_cap + (size_t)total_cmds * sizeof(BrCmd) +
+                   n_mbs * (16 + sizeof(BrCopyDesc)) + (1 << 16);
+    if (!job->arena2.reserve(need2)) return 0;
+    BrArena& B = job->arena2;
+    u8* scratch = B.take<u8>(scratch_total + 256); u32* outbits = B.take<u32>(outw_total + 64);
+    u32* out = B.take<u32>(out_cap / 4 + 16); BrCmd* cmds_all = B.take<BrCmd>((size_t)total_cmds + 1);
+    u64* d_soff = B.take<u64>(n_mbs); u64* d_ooff = B.take<u64>(n_mbs);
+    BrCopyDesc* desc = B.take<BrCopyDesc>(n_mbs); u32* res = B.take<u32>(16);
+    if (!res) return 0;
+    CK(cudaMemcpyAsync(d_soff, h_soff.data(), n_mbs * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ooff, h_ooff.data(), n_mbs * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(outbits, 0, (outw_total + 64) * 4, st));
+    CK(cudaMemsetAsync(out, 0, out_cap + 64, st));
+    k_compact<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s, cmds_all, block_mb);
+    k_encode_mb<<<n_mbs, 32, 0, st>>>(s, cmds_all, scratch, d_soff, outbits, d_ooff);
+    cudaEventRecord(ev[3], st);
+    k_assemble_scan<<<1, 32, 0, st>>>(s, d_ooff, out, desc, res);
+    CK(cudaMemcpyAsync(hp + 16, res, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hp[18]) {   // encode.c:604: the coded metablock is larger than the input -> store it raw and
+                    // redo the parse behind it with the restored distance cache
+      u32 idx = hp[18] - 1, one = 1;
+      CK(cudaMemcpyAsync(force_unc + idx, &one, 4, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      if (rounds > 256) return 0;
+      continue;
+    }
+    k_assemble_copy<<<dim3(64, n_mbs), 256, 0, st>>>(s, desc, outbits, out);
+    final_out = (const u8*)out; final_size = ((u64)hp[17] << 32) | hp[16];
+    break;
+  }
+  cudaEventRecord(ev[4], st);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  float ms;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]); job->stats.ms_index = ms;
+  cudaEventElapsedTime(&ms, ev[1], ev[2]); job->stats.ms_lz77 = ms;
+  cudaEventElapsedTime(&ms, ev[2], ev[3]); job->stats.ms_entropy = ms;
+  cudaEventElapsedTime(&ms, ev[3], ev[4]); job->stats.ms_assemble = ms;
+  cudaEventElapsedTime(&ms, ev[0], ev[4]); job->stats.ms_total = ms;
+  for (auto& e : ev) cudaEventDestroy(e);
+  job->stats.nblocks = nb; job->stats.n_metablocks = n_mbs; job->stats.rounds = (u32)rounds;
+  job->stats.out_bytes = final_size; job->stats.in_bytes = n;
+  *d_out = final_out; *out_size = final_size;
+  return 1;
+}
+
+// Debug / test hook: copies the position index of the last job to the host.
+extern "C" __attribute__((visibility("default"))) int br_debug_sort(int quality, int lgwin, const u8* h_in, u32 n, u32* h_S, u32* h_seg) {
+  BrParams P;
+  if (!br_derive_params(quality, lgwin, n, n, &P)) return 0;
+  u8* data; u16 *keys, *K1, *K2; u32 *V1, *S, *hist, *tmp, *seg;
+  const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
+  CK(cudaMalloc(&data, (size_t)n + 64)); CK(cudaMemset(data, 0, (size_t)n + 64));
+  CK(cudaMemcpy(data, h_in, n, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&keys, 2ull * n + 4)); CK(cudaMalloc(&K1, 2ull * n + 4)); CK(cudaMalloc(&K2, 2ull * n + 4));
+  CK(cudaMalloc(&V1, 4ull * n)); CK(cudaMalloc(&S, 4ull * n)); CK(cudaMalloc(&hist, 1024ull * ntiles));
+  CK(cudaMalloc(&tmp, scan_tmp_words(256ull * ntiles) * 4)); CK(cudaMalloc(&seg, (P.nbuckets + 4) * 4));
+  k_hash_keys<<<(n + 255) / 256, 256>>>(P, data, keys);
+  k_radix_count<0><<<ntiles, 256>>>(keys, n, hist, ntiles);
+  scan_exclusive(hist, 256 * ntiles, tmp, 0);
+  k_radix_scatter<0, false><<<ntiles, 256>>>(keys, nullptr, n, hist, ntiles, K1, V1);
+  k_radix_count<8><<<ntiles, 256>>>(K1, n, hist, ntiles);
+  scan_exclusive(hist, 256 * ntiles, tmp, 0);
+  k_radix_scatter<8, true><<<ntiles, 256>>>(K1, V1, n, hist, ntiles, K2, S);
+  k_seg<<<(n + 1 + 255) / 256, 256>>>(K2, n, P.nbuckets, seg);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h_S, S, 4ull * n, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_seg, seg, (P.nbuckets + 2) * 4ull, cudaMemcpyDeviceToHost));
+  cudaFree(data); cudaFree(keys); cudaFree(K1); cudaFree(K2); cudaFree(V1); cudaFree(S); cudaFree(hist); cudaFree(tmp); cudaFree(seg);
+  return 1;
+}

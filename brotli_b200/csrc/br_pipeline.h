@@ -1,0 +1,19 @@
+// br_pipeline.h -- host-visible interface of the per-stream GPU pipeline (br_kernels.cu).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+struct BrJob;
+struct BrJobStats {
+  float ms_total, ms_index, ms_lz77, ms_entropy, ms_assemble;
+  uint32_t lz77_iterations, nblocks, n_metablocks, rounds, launches;
+  uint64_t block_runs, in_bytes, out_bytes;
+};
+extern "C" {
+BrJob* br_job_create(void);
+void br_job_destroy(BrJob*);
+const BrJobStats* br_job_stats(const BrJob*);
+void* br_job_stream(BrJob*);
+int br_job_compress_device(BrJob* job, int quality, int lgwin, uint32_t size_hint,
+                           const uint8_t* d_in, uint32_t n, const uint8_t** d_out, size_t* out_size);
+int br_debug_sort(int quality, int lgwin, const uint8_t* h_in, uint32_t n, uint32_t* h_S, uint32_t* h_seg);
+}
