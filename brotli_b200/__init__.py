@@ -66,10 +66,11 @@ def available():
 
 def last_stats():
     """Timings of the calling thread's last compress call (ms) and pipeline counters."""
-    a = (C.c_double * 10)()
+    a = (C.c_double * 16)()
     lib().BrotliB200LastStats(a)
     keys = ["ms_total", "ms_index", "ms_lz77", "ms_entropy", "ms_assemble", "lz77_iterations",
-            "block_runs", "blocks", "metablocks", "launches"]
+            "block_runs", "blocks", "metablocks", "launches", "ms_walk", "ms_encode", "walk_launches",
+            "encode_launches", "walk_bytes", "total_cmds"]
     return dict(zip(keys, list(a)))
 
 

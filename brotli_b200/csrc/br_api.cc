@@ -17,7 +17,7 @@ namespace {
 struct TlsJob {
   BrJob* job = nullptr;
   uint8_t* d_in = nullptr; size_t d_in_cap = 0;
-  double last[10] = {0};
+  double last[16] = {0};
   ~TlsJob() { if (d_in) cudaFree(d_in); if (job) br_job_destroy(job); }
 };
 thread_local TlsJob tls;
@@ -40,6 +40,8 @@ void record_stats() {
   tls.last[0] = s->ms_total; tls.last[1] = s->ms_index; tls.last[2] = s->ms_lz77; tls.last[3] = s->ms_entropy;
   tls.last[4] = s->ms_assemble; tls.last[5] = s->lz77_iterations; tls.last[6] = (double)s->block_runs;
   tls.last[7] = s->nblocks; tls.last[8] = s->n_metablocks; tls.last[9] = s->launches;
+  tls.last[10] = s->ms_walk; tls.last[11] = s->ms_encode; tls.last[12] = s->walk_launches;
+  tls.last[13] = s->encode_launches; tls.last[14] = (double)s->walk_bytes; tls.last[15] = (double)s->total_cmds;
 }
 
 struct Params {
@@ -129,7 +131,7 @@ int BrotliB200Available(void) {
   return n > 0;
 }
 
-void BrotliB200LastStats(double out[10]) { memcpy(out, tls.last, sizeof(tls.last)); }
+void BrotliB200LastStats(double out[16]) { memcpy(out, tls.last, sizeof(tls.last)); }
 
 size_t BrotliEncoderMaxCompressedSize(size_t input_size) {  /* encode.c:1251 */
   size_t num_large_blocks = input_size >> 14;
@@ -152,9 +154,9 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
   size_t got = 0;
   int ok = compress_host(p, (uint32_t)input_size, input_buffer, input_size, encoded_buffer, out_size, &got, nullptr);
   if (ok && !(max_out_size && got > max_out_size)) { *encoded_size = got; return BROTLI_TRUE; }
-  /* encode.c:1345 fallback */
   *encoded_size = 0;
-  if (!ok && !BrotliB200Available()) return BROTLI_FALSE;
+  if (!ok) return BROTLI_FALSE;   /* GPU path failed: fail loudly, never substitute other bytes */
+  /* encode.c:1345: result larger than BrotliEncoderMaxCompressedSize -> raw stream */
   if (!max_out_size) return BROTLI_FALSE;
   if (out_size >= max_out_size) {
     *encoded_size = make_uncompressed_stream(input_buffer, input_size, encoded_buffer);

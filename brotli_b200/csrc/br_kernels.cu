@@ -365,7 +365,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   P.nblocks = nb;
   cudaStream_t st = job->st;
   memset(&job->stats, 0, sizeof(job->stats));
-  cudaEvent_t ev[6];
+  cudaEvent_t ev[10];
   for (auto& e : ev) cudaEventCreate(&e);
   cudaEventRecord(ev[0], st);
 
@@ -458,6 +458,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   u32* hp = job->h_pinned;
   u32 n_mbs = 0, total_cmds = 0;
   int rounds = 0;
+  bool walk_pending = false;
   const u8* final_out = nullptr; size_t final_size = 0;
   for (;;) {   // rounds: repeated only when a metablock needs the late uncompressed fallback
     ++rounds;
@@ -466,12 +467,17 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       CK(cudaMemcpyAsync(hp, counters, 32, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       u32 n_dirty = hp[0]; n_mbs = hp[1]; total_cmds = hp[2];
+      if (walk_pending) { float wms; cudaEventElapsedTime(&wms, ev[6], ev[7]); job->stats.ms_walk += wms; walk_pending = false; }
       if (n_dirty == 0) break;
       if (s.epoch + 2 >= BR_MAX_EPOCHS) { fprintf(stderr, "brotli_b200: LZ77 fixpoint did not converge\n"); return 0; }
       ++s.epoch; ++job->stats.lz77_iterations; job->stats.block_runs += n_dirty;
       k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
       scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
+      cudaEventRecord(ev[6], st);
       k_walk<<<(n_dirty + wpb - 1) / wpb, wpb * 32, walk_smem, st>>>(s, dirty_list, n_dirty, own_words);
+      cudaEventRecord(ev[7], st);
+      walk_pending = true; ++job->stats.walk_launches; job->stats.launches += 6;
+      job->stats.walk_bytes += (u64)n_dirty * bs;
       k_commit<<<(n_dirty * 32 + 127) / 128, 128, 0, st>>>(s, dirty_list, n_dirty);
     }
     cudaEventRecord(ev[2], st);
@@ -503,8 +509,11 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     CK(cudaMemsetAsync(outbits, 0, (outw_total + 64) * 4, st));
     CK(cudaMemsetAsync(out, 0, out_cap + 64, st));
     k_compact<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s, cmds_all, block_mb);
+    cudaEventRecord(ev[8], st);
     k_encode_mb<<<n_mbs, 32, 0, st>>>(s, cmds_all, scratch, d_soff, outbits, d_ooff);
+    cudaEventRecord(ev[9], st);
     cudaEventRecord(ev[3], st);
+    ++job->stats.encode_launches; job->stats.launches += 4;
     k_assemble_scan<<<1, 32, 0, st>>>(s, d_ooff, out, desc, res);
     CK(cudaMemcpyAsync(hp + 16, res, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -529,6 +538,8 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   cudaEventElapsedTime(&ms, ev[2], ev[3]); job->stats.ms_entropy = ms;
   cudaEventElapsedTime(&ms, ev[3], ev[4]); job->stats.ms_assemble = ms;
   cudaEventElapsedTime(&ms, ev[0], ev[4]); job->stats.ms_total = ms;
+  cudaEventElapsedTime(&ms, ev[8], ev[9]); job->stats.ms_encode = ms;
+  job->stats.total_cmds = total_cmds; job->stats.launches += 12;
   for (auto& e : ev) cudaEventDestroy(e);
   job->stats.nblocks = nb; job->stats.n_metablocks = n_mbs; job->stats.rounds = (u32)rounds;
   job->stats.out_bytes = final_size; job->stats.in_bytes = n;

@@ -85,9 +85,10 @@ BROTLI_B200_API BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, siz
  * Returns the number of streams compressed successfully. */
 BROTLI_B200_API size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8_t* const* inputs, const size_t* input_sizes, uint8_t* const* outputs, size_t* encoded_sizes, int threads);
 /* Timings (milliseconds, CUDA events) and counters of the calling thread's last compress call.
- * out[0..9]: total, index (hash+sort), lz77, entropy, assemble, lz77 iterations, block runs,
- * blocks, metablocks, kernel launches. */
-BROTLI_B200_API void BrotliB200LastStats(double out[10]);
+ * out[0..15]: total, index (hash+sort), lz77, entropy, assemble, lz77 iterations, block runs,
+ * blocks, metablocks, kernel launches, summed k_walk ms, k_encode_mb ms, k_walk launches,
+ * k_encode_mb launches, input bytes walked over all k_walk launches, commands emitted. */
+BROTLI_B200_API void BrotliB200LastStats(double out[16]);
 /* 1 if a usable CUDA device is present. */
 BROTLI_B200_API int BrotliB200Available(void);
 

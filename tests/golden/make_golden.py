@@ -1,0 +1,23 @@
+"""Generates tests/golden/golden.json: digests of the REFERENCE encoder's output
+(oracle/_ref/libbrotli_ref.so, built from /root/reference by oracle/Makefile) for seeded inputs
+that regenerate identically anywhere (tests/corpus.py).  The reference ships no encoder golden
+vectors of its own, so these pin the oracle and the GPU path."""
+import hashlib
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from brotli_libs import Ref
+from golden_cases import CASES, make_case
+
+ref = Ref()
+out = []
+for c in CASES:
+    d = make_case(c)
+    comp = ref.compress(d, c["q"], c["lgwin"])
+    out.append(dict(c, in_sha256=hashlib.sha256(d).hexdigest(), out_len=len(comp),
+                    out_sha256=hashlib.sha256(comp).hexdigest()))
+    print(c, len(d), len(comp))
+json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1)

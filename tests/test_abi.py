@@ -1,0 +1,77 @@
+"""CPU suite, part 3: the C-ABI library loads, exports every symbol include/brotli_b200.h
+declares, and fails loudly (never falls back) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from brotli_libs import ROOT
+
+SO = os.path.join(ROOT, "brotli_b200", "libbrotlienc_b200.so")
+HEADER = os.path.join(ROOT, "include", "brotli_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(SO):
+        import __graft_entry__
+        __graft_entry__.build_product()
+    return C.CDLL(SO, mode=os.RTLD_LOCAL)
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"BROTLI_B200_API[^;(]*?\b(Brotli\w+)\s*\(", text)))
+
+
+def test_header_declares_reference_api():
+    names = declared_symbols()
+    for n in ["BrotliEncoderSetParameter", "BrotliEncoderCreateInstance", "BrotliEncoderDestroyInstance",
+              "BrotliEncoderPrepareDictionary", "BrotliEncoderDestroyPreparedDictionary",
+              "BrotliEncoderAttachPreparedDictionary", "BrotliEncoderMaxCompressedSize", "BrotliEncoderCompress",
+              "BrotliEncoderCompressStream", "BrotliEncoderIsFinished", "BrotliEncoderHasMoreOutput",
+              "BrotliEncoderTakeOutput", "BrotliEncoderVersion"]:
+        assert n in names      # the 13 BROTLI_ENC_API functions of c/include/brotli/encode.h
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for n in declared_symbols():
+        assert hasattr(lib, n), n
+
+
+def test_host_only_entry_points(lib):
+    lib.BrotliEncoderMaxCompressedSize.restype = C.c_size_t
+    lib.BrotliEncoderMaxCompressedSize.argtypes = [C.c_size_t]
+    assert lib.BrotliEncoderMaxCompressedSize(0) == 2
+    assert lib.BrotliEncoderMaxCompressedSize(1 << 20) == (1 << 20) + 2 + 4 * 64 + 3 + 1   # encode.c:1251
+    lib.BrotliEncoderVersion.restype = C.c_uint32
+    assert lib.BrotliEncoderVersion() == 0x1002000
+    # empty input never needs the GPU: single byte 0x06 (encode.c:1310)
+    out = C.create_string_buffer(8)
+    n = C.c_size_t(8)
+    lib.BrotliEncoderCompress.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
+    assert lib.BrotliEncoderCompress(5, 22, 0, 0, None, C.byref(n), out) == 1 and out.raw[:n.value] == b"\x06"
+
+
+def test_state_api_and_loud_failure(lib):
+    lib.BrotliEncoderCreateInstance.restype = C.c_void_p
+    lib.BrotliEncoderCreateInstance.argtypes = [C.c_void_p] * 3
+    lib.BrotliEncoderSetParameter.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    lib.BrotliEncoderDestroyInstance.argtypes = [C.c_void_p]
+    s = lib.BrotliEncoderCreateInstance(None, None, None)
+    assert s
+    assert lib.BrotliEncoderSetParameter(s, 1, 5) == 1      # QUALITY
+    assert lib.BrotliEncoderSetParameter(s, 2, 22) == 1     # LGWIN
+    assert lib.BrotliEncoderSetParameter(s, 99, 0) == 0     # unknown parameter
+    lib.BrotliEncoderDestroyInstance(s)
+    import brotli_b200
+    if not brotli_b200.available():
+        with pytest.raises(brotli_b200.error):
+            brotli_b200.compress_oneshot(b"no gpu here " * 100, 5, 22)
+    # parameters outside the implemented path are refused instead of silently changed
+    out = C.create_string_buffer(4096)
+    n = C.c_size_t(4096)
+    assert lib.BrotliEncoderCompress(11, 22, 0, 100, b"x" * 100, C.byref(n), out) == 0
+    n = C.c_size_t(4096)
+    assert lib.BrotliEncoderCompress(5, 12, 0, 100, b"x" * 100, C.byref(n), out) == 0

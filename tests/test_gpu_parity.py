@@ -1,0 +1,104 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the golden vectors of the
+compiled reference, the oracle, and -- where it travelled -- oracle/_ref itself.  Bit-exact."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from brotli_libs import REF_SO, Oracle, Ref
+from golden_cases import make_case
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import brotli_b200
+    assert brotli_b200.available(), "no CUDA device"
+    return brotli_b200
+
+
+@pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%s-%d-q%d-w%d" % (g["kind"], g["n"], g["q"], g["lgwin"]))
+def test_golden(b200, g):
+    d = make_case(g)
+    assert hashlib.sha256(d).hexdigest() == g["in_sha256"]
+    out = b200.compress_oneshot(d, g["q"], g["lgwin"])
+    assert len(out) == g["out_len"]
+    assert hashlib.sha256(out).hexdigest() == g["out_sha256"]
+
+
+def test_against_oracle_all_qualities(b200):
+    ora = Oracle()
+    from corpus import synth_text, synth_web
+    d1, d2 = synth_text(700000, 31), synth_web(1300000, 32)
+    for q in (5, 6, 7, 8, 9):
+        for w in (17, 19, 22, 24):
+            for d in (d1, d2):
+                assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (q, w, len(d))
+
+
+def test_edge_sizes(b200):
+    ora = Oracle()
+    from corpus import synth_text
+    base = synth_text(200000, 33)
+    for n in (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 63, 64, 65, 511, 512, 4095, 65535, 65536, 65537, 131072, 131073):
+        d = base[:n]
+        assert b200.compress_oneshot(d, 5, 22) == ora.compress(d, 5, 22), n
+        assert b200.compress_oneshot(d, 9, 24) == ora.compress(d, 9, 24), n
+    assert b200.compress_oneshot(b"", 5, 22) == b"\x06"
+
+
+def test_streaming_api_equals_oneshot(b200):
+    from corpus import synth_text
+    d = synth_text(1500000, 34)
+    want = Oracle().compress(d, 5, 22)
+    c = b200.Compressor(quality=5, lgwin=22)
+    out = b""
+    # first call carries everything: the size hint freezes at the full length like the one-shot call
+    out += c.process(d)
+    out += c.finish()
+    assert out == want
+    assert b200.compress(d, quality=5, lgwin=22) == want
+    # empty stream through the streaming API
+    c2 = b200.Compressor(quality=5, lgwin=22)
+    assert c2.finish() == bytes([0x3B])   # window bits 1011 + ISLAST + ISEMPTY (encode.c:1006)
+
+
+def test_device_and_batch_api(b200):
+    import torch
+    from corpus import synth_text, synth_web
+    ora = Oracle()
+    L = b200.lib()
+    d = synth_text(2000000, 35)
+    want = ora.compress(d, 5, 22)
+    t = torch.frombuffer(bytearray(d), dtype=torch.uint8).cuda()
+    out = torch.empty(len(d) + 4096, dtype=torch.uint8, device="cuda")
+    sz = C.c_size_t(out.numel())
+    assert L.BrotliB200CompressDevice(5, 22, len(d), t.data_ptr(), C.byref(sz), out.data_ptr())
+    assert bytes(out[:sz.value].cpu().numpy().tobytes()) == want
+    # batch of independent streams over 4 host workers
+    ins = [synth_web(100000 + 7777 * i, 40 + i) for i in range(12)]
+    bufs = [C.create_string_buffer(len(x) + 4096) for x in ins]
+    inp = (C.c_void_p * 12)(*[C.cast(C.c_char_p(x), C.c_void_p) for x in ins])
+    outp = (C.c_void_p * 12)(*[C.cast(b, C.c_void_p) for b in bufs])
+    isz = (C.c_size_t * 12)(*[len(x) for x in ins])
+    osz = (C.c_size_t * 12)(*[len(x) + 4096 for x in ins])
+    assert L.BrotliB200CompressBatch(5, 22, 12, inp, isz, outp, osz, 4) == 12
+    for i in range(12):
+        assert bufs[i].raw[:osz[i]] == ora.compress(ins[i], 5, 22), i
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_full_size_properties(b200):
+    """BASELINE.json's full size (100 MB, q5, lgwin 22): equality with the reference run on the
+    box's CPU, and the size-independent property decode(encode(x)) == x via the reference decoder."""
+    from corpus import synth_text
+    ref = Ref()
+    d = synth_text(100_000_000)
+    out = b200.compress_oneshot(d, 5, 22)
+    assert ref.decompress(out, len(d)) == d
+    assert out == ref.compress(d, 5, 22)

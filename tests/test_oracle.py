@@ -1,0 +1,55 @@
+"""CPU suite, part 1: the oracle (oracle/brotli_oracle.c) against the golden vectors made from the
+compiled reference, and -- where oracle/_ref is present -- against the reference itself."""
+import hashlib
+import json
+import os
+
+import pytest
+
+from brotli_libs import REF_SO, Oracle, Ref
+from golden_cases import make_case
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+FAST = [g for g in GOLDEN if g["n"] <= 2_500_000]
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+@pytest.mark.parametrize("g", FAST, ids=lambda g: "%s-%d-q%d-w%d" % (g["kind"], g["n"], g["q"], g["lgwin"]))
+def test_oracle_matches_golden(oracle, g):
+    d = make_case(g)
+    assert hashlib.sha256(d).hexdigest() == g["in_sha256"], "corpus generator drifted"
+    out = oracle.compress(d, g["q"], g["lgwin"])
+    assert len(out) == g["out_len"]
+    assert hashlib.sha256(out).hexdigest() == g["out_sha256"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built")
+def test_oracle_matches_reference_and_roundtrips(oracle):
+    ref = Ref()
+    for g in FAST[:12]:
+        d = make_case(g)
+        a = ref.compress(d, g["q"], g["lgwin"])
+        assert a == oracle.compress(d, g["q"], g["lgwin"])
+        assert ref.decompress(a, len(d)) == d
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built")
+def test_empty_input_and_bounds():
+    ref = Ref()
+    assert ref.compress(b"", 5, 22) == b"\x06"
+    for n in (0, 1, 100, 1 << 14, (1 << 24) + 5):
+        assert ref.lib.BrotliEncoderMaxCompressedSize(n) >= n
+
+
+def test_fast_log2_table(oracle):
+    # c/enc/fast_log.c:13: the table literals carry an 'f' suffix -> float-rounded values
+    import math
+    import struct
+    for v in (1, 2, 3, 7, 100, 255):
+        f = struct.unpack("f", struct.pack("f", math.log2(v)))[0]
+        assert oracle.lib.oracle_fast_log2(v) == f
+    assert oracle.lib.oracle_fast_log2(4096) == 12.0

@@ -1,0 +1,42 @@
+"""CPU suite, part 2: the product's warp-task device code (LZ77 walkers, chain, entropy coder)
+compiled for the host by tests/sim/br_sim.cc with a one-lane warp, against the oracle.  This is
+how the bit-exact logic is debugged without a GPU; the CUDA build itself is checked by -m gpu."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from brotli_libs import ROOT, TABLES, Oracle
+from golden_cases import CASES, make_case
+
+SIM_SO = os.path.join(ROOT, "tests", "sim", "libbrsim.so")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    if not os.path.exists(SIM_SO):
+        import __graft_entry__
+        __graft_entry__.build_checkers()
+    L = C.CDLL(SIM_SO)
+    L.sim_init.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
+    L.sim_compress.restype = C.c_long
+    L.sim_compress.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
+    blob = open(TABLES, "rb").read()
+    L.sim_init(blob, len(blob), (1 << 22) + 2)
+    return L
+
+
+SMALL = [c for c in CASES if c["n"] <= 1_500_000 and not (c["kind"] in ("binary", "heavy") and c["q"] == 9)]
+
+
+@pytest.mark.parametrize("c", SMALL, ids=lambda c: "%s-%d-q%d-w%d" % (c["kind"], c["n"], c["q"], c["lgwin"]))
+def test_sim_matches_oracle(sim, c):
+    d = make_case(c)
+    want = Oracle().compress(d, c["q"], c["lgwin"])
+    cap = len(d) + len(d) // 2 + 4096
+    out = C.create_string_buffer(cap)
+    st = np.zeros(8, np.uint32)
+    r = sim.sim_compress(c["q"], c["lgwin"], d, len(d), out, cap, st.ctypes.data)
+    assert r >= 0
+    assert out.raw[:r] == want
