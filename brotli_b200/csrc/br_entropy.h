@@ -282,11 +282,22 @@ BR_DEV void br_store_huffman_tree(const u8* depths, u32 num, BrMbScratch* sc, Br
     else if (ix == 17) br_put_bits(w, 3, sc->hx[i]);
   }
 }
-// brotli_bit_stream.c:349 BuildAndStoreHuffmanTree (+ :242 StoreSimpleHuffmanTree).
-// Warp-uniform; the memory it writes is only touched through lane-0-equivalent code paths,
-// every lane executes the same stores with the same values.
-BR_DEV void br_build_and_store_tree(const u32* histo, u32 histo_len, u32 alphabet_size,
-                                    BrMbScratch* sc, u8* depth, u16* bits, BrBitW& w) {
+// brotli_bit_stream.c:349 BuildAndStoreHuffmanTree, split in two so that the construction of
+// all prefix codes of a metablock can run in parallel and only the (cheap) storing is serial.
+// Build: depth[] and bits[] (count <= 1 leaves depth 0 at the only symbol).
+BR_DEV void br_build_tree(const u32* histo, u32 histo_len, BrHTree* tree, u8* depth, u16* bits) {
+  u32 count = 0, first = 0;
+  for (u32 i = 0; i < histo_len; i++) {
+    if (histo[i]) { if (count == 0) first = i; if (++count > 1) break; }
+  }
+  if (count <= 1) { depth[first] = 0; bits[first] = 0; return; }
+  for (u32 i = 0; i < histo_len; ++i) depth[i] = 0;
+  br_create_huffman_tree(histo, histo_len, 15, tree, depth);
+  br_depths_to_symbols(depth, histo_len, bits);
+}
+// Store (+ :242 StoreSimpleHuffmanTree / :283 BrotliStoreHuffmanTree)
+BR_DEV void br_store_tree(const u32* histo, u32 histo_len, u32 alphabet_size, BrMbScratch* sc,
+                          const u8* depth, BrBitW& w) {
   u32 count = 0, s4[4] = {0, 0, 0, 0}, max_bits = 0;
   for (u32 i = 0; i < histo_len; i++) {
     if (histo[i]) {
@@ -298,12 +309,8 @@ BR_DEV void br_build_and_store_tree(const u32* histo, u32 histo_len, u32 alphabe
   if (count <= 1) {
     br_put_bits(w, 4, 1);
     br_put_bits(w, max_bits, s4[0]);
-    depth[s4[0]] = 0; bits[s4[0]] = 0;
     return;
   }
-  for (u32 i = 0; i < histo_len; ++i) depth[i] = 0;
-  br_create_huffman_tree(histo, histo_len, 15, sc->tree, depth);
-  br_depths_to_symbols(depth, histo_len, bits);
   if (count <= 4) {
     br_put_bits(w, 2, 1);
     br_put_bits(w, 2, count - 1);
@@ -315,6 +322,11 @@ BR_DEV void br_build_and_store_tree(const u32* histo, u32 histo_len, u32 alphabe
   } else {
     br_store_huffman_tree(depth, histo_len, sc, w);
   }
+}
+BR_DEV void br_build_and_store_tree(const u32* histo, u32 histo_len, u32 alphabet_size,
+                                    BrMbScratch* sc, u8* depth, u16* bits, BrBitW& w) {
+  br_build_tree(histo, histo_len, sc->tree, depth, bits);
+  br_store_tree(histo, histo_len, alphabet_size, sc, depth, w);
 }
 
 BR_DEV void br_store_varlen_uint8(u32 n, BrBitW& w) {

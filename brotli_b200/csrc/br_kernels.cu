@@ -15,6 +15,7 @@
 #include "br_lz77.h"
 #include "br_chain.h"
 #include "br_entropy.h"
+#include "br_entropy2.h"
 #include "br_pipeline.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -198,14 +199,80 @@ __global__ void k_compact(BrStream s, BrCmd* cmds_all, const u32* __restrict__ b
   if (t >= s.P.nblocks) return;
   br_compact_block(s, t, cmds_all, block_mb);
 }
-__global__ void __launch_bounds__(32) k_encode_mb(BrStream s, const BrCmd* __restrict__ cmds_all, u8* scratch,
-    const u64* __restrict__ scratch_off, u32* outbits, const u64* __restrict__ out_off /* in u32 words */) {
-  __shared__ u32 sm[4096];
-  u32 i = blockIdx.x;
-  BrMetaBlock mb = s.mbs[i];
+// ---- data-parallel entropy stage (br_entropy2.h)
+__global__ void k_cmd_scan_inputs(const BrCmd* __restrict__ cmds, u32 C, u32* ins, u32* span, u32* hasd) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > C) return;
+  u32 a = 0, b = 0, d = 0;
+  if (i < C) br_cmd_scan_inputs(cmds[i], &a, &b, &d);
+  ins[i] = a; span[i] = b; hasd[i] = d;
+}
+__global__ void k_cmd_mb(BrStream s, u32* cmd_mb) {
+  const BrMetaBlock mb = s.mbs[blockIdx.y];
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < mb.ncmd; i += gridDim.x * blockDim.x) cmd_mb[mb.cmd_off + i] = blockIdx.y;
+}
+__global__ void k_expand(BrEnt e) {
+  u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w * 32 >= e.total_cmds) return;
+  br_expand_cmds(e, w * 32);
+}
+// one warp per metablock: literal context model + bookkeeping
+__global__ void __launch_bounds__(32) k_mb_setup(BrStream s, BrEnt e) {
+  const u32 i = blockIdx.x;
+  const BrMetaBlock mb = s.mbs[i];
   if (!mb.compress) return;
-  u32 bits = br_encode_metablock(s, mb, cmds_all, scratch + scratch_off[i], outbits + out_off[i], sm);
-  if (threadIdx.x == 0) s.mbs[i].out_bits = bits;
+  u8* sc = e.scratch + e.scratch_off[i];
+  BrMbMem* M = (BrMbMem*)sc;
+  u32 which = br_decide_context_modeling(s, mb.start, mb.end - mb.start, M->sc.rle_syms);
+  if (threadIdx.x == 0) {
+    BrMbAux a; memset(&a, 0, sizeof(a));
+    a.which = which;
+    a.lit_base = e.lit_ord[mb.cmd_off]; a.dist_base = e.dist_ord[mb.cmd_off];
+    a.nsym[0] = mb.nlit; a.nsym[1] = mb.ncmd; a.nsym[2] = e.dist_ord[mb.cmd_off + mb.ncmd] - a.dist_base;
+    u32 off = br_align8((u32)sizeof(BrMbMem));
+    for (int cat = 0; cat < 3; ++cat) { a.var_off[cat] = off; off += br_mb2_var_bytes(br_mb2_nblk(cat, mb.nlit, mb.ncmd)); }
+    e.aux[i] = a;
+  }
+}
+__global__ void __launch_bounds__(256) k_split(BrStream s, BrEnt e) {
+  extern __shared__ u32 sm[];
+  const u32 i = blockIdx.x; const int cat = (int)blockIdx.y;
+  const BrMetaBlock mb = s.mbs[i];
+  if (!mb.compress) return;
+  BrMbAux& a = e.aux[i];
+  u8* sc = e.scratch + e.scratch_off[i];
+  BrMbMem* M = (BrMbMem*)sc;
+  const u32 A = cat == 0 ? 256u : cat == 1 ? 704u : 64u, nc = cat == 0 ? a.which : 1u;
+  const u32 minb = cat == 1 ? 1024u : 512u;
+  const double thr = cat == 0 ? 400.0 : cat == 1 ? 500.0 : 100.0;
+  u32* H = cat == 0 ? M->lit_H : cat == 1 ? M->cmd_H : M->dist_H;
+  u32 nblk = br_mb2_nblk(cat, mb.nlit, mb.ncmd);
+  br_split_cta(s, e, mb, a, cat, A, nc, minb, thr, a.nsym[cat], br_mb2_types(sc, a, cat, nblk),
+               br_mb2_lengths(sc, a, cat, nblk), H, sm);
+}
+__global__ void __launch_bounds__(64) k_prep(BrStream s, BrEnt e) {
+  const u32 i = blockIdx.x;
+  const BrMetaBlock mb = s.mbs[i];
+  if (!mb.compress) return;
+  br_prep_codes(s, mb, e.aux[i], e.scratch + e.scratch_off[i], e.outbits + e.out_off[i]);
+}
+__global__ void k_lit_bits(BrStream s, BrEnt e) {
+  u32 o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < e.total_lits) br_lit_bits(s, e, o);
+  else if (o == e.total_lits) e.lit_len[o] = 0;
+}
+__global__ void k_cmd_bits(BrStream s, BrEnt e) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < e.total_cmds) br_cmd_bits(s, e, i);
+  else if (i == e.total_cmds) e.cmd_len[i] = 0;
+}
+__global__ void k_emit_cmd(BrStream s, BrEnt e) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < e.total_cmds) br_emit_cmd(s, e, i);
+}
+__global__ void k_emit_lit(BrStream s, BrEnt e) {
+  u32 o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < e.total_lits) br_emit_lit(s, e, o);
 }
 
 // ---------------------------------------------------------------------------- stream assembly
@@ -490,30 +557,65 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     for (u32 i = 0; i < n_mbs; ++i) {
       h_soff[i] = scratch_total; h_ooff[i] = outw_total;
       if (hm[i].compress) {
-        scratch_total += ((size_t)br_mb_scratch_bytes(hm[i].nlit, hm[i].ncmd) + 255) & ~(size_t)255;
+        scratch_total += ((size_t)br_mb2_scratch_bytes(hm[i].nlit, hm[i].ncmd) + 255) & ~(size_t)255;
         outw_total += (2 * (size_t)(hm[i].end - hm[i].start) + 503) / 4 + 16;
       }
     }
     size_t out_cap = (size_t)n + ((size_t)n >> 3) + 4096 + 8ull * n_mbs;
-    size_t need2 = scratch_total + outw_total * 4 + out_cap + (size_t)total_cmds * sizeof(BrCmd) +
-                   n_mbs * (16 + sizeof(BrCopyDesc)) + (1 << 16);
+    const size_t C = total_cmds;
+    size_t need2 = scratch_total + outw_total * 4 + out_cap + (C + 2) * (sizeof(BrCmd) + 26) + ((size_t)n + 8) * 12 +
+                   scan_tmp_words((size_t)n + C + 8) * 4 * 2 + n_mbs * (32 + sizeof(BrCopyDesc) + sizeof(BrMbAux)) + (1 << 16);
     if (!job->arena2.reserve(need2)) return 0;
     BrArena& B = job->arena2;
     u8* scratch = B.take<u8>(scratch_total + 256); u32* outbits = B.take<u32>(outw_total + 64);
-    u32* out = B.take<u32>(out_cap / 4 + 16); BrCmd* cmds_all = B.take<BrCmd>((size_t)total_cmds + 1);
+    u32* out = B.take<u32>(out_cap / 4 + 16); BrCmd* cmds_all = B.take<BrCmd>(C + 1);
     u64* d_soff = B.take<u64>(n_mbs); u64* d_ooff = B.take<u64>(n_mbs);
     BrCopyDesc* desc = B.take<BrCopyDesc>(n_mbs); u32* res = B.take<u32>(16);
-    if (!res) return 0;
+    u32* lit_ord = B.take<u32>(C + 2); u32* cmd_pos = B.take<u32>(C + 2); u32* dist_ord = B.take<u32>(C + 2);
+    u32* cmd_len = B.take<u32>(C + 2); u32* lit_bit_base = B.take<u32>(C + 2); u32* cmd_mb = B.take<u32>(C + 2);
+    u16* dist_sym = B.take<u16>(C + 2);
+    u32* lit_pos = B.take<u32>((size_t)n + 2); u32* lit_cmd = B.take<u32>((size_t)n + 2); u32* lit_len = B.take<u32>((size_t)n + 2);
+    BrMbAux* aux = B.take<BrMbAux>(n_mbs);
+    u32* stmp = B.take<u32>(scan_tmp_words((size_t)n + C + 8) * 2);
+    if (!stmp) return 0;
     CK(cudaMemcpyAsync(d_soff, h_soff.data(), n_mbs * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_ooff, h_ooff.data(), n_mbs * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(outbits, 0, (outw_total + 64) * 4, st));
     CK(cudaMemsetAsync(out, 0, out_cap + 64, st));
     k_compact<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s, cmds_all, block_mb);
     cudaEventRecord(ev[8], st);
-    k_encode_mb<<<n_mbs, 32, 0, st>>>(s, cmds_all, scratch, d_soff, outbits, d_ooff);
+    // E0: ordinals
+    k_cmd_scan_inputs<<<(u32)((C + 1 + 255) / 256), 256, 0, st>>>(cmds_all, (u32)C, lit_ord, cmd_pos, dist_ord);
+    scan_exclusive(lit_ord, (u32)C + 1, stmp, st);
+    scan_exclusive(cmd_pos, (u32)C + 1, stmp, st);
+    scan_exclusive(dist_ord, (u32)C + 1, stmp, st);
+    CK(cudaMemcpyAsync(hp + 24, lit_ord + C, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp + 25, dist_ord + C, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    BrEnt e; memset(&e, 0, sizeof(e));
+    e.cmds = cmds_all; e.total_cmds = (u32)C; e.total_lits = hp[24]; e.total_dist = hp[25];
+    e.lit_ord = lit_ord; e.cmd_pos = cmd_pos; e.dist_ord = dist_ord; e.lit_pos = lit_pos; e.lit_cmd = lit_cmd;
+    e.dist_sym = dist_sym; e.lit_len = lit_len; e.cmd_len = cmd_len; e.lit_bit_base = lit_bit_base; e.cmd_mb = cmd_mb;
+    e.aux = aux; e.scratch = scratch; e.scratch_off = d_soff; e.outbits = outbits; e.out_off = d_ooff;
+    if (e.total_lits > n) return 0;
+    k_cmd_mb<<<dim3(64, n_mbs), 256, 0, st>>>(s, cmd_mb);
+    k_expand<<<(u32)((C + 127) / 128 + 1), 128, 0, st>>>(e);
+    k_mb_setup<<<n_mbs, 32, 0, st>>>(s, e);
+    {
+      const size_t smem_split = br_split_smem_bytes(256, 13) > br_split_smem_bytes(704, 1) ? br_split_smem_bytes(256, 13) : br_split_smem_bytes(704, 1);
+      CK(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_split));
+      k_split<<<dim3(n_mbs, 3), 256, smem_split, st>>>(s, e);
+    }
+    k_prep<<<n_mbs, 64, 0, st>>>(s, e);
+    k_lit_bits<<<(e.total_lits + 1 + 255) / 256, 256, 0, st>>>(s, e);
+    k_cmd_bits<<<(u32)((C + 1 + 255) / 256), 256, 0, st>>>(s, e);
+    scan_exclusive(lit_len, e.total_lits + 1, stmp, st);
+    scan_exclusive(cmd_len, (u32)C + 1, stmp, st);
+    k_emit_cmd<<<(u32)((C + 255) / 256), 256, 0, st>>>(s, e);
+    if (e.total_lits) k_emit_lit<<<(e.total_lits + 255) / 256, 256, 0, st>>>(s, e);
     cudaEventRecord(ev[9], st);
     cudaEventRecord(ev[3], st);
-    ++job->stats.encode_launches; job->stats.launches += 4;
+    ++job->stats.encode_launches; job->stats.launches += 24;
     k_assemble_scan<<<1, 32, 0, st>>>(s, d_ooff, out, desc, res);
     CK(cudaMemcpyAsync(hp + 16, res, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -14,6 +14,7 @@
 #include "../../brotli_b200/csrc/br_chain.h"
 #ifdef BR_SIM_ENTROPY
 #include "../../brotli_b200/csrc/br_entropy.h"
+#include "../../brotli_b200/csrc/br_entropy2.h"
 #endif
 
 struct SimTables {
@@ -173,6 +174,75 @@ static void put_bits_host(std::vector<u8>& o, u64& bit, u32 n, u64 v) {
     if ((v >> i) & 1) o[bit >> 3] |= (u8)(1u << (bit & 7));
   }
 }
+
+// ---- the data-parallel entropy stage (br_entropy2.h), run element by element
+struct SimEnt {
+  BrEnt e;
+  std::vector<u32> lit_ord, cmd_pos, dist_ord, lit_pos, lit_cmd, lit_len, cmd_len, lit_bit_base, cmd_mb, outbits;
+  std::vector<u16> dist_sym;
+  std::vector<BrMbAux> aux;
+  std::vector<u8> scratch;
+  std::vector<u64> scratch_off, out_off;
+};
+static void sim_entropy2(SimStream& m, SimEnt& E) {
+  BrStream& s = m.s;
+  u32 nm = s.counters[1], C = s.counters[2];
+  BrEnt& e = E.e;
+  e.cmds = m.cmds_all.data(); e.total_cmds = C;
+  E.lit_ord.assign(C + 1, 0); E.cmd_pos.assign(C + 1, 0); E.dist_ord.assign(C + 1, 0);
+  for (u32 i = 0; i < C; ++i) {
+    u32 a, b, d; br_cmd_scan_inputs(e.cmds[i], &a, &b, &d);
+    E.lit_ord[i + 1] = E.lit_ord[i] + a; E.cmd_pos[i + 1] = E.cmd_pos[i] + b; E.dist_ord[i + 1] = E.dist_ord[i] + d;
+  }
+  e.total_lits = E.lit_ord[C]; e.total_dist = E.dist_ord[C];
+  E.lit_pos.assign(e.total_lits + 1, 0); E.lit_cmd.assign(e.total_lits + 1, 0); E.dist_sym.assign(e.total_dist + 1, 0);
+  E.lit_len.assign(e.total_lits + 2, 0); E.cmd_len.assign(C + 2, 0); E.lit_bit_base.assign(C + 1, 0); E.cmd_mb.assign(C + 1, 0);
+  E.aux.assign(nm, BrMbAux());
+  E.scratch_off.assign(nm, 0); E.out_off.assign(nm, 0);
+  size_t st = 0, ot = 0;
+  for (u32 i = 0; i < nm; ++i) {
+    E.scratch_off[i] = st; E.out_off[i] = ot;
+    const BrMetaBlock& mb = s.mbs[i];
+    for (u32 c = mb.cmd_off; c < mb.cmd_off + mb.ncmd; ++c) E.cmd_mb[c] = i;
+    if (mb.compress) { st += (br_mb2_scratch_bytes(mb.nlit, mb.ncmd) + 255) & ~255u; ot += (2 * (size_t)(mb.end - mb.start) + 503) / 4 + 16; }
+  }
+  E.scratch.assign(st + 256, 0); E.outbits.assign(ot + 64, 0);
+  e.lit_ord = E.lit_ord.data(); e.cmd_pos = E.cmd_pos.data(); e.dist_ord = E.dist_ord.data();
+  e.lit_pos = E.lit_pos.data(); e.lit_cmd = E.lit_cmd.data(); e.dist_sym = E.dist_sym.data();
+  e.lit_len = E.lit_len.data(); e.cmd_len = E.cmd_len.data(); e.lit_bit_base = E.lit_bit_base.data();
+  e.cmd_mb = E.cmd_mb.data(); e.aux = E.aux.data(); e.scratch = E.scratch.data(); e.scratch_off = E.scratch_off.data();
+  e.outbits = E.outbits.data(); e.out_off = E.out_off.data();
+  for (u32 c = 0; c < C; c += BR_WARP) br_expand_cmds(e, c);
+  std::vector<u32> smem(64 * 1024);
+  for (u32 i = 0; i < nm; ++i) {
+    const BrMetaBlock& mb = s.mbs[i];
+    if (!mb.compress) continue;
+    BrMbAux& a = E.aux[i];
+    u8* sc = E.scratch.data() + E.scratch_off[i];
+    BrMbMem* M = (BrMbMem*)sc;
+    a.which = br_decide_context_modeling(s, mb.start, mb.end - mb.start, M->sc.rle_syms);
+    a.lit_base = E.lit_ord[mb.cmd_off]; a.dist_base = E.dist_ord[mb.cmd_off];
+    a.nsym[0] = mb.nlit; a.nsym[1] = mb.ncmd; a.nsym[2] = E.dist_ord[mb.cmd_off + mb.ncmd] - a.dist_base;
+    u32 off = br_align8((u32)sizeof(BrMbMem));
+    for (int cat = 0; cat < 3; ++cat) { a.var_off[cat] = off; off += br_mb2_var_bytes(br_mb2_nblk(cat, mb.nlit, mb.ncmd)); }
+    const u32 A[3] = {256, 704, 64}, NC[3] = {a.which, 1, 1}, MB[3] = {512, 1024, 512};
+    const double TH[3] = {400.0, 500.0, 100.0};
+    u32* H[3] = {M->lit_H, M->cmd_H, M->dist_H};
+    for (int cat = 0; cat < 3; ++cat) {
+      u32 nblk = br_mb2_nblk(cat, mb.nlit, mb.ncmd);
+      br_split_cta(s, e, mb, a, cat, A[cat], NC[cat], MB[cat], TH[cat], a.nsym[cat], br_mb2_types(sc, a, cat, nblk),
+                   br_mb2_lengths(sc, a, cat, nblk), H[cat], smem.data());
+    }
+    br_prep_codes(s, mb, a, sc, E.outbits.data() + E.out_off[i]);
+  }
+  for (u32 o = 0; o < e.total_lits; ++o) br_lit_bits(s, e, o);
+  for (u32 i = 0; i < C; ++i) br_cmd_bits(s, e, i);
+  { u32 acc = 0; for (u32 o = 0; o <= e.total_lits; ++o) { u32 v = E.lit_len[o]; E.lit_len[o] = acc; acc += v; } }
+  { u32 acc = 0; for (u32 i = 0; i <= C; ++i) { u32 v = E.cmd_len[i]; E.cmd_len[i] = acc; acc += v; } }
+  for (u32 i = 0; i < C; ++i) br_emit_cmd(s, e, i);
+  for (u32 o = 0; o < e.total_lits; ++o) br_emit_lit(s, e, o);
+}
+
 // Full pipeline; returns compressed size or negative error.
 extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, size_t out_cap, u32* stats) {
   if (n == 0) { if (out_cap < 1) return -3; out[0] = 6; return 1; }
@@ -188,6 +258,9 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
     u32 nm = s.counters[1];
     res.clear();
     u64 bit = 0;
+    const bool use_v2 = getenv("BR_SIM_V1") == nullptr;
+    SimEnt E;
+    if (use_v2) sim_entropy2(*m, E);
     if (lgwin == 17) put_bits_host(res, bit, 7, 1); else put_bits_host(res, bit, 4, ((lgwin - 17) << 1) | 1);
     bool redo = false;
     for (u32 i = 0; i < nm && !redo; ++i) {
@@ -197,7 +270,11 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
       if (compressed) {
         std::vector<u8> scratch(br_mb_scratch_bytes(mb.nlit, mb.ncmd) + 64);
         std::vector<u32> obuf((2 * (size_t)bytes + 503) / 4 + 8, 0);
-        u32 bits = br_encode_metablock(s, mb, m->cmds_all.data(), scratch.data(), obuf.data(), smem.data());
+        u32 bits;
+        if (use_v2) {
+          bits = s.mbs[i].out_bits;
+          memcpy(obuf.data(), E.outbits.data() + E.out_off[i], ((size_t)bits + 31) / 32 * 4);
+        } else bits = br_encode_metablock(s, mb, m->cmds_all.data(), scratch.data(), obuf.data(), smem.data());
         u64 storage_ix = (bit & 7) + bits;
         if (mb.is_last) storage_ix = (storage_ix + 7) & ~7ull;
         if ((u64)bytes + 4 < (storage_ix >> 3)) {
