@@ -1,32 +1,54 @@
 // br_chain.h -- the serial glue of one stream: replays what EncodeData (c/enc/encode.c:985)
-// does between blocks -- carrying distance cache / pending literals / dictionary counters
-// from block to block, ExtendLastCommand eligibility, the merge-or-flush policy
-// (encode.c:1141-1166), ShouldCompress (encode.c:457) -- over the walkers' per-block
-// summaries.  One warp, O(number of blocks) work.  It also decides which blocks must be
-// re-run: a block is dirty when the state it consumed differs from the state the chain now
-// derives for it, or when stored-bits it may have consulted were changed by a later commit.
+// does between input blocks -- carrying distance cache / pending literals / dictionary counters,
+// ExtendLastCommand eligibility, the merge-or-flush policy (encode.c:1141-1166), ShouldCompress
+// (encode.c:457) -- over the walkers' per-chunk summaries, and hands every chunk the state it must
+// start from.  Inside an input block the state simply flows from one chunk to the next.  It also
+// decides which chunks must be re-run: a chunk is dirty when the state it consumed differs from the
+// state the chain now derives for it, or when stored-bits it may have consulted were changed by a
+// later commit.
 #pragma once
 #include "br_cmd.h"
 
-// Compare and commit the stored-bits a walker just produced for block k (warp task).
+// Compare and commit the stored-bits a walker just produced for chunk k (warp task).  The
+// walker owns the positions [start_pos, out_pos).  StitchToPreviousBlock of the FOLLOWING input
+// block (hash_longest_match64_inc.h:127) stores the last three positions of a block after its
+// parse; that set is static, so it is added here, by whoever owns those positions.
 BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
   const BrBlockIn in = s.bin_used[k];
-  u32 w0 = in.pos >> 5, w1 = (in.end - 1) >> 5, diff = 0;
-  for (u32 x = w0 + (u32)br_lane(); x <= w1; x += BR_WARP) {
-    u32 m = 0xffffffffu;
-    if (x == w0) m &= 0xffffffffu << (in.pos & 31);
-    if (x == w1) m &= 0xffffffffu >> (31 - ((in.end - 1) & 31));
-    u32 nv = s.bits_cur[x] & m, ov = s.bits_latest[x] & m;
-    diff += (u32)br_popc(nv ^ ov);
-    if (nv != ov) {
-      if (m == 0xffffffffu) s.bits_latest[x] = nv;
-      else { br_atomic_and(s.bits_latest + x, ~m); br_atomic_or(s.bits_latest + x, nv); }
+  const u32 a = in.start_pos, b = s.bout[k].out_pos;
+  u32 diff = 0;
+  if (b > a) {
+    // stitch positions inside [a, b): the next block(s) starting at or shortly after blk_end
+    u32 st_lo = 0, st_hi = 0;   // [st_lo, st_hi) of stitch-stored positions (at most one run here)
+    if (in.last && b == in.blk_end) {
+      for (u32 nb = k + 1; nb < s.P.nblocks; ++nb) {
+        if (!s.bin[nb].first) continue;
+        u32 np = s.bin[nb].blk_start, ne = s.bin[nb].blk_end;
+        if (np >= in.blk_end + 3) break;
+        if (ne - np >= s.P.htl - 1 && np >= 3) { st_lo = np - 3; st_hi = np; }
+        break;
+      }
+    }
+    u32 w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (u32 x = w0 + (u32)br_lane(); x <= w1; x += BR_WARP) {
+      u32 m = 0xffffffffu;
+      if (x == w0) m &= 0xffffffffu << (a & 31);
+      if (x == w1) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+      u32 nv = s.bits_cur[x];
+      for (u32 q = st_lo; q < st_hi; ++q) if ((q >> 5) == x) nv |= 1u << (q & 31);
+      nv &= m;
+      u32 ov = s.bits_latest[x] & m;
+      diff += (u32)br_popc(nv ^ ov);
+      if (nv != ov) {
+        if (m == 0xffffffffu) s.bits_latest[x] = nv;
+        else { br_atomic_and(s.bits_latest + x, ~m); br_atomic_or(s.bits_latest + x, nv); }
+      }
     }
   }
   diff = br_warp_sum(diff);
   if (br_lane() == 0) {
     s.changed_bits[k] = diff;
-    if (diff) s.changed_epoch[k] = (int)s.epoch;
+    if (diff) { s.changed_epoch[k] = (int)s.epoch; br_atomic_max(&s.blk[in.blk].changed_epoch, (int)s.epoch); }
   }
 }
 
@@ -51,160 +73,251 @@ BR_DEV int br_should_compress(const BrStream& s, u32 start, u32 bytes, u32 num_l
   return 1;
 }
 
+#if BR_GPU
+#define BR_CH_TID ((u32)threadIdx.x)
+#define BR_CH_N ((u32)blockDim.x)
+BR_DEV void br_ch_sync() { __threadfence_block(); __syncthreads(); }
+#else
+#define BR_CH_TID 0u
+#define BR_CH_N 1u
+BR_DEV void br_ch_sync() {}
+#endif
+
+// One CTA per stream.  Phases 1, 2 and 4 are data-parallel over chunks / blocks; phase 3 (the
+// block-to-block recurrence of encode.c:985) runs on warp 0.
 BR_DEV void br_chain(const BrStream& s) {
   const BrParams& P = s.P;
+  const u32 tid = BR_CH_TID, nt = BR_CH_N;
+  const u32 nb = P.nblocks, nblk = s.nblk, t_now = s.epoch;
   const int lane = br_lane();
-  const u32 nb = P.nblocks, t_now = s.epoch;
-  // totals of this launch's commits
-  {
+  // ---- phase 0: totals of this launch's commits (for the counter-wrap rule)
+  if (tid < BR_WARP) {
     u32 tot = 0;
     for (u32 k = (u32)lane; k < nb; k += BR_WARP)
       if (s.bout[k].valid && s.bout[k].epoch == t_now) tot += s.changed_bits[k];
     tot = br_warp_sum(tot);
-    if (lane == 0 && t_now < BR_MAX_EPOCHS) s.epoch_changed[t_now] = tot;
-    for (u32 k = (u32)lane; k < nb; k += BR_WARP) s.ext_total[k] = 0;
-    br_syncwarp();
-  }
-  if (lane == 0) {
-    u32 acc = 0;
-    s.epoch_suffix[BR_MAX_EPOCHS] = 0;
-    for (int e = BR_MAX_EPOCHS - 1; e >= 0; --e) {
-      if ((u32)e <= t_now) acc += s.epoch_changed[e];
-      s.epoch_suffix[e] = acc;
-    }
-  }
-#if BR_GPU
-  __threadfence_block();
-#endif
-  br_syncwarp();
-
-  u32 num_cmds = 0, num_lits = 0, last_insert_len = 0;
-  int dc[4] = {4, 11, 15, 16}, saved_dc[4] = {4, 11, 15, 16};
-  u32 last_flush_pos = 0, first_block = 0, cmd_total = 0, n_mbs = 0, n_dirty = 0;
-  u64 dict_l = 0, dict_m = 0;
-  bool have_last = false;
-  u32 lc_copy_len = 0, lc_dist_prefix = 0, lc_dist_extra = 0, lc_block = 0;
-  const u32 blocksize = 1u << P.lgblock;
-
-  for (u32 k = 0; k < nb; ++k) {
-    const u32 pos = s.bin[k].pos, end = s.bin[k].end, is_last = s.bin[k].is_last;
-    // ---- state this block must start from
-    u32 ext_dist = 0;
-    if (num_cmds > 0 && last_insert_len == 0 && have_last) {
-      u32 dcode = br_cmd_restore_dcode(lc_dist_prefix, lc_dist_extra);
-      int cmd_dist = dc[0];
-      if (dcode < 16 || (cmd_dist > 0 && dcode - 15 == (u32)cmd_dist)) {
-        u32 lpp = pos - (lc_copy_len & 0x1FFFFFF);
-        u32 maxd = br_min(lpp, P.max_backward);
-        if (cmd_dist > 0 && (u32)cmd_dist <= maxd) ext_dist = (u32)cmd_dist;
-      }
-    }
-    const BrBlockOut out = s.bout[k];
-    u32 dirty = out.valid ? 0u : 1u;  // non-zero: reason code (1 never ran, 2 state, 3 dict gate, 4 window bits, 5 counter wrap)
-    if (!dirty) {
-      const BrBlockIn u = s.bin_used[k];
-      if (u.last_insert_len != last_insert_len || u.ext_dist != ext_dist ||
-          u.dc[0] != dc[0] || u.dc[1] != dc[1] || u.dc[2] != dc[2] || u.dc[3] != dc[3]) dirty = 2;
-#ifdef BR_SIM_DEBUG
-      if (dirty == 2 && getenv("BR_SIM_TRACE2")) fprintf(stderr, "  blk %u: lil %u->%u ext %u->%u dc %d,%d,%d,%d -> %d,%d,%d,%d | out ncmd %u lil %u\n", k, u.last_insert_len, last_insert_len, u.ext_dist, ext_dist, u.dc[0], u.dc[1], u.dc[2], u.dc[3], dc[0], dc[1], dc[2], dc[3], out.ncmd, out.last_insert_len);
-#endif
-      u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
-      if (!dirty && (ul != dict_l || um != dict_m) && out.gate_checks) {
-        bool all_open = out.gate_fail == 0, all_closed = out.gate_fail == out.gate_checks;
-        bool ok = (all_open && dict_m >= ((dict_l + out.dl) >> 7)) ||
-                  (all_closed && dict_m < (dict_l >> 7));
-        if (!ok) dirty = 3;
-      }
-      if (!dirty) {
-        // stored-bits committed at or after this block's last run, inside its window
-        u32 lowpos = pos > P.max_backward ? pos - P.max_backward : 0;
-        int seen = (int)out.epoch;
-        bool hit = false;
-        for (u32 base = 0; base < k && !hit; base += BR_WARP) {
-          u32 jj = k - 1 - base - (u32)lane;
-          bool has = (base + (u32)lane) < k;
-          bool inw = has && s.bin[jj].end > lowpos;
-          bool ch = inw && s.changed_epoch[jj] >= seen;
-          if (br_ballot(ch)) hit = true;
-          if (br_ballot(has && !inw) || br_ballot(!has)) break;
-        }
-        if (hit) dirty = 4;
-        u32 unseen = s.epoch_suffix[seen < BR_MAX_EPOCHS ? seen : BR_MAX_EPOCHS];
-        if (!dirty && unseen > out.min_wrap_dist) dirty = 5;
-      }
-    }
     if (lane == 0) {
+      if (t_now < BR_MAX_EPOCHS) s.epoch_changed[t_now] = tot;
+      u32 acc = 0;
+      s.epoch_suffix[BR_MAX_EPOCHS] = 0;
+      for (int e = BR_MAX_EPOCHS - 1; e >= 0; --e) {
+        if ((u32)e <= t_now) acc += s.epoch_changed[e];
+        s.epoch_suffix[e] = acc;
+      }
+      s.counters[0] = 0; s.counters[5] = 0;
+    }
+  }
+  for (u32 k = tid; k < nb; k += nt) s.ext_total[k] = 0;
+  // ---- phase 1+2: per input block, flow the state through its chunks and aggregate
+  for (u32 bi = tid; bi < nblk; bi += nt) {
+    BrBlk B = s.blk[bi];
+    u32 ncmd = 0, nlit_rel = 0, has_cmd = 0, lil_run = 0, lil_head = 0, last_cmd_chunk = 0, dl = 0, dm = 0;
+    u32 flow_pos = 0, flow_rh = 0, flow_se = 0; int fdc[4] = {0, 0, 0, 0};
+    bool all_valid = true;
+    for (u32 c = 0; c < B.nchunks; ++c) {
+      const u32 k = B.first_chunk + c;
+      const BrBlockOut out = s.bout[k];
+      if (c > 0) {
+        BrBlockIn ni = s.bin[k];
+        ni.start_pos = flow_pos; ni.apply_rh = flow_rh; ni.store_end = flow_se; ni.ext_dist = 0;
+        for (int i = 0; i < 4; ++i) ni.dc[i] = fdc[i];
+        s.bin[k] = ni;
+      }
+      // pending literals relative to the block start (true value = + block lil_in while no command seen)
+      s.lil_in[k] = lil_run | (has_cmd ? 0u : 0x80000000u);
+      if (out.valid) {
+        if (out.ncmd > 0) {
+          nlit_rel += out.nlit + lil_run;
+          if (!has_cmd) lil_head = lil_run; // (literals before the block's first command; block lil_in adds to it)
+          has_cmd = 1; lil_run = out.last_insert_len; last_cmd_chunk = k;
+        } else lil_run += out.last_insert_len;
+        ncmd += out.ncmd; dl += out.dl; dm += out.dm;
+        flow_pos = out.out_pos; flow_rh = out.apply_rh; flow_se = out.store_end;
+        for (int i = 0; i < 4; ++i) fdc[i] = out.dc[i];
+      } else {
+        // never ran: pretend it emitted nothing and stopped at its nominal end
+        all_valid = false;
+        const BrBlockIn cur = s.bin[k];
+        u32 sp = c == 0 ? cur.blk_start : cur.start_pos;
+        u32 from = sp > cur.pos ? sp : cur.pos, to = cur.last ? cur.blk_end : cur.end;
+        if (to > from) lil_run += to - from;
+        flow_pos = to > from ? to : sp; flow_rh = flow_pos + P.spree;
+        flow_se = cur.blk_end - cur.blk_start >= P.htl ? cur.blk_end - P.htl + 1 : cur.blk_start;
+        if (c == 0) { fdc[0] = 4; fdc[1] = 11; fdc[2] = 15; fdc[3] = 16; }
+      }
+    }
+    B.ncmd = ncmd; B.nlit_rel = nlit_rel; B.has_cmd = has_cmd; B.lil_head = lil_head; B.lil_tail = lil_run;
+    B.last_cmd_chunk = last_cmd_chunk; B.dl = dl; B.dm = dm; B.valid = all_valid ? 1u : 0u;
+    B.ext_len = s.bout[B.first_chunk].valid ? s.bout[B.first_chunk].ext_len : 0;
+    for (int i = 0; i < 4; ++i) B.out_dc[i] = fdc[i];
+    s.blk[bi] = B;
+  }
+  br_ch_sync();
+  // ---- phase 3: block-to-block recurrence (warp 0)
+  if (tid < BR_WARP) {
+    u32 num_cmds = 0, num_lits = 0, last_insert_len = 0;
+    int dc[4] = {4, 11, 15, 16}, saved_dc[4] = {4, 11, 15, 16};
+    u32 last_flush_pos = 0, first_blk = 0, cmd_total = 0, n_mbs = 0;
+    u64 dict_l = 0, dict_m = 0;
+    bool have_last = false;
+    u32 lc_copy_len = 0, lc_dist_prefix = 0, lc_dist_extra = 0, lc_chunk = 0;
+    const u32 blocksize = 1u << P.lgblock;
+    for (u32 bi = 0; bi < nblk; ++bi) {
+      const BrBlk B = s.blk[bi];
+      u32 ext_dist = 0;
+      if (num_cmds > 0 && last_insert_len == 0 && have_last) {
+        u32 dcode = br_cmd_restore_dcode(lc_dist_prefix, lc_dist_extra);
+        int cmd_dist = dc[0];
+        if (dcode < 16 || (cmd_dist > 0 && dcode - 15 == (u32)cmd_dist)) {
+          u32 lpp = B.start - (lc_copy_len & 0x1FFFFFF);
+          u32 maxd = br_min(lpp, P.max_backward);
+          if (cmd_dist > 0 && (u32)cmd_dist <= maxd) ext_dist = (u32)cmd_dist;
+        }
+      }
+      if (lane == 0) {
+        BrBlk W = B;
+        for (int i = 0; i < 4; ++i) W.in_dc[i] = dc[i];
+        W.in_ext_dist = ext_dist; W.lil_in = last_insert_len;
+        W.dict_l_lo = (u32)dict_l; W.dict_l_hi = (u32)(dict_l >> 32);
+        W.dict_m_lo = (u32)dict_m; W.dict_m_hi = (u32)(dict_m >> 32);
+        W.cmd_base = cmd_total; W.mb = n_mbs;
+        s.blk[bi] = W;
+      }
+      // carry on with the block's latest (possibly stale) summary
+      if (B.ext_len && have_last && s.bin_used[B.first_chunk].ext_dist) {
+        lc_copy_len += B.ext_len;
+        if (lane == 0) s.ext_total[lc_chunk] += B.ext_len;
+      }
+      if (B.has_cmd) {
+        const BrCmd c = s.cmd_blocks[(size_t)B.last_cmd_chunk * s.cmd_stride + s.bout[B.last_cmd_chunk].ncmd - 1];
+        lc_copy_len = c.copy_len; lc_dist_prefix = c.dist_prefix; lc_dist_extra = c.dist_extra;
+        lc_chunk = B.last_cmd_chunk; have_last = true;
+        num_lits += B.nlit_rel + last_insert_len;
+        last_insert_len = B.lil_tail;
+      } else last_insert_len += B.lil_tail;
+      num_cmds += B.ncmd;
+      for (int i = 0; i < 4; ++i) dc[i] = B.out_dc[i];
+      dict_l += B.dl; dict_m += B.dm;
+      cmd_total += B.ncmd;
+      // merge-or-flush (encode.c:1141)
+      const u32 end = B.end;
+      {
+        const u32 processed = end - last_flush_pos;
+        const bool next_fits = processed + blocksize <= P.max_mb;
+        if (!B.is_last && !B.force_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) continue;
+      }
+      u32 tail = 0;
+      if (last_insert_len > 0) { tail = last_insert_len; ++num_cmds; num_lits += tail; last_insert_len = 0; ++cmd_total; }
+      const u32 bytes = end - last_flush_pos;
+      int compress = br_should_compress(s, last_flush_pos, bytes, num_lits, num_cmds);
+      if (compress && s.force_unc[n_mbs]) compress = 0;
+      if (!compress) for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i];
+      if (lane == 0) {
+        BrMetaBlock m;
+        m.start = last_flush_pos; m.end = end;
+        m.first_block = s.blk[first_blk].first_chunk; m.last_block = B.first_chunk + B.nchunks - 1;
+        m.cmd_off = s.blk[first_blk].cmd_base; m.ncmd = num_cmds; m.nlit = num_lits;
+        m.is_last = B.is_last; m.compress = (u32)compress;
+        m.prev_byte = last_flush_pos > 0 ? s.data[last_flush_pos - 1] : 0;
+        m.prev_byte2 = last_flush_pos > 1 ? s.data[last_flush_pos - 2] : 0;
+        m.pad0 = m.pad1 = 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
+        s.mbs[n_mbs] = m;
+      }
+      br_syncwarp();
+      ++n_mbs;
+      last_flush_pos = end; num_cmds = 0; num_lits = 0; have_last = false; first_blk = bi + 1;
+      for (int i = 0; i < 4; ++i) saved_dc[i] = dc[i];
+    }
+    if (lane == 0) { s.counters[1] = n_mbs; s.counters[2] = cmd_total; }
+  }
+  br_ch_sync();
+  // ---- phase 4: per chunk: final in-state, dirty decision, offsets
+  for (u32 bi = tid; bi < nblk; bi += nt) {
+    const BrBlk B = s.blk[bi];
+    u64 dict_l = ((u64)B.dict_l_hi << 32) | B.dict_l_lo, dict_m = ((u64)B.dict_m_hi << 32) | B.dict_m_lo;
+    u32 cmd_off = B.cmd_base;
+    // stored-bits committed inside this block's window since a given launch: find the newest commit epoch
+    const u32 lowpos = B.start > P.max_backward ? B.start - P.max_backward : 0;
+    int newest = -1;
+    for (u32 j = bi; j-- > 0;) {
+      if (s.blk[j].end <= lowpos) break;
+      int ce = s.blk[j].changed_epoch;
+      if (ce > newest) newest = ce;
+    }
+    bool prev_dirty = false;
+    for (u32 c = 0; c < B.nchunks; ++c) {
+      const u32 k = B.first_chunk + c;
       BrBlockIn ni = s.bin[k];
-      ni.last_insert_len = last_insert_len;
-      for (int i = 0; i < 4; ++i) ni.dc[i] = dc[i];
-      ni.ext_dist = ext_dist;
+      if (c == 0) {
+        ni.start_pos = B.start; ni.ext_dist = B.in_ext_dist; ni.apply_rh = 0; ni.store_end = 0;
+        for (int i = 0; i < 4; ++i) ni.dc[i] = B.in_dc[i];
+      }
       ni.dict_l_lo = (u32)dict_l; ni.dict_l_hi = (u32)(dict_l >> 32);
       ni.dict_m_lo = (u32)dict_m; ni.dict_m_hi = (u32)(dict_m >> 32);
+      u32 rel = s.lil_in[k];
+      u32 lil_true = (rel & 0x7fffffffu) + ((rel & 0x80000000u) ? B.lil_in : 0u);
+      ni.last_insert_len = lil_true;
+      const BrBlockOut out = s.bout[k];
+      u32 dirty = out.valid ? 0u : 1u;  // reason: 1 never ran, 2 state, 3 dict gate, 4 window bits, 5 counter wrap
+      if (!dirty) {
+        const BrBlockIn u = s.bin_used[k];
+        if (u.ext_dist != ni.ext_dist || u.start_pos != ni.start_pos || u.apply_rh != ni.apply_rh ||
+            u.store_end != ni.store_end || u.dc[0] != ni.dc[0] || u.dc[1] != ni.dc[1] || u.dc[2] != ni.dc[2] ||
+            u.dc[3] != ni.dc[3]) dirty = 2;
+        u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
+        if (!dirty && (ul != dict_l || um != dict_m) && out.gate_checks) {
+          bool all_open = out.gate_fail == 0, all_closed = out.gate_fail == out.gate_checks;
+          bool ok = (all_open && dict_m >= ((dict_l + out.dl) >> 7)) || (all_closed && dict_m < (dict_l >> 7));
+          if (!ok) dirty = 3;
+        }
+        if (!dirty && out.out_pos > ni.start_pos) {
+          int seen = (int)out.epoch;
+          // earlier chunks of the own block count as window too
+          int own = s.blk[bi].changed_epoch;
+          if (newest >= seen || (c > 0 && own >= seen)) dirty = 4;
+          u32 unseen = s.epoch_suffix[seen < BR_MAX_EPOCHS ? seen : BR_MAX_EPOCHS];
+          if (!dirty && unseen > out.min_wrap_dist) dirty = 5;
+        }
+      }
+      // From the third launch on, a chunk whose only problem is the state handed over by a dirty
+      // predecessor is not scheduled: the predecessor's walker chases into it (br_walk_block), which
+      // resolves a serial ripple in one launch instead of one launch per chunk.
+      const bool defer = dirty == 2 && prev_dirty && t_now >= 2;
+      prev_dirty = dirty != 0;
       s.bin[k] = ni;
-      s.dirty[k] = dirty;
-      s.cmd_off[k] = cmd_total;
+      s.dirty[k] = defer ? 0u : dirty;
+      s.cmd_off[k] = cmd_off;
+      s.lil_in[k] = lil_true;
+      s.block_mb[k] = 0;
+      if (dirty) br_atomic_add(s.counters + 0, 1);
+      if (dirty && !defer) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; }
+      if (out.valid) { cmd_off += out.ncmd; dict_l += out.dl; dict_m += out.dm; }
     }
-    if (dirty) ++n_dirty;
-    // ---- carry on with the block's latest (possibly stale) summary
-    if (out.valid) {
-      if (out.ext_len && have_last) {
-        lc_copy_len += out.ext_len;
-        if (lane == 0) s.ext_total[lc_block] += out.ext_len;
-      }
-      if (out.ncmd > 0) {
-        const BrCmd c = s.cmd_blocks[(size_t)k * s.cmd_stride + out.ncmd - 1];
-        lc_copy_len = c.copy_len; lc_dist_prefix = c.dist_prefix; lc_dist_extra = c.dist_extra;
-        lc_block = k; have_last = true;
-      }
-      num_cmds += out.ncmd; num_lits += out.nlit; last_insert_len = out.last_insert_len;
-      for (int i = 0; i < 4; ++i) dc[i] = out.dc[i];
-      dict_l += out.dl; dict_m += out.dm;
-      cmd_total += out.ncmd;
-    } else {
-      last_insert_len += end - pos;
-    }
-    // ---- merge-or-flush (encode.c:1141)
-    {
-      const u32 processed = end - last_flush_pos;
-      const bool next_fits = processed + blocksize <= P.max_mb;
-      if (!is_last && !s.bin[k].force_flush && next_fits && num_lits < P.max_mb / 8 &&
-          num_cmds < P.max_mb / 8) continue;
-    }
-    u32 tail = 0;
-    if (last_insert_len > 0) {
-      tail = last_insert_len; ++num_cmds; num_lits += tail; last_insert_len = 0; ++cmd_total;
-    }
-    const u32 bytes = end - last_flush_pos;
-    int compress = br_should_compress(s, last_flush_pos, bytes, num_lits, num_cmds);
-    if (compress && s.force_unc[n_mbs]) compress = 0;
-    if (!compress) for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i];
-    if (lane == 0) {
-      BrMetaBlock m;
-      m.start = last_flush_pos; m.end = end; m.first_block = first_block; m.last_block = k;
-      m.cmd_off = s.cmd_off[first_block]; m.ncmd = num_cmds; m.nlit = num_lits;
-      m.is_last = is_last; m.compress = (u32)compress;
-      m.prev_byte = last_flush_pos > 0 ? s.data[last_flush_pos - 1] : 0;
-      m.prev_byte2 = last_flush_pos > 1 ? s.data[last_flush_pos - 2] : 0;
-      m.pad0 = m.pad1 = 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
-      s.mbs[n_mbs] = m;
-    }
-    br_syncwarp();
-    ++n_mbs;
-    last_flush_pos = end; num_cmds = 0; num_lits = 0; have_last = false; first_block = k + 1;
-    for (int i = 0; i < 4; ++i) saved_dc[i] = dc[i];
   }
-  if (lane == 0) { s.counters[0] = n_dirty; s.counters[1] = n_mbs; s.counters[2] = cmd_total; }
+  br_ch_sync();
+  // chunk -> metablock map
+  {
+    const u32 nm = s.counters[1];
+    for (u32 i = 0; i < nm; ++i) {
+      const u32 a = s.mbs[i].first_block, b = s.mbs[i].last_block;
+      for (u32 k = a + tid; k <= b; k += nt) s.block_mb[k] = i;
+    }
+  }
 }
 
-// Gather one block's commands into the stream-wide compacted array, applying the
+// Gather one chunk's commands into the stream-wide compacted array, applying the
 // ExtendLastCommand growth (encode.c:961) and the trailing insert-only command
-// (encode.c:1169).  Warp task per block.
+// (encode.c:1169).  Warp task per chunk.
 BR_DEV void br_compact_block(const BrStream& s, u32 k, BrCmd* cmds_all, const u32* block_mb) {
   const BrBlockOut out = s.bout[k];
   const BrCmd* src = s.cmd_blocks + (size_t)k * s.cmd_stride;
   BrCmd* dst = cmds_all + s.cmd_off[k];
   for (u32 i = (u32)br_lane(); i < out.ncmd; i += BR_WARP) {
     BrCmd c = src[i];
+    if (i == 0 && s.lil_in[k]) {   // literals pending when the chunk started belong to its first command
+      c.insert_len += s.lil_in[k];
+      c.cmd_prefix = br_length_code(c.insert_len, br_cmd_copy_len_code(c), (c.dist_prefix & 0x3FF) == 0);
+    }
     if (i + 1 == out.ncmd && s.ext_total[k]) {
       c.copy_len += s.ext_total[k];
       c.cmd_prefix = br_length_code(c.insert_len,

@@ -164,36 +164,17 @@ __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restr
 }
 
 // ---------------------------------------------------------------------------- warp-task kernels
-__global__ void k_walk(BrStream s, const u32* __restrict__ list, u32 count, u32 words_per_warp) {
-  extern __shared__ u32 sm[];
-  u32 warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  u32 t = blockIdx.x * wpb + warp;
-  if (t >= count) return;
-  br_walk_block(s, list[t], sm + warp * words_per_warp);
-}
-__global__ void k_commit(BrStream s, const u32* __restrict__ list, u32 count) {
+__global__ void __launch_bounds__(128) k_walk(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (t >= count) return;
-  br_commit_bits(s, list[t]);
+  if (t >= s.counters[5]) return;
+  br_walk_block(s, s.dirty_list[t]);
 }
-__global__ void k_chain(BrStream s, u32* dirty_list, u32* block_mb) {
-  br_chain(s);
-  __threadfence_block();
-  __syncwarp();
-  // compact the dirty flags into a work list; map blocks to metablocks
-  u32 lane = threadIdx.x, cnt = 0;
-  for (u32 base = 0; base < s.P.nblocks; base += 32) {
-    u32 k = base + lane;
-    bool d = k < s.P.nblocks && s.dirty[k] != 0;
-    u32 m = __ballot_sync(0xffffffffu, d);
-    if (d) dirty_list[cnt + __popc(m & ((1u << lane) - 1))] = k;
-    cnt += __popc(m);
-  }
-  __syncwarp();
-  u32 nm = s.counters[1];
-  for (u32 i = 0; i < nm; ++i)
-    for (u32 k = s.mbs[i].first_block + lane; k <= s.mbs[i].last_block; k += 32) block_mb[k] = i;
+__global__ void k_commit(BrStream s) {
+  u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= s.counters[4]) return;
+  br_commit_bits(s, s.ran_list[t]);
 }
+__global__ void __launch_bounds__(1024) k_chain(BrStream s) { br_chain(s); }
 __global__ void k_compact(BrStream s, BrCmd* cmds_all, const u32* __restrict__ block_mb) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.P.nblocks) return;
@@ -428,7 +409,24 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   BrStream s; memset(&s, 0, sizeof(s));
   if (!br_derive_params(quality, lgwin, size_hint, n, &s.P)) return 0;
   BrParams& P = s.P;
-  const u32 bs = 1u << P.lgblock, nb = (n + bs - 1) / bs;
+  const u32 bs = 1u << P.lgblock, ch = 1u << BR_CHUNK_BITS;
+  // chunk / block tables (one-shot call: uniform input blocks of 1 << lgblock bytes)
+  std::vector<BrBlockIn> hb; std::vector<BrBlk> hblk;
+  for (u64 bstart = 0; bstart < n; bstart += bs) {
+    u32 bend = (u32)(bstart + bs < n ? bstart + bs : n);
+    BrBlk B; memset(&B, 0, sizeof(B));
+    B.start = (u32)bstart; B.end = bend; B.is_last = (bend == n); B.changed_epoch = -1;
+    B.first_chunk = (u32)hb.size();
+    for (u64 c = bstart; c < bend; c += ch) {
+      BrBlockIn ci; memset(&ci, 0, sizeof(ci));
+      ci.pos = (u32)c; ci.end = (u32)(c + ch < bend ? c + ch : bend); ci.blk_start = (u32)bstart; ci.blk_end = bend;
+      ci.first = (c == bstart); ci.last = (ci.end == bend); ci.is_last = B.is_last; ci.blk = (u32)hblk.size();
+      hb.push_back(ci);
+    }
+    B.nchunks = (u32)hb.size() - B.first_chunk;
+    hblk.push_back(B);
+  }
+  const u32 nb = (u32)hb.size(), nblk = (u32)hblk.size();
   P.nblocks = nb;
   cudaStream_t st = job->st;
   memset(&job->stats, 0, sizeof(job->stats));
@@ -438,7 +436,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 
   const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
   const size_t nwords = (size_t)(n + 31) / 32 + 2;
-  const u32 cmd_stride = bs / 2 + 2;
+  const u32 cmd_stride = ch / 2 + 2;
   size_t need = 0;
   auto add = [&](size_t bytes) { need += (bytes + 255) & ~(size_t)255; };
   add((size_t)n + 64); add(2ull * n + 4); add(2ull * n + 4); add(4ull * n); add(2ull * n + 4); add(4ull * n); add(4ull * n);
@@ -446,7 +444,8 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
   add(scan_tmp_words((size_t)n / 1024 + 8) * 4);
   add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
-  for (int i = 0; i < 8; ++i) add(nb * 4ull + 64);
+  for (int i = 0; i < 12; ++i) add(nb * 4ull + 64);
+  add(nblk * sizeof(BrBlk));
   add(BR_MAX_EPOCHS * 8 + 64); add((nb + 1) * sizeof(BrMetaBlock)); add(4096);
   need += 1 << 20;
   if (!job->arena.reserve(need)) return 0;
@@ -466,6 +465,8 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   int* changed_epoch = A.take<int>(nb + 16); u32* ext_total = A.take<u32>(nb + 16);
   u32* cmd_off = A.take<u32>(nb + 16); u32* force_unc = A.take<u32>(nb + 16);
   u32* dirty_list = A.take<u32>(nb + 16); u32* block_mb = A.take<u32>(nb + 16);
+  u32* ran_list = A.take<u32>(nb + 16); u32* lil_in = A.take<u32>(nb + 16);
+  BrBlk* d_blk = A.take<BrBlk>(nblk);
   u32* epoch_changed = A.take<u32>(BR_MAX_EPOCHS); u32* epoch_suffix = A.take<u32>(BR_MAX_EPOCHS + 1);
   BrMetaBlock* mbs = A.take<BrMetaBlock>(nb + 1);
   u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256);
@@ -479,22 +480,15 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   s.changed_epoch = changed_epoch; s.epoch_changed = epoch_changed; s.epoch_suffix = epoch_suffix;
   s.ext_total = ext_total; s.cmd_off = cmd_off; s.mbs = mbs; s.force_unc = force_unc;
   s.counters = counters; s.hist_scratch = hist_scratch;
+  s.dirty_list = dirty_list; s.block_mb = block_mb; s.ran_list = ran_list; s.lil_in = lil_in; s.blk = d_blk; s.nblk = nblk;
   { const u8* p = T->blob + 8;
     s.dict_size_bits = p; p += 32; s.dict_offsets = (const u32*)p; p += 128; s.dict = p; p += 122784;
     s.dict_hash_words = (const u16*)p; p += 65536; s.dict_hash_lengths = p; p += 32768; s.ctx_lut = p; }
   s.log2tab = T->log2tab; s.log2tab_n = T->log2tab_n;
 
-  // block table (one-shot: uniform blocks) + zeroed state
-  {
-    std::vector<BrBlockIn> hb(nb);
-    memset(hb.data(), 0, nb * sizeof(BrBlockIn));
-    for (u32 k = 0; k < nb; ++k) {
-      hb[k].pos = k * bs; hb[k].end = (u64)(k + 1) * bs < n ? (k + 1) * bs : n;
-      hb[k].is_last = (k + 1 == nb);
-    }
-    CK(cudaMemcpyAsync(bin, hb.data(), nb * sizeof(BrBlockIn), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-  }
+  CK(cudaMemcpyAsync(bin, hb.data(), nb * sizeof(BrBlockIn), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_blk, hblk.data(), nblk * sizeof(BrBlk), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
   CK(cudaMemsetAsync(bout, 0, nb * sizeof(BrBlockOut), st));
   CK(cudaMemsetAsync(bin_used, 0, nb * sizeof(BrBlockIn), st));
   CK(cudaMemsetAsync(changed_bits, 0, (nb + 16) * 4, st));
@@ -518,10 +512,6 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   cudaEventRecord(ev[1], st);
 
   // ---- LZ77 fixpoint
-  const u32 own_words = bs / 32 + 2;
-  const u32 wpb = P.lgblock <= 16 ? 4 : 2;
-  const size_t walk_smem = (size_t)wpb * own_words * 4;
-  CK(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
   u32* hp = job->h_pinned;
   u32 n_mbs = 0, total_cmds = 0;
   int rounds = 0;
@@ -530,22 +520,25 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   for (;;) {   // rounds: repeated only when a metablock needs the late uncompressed fallback
     ++rounds;
     for (;;) {
-      k_chain<<<1, 32, 0, st>>>(s, dirty_list, block_mb);
+      k_chain<<<1, 1024, 0, st>>>(s);
       CK(cudaMemcpyAsync(hp, counters, 32, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      u32 n_dirty = hp[0]; n_mbs = hp[1]; total_cmds = hp[2];
+      u32 n_dirty = hp[0], n_sched = hp[5]; n_mbs = hp[1]; total_cmds = hp[2];
+      job->stats.block_runs += hp[4];
       if (walk_pending) { float wms; cudaEventElapsedTime(&wms, ev[6], ev[7]); job->stats.ms_walk += wms; walk_pending = false; }
       if (n_dirty == 0) break;
       if (s.epoch + 2 >= BR_MAX_EPOCHS) { fprintf(stderr, "brotli_b200: LZ77 fixpoint did not converge\n"); return 0; }
-      ++s.epoch; ++job->stats.lz77_iterations; job->stats.block_runs += n_dirty;
+      ++s.epoch; ++job->stats.lz77_iterations;
+      CK(cudaMemsetAsync(bits_cur, 0, nwords * 4, st));
+      CK(cudaMemsetAsync(counters + 4, 0, 4, st));
       k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
       scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
       cudaEventRecord(ev[6], st);
-      k_walk<<<(n_dirty + wpb - 1) / wpb, wpb * 32, walk_smem, st>>>(s, dirty_list, n_dirty, own_words);
+      k_walk<<<(n_sched + 3) / 4, 128, 0, st>>>(s);
       cudaEventRecord(ev[7], st);
       walk_pending = true; ++job->stats.walk_launches; job->stats.launches += 6;
-      job->stats.walk_bytes += (u64)n_dirty * bs;
-      k_commit<<<(n_dirty * 32 + 127) / 128, 128, 0, st>>>(s, dirty_list, n_dirty);
+      job->stats.walk_bytes += (u64)n_sched * ch;
+      k_commit<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s);
     }
     cudaEventRecord(ev[2], st);
     // ---- entropy stage

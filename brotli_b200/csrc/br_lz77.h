@@ -50,9 +50,7 @@ BR_DEV u32 br_hash_key(const BrParams& P, const u8* d, u32 pos) {
 struct BrWalk {
   const BrStream* s;
   const u8* d;
-  u32 p0, pend;
-  u32* own;        // stored bits of this block's own positions (shared memory)
-  u32 own_w0;
+  u32 p0, pend;    // p0: first position this walker owns; pend: end of the reference input block
   int dc[16];
   u64 dict_l, dict_m;
   u32 dl, dm, gate_checks, gate_fail;
@@ -60,11 +58,20 @@ struct BrWalk {
   u32 stale;       // the byte the reference finds just past the block end (see oracle)
 };
 
+// Stored-bits of the walker's own range [p0, ...) live in bits_cur (global): written with
+// atomic OR (other walkers own neighbouring bits of the same words), read around L1.
+BR_DEV u32 br_ld_cur(const u32* p) {
+#if BR_GPU
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
 BR_DEV int br_own_get(const BrWalk& w, u32 q) {
-  return (w.own[(q >> 5) - w.own_w0] >> (q & 31)) & 1;
+  return (br_ld_cur(w.s->bits_cur + (q >> 5)) >> (q & 31)) & 1;
 }
 BR_DEV void br_own_set(BrWalk& w, u32 q) {
-  if (br_lane() == 0) w.own[(q >> 5) - w.own_w0] |= 1u << (q & 31);
+  if (br_lane() == 0) br_atomic_or(w.s->bits_cur + (q >> 5), 1u << (q & 31));
   br_syncwarp();
 }
 BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
@@ -74,8 +81,11 @@ BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
     u32 m = 0xffffffffu;
     if (x == wa) m &= 0xffffffffu << (a & 31);
     if (x == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
-    w.own[x - w.own_w0] |= m;
+    br_atomic_or(w.s->bits_cur + x, m);
   }
+#if BR_GPU
+  __threadfence_block();
+#endif
   br_syncwarp();
 }
 BR_DEV int br_is_stored(const BrWalk& w, u32 q) {
@@ -290,52 +300,57 @@ BR_DEV u32 br_compute_distance_code(u32 distance, u32 max_distance, const int* d
   return distance + 15;
 }
 
-// One input block.  `own` must hold ((end-1)>>5) - (pos>>5) + 1 words.
-BR_DEV void br_walk_block(const BrStream& s, u32 b, u32* own) {
+// One chunk (see br_types.h).  The walker resumes the parse of its input block at
+// in.start_pos with the carried state and leaves when the position reaches the chunk end
+// (the last chunk of a block runs to the block end like the reference loop).
+BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOut& o) {
   const BrParams& P = s.P;
-  const BrBlockIn in = s.bin[b];
   const int lane = br_lane();
   BrWalk w;
-  w.s = &s; w.d = s.data; w.p0 = in.pos; w.pend = in.end;
-  w.own = own; w.own_w0 = in.pos >> 5;
+  w.s = &s; w.d = s.data; w.p0 = in.start_pos; w.pend = in.blk_end;
   w.dict_l = ((u64)in.dict_l_hi << 32) | in.dict_l_lo;
   w.dict_m = ((u64)in.dict_m_hi << 32) | in.dict_m_lo;
   w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
   w.min_wrap = 0xffffffffu;
-  w.stale = in.end <= P.rmask ? 0u : (u32)s.data[in.end - (P.rmask + 1)];
+  w.stale = in.blk_end <= P.rmask ? 0u : (u32)s.data[in.blk_end - (P.rmask + 1)];
   for (int i = 0; i < 4; ++i) w.dc[i] = in.dc[i];
   for (int i = 4; i < 16; ++i) w.dc[i] = 0;
-  {
-    u32 nw = ((in.end - 1) >> 5) - w.own_w0 + 1;
-    for (u32 x = (u32)lane; x < nw; x += BR_WARP) own[x] = 0;
-    br_syncwarp();
-  }
-  u32 position = in.pos, bytes = in.end - in.pos;
-  // ---- ExtendLastCommand (encode.c:941): grow the previous block's final copy.
+  const u32 pos_end = in.blk_end;
+  u32 position = in.start_pos;
   u32 ext = 0;
-  if (in.ext_dist) {
-    while (bytes) {
-      u32 chunk = bytes < BR_WARP ? bytes : BR_WARP;
-      bool eq = (u32)lane < chunk &&
-                s.data[position + lane] == s.data[position + lane - in.ext_dist];
-      u32 m = br_ballot(eq);
-      u32 run = (u32)br_ffs(~m) - 1u;  // leading equal lanes
-      if (BR_WARP == 1) run = m ? 1 : 0;
-      if (run > chunk) run = chunk;
-      ext += run; position += run; bytes -= run;
-      if (run < chunk) break;
-    }
-  }
-  // ---- CreateBackwardReferences (backward_references_inc.h:10)
-  const u32 pos_end = in.end;
-  const u32 store_end = bytes >= P.htl ? position + bytes - P.htl + 1 : position;
+  u32 apply_random_heuristics = in.apply_rh;
   const u32 window = P.spree;
-  u32 apply_random_heuristics = position + window;
-  u32 insert_length = in.last_insert_len;
+  u32 store_end;
+  if (in.first) {
+    u32 bytes = pos_end - position;
+    // ---- ExtendLastCommand (encode.c:941): grow the previous block's final copy.
+    if (in.ext_dist) {
+      while (bytes) {
+        u32 chunk = bytes < BR_WARP ? bytes : BR_WARP;
+        bool eq = (u32)lane < chunk && s.data[position + lane] == s.data[position + lane - in.ext_dist];
+        u32 m = br_ballot(eq);
+        u32 run = (u32)br_ffs(~m) - 1u;  // leading equal lanes
+        if (run > chunk) run = chunk;
+        ext += run; position += run; bytes -= run;
+        if (run < chunk) break;
+      }
+    }
+    apply_random_heuristics = position + window;
+  }
+  if (in.first) {
+    u32 bytes = pos_end - position;   // what CreateBackwardReferences receives after the extension
+    store_end = bytes >= P.htl ? pos_end - P.htl + 1 : position;
+  } else {
+    store_end = in.store_end;
+  }
+  // Pending literals are carried as an OFFSET: the parse does not depend on how many literals
+  // are pending at the chunk start, only the first command's insert length does.  The walker
+  // counts from zero and the chain / compaction add the true carry (BrStream::lil_in).
+  u32 insert_length = 0;
   u32 ncmd = 0, nlit = 0;
   BrCmd* cmds = s.cmd_blocks + (size_t)b * s.cmd_stride;
   br_prepare_dist_cache(w.dc, P.ndist);
-  while (position + P.htl < pos_end) {
+  while (position + P.htl < pos_end && (in.last || position < in.end)) {
     u32 max_length = pos_end - position;
     u32 max_distance = br_min(position, P.max_backward);
     BrSR sr; sr.len = 0; sr.delta = 0; sr.distance = 0; sr.score = BR_MIN_SCORE;
@@ -392,37 +407,56 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, u32* own) {
       }
     }
   }
-  insert_length += pos_end - position;
-  // ---- StitchToPreviousBlock of the FOLLOWING blocks (hash_longest_match64_inc.h:127) stores
-  // the last three positions of this block; the set is static, so this block owns the bits.
-  for (u32 nb = b + 1; nb < P.nblocks; ++nb) {
-    u32 np = s.bin[nb].pos, ne = s.bin[nb].end;
-    if (np >= pos_end + 3) break;
-    if (ne - np >= P.htl - 1 && np >= 3) {
-      for (u32 q = np - 3; q < np; ++q)
-        if (q >= in.pos && q < pos_end) br_own_set(w, q);
-    }
+  if (in.last) {
+    insert_length += pos_end - position;
+    position = pos_end;
   }
-  // ---- publish
   {
-    u32 w0 = in.pos >> 5, w1 = (pos_end - 1) >> 5;
-    for (u32 x = w0 + (u32)lane; x <= w1; x += BR_WARP) {
-      u32 m = 0xffffffffu;
-      if (x == w0) m &= 0xffffffffu << (in.pos & 31);
-      if (x == w1) m &= 0xffffffffu >> (31 - ((pos_end - 1) & 31));
-      u32 v = own[x - w0] & m;
-      if (m == 0xffffffffu) s.bits_cur[x] = v;
-      else { br_atomic_and(s.bits_cur + x, ~m); br_atomic_or(s.bits_cur + x, v); }
-    }
-  }
-  if (lane == 0) {
-    BrBlockOut o;
-    o.ncmd = ncmd; o.nlit = nlit; o.last_insert_len = insert_length;
+    o.ncmd = ncmd; o.nlit = nlit; o.out_pos = position; o.last_insert_len = insert_length;
     for (int i = 0; i < 4; ++i) o.dc[i] = w.dc[i];
+    o.apply_rh = apply_random_heuristics; o.store_end = store_end;
     o.ext_len = ext; o.dl = w.dl; o.dm = w.dm;
     o.gate_checks = w.gate_checks; o.gate_fail = w.gate_fail;
     o.min_wrap_dist = w.min_wrap; o.valid = 1; o.epoch = s.epoch;
+  }
+  if (lane == 0) {
     s.bout[b] = o;
     s.bin_used[b] = in;
+    u32 slot = br_atomic_add(s.counters + 4, 1);   // list of chunks to commit
+    s.ran_list[slot] = b;
+  }
+  br_syncwarp();
+}
+
+// Walk chunk b, then CHASE: while the state this walker leaves differs from what the next chunk
+// of the same input block consumed on its latest run -- and nobody else runs that chunk in this
+// launch -- keep going.  This resolves, inside one launch, the ripples that otherwise cost one
+// launch per chunk (e.g. a distance-cache change flowing through match-free data).
+BR_DEV void br_walk_block(const BrStream& s, u32 b) {
+  BrBlockIn in = s.bin[b];
+  for (;;) {
+    BrBlockOut o;
+    br_walk_one(s, b, in, o);
+    if (in.last) return;
+    const u32 nb = b + 1;
+    if (s.dirty[nb] != 0 || !s.bout[nb].valid) return;
+    const BrBlockIn u = s.bin_used[nb];
+    const u64 dl = (((u64)in.dict_l_hi << 32) | in.dict_l_lo) + o.dl, dm = (((u64)in.dict_m_hi << 32) | in.dict_m_lo) + o.dm;
+    bool same = u.start_pos == o.out_pos && u.apply_rh == o.apply_rh && u.store_end == o.store_end && u.ext_dist == 0 &&
+                u.dc[0] == o.dc[0] && u.dc[1] == o.dc[1] && u.dc[2] == o.dc[2] && u.dc[3] == o.dc[3];
+    if (same) {
+      const BrBlockOut uo = s.bout[nb];
+      const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
+      if ((ul != dl || um != dm) && uo.gate_checks) {
+        bool all_open = uo.gate_fail == 0, all_closed = uo.gate_fail == uo.gate_checks;
+        same = (all_open && dm >= ((dl + uo.dl) >> 7)) || (all_closed && dm < (dl >> 7));
+      }
+    }
+    if (same) return;
+    BrBlockIn ni = s.bin[nb];
+    ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0;
+    for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];
+    ni.dict_l_lo = (u32)dl; ni.dict_l_hi = (u32)(dl >> 32); ni.dict_m_lo = (u32)dm; ni.dict_m_hi = (u32)(dm >> 32);
+    in = ni; b = nb;
   }
 }

@@ -25,31 +25,54 @@ struct BrParams {
   u32 max_mb;       // MaxMetablockSize
   u32 size_hint;
   u32 n;            // input bytes
-  u32 nblocks;      // input blocks (EncodeData calls)
+  u32 nblocks;      // number of chunks (speculation units); input blocks are groups of them
   u32 nbuckets;     // 1 << bucket_bits (+1 overflow bucket for the unhashable tail positions)
 };
 
-// Per input block: what the serial chain hands to the block's walker.
+// The unit of speculation is a CHUNK: a slice (1 << BR_CHUNK_BITS bytes) of one of the
+// reference's input blocks.  Per chunk: what the chain hands to the chunk's walker.
+#define BR_CHUNK_BITS 12
 struct BrBlockIn {
-  u32 pos, end;          // [pos, end) of this input block
-  u32 last_insert_len;
-  int dc[4];             // distance cache at block start
-  u32 ext_dist;          // != 0: ExtendLastCommand applies with this distance (encode.c:905)
+  u32 pos, end;          // nominal slice [pos, end) of the input
+  u32 blk_start, blk_end;  // the reference input block (one EncodeData call) that contains it
+  u32 first, last;       // first / last chunk of that block
+  u32 blk;               // index of that block
+  u32 start_pos;         // where the parse resumes (first chunk: blk_start)
+  u32 last_insert_len;   // pending literals at start_pos (informational: walkers count from zero)
+  int dc[4];             // distance cache at start_pos
+  u32 ext_dist;          // first chunk, != 0: ExtendLastCommand applies with this distance (encode.c:905)
+  u32 apply_rh;          // apply_random_heuristics (backward_references_inc.h:29) carried into the chunk
+  u32 store_end;         // store_end of the block (backward_references_inc.h:24); set by its first chunk
   u32 dict_l_lo, dict_l_hi, dict_m_lo, dict_m_hi;  // dict_num_lookups / dict_num_matches (hash.h:49)
-  u32 is_last;
+  u32 is_last;           // block flags (copied to all its chunks)
   u32 force_flush;       // BROTLI_OPERATION_FLUSH ended the input here (encode.c:1700)
 };
 // What the walker reports back.
 struct BrBlockOut {
-  u32 ncmd, nlit;        // commands emitted, literals covered by them
-  u32 last_insert_len;   // pending literals at block end
+  u32 ncmd, nlit;        // commands emitted, literals covered by them (without the carried-in literals)
+  u32 out_pos;           // where the parse stands when the walker leaves the chunk
+  u32 last_insert_len;   // pending literals there, counted from the chunk start if it emitted no command
   int dc[4];
+  u32 apply_rh, store_end;
   u32 ext_len;           // bytes swallowed by ExtendLastCommand
   u32 dl, dm;            // static-dictionary counter deltas
   u32 gate_checks, gate_fail;
   u32 min_wrap_dist;     // see br_lz77.h (bucket counter wrap sensitivity)
   u32 valid;
   u32 epoch;             // walker launch that produced this record
+};
+
+// Per reference input block (one EncodeData call): static layout, aggregates over its chunks and
+// what the block-level chain derives for it.
+struct BrBlk {
+  u32 start, end, first_chunk, nchunks, is_last, force_flush;
+  // aggregates (chain phase 2)
+  u32 ncmd, nlit_rel, has_cmd, lil_head, lil_tail, last_cmd_chunk, dl, dm, ext_len, valid;
+  int out_dc[4];
+  // block-level chain (phase 3)
+  int in_dc[4];
+  u32 in_ext_dist, lil_in, dict_l_lo, dict_l_hi, dict_m_lo, dict_m_hi, cmd_base, mb;
+  int changed_epoch;     // last walker launch whose commit changed stored-bits inside this block (-1: never)
 };
 
 // Per metablock record produced by the chain kernel.
@@ -90,11 +113,17 @@ struct BrStream {
   u32* epoch_changed;    // [BR_MAX_EPOCHS] total changed bits committed per walker launch
   u32* epoch_suffix;     // [BR_MAX_EPOCHS + 1] suffix sums of the above (chain scratch)
   u32 epoch;             // current walker launch number (1-based)
-  u32* ext_total;        // [nblocks] bytes added to the block's last command by ExtendLastCommand
+  u32* ext_total;        // [nblocks] bytes added to the chunk's last command by ExtendLastCommand
+  u32* lil_in;           // [nblocks] true pending-literal count at the chunk start (added to its first command)
+  BrBlk* blk;            // [nblk] reference input blocks
+  u32 nblk;
+  u32* dirty_list;       // [nblocks] chunks scheduled for the next walker launch (counters[5] entries)
+  u32* ran_list;         // [nblocks] chunks walked in the current launch (counters[4] entries)
+  u32* block_mb;         // [nblocks] metablock of every chunk
   u32* cmd_off;          // [nblocks] offset of the block's commands in the compacted array
   BrMetaBlock* mbs;      // [max_mbs]
   u32* force_unc;        // [max_mbs] late fallback: store this metablock uncompressed
-  u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags
+  u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags, 4 chunks walked this launch, 5 chunks scheduled
   u32* hist_scratch;     // [256]
   // tables
   const u8* dict;        // RFC 7932 dictionary

@@ -36,12 +36,14 @@ struct SimStream {
   BrStream s;
   std::vector<u8> data;
   std::vector<u32> S, rank, seg, bits_latest, bits_cur, storedS, prefS, dirty, changed_bits,
-      epoch_changed, epoch_suffix, ext_total, cmd_off, force_unc, counters, hist, block_mb;
+      epoch_changed, epoch_suffix, ext_total, lil_in, cmd_off, force_unc, counters, hist, block_mb;
   std::vector<int> changed_epoch;
   std::vector<BrBlockIn> bin, bin_used;
   std::vector<BrBlockOut> bout;
   std::vector<BrCmd> cmd_blocks, cmds_all;
   std::vector<BrMetaBlock> mbs;
+  std::vector<BrBlk> blks;
+  std::vector<u32> dirty_list, ran_list;
   int iterations = 0;
   u64 block_runs = 0;
 };
@@ -80,27 +82,39 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   if (!br_derive_params(q, lgwin, n, n, &s.P)) { delete m; return nullptr; }
   BrParams& P = s.P;
   u32 bs = 1u << P.lgblock;
-  P.nblocks = (n + bs - 1) / bs;
+  const u32 ch = 1u << BR_CHUNK_BITS;
+  std::vector<BrBlockIn> chunks;
+  for (u32 bstart = 0; bstart < n; bstart += bs) {
+    u32 bend = std::min(n, bstart + bs);
+    for (u32 c = bstart; c < bend; c += ch) {
+      BrBlockIn ci; memset(&ci, 0, sizeof(ci));
+      ci.pos = c; ci.end = std::min(bend, c + ch); ci.blk_start = bstart; ci.blk_end = bend;
+      ci.first = (c == bstart); ci.last = (ci.end == bend); ci.is_last = (bend == n);
+      ci.blk = (u32)m->blks.size();
+      chunks.push_back(ci);
+    }
+    BrBlk B; memset(&B, 0, sizeof(B));
+    B.start = bstart; B.end = bend; B.is_last = (bend == n); B.changed_epoch = -1;
+    B.nchunks = (bend - bstart + ch - 1) / ch; B.first_chunk = (u32)chunks.size() - B.nchunks;
+    m->blks.push_back(B);
+  }
+  P.nblocks = (u32)chunks.size();
   m->data.assign(in, in + n); m->data.resize(n + 64, 0);
   s.data = m->data.data();
   u32 nb = P.nblocks, words = (n + 31) / 32 + 2;
-  m->bin.resize(nb); m->bin_used.resize(nb); m->bout.resize(nb);
-  memset(m->bin.data(), 0, nb * sizeof(BrBlockIn));
+  m->bin = chunks; m->bin_used.resize(nb); m->bout.resize(nb);
+  memset(m->bin_used.data(), 0, nb * sizeof(BrBlockIn));
   memset(m->bout.data(), 0, nb * sizeof(BrBlockOut));
-  for (u32 k = 0; k < nb; ++k) {
-    m->bin[k].pos = k * bs; m->bin[k].end = std::min(n, (k + 1) * bs);
-    m->bin[k].is_last = (k + 1 == nb);
-  }
   m->bits_latest.assign(words, 0); m->bits_cur.assign(words, 0);
   // initial guess: everything stored except the unsearchable tail of each block
   for (u32 k = 0; k < nb; ++k)
-    for (u32 p = m->bin[k].pos; p + P.htl <= m->bin[k].end; ++p) m->bits_latest[p >> 5] |= 1u << (p & 31);
+    for (u32 p = m->bin[k].pos; p < m->bin[k].end && p + P.htl <= m->bin[k].blk_end; ++p) m->bits_latest[p >> 5] |= 1u << (p & 31);
   m->storedS.assign(words + 32, 0); m->prefS.assign(n / 1024 + 4, 0);
   m->dirty.assign(nb, 0); m->changed_bits.assign(nb, 0); m->changed_epoch.assign(nb, -1);
   m->epoch_changed.assign(BR_MAX_EPOCHS, 0); m->epoch_suffix.assign(BR_MAX_EPOCHS + 1, 0);
-  m->ext_total.assign(nb, 0); m->cmd_off.assign(nb, 0); m->force_unc.assign(nb + 1, 0);
+  m->ext_total.assign(nb, 0); m->lil_in.assign(nb, 0); m->cmd_off.assign(nb, 0); m->force_unc.assign(nb + 1, 0);
   m->counters.assign(8, 0); m->hist.assign(256, 0); m->mbs.resize(nb + 1);
-  s.cmd_stride = bs / 2 + 2;
+  s.cmd_stride = ch / 2 + 2;
   m->cmd_blocks.resize((size_t)nb * s.cmd_stride);
   s.bits_latest = m->bits_latest.data(); s.bits_cur = m->bits_cur.data();
   s.storedS = m->storedS.data(); s.prefS = m->prefS.data();
@@ -108,9 +122,13 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   s.cmd_blocks = m->cmd_blocks.data(); s.dirty = m->dirty.data();
   s.changed_bits = m->changed_bits.data(); s.changed_epoch = m->changed_epoch.data();
   s.epoch_changed = m->epoch_changed.data(); s.epoch_suffix = m->epoch_suffix.data();
-  s.ext_total = m->ext_total.data(); s.cmd_off = m->cmd_off.data();
+  s.ext_total = m->ext_total.data(); s.lil_in = m->lil_in.data(); s.cmd_off = m->cmd_off.data();
   s.mbs = m->mbs.data(); s.force_unc = m->force_unc.data(); s.counters = m->counters.data();
   s.hist_scratch = m->hist.data();
+  s.blk = m->blks.data(); s.nblk = (u32)m->blks.size();
+  m->dirty_list.assign(nb + 1, 0); m->block_mb.assign(nb + 1, 0);
+  s.dirty_list = m->dirty_list.data(); s.block_mb = m->block_mb.data();
+  m->ran_list.assign(nb + 1, 0); s.ran_list = m->ran_list.data();
   const u8* p = g_t.blob.data() + 8;
   s.dict_size_bits = p; p += 32;
   s.dict_offsets = (const u32*)p; p += 128;
@@ -125,7 +143,6 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
 
 static void sim_lz77_fixpoint(SimStream& m) {
   BrStream& s = m.s; u32 nb = s.P.nblocks;
-  std::vector<u32> own((1u << s.P.lgblock) / 32 + 2);
   s.epoch = 0;
   for (;;) {
     br_chain(s);
@@ -134,16 +151,13 @@ static void sim_lz77_fixpoint(SimStream& m) {
     if (s.counters[0] == 0) break;
     ++s.epoch; ++m.iterations;
     sim_build_storedS(m);
-    std::vector<u32> ran;
-    for (u32 k = 0; k < nb; ++k) if (s.dirty[k]) { br_walk_block(s, k, own.data()); ran.push_back(k); }
-    m.block_runs += ran.size();
-    for (u32 k : ran) br_commit_bits(s, k);
+    std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0);
+    s.counters[4] = 0;
+    { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) br_walk_block(s, k); }
+    m.block_runs += s.counters[4];
+    for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
     if (s.epoch >= BR_MAX_EPOCHS - 1) { fprintf(stderr, "sim: no fixpoint\n"); break; }
   }
-  u32 nm = s.counters[1];
-  m.block_mb.assign(nb, 0);
-  for (u32 i = 0; i < nm; ++i)
-    for (u32 k = s.mbs[i].first_block; k <= s.mbs[i].last_block; ++k) m.block_mb[k] = i;
   m.cmds_all.resize(s.counters[2] + 1);
   for (u32 k = 0; k < nb; ++k) br_compact_block(s, k, m.cmds_all.data(), m.block_mb.data());
 }

@@ -64,10 +64,10 @@ def check(name, d, q, w, use_ref=True):
     k = -1
     if not ok:
         k = next((i for i in range(min(len(got), len(want))) if got[i] != want[i]), min(len(got), len(want)))
-    print("%s n=%d q=%d w=%d -> %d (want %d) %s  wall %.1f ms  gpu %.1f ms [index %.1f lz77 %.1f entropy %.1f asm %.1f] iters %d runs %d/%d mbs %d" % (
+    print("%s n=%d q=%d w=%d -> %d (want %d) %s  wall %.1f ms  gpu %.1f ms [index %.1f lz77 %.1f entropy %.1f asm %.1f] iters %d runs %d/%d mbs %d walk %.1f ms in %d launches" % (
         name, len(d), q, w, len(got), len(want), "OK" if ok else "DIFF at %d" % k, dt * 1e3, st["ms_total"],
         st["ms_index"], st["ms_lz77"], st["ms_entropy"], st["ms_assemble"], st["lz77_iterations"],
-        st["block_runs"], st["blocks"], st["metablocks"]), flush=True)
+        st["block_runs"], st["blocks"], st["metablocks"], st["ms_walk"], st["walk_launches"]), flush=True)
     return ok
 
 
