@@ -38,17 +38,50 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
       for (u32 q = st_lo; q < st_hi; ++q) if ((q >> 5) == x) nv |= 1u << (q & 31);
       nv &= m;
       u32 ov = s.bits_latest[x] & m;
-      diff += (u32)br_popc(nv ^ ov);
-      if (nv != ov) {
+      u32 flips = nv ^ ov;
+      {  // searched-positions bitmap of this run
+        u32 sv = s.srch_cur[x] & m, so = s.srch_latest[x] & m;
+        if (sv != so) {
+          if (m == 0xffffffffu) s.srch_latest[x] = sv;
+          else { br_atomic_and(s.srch_latest + x, ~m); br_atomic_or(s.srch_latest + x, sv); }
+        }
+      }
+      diff += (u32)br_popc(flips);
+      if (flips) {
         if (m == 0xffffffffu) s.bits_latest[x] = nv;
         else { br_atomic_and(s.bits_latest + x, ~m); br_atomic_or(s.bits_latest + x, nv); }
+        // Who may have consulted a flipped bit?  Position q sits in the bucket ring seen from a later
+        // position p of the same key until block_size stored positions lie between them.
+        const u32 reach = (1u << s.P.block_bits) + 2;
+        while (flips) {
+          const u32 q = (x << 5) + (u32)br_ffs(flips) - 1u;
+          flips &= flips - 1;
+          const u32 jq = s.rank[q];
+          const u16 key = s.skeys[jq];
+          if (s.seg[key + 1] - s.seg[key] >= 65536u) br_atomic_add(s.key_flips + key, 1);   // uint16 bucket counter may wrap
+          u32 cnt = 0, steps = 0;
+          for (u32 j = jq + 1; j < s.P.n && s.skeys[j] == key && cnt < reach; ++j) {
+            if (++steps > 512) {   // pathological bucket (long runs of unstored positions): give up precision,
+              br_atomic_max((int*)(s.counters + 6), (int)s.epoch + 1);   // everybody re-validates
+              break;
+            }
+            const u32 pp = s.S[j];
+            if (pp - q > s.P.max_backward) break;
+            if ((s.bits_latest[pp >> 5] >> (pp & 31)) & 1) ++cnt;
+            if (pp >= a && pp < b) continue;            // my own run is consistent with my own bits
+            if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
+            u32 c = ((pp >> s.P.lgblock) << s.P.cpb_shift) + ((pp & ((1u << s.P.lgblock) - 1)) >> BR_CHUNK_BITS);
+            br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
+            if (c > 0) br_atomic_max(s.bitdep_epoch + c - 1, (int)s.epoch);   // its owner may be the chunk before
+          }
+        }
       }
     }
   }
   diff = br_warp_sum(diff);
   if (br_lane() == 0) {
     s.changed_bits[k] = diff;
-    if (diff) { s.changed_epoch[k] = (int)s.epoch; br_atomic_max(&s.blk[in.blk].changed_epoch, (int)s.epoch); }
+    if (diff) s.changed_epoch[k] = (int)s.epoch;
   }
 }
 
@@ -73,31 +106,78 @@ BR_DEV int br_should_compress(const BrStream& s, u32 start, u32 bytes, u32 num_l
   return 1;
 }
 
-#if BR_GPU
-#define BR_CH_TID ((u32)threadIdx.x)
-#define BR_CH_N ((u32)blockDim.x)
-BR_DEV void br_ch_sync() { __threadfence_block(); __syncthreads(); }
-#else
-#define BR_CH_TID 0u
-#define BR_CH_N 1u
-BR_DEV void br_ch_sync() {}
-#endif
+// ---- The chain, three kernels per walker launch ------------------------------------------
+//   br_chain_a  (thread per input block)  state flow through the block's chunks + aggregates
+//   br_chain_b  (one warp)                block-to-block recurrence of encode.c:985
+//   br_chain_c  (thread per input block)  final in-state of every chunk, dirty decision, offsets
 
-// One CTA per stream.  Phases 1, 2 and 4 are data-parallel over chunks / blocks; phase 3 (the
-// block-to-block recurrence of encode.c:985) runs on warp 0.
-BR_DEV void br_chain(const BrStream& s) {
+BR_DEV void br_chain_a(const BrStream& s, u32 bi) {
   const BrParams& P = s.P;
-  const u32 tid = BR_CH_TID, nt = BR_CH_N;
-  const u32 nb = P.nblocks, nblk = s.nblk, t_now = s.epoch;
+  BrBlk B = s.blk[bi];
+  u32 ncmd = 0, nlit_rel = 0, has_cmd = 0, lil_run = 0, lil_head = 0, last_cmd_chunk = 0, dl = 0, dm = 0;
+  u32 flow_pos = 0, flow_rh = 0, flow_se = 0; int fdc[4] = {0, 0, 0, 0};
+  bool all_valid = true;
+  for (u32 c = 0; c < B.nchunks; ++c) {
+    const u32 k = B.first_chunk + c;
+    const BrBlockOut out = s.bout[k];
+    s.ext_total[k] = 0;
+    if (c > 0) {
+      BrBlockIn ni = s.bin[k];
+      ni.start_pos = flow_pos; ni.apply_rh = flow_rh; ni.store_end = flow_se; ni.ext_dist = 0;
+      for (int i = 0; i < 4; ++i) ni.dc[i] = fdc[i];
+      ni.warm = out.valid ? 0u : (u32)BR_WARM_BYTES;
+      s.bin[k] = ni;
+    }
+    // pending literals relative to the block start (true value = + block lil_in while no command seen)
+    s.lil_in[k] = lil_run | (has_cmd ? 0u : 0x80000000u);
+    if (out.valid) {
+      if (out.ncmd > 0) {
+        nlit_rel += out.nlit + lil_run;
+        if (!has_cmd) lil_head = lil_run;
+        has_cmd = 1; lil_run = out.last_insert_len; last_cmd_chunk = k;
+      } else lil_run += out.last_insert_len;
+      ncmd += out.ncmd; dl += out.dl; dm += out.dm;
+      flow_pos = out.out_pos; flow_rh = out.apply_rh; flow_se = out.store_end;
+      for (int i = 0; i < 4; ++i) fdc[i] = out.dc[i];
+    } else {
+      // never ran: pretend it emitted nothing and stopped at its nominal end
+      all_valid = false;
+      const BrBlockIn cur = s.bin[k];
+      u32 sp = c == 0 ? cur.blk_start : cur.start_pos;
+      u32 from = sp > cur.pos ? sp : cur.pos, to = cur.last ? cur.blk_end : cur.end;
+      if (to > from) lil_run += to - from;
+      flow_pos = to > from ? to : sp; flow_rh = flow_pos + P.spree;
+      flow_se = cur.blk_end - cur.blk_start >= P.htl ? cur.blk_end - P.htl + 1 : cur.blk_start;
+      if (c == 0) { fdc[0] = 4; fdc[1] = 11; fdc[2] = 15; fdc[3] = 16; }
+    }
+  }
+  B.ncmd = ncmd; B.nlit_rel = nlit_rel; B.has_cmd = has_cmd; B.lil_head = lil_head; B.lil_tail = lil_run;
+  B.last_cmd_chunk = last_cmd_chunk; B.dl = dl; B.dm = dm; B.valid = all_valid ? 1u : 0u;
+  B.ext_len = 0;
+  if (s.bout[B.first_chunk].valid && s.bin_used[B.first_chunk].ext_dist) B.ext_len = s.bout[B.first_chunk].ext_len;
+  for (int i = 0; i < 4; ++i) B.out_dc[i] = fdc[i];
+  B.lc_copy_len = B.lc_dist_prefix = B.lc_dist_extra = 0;
+  if (has_cmd) {
+    const BrCmd c = s.cmd_blocks[(size_t)last_cmd_chunk * s.cmd_stride + s.bout[last_cmd_chunk].ncmd - 1];
+    B.lc_copy_len = c.copy_len; B.lc_dist_prefix = c.dist_prefix; B.lc_dist_extra = c.dist_extra;
+  }
+  s.blk[bi] = B;
+}
+
+BR_DEV void br_chain_b(const BrStream& s) {
+  const BrParams& P = s.P;
+  const u32 nblk = s.nblk, t_now = s.epoch;
   const int lane = br_lane();
-  // ---- phase 0: totals of this launch's commits (for the counter-wrap rule)
-  if (tid < BR_WARP) {
-    u32 tot = 0;
-    for (u32 k = (u32)lane; k < nb; k += BR_WARP)
-      if (s.bout[k].valid && s.bout[k].epoch == t_now) tot += s.changed_bits[k];
-    tot = br_warp_sum(tot);
+#if BR_GPU
+  long long t_begin = clock64();
+#endif
+  // counter-wrap rule: per launch, the largest number of stored-bit flips any single (heavy) bucket saw
+  {
+    u32 mx = 0;
+    for (u32 k = (u32)lane; k <= P.nbuckets; k += BR_WARP) { u32 v = s.key_flips[k]; if (v > mx) mx = v; s.key_flips[k] = 0; }
+    mx = br_warp_max(mx);
     if (lane == 0) {
-      if (t_now < BR_MAX_EPOCHS) s.epoch_changed[t_now] = tot;
+      if (t_now < BR_MAX_EPOCHS) s.epoch_changed[t_now] = mx;
       u32 acc = 0;
       s.epoch_suffix[BR_MAX_EPOCHS] = 0;
       for (int e = BR_MAX_EPOCHS - 1; e >= 0; --e) {
@@ -105,204 +185,179 @@ BR_DEV void br_chain(const BrStream& s) {
         s.epoch_suffix[e] = acc;
       }
       s.counters[0] = 0; s.counters[5] = 0;
+      for (int i = 8; i < 16; ++i) s.counters[i] = 0;
     }
   }
-  for (u32 k = tid; k < nb; k += nt) s.ext_total[k] = 0;
-  // ---- phase 1+2: per input block, flow the state through its chunks and aggregate
-  for (u32 bi = tid; bi < nblk; bi += nt) {
-    BrBlk B = s.blk[bi];
-    u32 ncmd = 0, nlit_rel = 0, has_cmd = 0, lil_run = 0, lil_head = 0, last_cmd_chunk = 0, dl = 0, dm = 0;
-    u32 flow_pos = 0, flow_rh = 0, flow_se = 0; int fdc[4] = {0, 0, 0, 0};
-    bool all_valid = true;
-    for (u32 c = 0; c < B.nchunks; ++c) {
-      const u32 k = B.first_chunk + c;
-      const BrBlockOut out = s.bout[k];
-      if (c > 0) {
-        BrBlockIn ni = s.bin[k];
-        ni.start_pos = flow_pos; ni.apply_rh = flow_rh; ni.store_end = flow_se; ni.ext_dist = 0;
-        for (int i = 0; i < 4; ++i) ni.dc[i] = fdc[i];
-        s.bin[k] = ni;
-      }
-      // pending literals relative to the block start (true value = + block lil_in while no command seen)
-      s.lil_in[k] = lil_run | (has_cmd ? 0u : 0x80000000u);
-      if (out.valid) {
-        if (out.ncmd > 0) {
-          nlit_rel += out.nlit + lil_run;
-          if (!has_cmd) lil_head = lil_run; // (literals before the block's first command; block lil_in adds to it)
-          has_cmd = 1; lil_run = out.last_insert_len; last_cmd_chunk = k;
-        } else lil_run += out.last_insert_len;
-        ncmd += out.ncmd; dl += out.dl; dm += out.dm;
-        flow_pos = out.out_pos; flow_rh = out.apply_rh; flow_se = out.store_end;
-        for (int i = 0; i < 4; ++i) fdc[i] = out.dc[i];
-      } else {
-        // never ran: pretend it emitted nothing and stopped at its nominal end
-        all_valid = false;
-        const BrBlockIn cur = s.bin[k];
-        u32 sp = c == 0 ? cur.blk_start : cur.start_pos;
-        u32 from = sp > cur.pos ? sp : cur.pos, to = cur.last ? cur.blk_end : cur.end;
-        if (to > from) lil_run += to - from;
-        flow_pos = to > from ? to : sp; flow_rh = flow_pos + P.spree;
-        flow_se = cur.blk_end - cur.blk_start >= P.htl ? cur.blk_end - P.htl + 1 : cur.blk_start;
-        if (c == 0) { fdc[0] = 4; fdc[1] = 11; fdc[2] = 15; fdc[3] = 16; }
+#if BR_GPU
+  long long t_phase0 = clock64();
+#endif
+  u32 num_cmds = 0, num_lits = 0, last_insert_len = 0;
+  int dc[4] = {4, 11, 15, 16}, saved_dc[4] = {4, 11, 15, 16};
+  u32 last_flush_pos = 0, first_blk = 0, cmd_total = 0, n_mbs = 0;
+  u64 dict_l = 0, dict_m = 0;
+  bool have_last = false;
+  u32 lc_copy_len = 0, lc_dist_prefix = 0, lc_dist_extra = 0, lc_chunk = 0, first_blk_chunk = 0, first_blk_cmd_base = 0;
+  u32 dbg_slow = 0;
+  bool mb_valid = true;
+  const u32 blocksize = 1u << P.lgblock;
+  BrBlk Bnext = s.blk[0];
+  for (u32 bi = 0; bi < nblk; ++bi) {
+    const BrBlk B = Bnext;
+    if (bi + 1 < nblk) Bnext = s.blk[bi + 1];   // software prefetch: the loop-carried state is in registers only
+    u32 ext_dist = 0;
+    if (num_cmds > 0 && last_insert_len == 0 && have_last) {
+      u32 dcode = br_cmd_restore_dcode(lc_dist_prefix, lc_dist_extra);
+      int cmd_dist = dc[0];
+      if (dcode < 16 || (cmd_dist > 0 && dcode - 15 == (u32)cmd_dist)) {
+        u32 lpp = B.start - (lc_copy_len & 0x1FFFFFF);
+        u32 maxd = br_min(lpp, P.max_backward);
+        if (cmd_dist > 0 && (u32)cmd_dist <= maxd) ext_dist = (u32)cmd_dist;
       }
     }
-    B.ncmd = ncmd; B.nlit_rel = nlit_rel; B.has_cmd = has_cmd; B.lil_head = lil_head; B.lil_tail = lil_run;
-    B.last_cmd_chunk = last_cmd_chunk; B.dl = dl; B.dm = dm; B.valid = all_valid ? 1u : 0u;
-    B.ext_len = s.bout[B.first_chunk].valid ? s.bout[B.first_chunk].ext_len : 0;
-    for (int i = 0; i < 4; ++i) B.out_dc[i] = fdc[i];
-    s.blk[bi] = B;
-  }
-  br_ch_sync();
-  // ---- phase 3: block-to-block recurrence (warp 0)
-  if (tid < BR_WARP) {
-    u32 num_cmds = 0, num_lits = 0, last_insert_len = 0;
-    int dc[4] = {4, 11, 15, 16}, saved_dc[4] = {4, 11, 15, 16};
-    u32 last_flush_pos = 0, first_blk = 0, cmd_total = 0, n_mbs = 0;
-    u64 dict_l = 0, dict_m = 0;
-    bool have_last = false;
-    u32 lc_copy_len = 0, lc_dist_prefix = 0, lc_dist_extra = 0, lc_chunk = 0;
-    const u32 blocksize = 1u << P.lgblock;
-    for (u32 bi = 0; bi < nblk; ++bi) {
-      const BrBlk B = s.blk[bi];
-      u32 ext_dist = 0;
-      if (num_cmds > 0 && last_insert_len == 0 && have_last) {
-        u32 dcode = br_cmd_restore_dcode(lc_dist_prefix, lc_dist_extra);
-        int cmd_dist = dc[0];
-        if (dcode < 16 || (cmd_dist > 0 && dcode - 15 == (u32)cmd_dist)) {
-          u32 lpp = B.start - (lc_copy_len & 0x1FFFFFF);
-          u32 maxd = br_min(lpp, P.max_backward);
-          if (cmd_dist > 0 && (u32)cmd_dist <= maxd) ext_dist = (u32)cmd_dist;
+    if (lane == 0) {
+      BrBlkIn W;
+      for (int i = 0; i < 4; ++i) W.in_dc[i] = dc[i];
+      W.in_ext_dist = ext_dist; W.lil_in = last_insert_len;
+      W.dict_l_lo = (u32)dict_l; W.dict_l_hi = (u32)(dict_l >> 32);
+      W.dict_m_lo = (u32)dict_m; W.dict_m_hi = (u32)(dict_m >> 32);
+      W.cmd_base = cmd_total; W.mb = n_mbs;
+      s.blkin[bi] = W;
+    }
+    if (bi == first_blk) { first_blk_chunk = B.first_chunk; first_blk_cmd_base = cmd_total; mb_valid = true; }
+    if (!B.valid) mb_valid = false;
+    // carry on with the block's latest (possibly stale) summary
+    if (B.ext_len && have_last && ext_dist) {
+      lc_copy_len += B.ext_len;
+      if (lane == 0) s.ext_total[lc_chunk] += B.ext_len;
+    }
+    if (B.has_cmd) {
+      lc_copy_len = B.lc_copy_len; lc_dist_prefix = B.lc_dist_prefix; lc_dist_extra = B.lc_dist_extra;
+      lc_chunk = B.last_cmd_chunk; have_last = true;
+      num_lits += B.nlit_rel + last_insert_len;
+      last_insert_len = B.lil_tail;
+    } else last_insert_len += B.lil_tail;
+    num_cmds += B.ncmd;
+    for (int i = 0; i < 4; ++i) dc[i] = B.out_dc[i];
+    // dictionary counters: chunk by chunk only around the (single) point where the gate closes
+    if (!(dict_m < (dict_l >> 7))) {
+      if (dict_m >= ((dict_l + B.dl) >> 7)) { dict_l += B.dl; dict_m += B.dm; }
+      else {
+        ++dbg_slow;
+        for (u32 c = 0; c < B.nchunks; ++c) {
+          const BrBlockOut o = s.bout[B.first_chunk + c];
+          if (!o.valid || dict_m < (dict_l >> 7)) continue;
+          u32 edl = o.dl, edm = o.dm;
+          const BrBlockIn u = s.bin_used[B.first_chunk + c];
+          const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
+          if (ul != dict_l || um != dict_m) {
+            if (!br_dict_gate_valid(dict_l, dict_m, o.dl, o.dm, o.gate_checks, o.gate_fail, &edl, &edm)) { edl = o.dl; edm = o.dm; }
+          }
+          dict_l += edl; dict_m += edm;
         }
       }
-      if (lane == 0) {
-        BrBlk W = B;
-        for (int i = 0; i < 4; ++i) W.in_dc[i] = dc[i];
-        W.in_ext_dist = ext_dist; W.lil_in = last_insert_len;
-        W.dict_l_lo = (u32)dict_l; W.dict_l_hi = (u32)(dict_l >> 32);
-        W.dict_m_lo = (u32)dict_m; W.dict_m_hi = (u32)(dict_m >> 32);
-        W.cmd_base = cmd_total; W.mb = n_mbs;
-        s.blk[bi] = W;
-      }
-      // carry on with the block's latest (possibly stale) summary
-      if (B.ext_len && have_last && s.bin_used[B.first_chunk].ext_dist) {
-        lc_copy_len += B.ext_len;
-        if (lane == 0) s.ext_total[lc_chunk] += B.ext_len;
-      }
-      if (B.has_cmd) {
-        const BrCmd c = s.cmd_blocks[(size_t)B.last_cmd_chunk * s.cmd_stride + s.bout[B.last_cmd_chunk].ncmd - 1];
-        lc_copy_len = c.copy_len; lc_dist_prefix = c.dist_prefix; lc_dist_extra = c.dist_extra;
-        lc_chunk = B.last_cmd_chunk; have_last = true;
-        num_lits += B.nlit_rel + last_insert_len;
-        last_insert_len = B.lil_tail;
-      } else last_insert_len += B.lil_tail;
-      num_cmds += B.ncmd;
-      for (int i = 0; i < 4; ++i) dc[i] = B.out_dc[i];
-      dict_l += B.dl; dict_m += B.dm;
-      cmd_total += B.ncmd;
-      // merge-or-flush (encode.c:1141)
-      const u32 end = B.end;
-      {
-        const u32 processed = end - last_flush_pos;
-        const bool next_fits = processed + blocksize <= P.max_mb;
-        if (!B.is_last && !B.force_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) continue;
-      }
-      u32 tail = 0;
-      if (last_insert_len > 0) { tail = last_insert_len; ++num_cmds; num_lits += tail; last_insert_len = 0; ++cmd_total; }
-      const u32 bytes = end - last_flush_pos;
-      int compress = br_should_compress(s, last_flush_pos, bytes, num_lits, num_cmds);
-      if (compress && s.force_unc[n_mbs]) compress = 0;
-      if (!compress) for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i];
-      if (lane == 0) {
-        BrMetaBlock m;
-        m.start = last_flush_pos; m.end = end;
-        m.first_block = s.blk[first_blk].first_chunk; m.last_block = B.first_chunk + B.nchunks - 1;
-        m.cmd_off = s.blk[first_blk].cmd_base; m.ncmd = num_cmds; m.nlit = num_lits;
-        m.is_last = B.is_last; m.compress = (u32)compress;
-        m.prev_byte = last_flush_pos > 0 ? s.data[last_flush_pos - 1] : 0;
-        m.prev_byte2 = last_flush_pos > 1 ? s.data[last_flush_pos - 2] : 0;
-        m.pad0 = m.pad1 = 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
-        s.mbs[n_mbs] = m;
-      }
-      br_syncwarp();
-      ++n_mbs;
-      last_flush_pos = end; num_cmds = 0; num_lits = 0; have_last = false; first_blk = bi + 1;
-      for (int i = 0; i < 4; ++i) saved_dc[i] = dc[i];
     }
-    if (lane == 0) { s.counters[1] = n_mbs; s.counters[2] = cmd_total; }
+    cmd_total += B.ncmd;
+    // merge-or-flush (encode.c:1141)
+    const u32 end = B.end;
+    {
+      const u32 processed = end - last_flush_pos;
+      const bool next_fits = processed + blocksize <= P.max_mb;
+      if (!B.is_last && !B.force_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) continue;
+    }
+    u32 tail = 0;
+    if (last_insert_len > 0) { tail = last_insert_len; ++num_cmds; num_lits += tail; last_insert_len = 0; ++cmd_total; }
+    const u32 bytes = end - last_flush_pos;
+    // (summaries of chunks that never ran are placeholders: do not sample the input for them)
+    int compress = mb_valid ? br_should_compress(s, last_flush_pos, bytes, num_lits, num_cmds) : 1;
+    if (compress && s.force_unc[n_mbs]) compress = 0;
+    if (!compress) for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i];
+    if (lane == 0) {
+      BrMetaBlock m;
+      m.start = last_flush_pos; m.end = end;
+      m.first_block = first_blk_chunk; m.last_block = B.first_chunk + B.nchunks - 1;
+      m.cmd_off = first_blk_cmd_base; m.ncmd = num_cmds; m.nlit = num_lits;
+      m.is_last = B.is_last; m.compress = (u32)compress;
+      m.prev_byte = last_flush_pos > 0 ? s.data[last_flush_pos - 1] : 0;
+      m.prev_byte2 = last_flush_pos > 1 ? s.data[last_flush_pos - 2] : 0;
+      m.pad0 = m.pad1 = 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
+      s.mbs[n_mbs] = m;
+    }
+    br_syncwarp();
+    ++n_mbs;
+    last_flush_pos = end; num_cmds = 0; num_lits = 0; have_last = false; first_blk = bi + 1;
+    for (int i = 0; i < 4; ++i) saved_dc[i] = dc[i];
   }
-  br_ch_sync();
-  // ---- phase 4: per chunk: final in-state, dirty decision, offsets
-  for (u32 bi = tid; bi < nblk; bi += nt) {
-    const BrBlk B = s.blk[bi];
-    u64 dict_l = ((u64)B.dict_l_hi << 32) | B.dict_l_lo, dict_m = ((u64)B.dict_m_hi << 32) | B.dict_m_lo;
-    u32 cmd_off = B.cmd_base;
-    // stored-bits committed inside this block's window since a given launch: find the newest commit epoch
-    const u32 lowpos = B.start > P.max_backward ? B.start - P.max_backward : 0;
-    int newest = -1;
-    for (u32 j = bi; j-- > 0;) {
-      if (s.blk[j].end <= lowpos) break;
-      int ce = s.blk[j].changed_epoch;
-      if (ce > newest) newest = ce;
+  if (lane == 0) {
+    s.counters[1] = n_mbs; s.counters[2] = cmd_total;
+#if BR_GPU
+    long long t_end = clock64();
+    s.counters[20] = (u32)((t_phase0 - t_begin) >> 10); s.counters[21] = (u32)((t_end - t_phase0) >> 10); s.counters[22] = dbg_slow;
+#endif
+  }
+}
+
+BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
+  const BrBlk B = s.blk[bi];
+  const BrBlkIn W = s.blkin[bi];
+  u64 dict_l = ((u64)W.dict_l_hi << 32) | W.dict_l_lo, dict_m = ((u64)W.dict_m_hi << 32) | W.dict_m_lo;
+  u32 cmd_off = W.cmd_base;
+  const u32 t_now = s.epoch;
+  const int ovf = (int)s.counters[6] - 1;   // newest launch in which the precise bit tracking overflowed (-1: never)
+  bool prev_dirty = false;
+  for (u32 c = 0; c < B.nchunks; ++c) {
+    const u32 k = B.first_chunk + c;
+    BrBlockIn ni = s.bin[k];
+    if (c == 0) {
+      ni.start_pos = B.start; ni.ext_dist = W.in_ext_dist; ni.apply_rh = 0; ni.store_end = 0;
+      for (int i = 0; i < 4; ++i) ni.dc[i] = W.in_dc[i];
     }
-    bool prev_dirty = false;
-    for (u32 c = 0; c < B.nchunks; ++c) {
-      const u32 k = B.first_chunk + c;
-      BrBlockIn ni = s.bin[k];
-      if (c == 0) {
-        ni.start_pos = B.start; ni.ext_dist = B.in_ext_dist; ni.apply_rh = 0; ni.store_end = 0;
-        for (int i = 0; i < 4; ++i) ni.dc[i] = B.in_dc[i];
+    ni.dict_l_lo = (u32)dict_l; ni.dict_l_hi = (u32)(dict_l >> 32);
+    ni.dict_m_lo = (u32)dict_m; ni.dict_m_hi = (u32)(dict_m >> 32);
+    u32 rel = s.lil_in[k];
+    u32 lil_true = (rel & 0x7fffffffu) + ((rel & 0x80000000u) ? W.lil_in : 0u);
+    ni.last_insert_len = lil_true;
+    const BrBlockOut out = s.bout[k];
+    u32 dirty = out.valid ? 0u : 1u;  // reason: 1 never ran, 2 state, 3 dict gate, 4 stored-bits, 5 counter wrap
+    u32 edl = out.valid ? out.dl : 0, edm = out.valid ? out.dm : 0;
+    if (!dirty) {
+      const BrBlockIn u = s.bin_used[k];
+      if (u.ext_dist != ni.ext_dist || u.start_pos != ni.start_pos || u.apply_rh != ni.apply_rh ||
+          u.store_end != ni.store_end || u.dc[0] != ni.dc[0] || u.dc[1] != ni.dc[1] || u.dc[2] != ni.dc[2] ||
+          u.dc[3] != ni.dc[3]) dirty = 2;
+      u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
+      if (!dirty && (ul != dict_l || um != dict_m) &&
+          !br_dict_gate_valid(dict_l, dict_m, out.dl, out.dm, out.gate_checks, out.gate_fail, &edl, &edm)) dirty = 3;
+      if (!dirty && out.out_pos > ni.start_pos) {
+        int seen = (int)out.epoch;
+        if (s.bitdep_epoch[k] >= seen || ovf >= seen) dirty = 4;
+        u32 unseen = s.epoch_suffix[seen < BR_MAX_EPOCHS ? seen : BR_MAX_EPOCHS];
+        if (!dirty && unseen > out.min_wrap_dist) dirty = 5;
       }
-      ni.dict_l_lo = (u32)dict_l; ni.dict_l_hi = (u32)(dict_l >> 32);
-      ni.dict_m_lo = (u32)dict_m; ni.dict_m_hi = (u32)(dict_m >> 32);
-      u32 rel = s.lil_in[k];
-      u32 lil_true = (rel & 0x7fffffffu) + ((rel & 0x80000000u) ? B.lil_in : 0u);
-      ni.last_insert_len = lil_true;
-      const BrBlockOut out = s.bout[k];
-      u32 dirty = out.valid ? 0u : 1u;  // reason: 1 never ran, 2 state, 3 dict gate, 4 window bits, 5 counter wrap
-      if (!dirty) {
-        const BrBlockIn u = s.bin_used[k];
-        if (u.ext_dist != ni.ext_dist || u.start_pos != ni.start_pos || u.apply_rh != ni.apply_rh ||
-            u.store_end != ni.store_end || u.dc[0] != ni.dc[0] || u.dc[1] != ni.dc[1] || u.dc[2] != ni.dc[2] ||
-            u.dc[3] != ni.dc[3]) dirty = 2;
-        u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
-        if (!dirty && (ul != dict_l || um != dict_m) && out.gate_checks) {
-          bool all_open = out.gate_fail == 0, all_closed = out.gate_fail == out.gate_checks;
-          bool ok = (all_open && dict_m >= ((dict_l + out.dl) >> 7)) || (all_closed && dict_m < (dict_l >> 7));
-          if (!ok) dirty = 3;
-        }
-        if (!dirty && out.out_pos > ni.start_pos) {
-          int seen = (int)out.epoch;
-          // earlier chunks of the own block count as window too
-          int own = s.blk[bi].changed_epoch;
-          if (newest >= seen || (c > 0 && own >= seen)) dirty = 4;
-          u32 unseen = s.epoch_suffix[seen < BR_MAX_EPOCHS ? seen : BR_MAX_EPOCHS];
-          if (!dirty && unseen > out.min_wrap_dist) dirty = 5;
-        }
-      }
-      // From the third launch on, a chunk whose only problem is the state handed over by a dirty
-      // predecessor is not scheduled: the predecessor's walker chases into it (br_walk_block), which
-      // resolves a serial ripple in one launch instead of one launch per chunk.
-      const bool defer = dirty == 2 && prev_dirty && t_now >= 2;
-      prev_dirty = dirty != 0;
-      s.bin[k] = ni;
-      s.dirty[k] = defer ? 0u : dirty;
-      s.cmd_off[k] = cmd_off;
-      s.lil_in[k] = lil_true;
-      s.block_mb[k] = 0;
-      if (dirty) br_atomic_add(s.counters + 0, 1);
-      if (dirty && !defer) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; }
-      if (out.valid) { cmd_off += out.ncmd; dict_l += out.dl; dict_m += out.dm; }
+    }
+    // From the third launch on, a chunk whose only problem is the state handed over by a dirty
+    // predecessor is not scheduled: the predecessor's walker chases into it (br_walk_block), which
+    // resolves a serial ripple in one launch instead of one launch per chunk.
+    const bool defer = dirty == 2 && prev_dirty && t_now >= 2;
+    prev_dirty = dirty != 0;
+    s.bin[k] = ni;
+    s.dirty[k] = defer ? 0u : dirty;
+    s.cmd_off[k] = cmd_off;
+    s.lil_in[k] = lil_true;
+    s.block_mb[k] = W.mb;
+    if (dirty) { br_atomic_add(s.counters + 0, 1); br_atomic_add(s.counters + 8 + (dirty < 6 ? dirty : 6), 1); }
+    if (dirty && !defer) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; }
+    if (out.valid) {
+      cmd_off += out.ncmd;
+      if (!(dict_m < (dict_l >> 7))) { dict_l += edl; dict_m += edm; }
     }
   }
-  br_ch_sync();
-  // chunk -> metablock map
-  {
-    const u32 nm = s.counters[1];
-    for (u32 i = 0; i < nm; ++i) {
-      const u32 a = s.mbs[i].first_block, b = s.mbs[i].last_block;
-      for (u32 k = a + tid; k <= b; k += nt) s.block_mb[k] = i;
-    }
-  }
+}
+
+// sequential driver for the CPU sim / single-thread use
+BR_DEV void br_chain(const BrStream& s) {
+  for (u32 bi = 0; bi < s.nblk; ++bi) br_chain_a(s, bi);
+  br_chain_b(s);
+  for (u32 bi = 0; bi < s.nblk; ++bi) br_chain_c(s, bi);
 }
 
 // Gather one chunk's commands into the stream-wide compacted array, applying the

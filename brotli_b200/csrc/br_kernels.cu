@@ -144,6 +144,11 @@ __global__ void k_init_bits(BrStream s) {
     if (p >= s.P.n) break;
     u32 blk_end = (p / bs + 1) * bs; if (blk_end > s.P.n) blk_end = s.P.n;   // uniform blocks (one-shot)
     if (p + s.P.htl <= blk_end) v |= 1u << b;
+    // StitchToPreviousBlock of the next block stores the last three positions of this one
+    if (blk_end < s.P.n && p + 3 >= blk_end) {
+      u32 nxt = s.P.n - blk_end < bs ? s.P.n - blk_end : bs;
+      if (nxt >= s.P.htl - 1) v |= 1u << b;
+    }
   }
   s.bits_latest[wi] = v;
 }
@@ -174,7 +179,15 @@ __global__ void k_commit(BrStream s) {
   if (t >= s.counters[4]) return;
   br_commit_bits(s, s.ran_list[t]);
 }
-__global__ void __launch_bounds__(1024) k_chain(BrStream s) { br_chain(s); }
+__global__ void k_chain_a(BrStream s) {
+  u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi < s.nblk) br_chain_a(s, bi);
+}
+__global__ void __launch_bounds__(32) k_chain_b(BrStream s) { br_chain_b(s); }
+__global__ void k_chain_c(BrStream s) {
+  u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi < s.nblk) br_chain_c(s, bi);
+}
 __global__ void k_compact(BrStream s, BrCmd* cmds_all, const u32* __restrict__ block_mb) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.P.nblocks) return;
@@ -441,11 +454,11 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   auto add = [&](size_t bytes) { need += (bytes + 255) & ~(size_t)255; };
   add((size_t)n + 64); add(2ull * n + 4); add(2ull * n + 4); add(4ull * n); add(2ull * n + 4); add(4ull * n); add(4ull * n);
   add(256ull * ntiles * 4); add(scan_tmp_words(256ull * ntiles) * 4);
-  add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
+  add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
   add(scan_tmp_words((size_t)n / 1024 + 8) * 4);
   add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
-  for (int i = 0; i < 12; ++i) add(nb * 4ull + 64);
-  add(nblk * sizeof(BrBlk));
+  for (int i = 0; i < 14; ++i) add(nb * 4ull + 64);
+  add(nblk * sizeof(BrBlk)); add(nblk * sizeof(BrBlkIn)); add((P.nbuckets + 8) * 4ull);
   add(BR_MAX_EPOCHS * 8 + 64); add((nb + 1) * sizeof(BrMetaBlock)); add(4096);
   need += 1 << 20;
   if (!job->arena.reserve(need)) return 0;
@@ -456,6 +469,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   u32* hist = A.take<u32>(256ull * ntiles); u32* scan_tmp = A.take<u32>(scan_tmp_words(256ull * ntiles));
   u32* seg = A.take<u32>(P.nbuckets + 4);
   u32* bits_latest = A.take<u32>(nwords); u32* bits_cur = A.take<u32>(nwords);
+  u32* srch_latest = A.take<u32>(nwords); u32* srch_cur = A.take<u32>(nwords);
   u32* storedS = A.take<u32>(nwords + 64); u32* prefS = A.take<u32>((size_t)n / 1024 + 8);
   u32* scan_tmp2 = A.take<u32>(scan_tmp_words((size_t)n / 1024 + 8));
   BrBlockIn* bin = A.take<BrBlockIn>(nb); BrBlockIn* bin_used = A.take<BrBlockIn>(nb);
@@ -466,7 +480,9 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   u32* cmd_off = A.take<u32>(nb + 16); u32* force_unc = A.take<u32>(nb + 16);
   u32* dirty_list = A.take<u32>(nb + 16); u32* block_mb = A.take<u32>(nb + 16);
   u32* ran_list = A.take<u32>(nb + 16); u32* lil_in = A.take<u32>(nb + 16);
-  BrBlk* d_blk = A.take<BrBlk>(nblk);
+  int* bitdep_epoch = A.take<int>(nb + 16);
+  BrBlk* d_blk = A.take<BrBlk>(nblk); BrBlkIn* d_blkin = A.take<BrBlkIn>(nblk);
+  u32* key_flips = A.take<u32>(P.nbuckets + 8);
   u32* epoch_changed = A.take<u32>(BR_MAX_EPOCHS); u32* epoch_suffix = A.take<u32>(BR_MAX_EPOCHS + 1);
   BrMetaBlock* mbs = A.take<BrMetaBlock>(nb + 1);
   u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256);
@@ -480,7 +496,8 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   s.changed_epoch = changed_epoch; s.epoch_changed = epoch_changed; s.epoch_suffix = epoch_suffix;
   s.ext_total = ext_total; s.cmd_off = cmd_off; s.mbs = mbs; s.force_unc = force_unc;
   s.counters = counters; s.hist_scratch = hist_scratch;
-  s.dirty_list = dirty_list; s.block_mb = block_mb; s.ran_list = ran_list; s.lil_in = lil_in; s.blk = d_blk; s.nblk = nblk;
+  s.srch_latest = srch_latest; s.srch_cur = srch_cur; s.bitdep_epoch = bitdep_epoch; s.skeys = K2;
+  s.dirty_list = dirty_list; s.block_mb = block_mb; s.ran_list = ran_list; s.lil_in = lil_in; s.blk = d_blk; s.nblk = nblk; s.blkin = d_blkin; s.key_flips = key_flips;
   { const u8* p = T->blob + 8;
     s.dict_size_bits = p; p += 32; s.dict_offsets = (const u32*)p; p += 128; s.dict = p; p += 122784;
     s.dict_hash_words = (const u16*)p; p += 65536; s.dict_hash_lengths = p; p += 32768; s.ctx_lut = p; }
@@ -493,6 +510,9 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   CK(cudaMemsetAsync(bin_used, 0, nb * sizeof(BrBlockIn), st));
   CK(cudaMemsetAsync(changed_bits, 0, (nb + 16) * 4, st));
   CK(cudaMemsetAsync(changed_epoch, 0xFF, (nb + 16) * 4, st));
+  CK(cudaMemsetAsync(bitdep_epoch, 0xFF, (nb + 16) * 4, st));
+  CK(cudaMemsetAsync(srch_latest, 0, nwords * 4, st));
+  CK(cudaMemsetAsync(key_flips, 0, (P.nbuckets + 8) * 4, st));
   CK(cudaMemsetAsync(force_unc, 0, (nb + 16) * 4, st));
   CK(cudaMemsetAsync(epoch_changed, 0, BR_MAX_EPOCHS * 4, st));
   CK(cudaMemsetAsync(counters, 0, 256, st));
@@ -520,16 +540,20 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   for (;;) {   // rounds: repeated only when a metablock needs the late uncompressed fallback
     ++rounds;
     for (;;) {
-      k_chain<<<1, 1024, 0, st>>>(s);
-      CK(cudaMemcpyAsync(hp, counters, 32, cudaMemcpyDeviceToHost, st));
+      k_chain_a<<<(nblk + 31) / 32, 32, 0, st>>>(s);
+      k_chain_b<<<1, 32, 0, st>>>(s);
+      k_chain_c<<<(nblk + 31) / 32, 32, 0, st>>>(s);
+      CK(cudaMemcpyAsync(hp, counters, 128, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       u32 n_dirty = hp[0], n_sched = hp[5]; n_mbs = hp[1]; total_cmds = hp[2];
       job->stats.block_runs += hp[4];
+      if (getenv("BR_TRACE")) fprintf(stderr, "epoch %u: dirty %u sched %u ran %u | never %u state %u dict %u bits %u wrap %u\n", s.epoch, hp[0], hp[5], hp[4], hp[9], hp[10], hp[11], hp[12], hp[13]), fprintf(stderr, "   chain_b: phase0 %u kcyc, blocks %u kcyc, slow-dict blocks %u\n", hp[20], hp[21], hp[22]);
       if (walk_pending) { float wms; cudaEventElapsedTime(&wms, ev[6], ev[7]); job->stats.ms_walk += wms; walk_pending = false; }
       if (n_dirty == 0) break;
       if (s.epoch + 2 >= BR_MAX_EPOCHS) { fprintf(stderr, "brotli_b200: LZ77 fixpoint did not converge\n"); return 0; }
       ++s.epoch; ++job->stats.lz77_iterations;
       CK(cudaMemsetAsync(bits_cur, 0, nwords * 4, st));
+      CK(cudaMemsetAsync(srch_cur, 0, nwords * 4, st));
       CK(cudaMemsetAsync(counters + 4, 0, 4, st));
       k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
       scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);

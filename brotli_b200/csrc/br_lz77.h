@@ -56,6 +56,7 @@ struct BrWalk {
   u32 dl, dm, gate_checks, gate_fail;
   u32 min_wrap;
   u32 stale;       // the byte the reference finds just past the block end (see oracle)
+  bool warming;    // warm-up (state refinement before the chunk proper): reads the snapshot, records nothing
 };
 
 // Stored-bits of the walker's own range [p0, ...) live in bits_cur (global): written with
@@ -70,12 +71,15 @@ BR_DEV u32 br_ld_cur(const u32* p) {
 BR_DEV int br_own_get(const BrWalk& w, u32 q) {
   return (br_ld_cur(w.s->bits_cur + (q >> 5)) >> (q & 31)) & 1;
 }
+BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b);
 BR_DEV void br_own_set(BrWalk& w, u32 q) {
+  if (w.warming) return;   // warm-up: the snapshot is read, nothing is recorded
   if (br_lane() == 0) br_atomic_or(w.s->bits_cur + (q >> 5), 1u << (q & 31));
   br_syncwarp();
 }
 BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
   if (a >= b) return;
+  if (w.warming) return;
   u32 wa = a >> 5, wb = (b - 1) >> 5;
   for (u32 x = wa + (u32)br_lane(); x <= wb; x += BR_WARP) {
     u32 m = 0xffffffffu;
@@ -92,7 +96,6 @@ BR_DEV int br_is_stored(const BrWalk& w, u32 q) {
   if (q >= w.p0) return br_own_get(w, q);
   return (br_ldg(w.s->bits_latest + (q >> 5)) >> (q & 31)) & 1;
 }
-
 // Number of stored positions (latest snapshot) among S[a .. b).
 BR_DEV u32 br_countS_upto(const BrStream& s, u32 x) {
   u32 base = br_ldg(s.prefS + (x >> 10));
@@ -270,6 +273,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
       jj = jj > BR_WARP ? jj - BR_WARP : 0;
     }
     br_own_set(w, cur);  // the insertion at hash_longest_match64_inc.h:268
+    if (!w.warming && br_lane() == 0) br_atomic_or(s.srch_cur + (cur >> 5), 1u << (cur & 31));
   }
   if (min_score == out.score) br_search_static_dict(w, cur, max_length, dict_distance, out);
 }
@@ -319,6 +323,18 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   u32 position = in.start_pos;
   u32 ext = 0;
   u32 apply_random_heuristics = in.apply_rh;
+  BrBlockIn used = in;     // the state this run really starts from (refined by the warm-up)
+  used.warm = 0;
+  w.warming = false;
+  if (in.warm && !in.first && in.pos >= in.blk_start + in.warm) {
+    // State refinement: parse the last `warm` bytes before the chunk from a neutral state; by the
+    // time the parse crosses into the chunk it has usually synchronised with the true parse.
+    w.warming = true;
+    position = in.pos - in.warm;
+    w.p0 = 0xffffffffu;
+    apply_random_heuristics = position + P.spree;
+  }
+  const u64 dict_l0 = w.dict_l, dict_m0 = w.dict_m;
   const u32 window = P.spree;
   u32 store_end;
   if (in.first) {
@@ -351,6 +367,16 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   BrCmd* cmds = s.cmd_blocks + (size_t)b * s.cmd_stride;
   br_prepare_dist_cache(w.dc, P.ndist);
   while (position + P.htl < pos_end && (in.last || position < in.end)) {
+    if (w.warming && position >= in.pos) {
+      // crossing: from here on this is the chunk's own run
+      w.warming = false; w.p0 = position;
+      used.start_pos = position; used.apply_rh = apply_random_heuristics;
+      for (int i = 0; i < 4; ++i) used.dc[i] = w.dc[i];
+      insert_length = 0; ncmd = 0; nlit = 0;
+      w.dict_l = dict_l0; w.dict_m = dict_m0; w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
+      w.min_wrap = 0xffffffffu;
+      if (position >= in.end && !in.last) break;
+    }
     u32 max_length = pos_end - position;
     u32 max_distance = br_min(position, P.max_backward);
     BrSR sr; sr.len = 0; sr.delta = 0; sr.distance = 0; sr.score = BR_MIN_SCORE;
@@ -375,7 +401,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
         w.dc[3] = w.dc[2]; w.dc[2] = w.dc[1]; w.dc[1] = w.dc[0]; w.dc[0] = (int)sr.distance;
         br_prepare_dist_cache(w.dc, P.ndist);
       }
-      if (lane == 0) cmds[ncmd] = br_init_cmd(insert_length, sr.len, sr.delta, dcode);
+      if (lane == 0 && !w.warming) cmds[ncmd] = br_init_cmd(insert_length, sr.len, sr.delta, dcode);
       ++ncmd;
       nlit += insert_length;
       insert_length = 0;
@@ -407,6 +433,14 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
       }
     }
   }
+  if (w.warming) {   // the warm-up parse jumped over the whole chunk (or the block ended)
+    w.warming = false; w.p0 = position;
+    used.start_pos = position; used.apply_rh = apply_random_heuristics;
+    for (int i = 0; i < 4; ++i) used.dc[i] = w.dc[i];
+    insert_length = 0; ncmd = 0; nlit = 0;
+    w.dict_l = dict_l0; w.dict_m = dict_m0; w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
+    w.min_wrap = 0xffffffffu;
+  }
   if (in.last) {
     insert_length += pos_end - position;
     position = pos_end;
@@ -421,7 +455,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   }
   if (lane == 0) {
     s.bout[b] = o;
-    s.bin_used[b] = in;
+    s.bin_used[b] = used;
     u32 slot = br_atomic_add(s.counters + 4, 1);   // list of chunks to commit
     s.ran_list[slot] = b;
   }
@@ -441,20 +475,18 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b) {
     const u32 nb = b + 1;
     if (s.dirty[nb] != 0 || !s.bout[nb].valid) return;
     const BrBlockIn u = s.bin_used[nb];
-    const u64 dl = (((u64)in.dict_l_hi << 32) | in.dict_l_lo) + o.dl, dm = (((u64)in.dict_m_hi << 32) | in.dict_m_lo) + o.dm;
+    const u64 dl = (((u64)in.dict_l_hi << 32) | in.dict_l_lo) + o.dl, dm = (((u64)in.dict_m_hi << 32) | in.dict_m_lo) + o.dm;   // (a closed gate reports dl = dm = 0)
     bool same = u.start_pos == o.out_pos && u.apply_rh == o.apply_rh && u.store_end == o.store_end && u.ext_dist == 0 &&
                 u.dc[0] == o.dc[0] && u.dc[1] == o.dc[1] && u.dc[2] == o.dc[2] && u.dc[3] == o.dc[3];
     if (same) {
       const BrBlockOut uo = s.bout[nb];
       const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
-      if ((ul != dl || um != dm) && uo.gate_checks) {
-        bool all_open = uo.gate_fail == 0, all_closed = uo.gate_fail == uo.gate_checks;
-        same = (all_open && dm >= ((dl + uo.dl) >> 7)) || (all_closed && dm < (dl >> 7));
-      }
+      u32 edl, edm;
+      if (ul != dl || um != dm) same = br_dict_gate_valid(dl, dm, uo.dl, uo.dm, uo.gate_checks, uo.gate_fail, &edl, &edm) != 0;
     }
     if (same) return;
     BrBlockIn ni = s.bin[nb];
-    ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0;
+    ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0; ni.warm = 0;
     for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];
     ni.dict_l_lo = (u32)dl; ni.dict_l_hi = (u32)(dl >> 32); ni.dict_m_lo = (u32)dm; ni.dict_m_hi = (u32)(dm >> 32);
     in = ni; b = nb;

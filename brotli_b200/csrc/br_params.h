@@ -26,5 +26,6 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->size_hint = size_hint;
   P->n = n;
   P->nbuckets = 1u << P->bucket_bits;
+  P->cpb_shift = (u32)P->lgblock - BR_CHUNK_BITS;
   return 1;
 }

@@ -27,6 +27,7 @@ struct BrParams {
   u32 n;            // input bytes
   u32 nblocks;      // number of chunks (speculation units); input blocks are groups of them
   u32 nbuckets;     // 1 << bucket_bits (+1 overflow bucket for the unhashable tail positions)
+  u32 cpb_shift;    // lgblock - BR_CHUNK_BITS: chunks per full input block = 1 << cpb_shift
 };
 
 // The unit of speculation is a CHUNK: a slice (1 << BR_CHUNK_BITS bytes) of one of the
@@ -46,7 +47,9 @@ struct BrBlockIn {
   u32 dict_l_lo, dict_l_hi, dict_m_lo, dict_m_hi;  // dict_num_lookups / dict_num_matches (hash.h:49)
   u32 is_last;           // block flags (copied to all its chunks)
   u32 force_flush;       // BROTLI_OPERATION_FLUSH ended the input here (encode.c:1700)
+  u32 warm;              // != 0: the state above is a guess; walk this many bytes before `pos` first to refine it
 };
+#define BR_WARM_BYTES 1024
 // What the walker reports back.
 struct BrBlockOut {
   u32 ncmd, nlit;        // commands emitted, literals covered by them (without the carried-in literals)
@@ -69,10 +72,13 @@ struct BrBlk {
   // aggregates (chain phase 2)
   u32 ncmd, nlit_rel, has_cmd, lil_head, lil_tail, last_cmd_chunk, dl, dm, ext_len, valid;
   int out_dc[4];
-  // block-level chain (phase 3)
+  u32 lc_copy_len, lc_dist_prefix, lc_dist_extra;   // the block's last command
+  int changed_epoch;
+};
+// What the block-to-block recurrence derives for an input block (br_chain_b -> br_chain_c).
+struct BrBlkIn {
   int in_dc[4];
   u32 in_ext_dist, lil_in, dict_l_lo, dict_l_hi, dict_m_lo, dict_m_hi, cmd_base, mb;
-  int changed_epoch;     // last walker launch whose commit changed stored-bits inside this block (-1: never)
 };
 
 // Per metablock record produced by the chain kernel.
@@ -100,6 +106,8 @@ struct BrStream {
   const u32* seg;        // seg[key] = first index of bucket key in S; nbuckets + 2 entries
   u32* bits_latest;      // stored-position bitmap, latest run of every block
   u32* bits_cur;         // written by the walkers of this iteration
+  u32* srch_latest;      // positions FindLongestMatch was called on (latest run of their owner) ...
+  u32* srch_cur;         // ... and in this iteration
   const u32* storedS;    // bits_latest permuted into S order ...
   const u32* prefS;      // ... with exclusive popcount prefix every 1024 bits
   BrBlockIn* bin;        // [nblocks]   chain state handed to walkers
@@ -109,13 +117,17 @@ struct BrStream {
   u32 cmd_stride;
   u32* dirty;            // [nblocks] run this block in the next walker launch
   u32* changed_bits;     // [nblocks] popcount of bitmap changes of the latest run
-  int* changed_epoch;    // [nblocks] last walker launch whose commit changed this block's bits (-1: never)
+  int* changed_epoch;    // [nblocks] last walker launch whose commit changed this chunk's bits (-1: never)
+  int* bitdep_epoch;     // [nblocks] last launch that changed a stored-bit this chunk's searches may consult
+  const u16* skeys;      // bucket key of S[j]
   u32* epoch_changed;    // [BR_MAX_EPOCHS] total changed bits committed per walker launch
   u32* epoch_suffix;     // [BR_MAX_EPOCHS + 1] suffix sums of the above (chain scratch)
   u32 epoch;             // current walker launch number (1-based)
   u32* ext_total;        // [nblocks] bytes added to the chunk's last command by ExtendLastCommand
   u32* lil_in;           // [nblocks] true pending-literal count at the chunk start (added to its first command)
   BrBlk* blk;            // [nblk] reference input blocks
+  BrBlkIn* blkin;        // [nblk]
+  u32* key_flips;        // [nbuckets + 1] stored-bit flips per heavy bucket in the current launch
   u32 nblk;
   u32* dirty_list;       // [nblocks] chunks scheduled for the next walker launch (counters[5] entries)
   u32* ran_list;         // [nblocks] chunks walked in the current launch (counters[4] entries)
@@ -123,7 +135,7 @@ struct BrStream {
   u32* cmd_off;          // [nblocks] offset of the block's commands in the compacted array
   BrMetaBlock* mbs;      // [max_mbs]
   u32* force_unc;        // [max_mbs] late fallback: store this metablock uncompressed
-  u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags, 4 chunks walked this launch, 5 chunks scheduled
+  u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags, 4 chunks walked this launch, 5 chunks scheduled, 6 last launch whose bit tracking overflowed (+1), 8.. dirty reasons
   u32* hist_scratch;     // [256]
   // tables
   const u8* dict;        // RFC 7932 dictionary

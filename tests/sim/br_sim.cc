@@ -35,14 +35,17 @@ extern "C" int sim_init(const u8* blob, size_t len, u32 log2n) {
 struct SimStream {
   BrStream s;
   std::vector<u8> data;
-  std::vector<u32> S, rank, seg, bits_latest, bits_cur, storedS, prefS, dirty, changed_bits,
+  std::vector<u32> S, rank, seg, bits_latest, bits_cur, srch_latest, srch_cur, storedS, prefS, dirty, changed_bits,
       epoch_changed, epoch_suffix, ext_total, lil_in, cmd_off, force_unc, counters, hist, block_mb;
-  std::vector<int> changed_epoch;
+  std::vector<int> changed_epoch, bitdep_epoch;
+  std::vector<u16> skeys;
   std::vector<BrBlockIn> bin, bin_used;
   std::vector<BrBlockOut> bout;
   std::vector<BrCmd> cmd_blocks, cmds_all;
   std::vector<BrMetaBlock> mbs;
   std::vector<BrBlk> blks;
+  std::vector<BrBlkIn> blkin;
+  std::vector<u32> key_flips;
   std::vector<u32> dirty_list, ran_list;
   int iterations = 0;
   u64 block_runs = 0;
@@ -58,7 +61,9 @@ static void sim_build_sorted(SimStream& m) {
   for (u32 k = 0; k <= P.nbuckets; ++k) m.seg[k + 1] += m.seg[k];
   std::vector<u32> cur(m.seg.begin(), m.seg.end() - 1);
   m.S.resize(n); m.rank.resize(n);
-  for (u32 p = 0; p < n; ++p) { u32 j = cur[key[p]]++; m.S[j] = p; m.rank[p] = j; }
+  m.skeys.resize(n + 1);
+  for (u32 p = 0; p < n; ++p) { u32 j = cur[key[p]]++; m.S[j] = p; m.rank[p] = j; m.skeys[j] = (u16)key[p]; }
+  s.skeys = m.skeys.data();
   s.S = m.S.data(); s.rank = m.rank.data(); s.seg = m.seg.data();
 }
 static void sim_build_storedS(SimStream& m) {
@@ -105,27 +110,35 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   m->bin = chunks; m->bin_used.resize(nb); m->bout.resize(nb);
   memset(m->bin_used.data(), 0, nb * sizeof(BrBlockIn));
   memset(m->bout.data(), 0, nb * sizeof(BrBlockOut));
-  m->bits_latest.assign(words, 0); m->bits_cur.assign(words, 0);
+  m->bits_latest.assign(words, 0); m->bits_cur.assign(words, 0); m->srch_latest.assign(words, 0); m->srch_cur.assign(words, 0);
   // initial guess: everything stored except the unsearchable tail of each block
   for (u32 k = 0; k < nb; ++k)
     for (u32 p = m->bin[k].pos; p < m->bin[k].end && p + P.htl <= m->bin[k].blk_end; ++p) m->bits_latest[p >> 5] |= 1u << (p & 31);
+  for (size_t bi = 1; bi < m->blks.size(); ++bi) {   // StitchToPreviousBlock positions
+    const BrBlk& B = m->blks[bi];
+    if (B.end - B.start >= P.htl - 1 && B.start >= 3)
+      for (u32 q = B.start - 3; q < B.start; ++q) m->bits_latest[q >> 5] |= 1u << (q & 31);
+  }
   m->storedS.assign(words + 32, 0); m->prefS.assign(n / 1024 + 4, 0);
-  m->dirty.assign(nb, 0); m->changed_bits.assign(nb, 0); m->changed_epoch.assign(nb, -1);
+  m->dirty.assign(nb, 0); m->changed_bits.assign(nb, 0); m->changed_epoch.assign(nb, -1); m->bitdep_epoch.assign(nb + 1, -1);
   m->epoch_changed.assign(BR_MAX_EPOCHS, 0); m->epoch_suffix.assign(BR_MAX_EPOCHS + 1, 0);
   m->ext_total.assign(nb, 0); m->lil_in.assign(nb, 0); m->cmd_off.assign(nb, 0); m->force_unc.assign(nb + 1, 0);
-  m->counters.assign(8, 0); m->hist.assign(256, 0); m->mbs.resize(nb + 1);
+  m->counters.assign(64, 0); m->hist.assign(256, 0); m->mbs.resize(nb + 1);
   s.cmd_stride = ch / 2 + 2;
   m->cmd_blocks.resize((size_t)nb * s.cmd_stride);
   s.bits_latest = m->bits_latest.data(); s.bits_cur = m->bits_cur.data();
+  s.srch_latest = m->srch_latest.data(); s.srch_cur = m->srch_cur.data();
   s.storedS = m->storedS.data(); s.prefS = m->prefS.data();
   s.bin = m->bin.data(); s.bin_used = m->bin_used.data(); s.bout = m->bout.data();
   s.cmd_blocks = m->cmd_blocks.data(); s.dirty = m->dirty.data();
-  s.changed_bits = m->changed_bits.data(); s.changed_epoch = m->changed_epoch.data();
+  s.changed_bits = m->changed_bits.data(); s.changed_epoch = m->changed_epoch.data(); s.bitdep_epoch = m->bitdep_epoch.data();
   s.epoch_changed = m->epoch_changed.data(); s.epoch_suffix = m->epoch_suffix.data();
   s.ext_total = m->ext_total.data(); s.lil_in = m->lil_in.data(); s.cmd_off = m->cmd_off.data();
   s.mbs = m->mbs.data(); s.force_unc = m->force_unc.data(); s.counters = m->counters.data();
   s.hist_scratch = m->hist.data();
   s.blk = m->blks.data(); s.nblk = (u32)m->blks.size();
+  m->blkin.resize(m->blks.size()); s.blkin = m->blkin.data();
+  m->key_flips.assign(P.nbuckets + 2, 0); s.key_flips = m->key_flips.data();
   m->dirty_list.assign(nb + 1, 0); m->block_mb.assign(nb + 1, 0);
   s.dirty_list = m->dirty_list.data(); s.block_mb = m->block_mb.data();
   m->ran_list.assign(nb + 1, 0); s.ran_list = m->ran_list.data();
@@ -147,11 +160,11 @@ static void sim_lz77_fixpoint(SimStream& m) {
   for (;;) {
     br_chain(s);
     if (getenv("BR_SIM_TRACE")) { u32 h[6] = {0}; u32 first = nb; for (u32 k = 0; k < nb; ++k) { h[s.dirty[k]]++; if (s.dirty[k] && first == nb) first = k; }
-      fprintf(stderr, "epoch %u dirty %u first %u: never %u state %u dict %u window %u wrap %u\n", s.epoch, s.counters[0], first, h[1], h[2], h[3], h[4], h[5]); }
+      fprintf(stderr, "epoch %u dirty %u first %u: never %u state %u dict %u window %u wrap %u | flipped bits %u\n", s.epoch, s.counters[0], first, h[1], h[2], h[3], h[4], h[5], s.epoch_changed[s.epoch]); }
     if (s.counters[0] == 0) break;
     ++s.epoch; ++m.iterations;
     sim_build_storedS(m);
-    std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0);
+    std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
     s.counters[4] = 0;
     { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) br_walk_block(s, k); }
     m.block_runs += s.counters[4];
