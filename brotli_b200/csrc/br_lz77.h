@@ -38,6 +38,22 @@ BR_DEV u32 br_match_len(const u8* d, u32 a, u32 b, u32 limit) {
   return len;
 }
 
+// Same, with the first 16 bytes at `b` (the search position, identical for all candidates of one
+// search) already in registers.
+BR_DEV u32 br_match_len_c(const u8* d, u32 a, u32 b, u32 limit, u64 c0, u64 c1) {
+  if (limit >= 8) {
+    u64 x = br_ld64u(d, a) ^ c0;
+    if (x) return (u32)(br_ctz64(x) >> 3);
+    if (limit >= 16) {
+      x = br_ld64u(d, a + 8) ^ c1;
+      if (x) return 8u + (u32)(br_ctz64(x) >> 3);
+      return 16u + br_match_len(d, a + 16, b + 16, limit - 16);
+    }
+    return 8u + br_match_len(d, a + 8, b + 8, limit - 8);
+  }
+  return br_match_len(d, a, b, limit);
+}
+
 // hash_longest_match64_inc.h:23 / hash_longest_match_inc.h:23 HashBytes
 BR_DEV u32 br_hash_key(const BrParams& P, const u8* d, u32 pos) {
   if (P.hash64) {
@@ -51,7 +67,7 @@ struct BrWalk {
   const BrStream* s;
   const u8* d;
   u32 p0, pend;    // p0: first position this walker owns; pend: end of the reference input block
-  int dc[16];
+  int dc[4];       // distance cache; entries 4..15 of the reference (hash.h:80) are derived on the fly
   u64 dict_l, dict_m;
   u32 dl, dm, gate_checks, gate_fail;
   u32 min_wrap;
@@ -163,36 +179,39 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   u32 best_score = out.score, best_len = out.len;
   out.len = 0; out.delta = 0;
   bool brk = false;
-  // ---- distance cache probes
+  // the bytes at the search position, shared by every candidate comparison below
+  const u64 c0 = br_ld64u(d, cur), c1 = br_ld64u(d, cur + 8);
+  // ---- distance cache probes: lane k owns candidate k (hash.h:80 PrepareDistanceCache layout)
   for (int base = 0; base < P.ndist && !brk; base += BR_WARP) {
-    int k = base + lane;
-    int back_i = (k < P.ndist) ? w.dc[k] : 0;
-    bool valid = (k < P.ndist) && back_i > 0 && (u32)back_i <= max_backward;
-    u32 back = (u32)back_i, len = 0; int eqmax = 0;
+    const int k = base + lane;
+    int back_i = 0;
+    if (k < 4) back_i = k == 0 ? w.dc[0] : k == 1 ? w.dc[1] : k == 2 ? w.dc[2] : w.dc[3];
+    else if (k < 16) { int j = (k - 4) % 6, mag = (j >> 1) + 1; back_i = (k < 10 ? w.dc[0] : w.dc[1]) + ((j & 1) ? mag : -mag); }
+    const bool valid = (k < P.ndist) && back_i > 0 && (u32)back_i <= max_backward;
+    const u32 back = (u32)back_i;
+    u32 len = 0; int eqmax = 0;
     if (valid) {
-      len = br_match_len(d, cur - back, cur, max_length);
+      len = br_match_len_c(d, cur - back, cur, max_length, c0, c1);
       if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + (cur - back) + max_length));
     }
-    int cnt = P.ndist - base < BR_WARP ? P.ndist - base : BR_WARP;
-    for (int t = 0; t < cnt; ++t) {
-      if (!br_shfl((int)valid, t)) continue;
-      u32 l = br_shfl(len, t), bk = br_shfl(back, t);
-      int em = br_shfl(eqmax, t);
-      u32 pm = (cur - bk) & rmask;
+    u32 score = 135u * len + BR_SCORE_BASE + 15u;
+    if (k != 0) score -= 39u + ((0x1CA10u >> (k & 0xE)) & 0xEu);
+    const bool lenok = valid && (len >= 3 || (len == 2 && k < 2));
+    const u32 pm = (cur - back) & rmask;
+    int last = -1;
+    for (;;) {
+      // candidates are examined in order; everything up to `last` has been decided
+      u32 pending = br_ballot(valid && lane > last);
+      if (!pending) break;
       if (cur_m + best_len > rmask) { brk = true; break; }
-      if (pm + best_len > rmask) continue;
-      if (!(l > best_len || (l == best_len && best_len == max_length && em))) continue;
-      int kk = base + t;
-      if (l >= 3 || (l == 2 && kk < 2)) {
-        u32 score = 135u * l + BR_SCORE_BASE + 15u;
-        if (best_score < score) {
-          if (kk != 0) score -= 39u + ((0x1CA10u >> (kk & 0xE)) & 0xEu);
-          if (best_score < score) {
-            best_score = score; best_len = l;
-            out.len = l; out.distance = bk; out.score = score;
-          }
-        }
-      }
+      bool ok = lenok && lane > last && !(pm + best_len > rmask) &&
+                (len > best_len || (len == best_len && best_len == max_length && eqmax)) && score > best_score;
+      u32 mm = br_ballot(ok);
+      if (!mm) break;
+      int f = br_ffs(mm) - 1;
+      best_len = br_shfl(len, f); best_score = br_shfl(score, f);
+      out.len = best_len; out.distance = br_shfl(back, f); out.score = best_score;
+      last = f;
     }
   }
   if (best_len < 3) best_len = 3;
@@ -228,7 +247,6 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
         if (m < w.min_wrap) w.min_wrap = m;
       }
     }
-    const u32 first4 = br_ld32u(d, cur);
     u32 collected = 0, jj = j;
     bool done = false;
     while (!done && collected < V && jj > lo) {
@@ -246,12 +264,9 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
       // full match length of every taken candidate
       u32 len = 0; int eqmax = 0;
       if (take) {
-        if (P.hash64) {
-          if (br_ld32u(d, q) == first4) len = 4 + br_match_len(d, q + 4, cur + 4, max_length - 4);
-        } else {
-          len = br_match_len(d, q, cur, max_length);
-          if (len < 4) len = 0;
-        }
+        // H6: the first four bytes must agree, then the length counts on; H5: length >= 4.  Same thing.
+        len = br_match_len_c(d, q, cur, max_length, c0, c1);
+        if (len < 4) len = 0;
         if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + q + max_length));
       }
       u32 score = len ? BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward) : 0;
@@ -278,17 +293,6 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   if (min_score == out.score) br_search_static_dict(w, cur, max_length, dict_distance, out);
 }
 
-// hash.h:80 PrepareDistanceCache
-BR_DEV void br_prepare_dist_cache(int* dc, int nd) {
-  if (nd > 4) {
-    int l = dc[0];
-    dc[4] = l - 1; dc[5] = l + 1; dc[6] = l - 2; dc[7] = l + 2; dc[8] = l - 3; dc[9] = l + 3;
-    if (nd > 10) {
-      int n = dc[1];
-      dc[10] = n - 1; dc[11] = n + 1; dc[12] = n - 2; dc[13] = n + 2; dc[14] = n - 3; dc[15] = n + 3;
-    }
-  }
-}
 // backward_references.c:87 ComputeDistanceCode
 BR_DEV u32 br_compute_distance_code(u32 distance, u32 max_distance, const int* dc) {
   if (distance <= max_distance) {
@@ -318,7 +322,6 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   w.min_wrap = 0xffffffffu;
   w.stale = in.blk_end <= P.rmask ? 0u : (u32)s.data[in.blk_end - (P.rmask + 1)];
   for (int i = 0; i < 4; ++i) w.dc[i] = in.dc[i];
-  for (int i = 4; i < 16; ++i) w.dc[i] = 0;
   const u32 pos_end = in.blk_end;
   u32 position = in.start_pos;
   u32 ext = 0;
@@ -365,7 +368,6 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   u32 insert_length = 0;
   u32 ncmd = 0, nlit = 0;
   BrCmd* cmds = s.cmd_blocks + (size_t)b * s.cmd_stride;
-  br_prepare_dist_cache(w.dc, P.ndist);
   while (position + P.htl < pos_end && (in.last || position < in.end)) {
     if (w.warming && position >= in.pos) {
       // crossing: from here on this is the chunk's own run
@@ -399,7 +401,6 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
       u32 dcode = br_compute_distance_code(sr.distance, dictionary_start, w.dc);
       if (sr.distance <= dictionary_start && dcode > 0) {
         w.dc[3] = w.dc[2]; w.dc[2] = w.dc[1]; w.dc[1] = w.dc[0]; w.dc[0] = (int)sr.distance;
-        br_prepare_dist_cache(w.dc, P.ndist);
       }
       if (lane == 0 && !w.warming) cmds[ncmd] = br_init_cmd(insert_length, sr.len, sr.delta, dcode);
       ++ncmd;
