@@ -32,7 +32,7 @@ struct BrParams {
 
 // The unit of speculation is a CHUNK: a slice (1 << BR_CHUNK_BITS bytes) of one of the
 // reference's input blocks.  Per chunk: what the chain hands to the chunk's walker.
-#define BR_CHUNK_BITS 12
+#define BR_CHUNK_BITS 11
 struct BrBlockIn {
   u32 pos, end;          // nominal slice [pos, end) of the input
   u32 blk_start, blk_end;  // the reference input block (one EncodeData call) that contains it
@@ -49,7 +49,7 @@ struct BrBlockIn {
   u32 force_flush;       // BROTLI_OPERATION_FLUSH ended the input here (encode.c:1700)
   u32 warm;              // != 0: the state above is a guess; walk this many bytes before `pos` first to refine it
 };
-#define BR_WARM_BYTES 1024
+#define BR_WARM_BYTES 256
 // What the walker reports back.
 struct BrBlockOut {
   u32 ncmd, nlit;        // commands emitted, literals covered by them (without the carried-in literals)
