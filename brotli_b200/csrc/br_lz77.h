@@ -186,7 +186,10 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
     const int k = base + lane;
     int back_i = 0;
     if (k < 4) back_i = k == 0 ? w.dc[0] : k == 1 ? w.dc[1] : k == 2 ? w.dc[2] : w.dc[3];
-    else if (k < 16) { int j = (k - 4) % 6, mag = (j >> 1) + 1; back_i = (k < 10 ? w.dc[0] : w.dc[1]) + ((j & 1) ? mag : -mag); }
+    else if (k < 16) {   // dc[4..15] = last -1, +1, -2, +2, -3, +3; second last likewise (hash.h:83-97)
+      int mag = (int)((0xE79u >> (2 * ((k - 4) >> 1))) & 3u);
+      back_i = (k < 10 ? w.dc[0] : w.dc[1]) + ((k & 1) ? mag : -mag);
+    }
     const bool valid = (k < P.ndist) && back_i > 0 && (u32)back_i <= max_backward;
     const u32 back = (u32)back_i;
     u32 len = 0; int eqmax = 0;

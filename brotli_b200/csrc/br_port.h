@@ -28,7 +28,10 @@ BR_DEV void br_syncwarp() { __syncwarp(); }
 BR_DEV int br_popc(u32 x) { return __popc(x); }
 BR_DEV int br_ffs(u32 x) { return __ffs((int)x); }  // 1-based, 0 if none
 BR_DEV int br_clz(u32 x) { return __clz((int)x); }
-BR_DEV int br_ctz64(u64 x) { return __ffsll((long long)x) - 1; }
+BR_DEV int br_ctz64(u64 x) {   // x != 0
+  u32 lo = (u32)x;
+  return lo ? __ffs((int)lo) - 1 : 31 + __ffs((int)(u32)(x >> 32));
+}
 BR_DEV u32 br_lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 BR_DEV u32 br_atomic_or(u32* p, u32 v) { return atomicOr(p, v); }
 BR_DEV u32 br_atomic_and(u32* p, u32 v) { return atomicAnd(p, v); }

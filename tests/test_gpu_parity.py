@@ -102,3 +102,23 @@ def test_full_size_properties(b200):
     out = b200.compress_oneshot(d, 5, 22)
     assert ref.decompress(out, len(d)) == d
     assert out == ref.compress(d, 5, 22)
+
+
+def test_cli_dropin(b200, tmp_path):
+    """The reference's own CLI (c/tools/brotli.c, unmodified) linked against this library instead of
+    libbrotlienc produces the same file as the CLI linked against the reference encoder."""
+    import subprocess
+    from brotli_libs import ROOT
+    cli_ref = os.path.join(ROOT, "oracle", "_ref", "brotli_cli_ref")
+    cli_b200 = os.path.join(ROOT, "oracle", "_ref", "brotli_cli_b200")
+    if not (os.path.exists(cli_ref) and os.path.exists(cli_b200)):
+        pytest.skip("CLI binaries were not built (oracle/Makefile ref)")
+    from corpus import synth_text
+    src = tmp_path / "in.txt"
+    src.write_bytes(synth_text(3_000_000, 77))
+    outs = []
+    for cli in (cli_ref, cli_b200):
+        dst = tmp_path / (os.path.basename(cli) + ".br")
+        subprocess.check_call([cli, "-q", "5", "-w", "22", "-f", "-o", str(dst), str(src)])
+        outs.append(dst.read_bytes())
+    assert outs[0] == outs[1] and len(outs[0]) > 0
