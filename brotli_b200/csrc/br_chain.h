@@ -59,17 +59,38 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
           const u32 jq = s.rank[q];
           const u16 key = s.skeys[jq];
           if (s.seg[key + 1] - s.seg[key] >= 65536u) br_atomic_add(s.key_flips + key, 1);   // uint16 bucket counter may wrap
-          u32 cnt = 0, steps = 0;
+          const u32 V = 1u << s.P.block_bits;
+          // B: stored same-bucket positions older than q that a later search could still see (capped at V)
+          u32 B = 0;
+          {
+            const u32 lo = s.seg[key];
+            u32 steps = 0;
+            for (u32 j = jq; j > lo && B < V; ) {
+              --j;
+              const u32 pp = s.S[j];
+              if (q - pp > s.P.max_backward || ++steps > 1024) { if (steps > 1024) B = V; break; }
+              if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5]) >> (pp & 31)) & 1) ++B;   // stored before or after this launch
+            }
+          }
+          const u32 q4 = br_ld32u(s.data, q);
+          // cnt: stored (snapshot the walkers read) strictly between q and pp -> is q inside pp's view;
+          // cnt_e: stored before OR after this launch -> upper bound of the view size in both snapshots
+          u32 cnt = 0, cnt_e = 0, steps = 0;
           for (u32 j = jq + 1; j < s.P.n && s.skeys[j] == key && cnt < reach; ++j) {
-            if (++steps > 512) {   // pathological bucket (long runs of unstored positions): give up precision,
-              br_atomic_max((int*)(s.counters + 6), (int)s.epoch + 1);   // everybody re-validates
+            if (++steps > 4096) {  // pathological bucket (long runs of unstored positions): give up precision,
+              br_atomic_max(&s.blk[in.blk].changed_epoch, (int)s.epoch);   // block-level window rule (br_chain_c)
               break;
             }
             const u32 pp = s.S[j];
             if (pp - q > s.P.max_backward) break;
-            if ((s.bits_latest[pp >> 5] >> (pp & 31)) & 1) ++cnt;
+            const u32 before = cnt_e;
+            if ((s.bits_prev[pp >> 5] >> (pp & 31)) & 1) ++cnt;
+            if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5]) >> (pp & 31)) & 1) ++cnt_e;
             if (pp >= a && pp < b) continue;            // my own run is consistent with my own bits
             if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
+            // q itself can only be chosen at pp if at least four bytes agree; and it can only push another
+            // candidate out of (or pull one into) pp's view if that view is full
+            if (br_ld32u(s.data, pp) != q4 && before + 1 + B < V) continue;
             u32 c = ((pp >> s.P.lgblock) << s.P.cpb_shift) + ((pp & ((1u << s.P.lgblock) - 1)) >> BR_CHUNK_BITS);
             br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
             if (c > 0) br_atomic_max(s.bitdep_epoch + c - 1, (int)s.epoch);   // its owner may be the chunk before
@@ -302,7 +323,17 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
   u64 dict_l = ((u64)W.dict_l_hi << 32) | W.dict_l_lo, dict_m = ((u64)W.dict_m_hi << 32) | W.dict_m_lo;
   u32 cmd_off = W.cmd_base;
   const u32 t_now = s.epoch;
-  const int ovf = (int)s.counters[6] - 1;   // newest launch in which the precise bit tracking overflowed (-1: never)
+  // conservative fallback for buckets where the precise tracking gave up: newest such commit among the
+  // blocks inside this block's window (including itself)
+  int ovf = B.changed_epoch;
+  {
+    const u32 lowpos = B.start > s.P.max_backward ? B.start - s.P.max_backward : 0;
+    for (u32 j = bi; j-- > 0;) {
+      if (s.blk[j].end <= lowpos) break;
+      int ce = s.blk[j].changed_epoch;
+      if (ce > ovf) ovf = ce;
+    }
+  }
   bool prev_dirty = false;
   for (u32 c = 0; c < B.nchunks; ++c) {
     const u32 k = B.first_chunk + c;

@@ -106,6 +106,7 @@ struct BrStream {
   const u32* seg;        // seg[key] = first index of bucket key in S; nbuckets + 2 entries
   u32* bits_latest;      // stored-position bitmap, latest run of every block
   u32* bits_cur;         // written by the walkers of this iteration
+  const u32* bits_prev;  // copy of bits_latest taken before the commits of this iteration
   u32* srch_latest;      // positions FindLongestMatch was called on (latest run of their owner) ...
   u32* srch_cur;         // ... and in this iteration
   const u32* storedS;    // bits_latest permuted into S order ...

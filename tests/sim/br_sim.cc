@@ -35,7 +35,7 @@ extern "C" int sim_init(const u8* blob, size_t len, u32 log2n) {
 struct SimStream {
   BrStream s;
   std::vector<u8> data;
-  std::vector<u32> S, rank, seg, bits_latest, bits_cur, srch_latest, srch_cur, storedS, prefS, dirty, changed_bits,
+  std::vector<u32> S, rank, seg, bits_latest, bits_cur, bits_prev, srch_latest, srch_cur, storedS, prefS, dirty, changed_bits,
       epoch_changed, epoch_suffix, ext_total, lil_in, cmd_off, force_unc, counters, hist, block_mb;
   std::vector<int> changed_epoch, bitdep_epoch;
   std::vector<u16> skeys;
@@ -168,6 +168,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     s.counters[4] = 0;
     { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) br_walk_block(s, k); }
     m.block_runs += s.counters[4];
+    m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
     if (s.epoch >= BR_MAX_EPOCHS - 1) { fprintf(stderr, "sim: no fixpoint\n"); break; }
   }
