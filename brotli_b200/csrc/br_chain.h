@@ -58,7 +58,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
           flips &= flips - 1;
           const u32 jq = s.rank[q];
           const u16 key = s.skeys[jq];
-          if (s.seg[key + 1] - s.seg[key] >= 65536u) br_atomic_add(s.key_flips + key, 1);   // uint16 bucket counter may wrap
+          if (s.seg[key + 1] - s.seg[key] >= s.P.heavy_min) br_atomic_add(s.key_flips + key, 1);   // uint16 bucket counter may wrap
           const u32 V = 1u << s.P.block_bits;
           // B: stored same-bucket positions older than q that a later search could still see (capped at V)
           u32 B = 0;
@@ -90,7 +90,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
             if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
             // q itself can only be chosen at pp if at least four bytes agree; and it can only push another
             // candidate out of (or pull one into) pp's view if that view is full
-            if (br_ld32u(s.data, pp) != q4 && before + 1 + B < V) continue;
+            if (!(s.P.dbg_flags & 1) && br_ld32u(s.data, pp) != q4 && before + 1 + B < V) continue;
             u32 c = ((pp >> s.P.lgblock) << s.P.cpb_shift) + ((pp & ((1u << s.P.lgblock) - 1)) >> BR_CHUNK_BITS);
             br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
             if (c > 0) br_atomic_max(s.bitdep_epoch + c - 1, (int)s.epoch);   // its owner may be the chunk before

@@ -91,6 +91,9 @@ BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b);
 BR_DEV void br_own_set(BrWalk& w, u32 q) {
   if (w.warming) return;   // warm-up: the snapshot is read, nothing is recorded
   if (br_lane() == 0) br_atomic_or(w.s->bits_cur + (q >> 5), 1u << (q & 31));
+#if BR_GPU
+  __threadfence_block();   // the next search may consult this very bit (runs: cur and cur + 1 share a bucket)
+#endif
   br_syncwarp();
 }
 BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
@@ -225,7 +228,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
     const u32 j = br_ldg(s.rank + cur);
     const u32 block_size = 1u << P.block_bits;
     u32 V = block_size;
-    if (hi - lo >= 65536u) {
+    if (hi - lo >= P.heavy_min) {
       // The reference's per-bucket counter is a uint16 (hash_longest_match64_inc.h:52): after
       // 65536 insertions it wraps and the ring looks empty again.  c = insertions so far.
       u32 own_cnt = 0, jj = j, n_own = 0;

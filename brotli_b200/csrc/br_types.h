@@ -28,6 +28,8 @@ struct BrParams {
   u32 nblocks;      // number of chunks (speculation units); input blocks are groups of them
   u32 nbuckets;     // 1 << bucket_bits (+1 overflow bucket for the unhashable tail positions)
   u32 cpb_shift;    // lgblock - BR_CHUNK_BITS: chunks per full input block = 1 << cpb_shift
+  u32 dbg_flags;    // bit 0: disable the candidate-relevance filter of the dependency marking (default: disabled)
+  u32 heavy_min;    // buckets with at least this many positions take the counter-wrap path (65536; tests lower it)
 };
 
 // The unit of speculation is a CHUNK: a slice (1 << BR_CHUNK_BITS bytes) of one of the

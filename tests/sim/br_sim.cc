@@ -86,6 +86,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   memset(&s, 0, sizeof(s));
   if (!br_derive_params(q, lgwin, n, n, &s.P)) { delete m; return nullptr; }
   BrParams& P = s.P;
+  if (getenv("BR_SIM_HEAVY_MIN")) P.heavy_min = (u32)atoi(getenv("BR_SIM_HEAVY_MIN"));
   u32 bs = 1u << P.lgblock;
   const u32 ch = 1u << BR_CHUNK_BITS;
   std::vector<BrBlockIn> chunks;
