@@ -128,6 +128,10 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of k_walk's first launch on this workload (profiles/r01f_summary.md)
+WALK_DRAM_GB = 27.68
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -260,7 +264,10 @@ def main():
                 "e2e": {"value": round(e2e, 2), "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": out_size},
                 "gpu_launches": int(st["launches"]) * args.steps,
                 "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 6), "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"},
+                             "frac": round(achieved / peak, 6), "traffic": WALK_DRAM_GB if kname == "k_walk" else None,
+                             "traffic_unit": "GB of DRAM read+write per launch (ncu --set full, first = dominant k_walk launch of this workload, profiles/r01f_summary.md)",
+                             "algorithmic_gb_per_launch": round(per_launch / 1e9, 4),
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"},
                 "cpu_baseline": cpu,
                 "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_index", "ms_lz77", "ms_entropy", "ms_assemble", "ms_walk", "ms_encode")},
                 "lz77": {"iterations": int(st["lz77_iterations"]), "block_runs": int(st["block_runs"]), "blocks": int(st["blocks"]),

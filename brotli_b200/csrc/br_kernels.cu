@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restr
 }
 
 // ---------------------------------------------------------------------------- warp-task kernels
-__global__ void __launch_bounds__(128) k_walk(BrStream s) {
+#ifndef BR_WALK_MINB
+#define BR_WALK_MINB 8
+#endif
+__global__ void __launch_bounds__(128, BR_WALK_MINB) k_walk(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.counters[5]) return;
   br_walk_block(s, s.dirty_list[t]);

@@ -1420,8 +1420,44 @@ static int oracle_compress_impl(int quality, int lgwin, size_t n, const uint8_t*
   return 1;
 }
 
+#include "brotli_oracle_q1.h"
+
 int oracle_brotli_compress(int quality, int lgwin, size_t n, const uint8_t* in,
                            size_t* out_n, uint8_t* out) {
+  if (quality == 1) {
+    if (n == 0) { if (*out_n < 1) return 0; out[0] = 6; *out_n = 1; return 1; }   /* encode.c:1310 */
+    {
+      /* encode.c:1345: a stream longer than BrotliEncoderMaxCompressedSize (:1251) is replaced by
+         the raw stream of :1264 MakeUncompressedStream (window 10, empty metadata block, raw
+         meta-blocks of at most 2^24 bytes, empty last meta-block) */
+      const size_t cap = *out_n, bound = n + 4 * (n >> 14) + 6;
+      size_t got = cap + 2 * n + 65536;
+      uint8_t* tmp = (uint8_t*)malloc(got);
+      int ok = oracle_brotli_compress_q1(lgwin, n, in, 0, NULL, &got, tmp);
+      if (ok && got <= bound) {
+        ok = got <= cap;
+        if (ok) { memcpy(out, tmp, got); *out_n = got; }
+      } else if (ok) {
+        size_t o = 0, off = 0;
+        ok = cap >= bound;
+        if (ok) {
+          out[o++] = 0x21; out[o++] = 0x03;
+          while (off < n) {
+            const uint32_t len = n - off > (1u << 24) ? (1u << 24) : (uint32_t)(n - off);
+            const uint32_t nib = len > (1u << 20) ? 2 : len > (1u << 16) ? 1 : 0;   /* MNIBBLES - 4 */
+            const uint32_t hdr = (nib << 1) | ((len - 1) << 3) | (1u << (19 + 4 * nib));
+            uint32_t k;
+            for (k = 0; k < 3 + (nib == 2); ++k) out[o++] = (uint8_t)(hdr >> (8 * k));
+            memcpy(out + o, in + off, len); o += len; off += len;
+          }
+          out[o++] = 3;
+          *out_n = o;
+        }
+      }
+      free(tmp);
+      return ok;
+    }
+  }
   return oracle_compress_impl(quality, lgwin, n, in, out_n, out, NULL);
 }
 /* tests: cb(cmds(16B each), ncmds, metablock_start, metablock_bytes) */
