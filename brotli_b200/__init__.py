@@ -55,6 +55,7 @@ def lib():
                                               C.c_void_p, C.c_void_p, C.c_int]
         L.BrotliB200CompressBatch.restype = C.c_size_t
         L.BrotliB200LastStats.argtypes = [C.POINTER(C.c_double)]
+        L.BrotliB200LastStatsQ1.argtypes = [C.POINTER(C.c_double)]
         L.BrotliB200Available.restype = C.c_int
         _lib = L
     return _lib
@@ -72,6 +73,32 @@ def last_stats():
             "block_runs", "blocks", "metablocks", "launches", "ms_walk", "ms_encode", "walk_launches",
             "encode_launches", "walk_bytes", "total_cmds"]
     return dict(zip(keys, list(a)))
+
+
+def last_stats_q1():
+    """Timings (ms) and counters of the calling thread's last quality-1 batch."""
+    a = (C.c_double * 12)()
+    lib().BrotliB200LastStatsQ1(a)
+    keys = ["ms_total", "ms_h2d", "ms_parse", "ms_code", "ms_pack", "ms_d2h", "streams", "fragments", "blocks",
+            "in_bytes", "out_bytes", "launches"]
+    return dict(zip(keys, list(a)))
+
+
+def compress_batch(streams, quality, lgwin, threads=8):
+    """Many independent one-shot streams in one call (BrotliB200CompressBatch); returns a list of bytes."""
+    L = lib()
+    n = len(streams)
+    bufs = [C.create_string_buffer(bytes(s), max(1, len(s))) for s in streams]
+    sizes = (C.c_size_t * n)(*[len(s) for s in streams])
+    caps = [L.BrotliEncoderMaxCompressedSize(len(s)) + 16 for s in streams]
+    outs = [C.create_string_buffer(c) for c in caps]
+    in_ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+    out_ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in outs])
+    out_sizes = (C.c_size_t * n)(*caps)
+    good = L.BrotliB200CompressBatch(quality, lgwin, n, in_ptrs, sizes, out_ptrs, out_sizes, threads)
+    if good != n:
+        raise error("BrotliB200CompressBatch: %d of %d streams failed" % (n - good, n))
+    return [outs[i].raw[:out_sizes[i]] for i in range(n)]
 
 
 def compress(string, mode=MODE_GENERIC, quality=11, lgwin=22, lgblock=0):

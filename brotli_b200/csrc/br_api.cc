@@ -11,16 +11,43 @@
 #include <vector>
 #include "../../include/brotli_b200.h"
 #include "br_pipeline.h"
+#include "br_q1_host.h"
 
 namespace {
 
 struct TlsJob {
   BrJob* job = nullptr;
+  BrQ1Job* q1 = nullptr;
   uint8_t* d_in = nullptr; size_t d_in_cap = 0;
   double last[16] = {0};
-  ~TlsJob() { if (d_in) cudaFree(d_in); if (job) br_job_destroy(job); }
+  double last_q1[12] = {0};
+  ~TlsJob() { if (d_in) cudaFree(d_in); if (job) br_job_destroy(job); if (q1) br_q1_job_destroy(q1); }
 };
 thread_local TlsJob tls;
+
+bool have_device() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    static bool warned = false;
+    if (!warned) { warned = true; fprintf(stderr, "brotli_b200: no CUDA device; this library has no CPU path\n"); }
+    return false;
+  }
+  return true;
+}
+bool ensure_q1() {
+  if (tls.q1) return true;
+  if (!have_device()) return false;
+  tls.q1 = br_q1_job_create();
+  return tls.q1 != nullptr;
+}
+void record_q1_stats() {
+  const BrQ1Stats* s = br_q1_job_stats(tls.q1);
+  double* o = tls.last_q1;
+  o[0] = s->ms_total; o[1] = s->ms_h2d; o[2] = s->ms_parse; o[3] = s->ms_code; o[4] = s->ms_pack; o[5] = s->ms_d2h;
+  o[6] = (double)s->streams; o[7] = (double)s->fragments; o[8] = (double)s->blocks; o[9] = (double)s->in_bytes;
+  o[10] = (double)s->out_bytes; o[11] = (double)s->launches;
+}
 
 bool ensure_job() {
   if (tls.job) return true;
@@ -55,8 +82,8 @@ bool supported(Params p) {
   if (p.quality < 0) p.quality = 0;
   if (p.lgwin < 10) p.lgwin = 10;
   if (p.lgwin > 24 && !p.large_window) p.lgwin = 24;
-  if (p.quality < 5 || p.quality > 9) return false;
-  if (p.lgwin < 17 || p.lgwin > 24) return false;
+  if (p.quality != 1 && (p.quality < 5 || p.quality > 9)) return false;
+  if (p.quality == 1 ? p.lgwin > 24 : (p.lgwin < 17 || p.lgwin > 24)) return false;
   if (p.large_window || p.npostfix || p.ndirect || p.stream_offset || p.base64 || p.disable_ctx) return false;
   if (p.lgblock != 0) return false;
   if (p.mode == BROTLI_MODE_FONT) return false;
@@ -110,6 +137,27 @@ int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t
   return 1;
 }
 
+// Quality 1 (two-pass fragment coder, br_q1.cu): one stream = a batch of one.  `calls`: sizes of the
+// CompressStream calls that delivered the input (nullptr: a single call).
+int compress_host_q1(const Params& p0, const uint8_t* in, size_t n, const std::vector<size_t>* calls,
+                     std::vector<uint8_t>* out_vec) {
+  Params p = p0;
+  if (p.lgwin < 10) p.lgwin = 10;      // quality.h:60 SanitizeParams
+  if (p.lgwin > 24) p.lgwin = 24;
+  if (!ensure_q1() || n > (1u << 28)) return 0;
+  size_t cap = n + 16;
+  { size_t lim = (size_t)1 << p.lgwin, nc = calls ? calls->size() : 1; cap += 12 * (n / lim + nc + 2); }
+  out_vec->resize(cap);
+  const uint8_t* ins[1] = {in}; size_t in_n[1] = {n};
+  const size_t* cl[1] = {calls ? calls->data() : nullptr}; size_t ncl[1] = {calls ? calls->size() : 0};
+  uint8_t* outs[1] = {out_vec->data()}; size_t out_n[1] = {cap}; int ok[1] = {0};
+  if (!br_q1_compress_batch(tls.q1, p.lgwin, 1, ins, in_n, calls ? cl : nullptr, calls ? ncl : nullptr, 0, outs, out_n, ok, 1))
+    return 0;
+  record_q1_stats();
+  out_vec->resize(out_n[0]);
+  return 1;
+}
+
 }  // namespace
 
 struct BrotliEncoderStateStruct {
@@ -117,6 +165,7 @@ struct BrotliEncoderStateStruct {
   Params params;
   bool initialized = false, finished = false, compressed = false, hint_fixed = false;
   std::vector<uint8_t> input, output;
+  std::vector<size_t> calls;     // quality 1: bytes brought by each CompressStream call (encode.c:1425 cuts fragments per call)
   size_t out_pos = 0;
   uint64_t total_out = 0;
 };
@@ -132,6 +181,7 @@ int BrotliB200Available(void) {
 }
 
 void BrotliB200LastStats(double out[16]) { memcpy(out, tls.last, sizeof(tls.last)); }
+void BrotliB200LastStatsQ1(double out[12]) { memcpy(out, tls.last_q1, sizeof(tls.last_q1)); }
 
 size_t BrotliEncoderMaxCompressedSize(size_t input_size) {  /* encode.c:1251 */
   size_t num_large_blocks = input_size >> 14;
@@ -152,7 +202,18 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
   if (lgwin > 24) p.large_window = 1;
   if (!supported(p)) { *encoded_size = 0; return BROTLI_FALSE; }
   size_t got = 0;
-  int ok = compress_host(p, (uint32_t)input_size, input_buffer, input_size, encoded_buffer, out_size, &got, nullptr);
+  int ok;
+  if (quality == 1) {
+    std::vector<uint8_t> tmp;
+    ok = compress_host_q1(p, input_buffer, input_size, nullptr, &tmp);
+    got = tmp.size();
+    if (ok && got <= max_out_size) {
+      if (got > out_size) { *encoded_size = 0; return BROTLI_FALSE; }
+      memcpy(encoded_buffer, tmp.data(), got);
+    }
+  } else {
+    ok = compress_host(p, (uint32_t)input_size, input_buffer, input_size, encoded_buffer, out_size, &got, nullptr);
+  }
   if (ok && !(max_out_size && got > max_out_size)) { *encoded_size = got; return BROTLI_TRUE; }
   *encoded_size = 0;
   if (!ok) return BROTLI_FALSE;   /* GPU path failed: fail loudly, never substitute other bytes */
@@ -184,6 +245,31 @@ BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, size_t input_size, 
 size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8_t* const* inputs,
     const size_t* input_sizes, uint8_t* const* outputs, size_t* encoded_sizes, int threads) {
   if (threads < 1) threads = 1;
+  if (quality == 1 && count) {
+    /* one device batch: all streams through the same four launches (br_q1.cu) */
+    Params p; p.quality = 1; p.lgwin = lgwin;
+    if (!supported(p) || !ensure_q1()) { for (size_t i = 0; i < count; ++i) encoded_sizes[i] = 0; return 0; }
+    int w = lgwin < 10 ? 10 : lgwin;
+    std::vector<int> ok(count, 0);
+    std::vector<size_t> caps(encoded_sizes, encoded_sizes + count);
+    br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, 0, outputs, encoded_sizes, ok.data(), threads);
+    record_q1_stats();
+    size_t good = 0;
+    for (size_t i = 0; i < count; ++i) {
+      /* what the one-shot wrapper adds per stream: encode.c:1310 (empty input) and :1345 (raw-stream rule) */
+      const size_t bound = BrotliEncoderMaxCompressedSize(input_sizes[i]);
+      if (input_sizes[i] == 0) {
+        if (caps[i] >= 1) { outputs[i][0] = 6; encoded_sizes[i] = 1; ++good; } else encoded_sizes[i] = 0;
+      } else if (ok[i] && encoded_sizes[i] <= bound) {
+        ++good;
+      } else if (ok[i] && caps[i] >= bound) {
+        encoded_sizes[i] = make_uncompressed_stream(inputs[i], input_sizes[i], outputs[i]); ++good;
+      } else {
+        encoded_sizes[i] = 0;
+      }
+    }
+    return good;
+  }
   if ((size_t)threads > count) threads = (int)count;
   std::vector<size_t> okc((size_t)threads, 0);
   int dev = 0; cudaGetDevice(&dev);
@@ -268,6 +354,7 @@ BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOper
   }
   if (s->compressed && *available_in != 0) return BROTLI_FALSE;   /* input after finish */
   if (!supported(s->params)) return BROTLI_FALSE;
+  if (!s->compressed && (*available_in || op == BROTLI_OPERATION_FINISH)) s->calls.push_back(*available_in);
   if (*available_in) {
     s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
     *next_in += *available_in; *available_in = 0;
@@ -288,13 +375,16 @@ BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOper
     if (s->input.empty()) {
       /* encode.c:1006: empty stream = window bits + ISLAST + ISEMPTY */
       int lgwin = s->params.lgwin > 24 ? 24 : s->params.lgwin;
+      if (s->params.quality == 1 && lgwin < 18) lgwin = 18;      /* encode.c:673 */
       uint32_t bits = lgwin == 17 ? 1u : (uint32_t)(((lgwin - 17) << 1) | 1), nb = lgwin == 17 ? 7 : 4;
       bits |= 3u << nb; nb += 2;
       s->output.assign((nb + 7) / 8, 0);
       for (uint32_t i = 0; i < (nb + 7) / 8; ++i) s->output[i] = (uint8_t)(bits >> (8 * i));
     } else {
       size_t got = 0;
-      if (!compress_host(s->params, s->params.size_hint, s->input.data(), s->input.size(), nullptr, 0, &got, &s->output))
+      if (s->params.quality == 1) {
+        if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &s->output)) return BROTLI_FALSE;
+      } else if (!compress_host(s->params, s->params.size_hint, s->input.data(), s->input.size(), nullptr, 0, &got, &s->output))
         return BROTLI_FALSE;
     }
     s->compressed = true;

@@ -246,7 +246,7 @@ struct BrMbScratch {
 };
 
 // brotli_bit_stream.c:165 + :283 BrotliStoreHuffmanTree
-BR_DEV void br_store_huffman_tree(const u8* depths, u32 num, BrMbScratch* sc, BrBitW& w) {
+template <class SC> BR_DEV void br_store_huffman_tree(const u8* depths, u32 num, SC* sc, BrBitW& w) {
   const u8 kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
   const u8 kSym[6] = {0, 7, 3, 2, 1, 15};
   const u8 kLen[6] = {2, 4, 3, 2, 2, 4};

@@ -63,6 +63,15 @@ BR_DEV u32 br_hash_key(const BrParams& P, const u8* d, u32 pos) {
   return (br_ld32u(d, pos) * 0x1E35A7BDu) >> (32 - P.bucket_bits);
 }
 
+// same, from the 8 bytes at the position
+BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
+  if (P.hash64) return (u32)((v * (0x1FE35A7BD3579BD3ull << 24)) >> (64 - 15));
+  return ((u32)v * 0x1E35A7BDu) >> (32 - P.bucket_bits);
+}
+#ifndef BR_WALK_PREFETCH
+#define BR_WALK_PREFETCH 1
+#endif
+
 struct BrWalk {
   const BrStream* s;
   const u8* d;
@@ -73,6 +82,7 @@ struct BrWalk {
   u32 min_wrap;
   u32 stale;       // the byte the reference finds just past the block end (see oracle)
   bool warming;    // warm-up (state refinement before the chunk proper): reads the snapshot, records nothing
+  u32 pf_pos, pf_lo, pf_hi, pf_j;   // prefetched index entry (bucket bounds, rank) of position pf_pos
 };
 
 // Stored-bits of the walker's own range [p0, ...) live in bits_cur (global): written with
@@ -223,9 +233,27 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   if (best_len < 3) best_len = 3;
   // ---- bucket ring
   {
-    const u32 key = br_hash_key(P, d, cur);
-    const u32 lo = br_ldg(s.seg + key), hi = br_ldg(s.seg + key + 1);
-    const u32 j = br_ldg(s.rank + cur);
+    // Index entry of `cur`: bucket bounds and the position's rank.  Most searches follow each
+    // other at consecutive positions, so the entry of cur + 1 is requested now and consumed by the
+    // next call: its latency hides behind this search's gather chain.
+    u32 lo, hi, j;
+#if BR_WALK_PREFETCH
+    if (w.pf_pos == cur) { lo = w.pf_lo; hi = w.pf_hi; j = w.pf_j; }
+    else
+#endif
+    {
+      const u32 key = br_hash_key_v(P, c0);
+      lo = br_ldg(s.seg + key); hi = br_ldg(s.seg + key + 1);
+      j = br_ldg(s.rank + cur);
+    }
+#if BR_WALK_PREFETCH
+    {
+      const u32 k1 = br_hash_key_v(P, (c0 >> 8) | (c1 << 56));
+      w.pf_lo = br_ldg(s.seg + k1); w.pf_hi = br_ldg(s.seg + k1 + 1);
+      w.pf_j = br_ldg(s.rank + cur + 1);
+      w.pf_pos = cur + 1;
+    }
+#endif
     const u32 block_size = 1u << P.block_bits;
     u32 V = block_size;
     if (hi - lo >= P.heavy_min) {
@@ -326,6 +354,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   w.dict_m = ((u64)in.dict_m_hi << 32) | in.dict_m_lo;
   w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
   w.min_wrap = 0xffffffffu;
+  w.pf_pos = 0xffffffffu; w.pf_lo = w.pf_hi = w.pf_j = 0;
   w.stale = in.blk_end <= P.rmask ? 0u : (u32)s.data[in.blk_end - (P.rmask + 1)];
   for (int i = 0; i < 4; ++i) w.dc[i] = in.dc[i];
   const u32 pos_end = in.blk_end;
@@ -385,23 +414,30 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
       w.min_wrap = 0xffffffffu;
       if (position >= in.end && !in.last) break;
     }
+    // One search call site for the primary search and the (up to 4) lazy ones at position + 1
+    // (backward_references_inc.h:58-101): the walker's code is dominated by the inlined search.
     u32 max_length = pos_end - position;
-    u32 max_distance = br_min(position, P.max_backward);
     BrSR sr; sr.len = 0; sr.delta = 0; sr.distance = 0; sr.score = BR_MIN_SCORE;
-    br_find_longest_match(w, position, max_length, max_distance, max_distance, sr);
-    if (sr.score > BR_MIN_SCORE) {
-      int delayed = 0;
-      --max_length;
-      for (;; --max_length) {
-        BrSR sr2; sr2.len = 0; sr2.delta = 0; sr2.distance = 0; sr2.score = BR_MIN_SCORE;
-        max_distance = br_min(position + 1, P.max_backward);
-        br_find_longest_match(w, position + 1, max_length, max_distance, max_distance, sr2);
-        if (sr2.score >= sr.score + 175u) {
-          ++position; ++insert_length; sr = sr2;
-          if (++delayed < 4 && position + P.htl < pos_end) continue;
-        }
-        break;
+    bool have = false;
+    int delayed = 0;
+    for (;;) {
+      const u32 sp = position + (have ? 1u : 0u);
+      const u32 md = br_min(sp, P.max_backward);
+      BrSR cur; cur.len = 0; cur.delta = 0; cur.distance = 0; cur.score = BR_MIN_SCORE;
+      br_find_longest_match(w, sp, max_length, md, md, cur);
+      if (!have) {
+        sr = cur;
+        if (!(sr.score > BR_MIN_SCORE)) break;
+        have = true; --max_length;
+        continue;
       }
+      if (cur.score >= sr.score + 175u) {
+        ++position; ++insert_length; sr = cur;
+        if (++delayed < 4 && position + P.htl < pos_end) { --max_length; continue; }
+      }
+      break;
+    }
+    if (have) {
       apply_random_heuristics = position + 2 * sr.len + window;
       u32 dictionary_start = br_min(position, P.max_backward);
       u32 dcode = br_compute_distance_code(sr.distance, dictionary_start, w.dc);

@@ -1,0 +1,239 @@
+// br_q1.cu -- kernels and host orchestration of the quality-1 path (br_q1.h): a BATCH of
+// independent streams goes through four launches, whatever its size.
+//
+//   k_q1_parse   persistent warps pull fragments from a queue (one 2^table_bits-entry table per warp)
+//   k_q1_prep    one CTA per 128 KiB block
+//   k_q1_chain   one thread per stream
+//   k_q1_emit    one CTA per block
+//   k_q1_pack    dense packing of the compressed streams for one device->host copy
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <functional>
+#include <thread>
+#include <vector>
+#include "br_q1.h"
+#include "br_q1_host.h"
+#include "br_q1_plan.h"
+
+__global__ void __launch_bounds__(128) k_q1_parse(BrQ1 q) {
+  const u32 slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int* table = q.tables + (size_t)slot * q.table_slot;
+  for (;;) {
+    u32 f = 0;
+    if ((threadIdx.x & 31u) == 0) f = atomicAdd(q.counters, 1u);
+    f = __shfl_sync(0xffffffffu, f, 0);
+    if (f >= q.nfrags) return;
+    br_q1_parse_fragment(q, f, table);
+  }
+}
+__global__ void __launch_bounds__(128) k_q1_prep(BrQ1 q) {
+  __shared__ BrQ1Smem sm;
+  br_q1_prep_block(q, blockIdx.x, &sm);
+}
+__global__ void k_q1_chain(BrQ1 q) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < q.nstreams) br_q1_chain_stream(q, s);
+}
+__global__ void __launch_bounds__(128) k_q1_emit(BrQ1 q) {
+  __shared__ u32 scratch[8];
+  br_q1_emit_block(q, blockIdx.x, scratch);
+}
+// dense offsets (16-aligned) of the compressed streams; one thread, the batch has <= ~10^6 streams
+__global__ void k_q1_offsets(BrQ1 q, u64* dense_off) {
+  u64 o = 0;
+  for (u32 s = 0; s < q.nstreams; ++s) { dense_off[s] = o; o += (q.streams[s].out_bytes + 15u) & ~15u; }
+  dense_off[q.nstreams] = o;
+}
+__global__ void __launch_bounds__(256) k_q1_pack(BrQ1 q, const u64* dense_off, uint4* dense) {
+  const u32 s = blockIdx.x;
+  const uint4* src = (const uint4*)((const u8*)q.out + q.streams[s].out_off);
+  uint4* dst = dense + (dense_off[s] >> 4);
+  const u32 n = (q.streams[s].out_bytes + 15u) >> 4;
+  for (u32 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ host
+namespace {
+struct Arena {
+  void* p = nullptr; size_t cap = 0;
+  bool need(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 4096;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = want; return true;
+  }
+  ~Arena() { if (p) cudaFree(p); }
+};
+struct Pinned {
+  void* p = nullptr; size_t cap = 0;
+  bool need(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 4096;
+    if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = want; return true;
+  }
+  ~Pinned() { if (p) cudaFreeHost(p); }
+};
+}  // namespace
+
+struct BrQ1Job {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[6] = {};
+  Arena in, out, dense, cmds, lits, streams, frags, blocks, codes, hdr, tables, counters, dense_off, log2;
+  Pinned h_in, h_out, h_off;
+  u32 log2_n = 0;
+  int sm_count = 0;
+  BrQ1Stats stats = {};
+};
+
+extern "C" const double* br_host_log2_table(u32* n);   // br_host.cc
+
+extern "C" BrQ1Job* br_q1_job_create(void) {
+  BrQ1Job* j = new BrQ1Job();
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError(); delete j; return nullptr;
+  }
+  cudaDeviceGetAttribute(&j->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  for (auto& e : j->ev) cudaEventCreate(&e);
+  // bit_cost.c:18 needs FastLog2 of sampled counts only (<= 2^17 / 43): the first 4096 entries
+  u32 n = 0; const double* h = br_host_log2_table(&n);
+  j->log2_n = n < 4096 ? n : 4096;
+  if (!j->log2.need((size_t)j->log2_n * 8)) { delete j; return nullptr; }
+  cudaMemcpy(j->log2.p, h, (size_t)j->log2_n * 8, cudaMemcpyHostToDevice);
+  return j;
+}
+extern "C" void br_q1_job_destroy(BrQ1Job* j) {
+  if (!j) return;
+  for (auto& e : j->ev) if (e) cudaEventDestroy(e);
+  if (j->st) cudaStreamDestroy(j->st);
+  delete j;
+}
+extern "C" const BrQ1Stats* br_q1_job_stats(const BrQ1Job* j) { return &j->stats; }
+
+static void run_threads(int threads, size_t count, const std::function<void(size_t, size_t)>& fn) {
+  if (threads <= 1 || count < 64) { fn(0, count); return; }
+  std::vector<std::thread> th;
+  size_t per = (count + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    size_t a = (size_t)t * per, b = a + per < count ? a + per : count;
+    if (a >= b) break;
+    th.emplace_back([=, &fn] { fn(a, b); });
+  }
+  for (auto& t : th) t.join();
+}
+
+extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const uint8_t* const* in, const size_t* in_n,
+                                    const size_t* const* calls, const size_t* ncalls, int inputs_on_device,
+                                    uint8_t* const* out, size_t* out_n, int* ok, int threads) {
+  if (!j || lgwin < 10 || lgwin > 24 || count == 0 || count > (1u << 24)) return 0;
+  std::vector<BrQ1Stream> streams; std::vector<BrQ1Frag> frags; std::vector<BrQ1Block> blocks;
+  streams.reserve(count);
+  u64 in_off = 0, out_off = 0;
+  u32 max_tb = 8;
+  for (size_t s = 0; s < count; ++s) {
+    if (in_n[s] > (1u << 28)) return 0;         // bit offsets of a stream are 32-bit
+    br_q1_plan_stream(lgwin, (u32)s, in_off, out_off, in_n[s], calls ? calls[s] : nullptr, calls ? ncalls[s] : 0, streams, frags, blocks);
+    in_off += (in_n[s] + 15 + 16) & ~(u64)15;   // >= 16 bytes of slack behind every stream (unaligned 8-byte loads)
+    out_off += br_q1_stream_bound(frags, streams.back());
+  }
+  for (auto& f : frags) if (f.table_bits > max_tb) max_tb = f.table_bits;
+  const u64 total_in = in_off, total_out = out_off;
+  const u32 nfr = (u32)frags.size(), nbl = (u32)blocks.size();
+  const u32 table_slot = 1u << max_tb;
+  u32 nwarps = (u32)j->sm_count * 32u;
+  if (nwarps > nfr) nwarps = nfr ? nfr : 1;
+  nwarps = (nwarps + 3u) & ~3u;
+
+  if (!j->in.need(total_in + 64) || !j->out.need(total_out + 64) || !j->dense.need(total_out + 64) ||
+      !j->lits.need(total_in + 64) || !j->cmds.need(4 * total_in + 64) ||
+      !j->streams.need(streams.size() * sizeof(BrQ1Stream)) || !j->frags.need((size_t)nfr * sizeof(BrQ1Frag) + 16) ||
+      !j->blocks.need((size_t)nbl * sizeof(BrQ1Block) + 16) || !j->codes.need((size_t)nbl * sizeof(BrQ1Codes) + 16) ||
+      !j->hdr.need((size_t)nbl * BR_Q1_HDR_WORDS * 4 + 16) || !j->tables.need((size_t)nwarps * table_slot * 4) ||
+      !j->counters.need(64) || !j->dense_off.need((count + 1) * 8))
+    return 0;
+  cudaStream_t st = j->st;
+  cudaEventRecord(j->ev[0], st);
+  // ---- inputs
+  if (inputs_on_device) {
+    for (size_t s = 0; s < count; ++s)
+      if (in_n[s]) cudaMemcpyAsync((u8*)j->in.p + streams[s].in_off, in[s], in_n[s], cudaMemcpyDeviceToDevice, st);
+  } else {
+    if (!j->h_in.need(total_in + 64)) return 0;
+    u8* hp = (u8*)j->h_in.p;
+    run_threads(threads, count, [&](size_t a, size_t b) {
+      for (size_t s = a; s < b; ++s) if (in_n[s]) memcpy(hp + streams[s].in_off, in[s], in_n[s]);
+    });
+    cudaMemcpyAsync(j->in.p, hp, total_in, cudaMemcpyHostToDevice, st);
+  }
+  cudaMemcpyAsync(j->streams.p, streams.data(), streams.size() * sizeof(BrQ1Stream), cudaMemcpyHostToDevice, st);
+  if (nfr) cudaMemcpyAsync(j->frags.p, frags.data(), (size_t)nfr * sizeof(BrQ1Frag), cudaMemcpyHostToDevice, st);
+  if (nbl) cudaMemcpyAsync(j->blocks.p, blocks.data(), (size_t)nbl * sizeof(BrQ1Block), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(j->counters.p, 0, 64, st);
+  cudaMemsetAsync(j->out.p, 0, total_out + 64, st);
+  cudaEventRecord(j->ev[1], st);
+
+  BrQ1 q; memset(&q, 0, sizeof(q));
+  q.in = (const u8*)j->in.p; q.out = (u32*)j->out.p; q.cmds = (u32*)j->cmds.p; q.lits = (u8*)j->lits.p;
+  q.streams = (BrQ1Stream*)j->streams.p; q.frags = (BrQ1Frag*)j->frags.p; q.blocks = (BrQ1Block*)j->blocks.p;
+  q.codes = (BrQ1Codes*)j->codes.p; q.hdr = (u32*)j->hdr.p; q.tables = (int*)j->tables.p; q.table_slot = table_slot;
+  q.nstreams = (u32)count; q.nfrags = nfr; q.nblocks = nbl; q.counters = (u32*)j->counters.p;
+  q.log2tab = (const double*)j->log2.p; q.log2tab_n = j->log2_n;
+
+  if (nfr) k_q1_parse<<<nwarps / 4, 128, 0, st>>>(q);
+  cudaEventRecord(j->ev[2], st);
+  if (nbl) k_q1_prep<<<nbl, 128, 0, st>>>(q);
+  k_q1_chain<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(q);
+  if (nbl) k_q1_emit<<<nbl, 128, 0, st>>>(q);
+  cudaEventRecord(j->ev[3], st);
+  k_q1_offsets<<<1, 1, 0, st>>>(q, (u64*)j->dense_off.p);
+  k_q1_pack<<<(unsigned)count, 256, 0, st>>>(q, (const u64*)j->dense_off.p, (uint4*)j->dense.p);
+  cudaEventRecord(j->ev[4], st);
+  // ---- results
+  if (!j->h_off.need((count + 1) * 8 + streams.size() * sizeof(BrQ1Stream))) return 0;
+  u64* h_off = (u64*)j->h_off.p;
+  BrQ1Stream* h_streams = (BrQ1Stream*)(h_off + count + 1);
+  cudaMemcpyAsync(h_off, j->dense_off.p, (count + 1) * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(h_streams, j->streams.p, streams.size() * sizeof(BrQ1Stream), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { fprintf(stderr, "brotli_b200 q1: %s\n", cudaGetErrorString(cudaGetLastError())); return 0; }
+  const u64 dense_bytes = h_off[count];
+  size_t good = 0;
+  if (inputs_on_device) {
+    // device-resident variant: outputs are device pointers too
+    for (size_t s = 0; s < count; ++s) {
+      const size_t sz = h_streams[s].out_bytes;
+      ok[s] = sz <= out_n[s];
+      if (ok[s]) { cudaMemcpyAsync(out[s], (const u8*)j->dense.p + h_off[s], sz, cudaMemcpyDeviceToDevice, st); out_n[s] = sz; ++good; }
+    }
+    cudaEventRecord(j->ev[5], st);
+    cudaStreamSynchronize(st);
+  } else {
+    if (!j->h_out.need(dense_bytes + 64)) return 0;
+    cudaMemcpyAsync(j->h_out.p, j->dense.p, dense_bytes, cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(j->ev[5], st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 0;
+    const u8* hp = (const u8*)j->h_out.p;
+    std::vector<int> okv(count, 0);
+    run_threads(threads, count, [&](size_t a, size_t b) {
+      for (size_t s = a; s < b; ++s) {
+        const size_t sz = h_streams[s].out_bytes;
+        if (sz <= out_n[s]) { memcpy(out[s], hp + h_off[s], sz); out_n[s] = sz; okv[s] = 1; }
+      }
+    });
+    for (size_t s = 0; s < count; ++s) { ok[s] = okv[s]; good += okv[s]; }
+  }
+  BrQ1Stats& S = j->stats;
+  cudaEventElapsedTime(&S.ms_h2d, j->ev[0], j->ev[1]);
+  cudaEventElapsedTime(&S.ms_parse, j->ev[1], j->ev[2]);
+  cudaEventElapsedTime(&S.ms_code, j->ev[2], j->ev[3]);
+  cudaEventElapsedTime(&S.ms_pack, j->ev[3], j->ev[4]);
+  cudaEventElapsedTime(&S.ms_d2h, j->ev[4], j->ev[5]);
+  cudaEventElapsedTime(&S.ms_total, j->ev[0], j->ev[5]);
+  S.streams = count; S.fragments = nfr; S.blocks = nbl; S.in_bytes = total_in; S.out_bytes = dense_bytes; S.launches = 6;
+  return (int)(good == count);
+}

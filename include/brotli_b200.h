@@ -80,8 +80,10 @@ BROTLI_B200_API uint32_t BrotliEncoderVersion(void);
  * CUDA device (plain device pointers).  *encoded_size: in = capacity, out = bytes written. */
 BROTLI_B200_API BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, size_t input_size, const void* d_input, size_t* encoded_size, void* d_encoded);
 /* Many independent streams (one stream per shard / per object).  Inputs and
- * outputs are host pointers; streams are spread over `threads` host workers, each with its own
- * CUDA stream.  encoded_sizes[i]: in = capacity of outputs[i], out = bytes written.
+ * outputs are host pointers.  Quality 5..9: streams are spread over `threads` host workers, each with
+ * its own CUDA stream.  Quality 1 (compress_fragment_two_pass.c:612, one independent fragment coder per
+ * stream): the whole batch is ONE device batch -- four kernel launches, one copy each way -- and `threads`
+ * only parallelises the host-side packing.  encoded_sizes[i]: in = capacity of outputs[i], out = bytes written.
  * Returns the number of streams compressed successfully. */
 BROTLI_B200_API size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8_t* const* inputs, const size_t* input_sizes, uint8_t* const* outputs, size_t* encoded_sizes, int threads);
 /* Timings (milliseconds, CUDA events) and counters of the calling thread's last compress call.
@@ -89,6 +91,9 @@ BROTLI_B200_API size_t BrotliB200CompressBatch(int quality, int lgwin, size_t co
  * blocks, metablocks, kernel launches, summed k_walk ms, k_encode_mb ms, k_walk launches,
  * k_encode_mb launches, input bytes walked over all k_walk launches, commands emitted. */
 BROTLI_B200_API void BrotliB200LastStats(double out[16]);
+/* quality-1 batch pipeline of the calling thread's last call: ms total / h2d / parse / code / pack / d2h, then
+   streams, fragments, blocks, input bytes, compressed bytes, launches */
+BROTLI_B200_API void BrotliB200LastStatsQ1(double out[12]);
 /* 1 if a usable CUDA device is present. */
 BROTLI_B200_API int BrotliB200Available(void);
 

@@ -64,6 +64,18 @@ class Oracle:
         blob = open(TABLES, "rb").read()
         assert L.oracle_init(blob, len(blob)) == 1
 
+    def compress_q1_stream(self, data, lgwin, calls=None):
+        """The quality-1 stream for a sequence of CompressStream calls (sizes); None = one call."""
+        L = self.lib
+        L.oracle_brotli_compress_q1.argtypes = [C.c_int, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
+                                                C.POINTER(C.c_size_t), C.c_void_p]
+        cap = 2 * len(data) + 100000
+        out = C.create_string_buffer(cap)
+        n = C.c_size_t(cap)
+        arr = (C.c_size_t * len(calls))(*calls) if calls is not None else None
+        assert L.oracle_brotli_compress_q1(lgwin, len(data), data, len(calls) if calls is not None else 0, arr, C.byref(n), out) == 1
+        return out.raw[:n.value]
+
     def compress(self, data, quality, lgwin):
         n = len(data)
         cap = n + (n >> 1) + 4096
@@ -72,3 +84,43 @@ class Oracle:
         ok = self.lib.oracle_brotli_compress(quality, lgwin, n, data, C.byref(out_n), out)
         assert ok == 1
         return out.raw[:out_n.value]
+
+
+def ref_compress_stream(ref, data, quality, lgwin, chunk, out_buf=1 << 19):
+    """Drives the reference's streaming API the way c/tools/brotli.c:1357 does: PROCESS calls of
+    `chunk` bytes, FINISH once the input is exhausted (an extra empty call when the size is a
+    multiple of `chunk`, like feof() after a full read)."""
+    L = ref.lib
+    L.BrotliEncoderCreateInstance.restype = C.c_void_p
+    L.BrotliEncoderCreateInstance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.BrotliEncoderSetParameter.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    L.BrotliEncoderDestroyInstance.argtypes = [C.c_void_p]
+    L.BrotliEncoderIsFinished.argtypes = [C.c_void_p]
+    L.BrotliEncoderCompressStream.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.c_void_p]
+    s = L.BrotliEncoderCreateInstance(None, None, None)
+    L.BrotliEncoderSetParameter(s, 1, quality)
+    L.BrotliEncoderSetParameter(s, 2, lgwin)
+    src = C.create_string_buffer(data, max(1, len(data)))
+    dst = C.create_string_buffer(out_buf)
+    out = bytearray()
+    pos, eof = 0, False
+    avail_in = C.c_size_t(0); next_in = C.c_void_p(C.addressof(src))
+    avail_out = C.c_size_t(out_buf); next_out = C.c_void_p(C.addressof(dst))
+    while True:
+        if avail_in.value == 0 and not eof:
+            n = min(chunk, len(data) - pos)
+            next_in = C.c_void_p(C.addressof(src) + pos); avail_in = C.c_size_t(n)
+            pos += n
+            eof = n < chunk          # fread() came back short
+        ok = L.BrotliEncoderCompressStream(s, 2 if eof else 0, C.byref(avail_in), C.byref(next_in),
+                                           C.byref(avail_out), C.byref(next_out), None)
+        assert ok == 1
+        if avail_out.value == 0:
+            out += dst.raw[:out_buf]
+            avail_out = C.c_size_t(out_buf); next_out = C.c_void_p(C.addressof(dst))
+        if L.BrotliEncoderIsFinished(s):
+            out += dst.raw[:out_buf - avail_out.value]
+            break
+    L.BrotliEncoderDestroyInstance(s)
+    return bytes(out)

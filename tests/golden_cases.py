@@ -62,4 +62,20 @@ CASES = [
     dict(kind="mixed", n=2500000, seed=13, q=8, lgwin=24),
     dict(kind="text", n=9500000, seed=14, q=5, lgwin=22),    # > 8 MiB ring buffer of the reference: wrap rules
     dict(kind="text", n=5000000, seed=15, q=5, lgwin=17),    # small window: ring wraps many times
+    # quality 1: the two-pass fragment coder
+    dict(kind="text", n=1, seed=1, q=1, lgwin=22),
+    dict(kind="text", n=15, seed=1, q=1, lgwin=22),           # below the 16-byte input margin: literals only
+    dict(kind="text", n=16, seed=1, q=1, lgwin=22),
+    dict(kind="text", n=17, seed=1, q=1, lgwin=22),
+    dict(kind="text", n=1000, seed=3, q=1, lgwin=16),         # 2^10-entry table, min_match 4
+    dict(kind="web", n=65536, seed=16, q=1, lgwin=22),        # BASELINE config C5 shape: 2^16 table, min_match 6
+    dict(kind="text", n=300000, seed=5, q=1, lgwin=22),       # three 128 KiB blocks sharing one table
+    dict(kind="text", n=300000, seed=5, q=1, lgwin=10),       # 1 KiB fragments
+    dict(kind="web", n=1200000, seed=8, q=1, lgwin=18),       # 256 KiB fragments
+    dict(kind="binary", n=1500000, seed=9, q=1, lgwin=22),
+    dict(kind="zeros", n=400000, seed=0, q=1, lgwin=22),
+    dict(kind="random", n=300000, seed=10, q=1, lgwin=22),    # raw meta-blocks (ShouldCompress)
+    dict(kind="random", n=300000, seed=10, q=1, lgwin=10),    # larger than MaxCompressedSize: raw stream
+    dict(kind="mixed", n=2500000, seed=13, q=1, lgwin=22),
+    dict(kind="text", n=5000000, seed=15, q=1, lgwin=20),     # five fragments
 ]

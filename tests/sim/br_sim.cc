@@ -334,3 +334,35 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
   return (long)res.size();
 }
 #endif
+
+// ------------------------------------------------------------------ quality 1 (br_q1.h)
+#ifdef BR_SIM_ENTROPY
+#include "../../brotli_b200/csrc/br_q1_plan.h"
+// One stream through the q1 device code with a one-lane warp and a one-thread CTA.
+extern "C" long sim_q1_compress(int lgwin, const u8* in, u32 n, const size_t* calls, size_t ncalls, u8* out, size_t out_cap) {
+  std::vector<BrQ1Stream> streams; std::vector<BrQ1Frag> frags; std::vector<BrQ1Block> blocks;
+  br_q1_plan_stream(lgwin, 0, 0, 0, n, calls, ncalls, streams, frags, blocks);
+  const size_t bound = br_q1_stream_bound(frags, streams[0]);
+  std::vector<u8> din((size_t)n + 64, 0); memcpy(din.data(), in, n);
+  std::vector<u32> dout(bound / 4 + 16, 0), cmds((size_t)n + 16), hdr(blocks.size() * BR_Q1_HDR_WORDS + 1, 0), counters(16, 0);
+  std::vector<u8> lits((size_t)n + 16);
+  std::vector<BrQ1Codes> codes(blocks.size() + 1);
+  std::vector<int> table((size_t)1 << 17);
+  BrQ1 q; memset(&q, 0, sizeof(q));
+  q.in = din.data(); q.out = dout.data(); q.cmds = cmds.data(); q.lits = lits.data();
+  q.streams = streams.data(); q.frags = frags.data(); q.blocks = blocks.data(); q.codes = codes.data(); q.hdr = hdr.data();
+  q.tables = table.data(); q.table_slot = 1u << 17; q.nstreams = 1; q.nfrags = (u32)frags.size(); q.nblocks = (u32)blocks.size();
+  q.counters = counters.data(); q.log2tab = g_t.log2tab.data(); q.log2tab_n = (u32)std::min<size_t>(g_t.log2tab.size(), 4096);
+  for (u32 f = 0; f < q.nfrags; ++f) br_q1_parse_fragment(q, f, table.data());
+  BrQ1Smem* sm = new BrQ1Smem();
+  for (u32 b = 0; b < q.nblocks; ++b) br_q1_prep_block(q, b, sm);
+  delete sm;
+  br_q1_chain_stream(q, 0);
+  u32 scratch[8];
+  for (u32 b = 0; b < q.nblocks; ++b) br_q1_emit_block(q, b, scratch);
+  const size_t sz = streams[0].out_bytes;
+  if (sz > out_cap) return -1;
+  memcpy(out, dout.data(), sz);
+  return (long)sz;
+}
+#endif

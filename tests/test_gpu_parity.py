@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from brotli_libs import REF_SO, Oracle, Ref
+from brotli_libs import REF_SO, Oracle, Ref, ref_compress_stream
 from golden_cases import make_case
 
 pytestmark = pytest.mark.gpu
@@ -122,3 +122,80 @@ def test_cli_dropin(b200, tmp_path):
         subprocess.check_call([cli, "-q", "5", "-w", "22", "-f", "-o", str(dst), str(src)])
         outs.append(dst.read_bytes())
     assert outs[0] == outs[1] and len(outs[0]) > 0
+
+
+def test_q1_oneshot_against_oracle(b200):
+    """Quality 1 through BrotliEncoderCompress: every hash-table size / min_match, block and fragment
+    boundaries, raw meta-blocks, the raw-stream rule."""
+    ora = Oracle()
+    from corpus import synth_binary, synth_text, synth_web
+    base = synth_web(3_000_000, 51)
+    for n in (0, 1, 15, 16, 17, 255, 256, 257, 1000, 5000, 40000, 65535, 65536, 65537, 131072, 131073, 300000, 1 << 20, 3_000_000):
+        for w in (10, 16, 18, 22, 24):
+            assert b200.compress_oneshot(base[:n], 1, w) == ora.compress(base[:n], 1, w), (n, w)
+    rnd = np.random.RandomState(5).randint(0, 256, 500000, dtype=np.uint8).tobytes()
+    for d in (synth_text(1_400_000, 52), synth_binary(1_400_000, 53), bytes(300000), rnd, rnd[:70000] + bytes(70000) + rnd[:70000]):
+        for w in (12, 17, 22):
+            assert b200.compress_oneshot(d, 1, w) == ora.compress(d, 1, w), (len(d), w)
+
+
+def test_q1_batch_c5_shape(b200):
+    """BASELINE config C5 in small: many independent 64 KiB streams, quality 1, one device batch; plus
+    ragged and empty members."""
+    ora = Oracle()
+    from corpus import synth_web
+    src = synth_web(6_000_000, 54)
+    offs = [(i * 104729) % (len(src) - 65536) for i in range(300)]
+    streams = [src[o:o + 65536] for o in offs]
+    streams += [b"", b"x", src[:15], src[:16], src[:17], src[:100000], src[:300001], bytes(5000),
+                np.random.RandomState(6).randint(0, 256, 20000, dtype=np.uint8).tobytes()]
+    got = b200.compress_batch(streams, 1, 22)
+    assert len(got) == len(streams)
+    for i, (g, d) in enumerate(zip(got, streams)):
+        assert g == ora.compress(d, 1, 22), i
+    st = b200.last_stats_q1()
+    assert st["streams"] == len(streams) and st["launches"] > 0
+
+
+def test_q1_streaming_call_pattern(b200):
+    """Quality 1 cuts fragments per CompressStream call: Compressor.process() chunks must give the
+    bytes the reference gives for the same calls."""
+    from corpus import synth_web
+    ora = Oracle()
+    d = synth_web(1_700_000, 55)
+    for sizes in ([1_700_000], [524288, 524288, 524288, 127136], [1, 15, 16, 17, 1_699_951], [600000, 0, 1_100_000]):
+        c = b200.Compressor(quality=1, lgwin=22)
+        out, o = b"", 0
+        for a in sizes:
+            out += c.process(d[o:o + a]); o += a
+        out += c.finish()
+        calls = [a for a in sizes if a] + [0]
+        assert out == ora.compress_q1_stream(d, 22, calls), sizes
+    if os.path.exists(REF_SO):
+        ref = Ref()
+        c = b200.Compressor(quality=1, lgwin=18)
+        out = b""
+        for o in range(0, len(d), 1 << 19):
+            out += c.process(d[o:o + (1 << 19)])
+        out += c.finish()
+        assert out == ref_compress_stream(ref, d, 1, 18, 1 << 19)
+        assert ref.decompress(out, len(d)) == d
+
+
+def test_q1_cli_dropin(b200, tmp_path):
+    import subprocess
+    from brotli_libs import ROOT
+    cli_ref = os.path.join(ROOT, "oracle", "_ref", "brotli_cli_ref")
+    cli_b200 = os.path.join(ROOT, "oracle", "_ref", "brotli_cli_b200")
+    if not (os.path.exists(cli_ref) and os.path.exists(cli_b200)):
+        pytest.skip("CLI binaries were not built (oracle/Makefile ref)")
+    from corpus import synth_web
+    for n in (3_000_000, 1 << 20):       # the second one ends exactly on a 512 KiB read: empty FINISH call
+        src = tmp_path / ("in%d.html" % n)
+        src.write_bytes(synth_web(n, 78))
+        outs = []
+        for cli in (cli_ref, cli_b200):
+            dst = tmp_path / (os.path.basename(cli) + ".br")
+            subprocess.check_call([cli, "-q", "1", "-w", "22", "-f", "-o", str(dst), str(src)])
+            outs.append(dst.read_bytes())
+        assert outs[0] == outs[1] and len(outs[0]) > 0

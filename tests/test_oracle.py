@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from brotli_libs import REF_SO, Oracle, Ref
+from brotli_libs import REF_SO, Oracle, Ref, ref_compress_stream
 from golden_cases import make_case
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
@@ -53,3 +53,26 @@ def test_fast_log2_table(oracle):
         f = struct.unpack("f", struct.pack("f", math.log2(v)))[0]
         assert oracle.lib.oracle_fast_log2(v) == f
     assert oracle.lib.oracle_fast_log2(4096) == 12.0
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built")
+def test_q1_oracle_against_reference(oracle):
+    """Quality 1 (compress_fragment_two_pass.c): one-shot calls over every table size / min_match the
+    reference can pick, and the streaming call pattern of c/tools/brotli.c (512 KiB PROCESS calls)."""
+    from corpus import synth_binary, synth_text, synth_web
+    ref = Ref()
+    base = synth_web(3_000_000, 51)
+    for n in (0, 1, 15, 16, 17, 255, 256, 257, 1000, 5000, 40000, 65536, 131072, 131073, 300000, 1 << 20, 3_000_000):
+        for w in (10, 16, 18, 22, 24):
+            assert oracle.compress(base[:n], 1, w) == ref.compress(base[:n], 1, w), (n, w)
+    for d in (synth_text(1_400_000, 52), synth_binary(1_400_000, 53), bytes(300000)):
+        for w in (17, 22):
+            assert oracle.compress(d, 1, w) == ref.compress(d, 1, w)
+    chunk = 1 << 19
+    for n in (0, 100, chunk, chunk + 1, 3 * chunk, 3_000_000):
+        d = base[:n]
+        calls = [min(chunk, n - o) for o in range(0, n, chunk)]
+        if n % chunk == 0:
+            calls.append(0)
+        for w in (16, 22):
+            assert oracle.compress_q1_stream(d, w, calls) == ref_compress_stream(ref, d, 1, w, chunk), (n, w)

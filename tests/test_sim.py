@@ -24,6 +24,8 @@ def sim():
     L.sim_compress.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
     blob = open(TABLES, "rb").read()
     L.sim_init(blob, len(blob), (1 << 22) + 2)
+    L.sim_q1_compress.restype = C.c_long
+    L.sim_q1_compress.argtypes = [C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     return L
 
 
@@ -33,6 +35,15 @@ SMALL = [c for c in CASES if c["n"] <= 1_500_000 and not (c["kind"] in ("binary"
 @pytest.mark.parametrize("c", SMALL, ids=lambda c: "%s-%d-q%d-w%d" % (c["kind"], c["n"], c["q"], c["lgwin"]))
 def test_sim_matches_oracle(sim, c):
     d = make_case(c)
+    if c["q"] == 1:
+        # quality 1: the stream as the device code makes it (the one-shot wrapper's empty-input and
+        # raw-stream rules live in br_api.cc)
+        want = Oracle().compress_q1_stream(d, c["lgwin"])
+        cap = 2 * len(d) + 100000
+        out = C.create_string_buffer(cap)
+        r = sim.sim_q1_compress(c["lgwin"], d, len(d), None, 0, out, cap)
+        assert r >= 0 and out.raw[:r] == want
+        return
     want = Oracle().compress(d, c["q"], c["lgwin"])
     cap = len(d) + len(d) // 2 + 4096
     out = C.create_string_buffer(cap)
@@ -40,3 +51,19 @@ def test_sim_matches_oracle(sim, c):
     r = sim.sim_compress(c["q"], c["lgwin"], d, len(d), out, cap, st.ctypes.data)
     assert r >= 0
     assert out.raw[:r] == want
+
+
+def test_sim_q1_call_patterns(sim):
+    """Quality 1 cuts fragments per CompressStream call (encode.c:1425): the device code planned with
+    the same call sizes gives the oracle's stream."""
+    from corpus import synth_web
+    d = synth_web(700000, 41)
+    ora = Oracle()
+    for calls in ([700000], [524288, 175712], [100000] * 7 + [0], [1, 15, 16, 17, 699951], [0, 700000, 0]):
+        for w in (12, 18, 22):
+            want = ora.compress_q1_stream(d, w, calls)
+            arr = (C.c_size_t * len(calls))(*calls)
+            cap = 2 * len(d) + 100000
+            out = C.create_string_buffer(cap)
+            r = sim.sim_q1_compress(w, d, len(d), arr, len(calls), out, cap)
+            assert r >= 0 and out.raw[:r] == want, (calls, w)
