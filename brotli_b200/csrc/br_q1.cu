@@ -8,6 +8,7 @@
 //   k_q1_pack    dense packing of the compressed streams for one device->host copy
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <functional>
 #include <thread>
@@ -16,7 +17,7 @@
 #include "br_q1_host.h"
 #include "br_q1_plan.h"
 
-__global__ void __launch_bounds__(128) k_q1_parse(BrQ1 q) {
+__global__ void __launch_bounds__(128, 12) k_q1_parse(BrQ1 q) {
   const u32 slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int* table = q.tables + (size_t)slot * q.table_slot;
   for (;;) {
@@ -88,6 +89,7 @@ struct BrQ1Job {
   Pinned h_in, h_out, h_off;
   u32 log2_n = 0;
   int sm_count = 0;
+  u32 warps_per_sm = 32, first_width = 32;   // tuning knobs (env BR_Q1_WARPS_PER_SM, BR_Q1_FIRST_WIDTH)
   BrQ1Stats stats = {};
 };
 
@@ -101,6 +103,8 @@ extern "C" BrQ1Job* br_q1_job_create(void) {
   }
   cudaDeviceGetAttribute(&j->sm_count, cudaDevAttrMultiProcessorCount, dev);
   for (auto& e : j->ev) cudaEventCreate(&e);
+  if (const char* e = getenv("BR_Q1_WARPS_PER_SM")) { int v = atoi(e); if (v >= 4 && v <= 48) j->warps_per_sm = (u32)v; }
+  if (const char* e = getenv("BR_Q1_FIRST_WIDTH")) { int v = atoi(e); if (v >= 1 && v <= 32) j->first_width = (u32)v; }
   // bit_cost.c:18 needs FastLog2 of sampled counts only (<= 2^17 / 43): the first 4096 entries
   u32 n = 0; const double* h = br_host_log2_table(&n);
   j->log2_n = n < 4096 ? n : 4096;
@@ -146,7 +150,7 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   const u64 total_in = in_off, total_out = out_off;
   const u32 nfr = (u32)frags.size(), nbl = (u32)blocks.size();
   const u32 table_slot = 1u << max_tb;
-  u32 nwarps = (u32)j->sm_count * 32u;
+  u32 nwarps = (u32)j->sm_count * j->warps_per_sm;
   if (nwarps > nfr) nwarps = nfr ? nfr : 1;
   nwarps = (nwarps + 3u) & ~3u;
 
@@ -184,6 +188,7 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   q.codes = (BrQ1Codes*)j->codes.p; q.hdr = (u32*)j->hdr.p; q.tables = (int*)j->tables.p; q.table_slot = table_slot;
   q.nstreams = (u32)count; q.nfrags = nfr; q.nblocks = nbl; q.counters = (u32*)j->counters.p;
   q.log2tab = (const double*)j->log2.p; q.log2tab_n = j->log2_n;
+  q.first_width = j->first_width;
 
   if (nfr) k_q1_parse<<<nwarps / 4, 128, 0, st>>>(q);
   cudaEventRecord(j->ev[2], st);

@@ -66,6 +66,7 @@ struct BrQ1 {
   u32 nstreams, nfrags, nblocks;
   u32* counters;           // [0] fragment queue head
   const double* log2tab; u32 log2tab_n;
+  u32 first_width;         // lanes probing in the first step of a trawl (matches tend to follow matches)
 };
 struct BrQ1Smem {          // shared memory of one prep CTA
   u32 lit_histo[256], cmd_histo[128];
@@ -173,11 +174,15 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
       // ---- trawl (:262-304), BR_WARP probes per step
       u32 skip = 32, cand = 0;
       bool hit = false;
+      // Right behind a copy the next match is usually close: the first step probes fewer positions,
+      // so fewer table / candidate sectors are fetched for nothing.
+      u32 width = br_min(q.first_width, (u32)BR_WARP);
       for (;;) {
         const u32 m1 = skip + (u32)lane;
         const u32 pos = ip + (br_q1_skip_sum(m1) - br_q1_skip_sum(skip));
         const u32 nxt = pos + (m1 >> 5);
-        const bool valid = nxt <= ip_limit;       // else the reference leaves for emit_remainder first (:283)
+        const bool act = (u32)lane < width;
+        const bool valid = act && nxt <= ip_limit;       // else the reference leaves for emit_remainder first (:283)
         u64 v = 0; u32 h = 0xFFFFFFFFu - (u32)lane; u32 t = 0;
         if (valid) { v = br_ld64u(d, pos); h = br_q1_hash(v, shift, mm); t = (u32)table[h]; }
         const u32 peers = br_match_any(h);
@@ -191,9 +196,9 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
           if (!m_last) m_tab = br_q1_is_match(d, v, ctab, mm) && pos - ctab <= BR_Q1_MAX_DISTANCE;
         }
         const u32 hits = br_ballot(valid && (m_last || m_tab));
-        const u32 inval = br_ballot(!valid);
+        const u32 inval = br_ballot(act && !valid);
         // lanes up to and including `lim` performed their probe: they file their position
-        const int lim = hits ? br_ffs(hits) - 1 : inval ? br_ffs(inval) - 2 : (int)BR_WARP - 1;
+        const int lim = hits ? br_ffs(hits) - 1 : inval ? br_ffs(inval) - 2 : (int)width - 1;
         const u32 upto = lim >= 31 ? 0xFFFFFFFFu : ((1u << (lim + 1)) - 1u);
         const u32 mine = peers & upto;
         if (valid && lane <= lim && 31 - br_clz(mine) == lane) table[h] = (int)(pos - base);
@@ -205,8 +210,9 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
           hit = true; break;
         }
         if (inval) break;
-        ip = br_shfl(nxt, (int)BR_WARP - 1);
-        skip += BR_WARP;
+        ip = br_shfl(nxt, (int)width - 1);
+        skip += width;
+        width = BR_WARP;
       }
       if (!hit) break;
       // ---- first copy of the run, with its literals (:309-360)

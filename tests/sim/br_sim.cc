@@ -352,7 +352,7 @@ extern "C" long sim_q1_compress(int lgwin, const u8* in, u32 n, const size_t* ca
   q.in = din.data(); q.out = dout.data(); q.cmds = cmds.data(); q.lits = lits.data();
   q.streams = streams.data(); q.frags = frags.data(); q.blocks = blocks.data(); q.codes = codes.data(); q.hdr = hdr.data();
   q.tables = table.data(); q.table_slot = 1u << 17; q.nstreams = 1; q.nfrags = (u32)frags.size(); q.nblocks = (u32)blocks.size();
-  q.counters = counters.data(); q.log2tab = g_t.log2tab.data(); q.log2tab_n = (u32)std::min<size_t>(g_t.log2tab.size(), 4096);
+  q.first_width = 8; q.counters = counters.data(); q.log2tab = g_t.log2tab.data(); q.log2tab_n = (u32)std::min<size_t>(g_t.log2tab.size(), 4096);
   for (u32 f = 0; f < q.nfrags; ++f) br_q1_parse_fragment(q, f, table.data());
   BrQ1Smem* sm = new BrQ1Smem();
   for (u32 b = 0; b < q.nblocks; ++b) br_q1_prep_block(q, b, sm);

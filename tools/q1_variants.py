@@ -1,0 +1,23 @@
+"""Tuning runs of the quality-1 batch (config-5 shape on a smaller source): warps per SM x first probe width."""
+import os, sys, threading, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import brotli_b200
+from corpus import synth_web
+total, count = 200_000_000, 10000
+src = synth_web(total)
+streams = [src[o:o + 65536] for o in [(i * 104729) % (total - 65536) for i in range(count)]]
+nbytes = sum(len(s) for s in streams)
+variants = [(32, 32)] if "--one" in sys.argv else [(32, 32), (48, 32), (32, 8), (48, 8), (48, 16), (48, 4), (24, 8)]
+base = None
+def run(w, f):
+    global base
+    for rep in range(2):
+        got = brotli_b200.compress_batch(streams, 1, 22, threads=16)
+    st = brotli_b200.last_stats_q1()
+    if base is None: base = got
+    print("warps/SM %2d first width %2d: parse %.1f ms code %.1f ms total %.1f ms  same bytes as first variant: %s" % (
+        w, f, st["ms_parse"], st["ms_code"], st["ms_total"], got == base), flush=True)
+for w, f in variants:
+    os.environ["BR_Q1_WARPS_PER_SM"] = str(w); os.environ["BR_Q1_FIRST_WIDTH"] = str(f)
+    t = threading.Thread(target=run, args=(w, f)); t.start(); t.join()
