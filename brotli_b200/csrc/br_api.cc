@@ -140,7 +140,7 @@ int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t
 // Quality 1 (two-pass fragment coder, br_q1.cu): one stream = a batch of one.  `calls`: sizes of the
 // CompressStream calls that delivered the input (nullptr: a single call).
 int compress_host_q1(const Params& p0, const uint8_t* in, size_t n, const std::vector<size_t>* calls,
-                     std::vector<uint8_t>* out_vec) {
+                     std::vector<uint8_t>* out_vec, int with_header = 1, int end_op = 2) {
   Params p = p0;
   if (p.lgwin < 10) p.lgwin = 10;      // quality.h:60 SanitizeParams
   if (p.lgwin > 24) p.lgwin = 24;
@@ -151,7 +151,7 @@ int compress_host_q1(const Params& p0, const uint8_t* in, size_t n, const std::v
   const uint8_t* ins[1] = {in}; size_t in_n[1] = {n};
   const size_t* cl[1] = {calls ? calls->data() : nullptr}; size_t ncl[1] = {calls ? calls->size() : 0};
   uint8_t* outs[1] = {out_vec->data()}; size_t out_n[1] = {cap}; int ok[1] = {0};
-  if (!br_q1_compress_batch(tls.q1, p.lgwin, 1, ins, in_n, calls ? cl : nullptr, calls ? ncl : nullptr, 0, outs, out_n, ok, 1))
+  if (!br_q1_compress_batch(tls.q1, p.lgwin, 1, ins, in_n, calls ? cl : nullptr, calls ? ncl : nullptr, 0, outs, out_n, ok, 1, with_header, end_op))
     return 0;
   record_q1_stats();
   out_vec->resize(out_n[0]);
@@ -164,6 +164,7 @@ struct BrotliEncoderStateStruct {
   brotli_alloc_func alloc_func; brotli_free_func free_func; void* opaque;
   Params params;
   bool initialized = false, finished = false, compressed = false, hint_fixed = false;
+  bool q1_header_done = false;   // quality 1: a FLUSH already delivered the window bits
   std::vector<uint8_t> input, output;
   std::vector<size_t> calls;     // quality 1: bytes brought by each CompressStream call (encode.c:1425 cuts fragments per call)
   size_t out_pos = 0;
@@ -252,7 +253,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
     int w = lgwin < 10 ? 10 : lgwin;
     std::vector<int> ok(count, 0);
     std::vector<size_t> caps(encoded_sizes, encoded_sizes + count);
-    br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, 0, outputs, encoded_sizes, ok.data(), threads);
+    br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, 0, outputs, encoded_sizes, ok.data(), threads, 1, 2);
     record_q1_stats();
     size_t good = 0;
     for (size_t i = 0; i < count; ++i) {
@@ -348,6 +349,26 @@ BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOper
     const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out) {
   s->initialized = true;
   if (op == BROTLI_OPERATION_EMIT_METADATA) return BROTLI_FALSE;
+  if (op == BROTLI_OPERATION_FLUSH && s->params.quality == 1 && supported(s->params) && !s->compressed) {
+    /* Quality 1 (encode.c:1425): the fragments of this call are compressed now, then the stream is padded
+       to a byte boundary (encode.c:1356), so everything delivered so far is decodable. */
+    if (*available_in) {
+      s->calls.push_back(*available_in);
+      s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
+      *next_in += *available_in; *available_in = 0;
+    }
+    if (!s->input.empty() || !s->q1_header_done) {
+      std::vector<uint8_t> seg;
+      if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &seg, !s->q1_header_done, 1))
+        return BROTLI_FALSE;
+      s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
+      s->output.insert(s->output.end(), seg.begin(), seg.end());
+      s->q1_header_done = true;
+      s->input.clear(); s->calls.clear();
+    }
+    push_output(s, available_out, next_out, total_out);
+    return BROTLI_TRUE;
+  }
   if (op == BROTLI_OPERATION_FLUSH) {
     if (*available_in == 0 && s->input.empty()) { push_output(s, available_out, next_out, total_out); return BROTLI_TRUE; }
     return BROTLI_FALSE;
@@ -370,6 +391,16 @@ BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOper
       }
       s->hint_fixed = true;
     }
+  }
+  if (op == BROTLI_OPERATION_FINISH && !s->compressed && s->q1_header_done) {
+    /* quality 1 behind a FLUSH: the last segment has no window bits */
+    std::vector<uint8_t> seg;
+    if (s->input.empty()) seg.assign(1, 3);          /* ISLAST + ISEMPTY on a byte boundary */
+    else if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &seg, 0, 2)) return BROTLI_FALSE;
+    s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
+    s->output.insert(s->output.end(), seg.begin(), seg.end());
+    s->compressed = true;
+    std::vector<uint8_t>().swap(s->input);
   }
   if (op == BROTLI_OPERATION_FINISH && !s->compressed) {
     if (s->input.empty()) {

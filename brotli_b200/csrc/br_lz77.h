@@ -73,6 +73,10 @@ BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
 #define BR_WALK_PREFETCH 0
 #endif
 
+#ifndef BR_WALK_SPECLEN
+#define BR_WALK_SPECLEN 1
+#endif
+
 struct BrWalk {
   const BrStream* s;
   const u8* d;
@@ -290,6 +294,16 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
       u32 q = has ? br_ldg(s.S + idx) : 0;
       u32 backward = cur - q;
       bool inwin = has && backward <= max_backward;
+#if BR_WALK_SPECLEN
+      // The candidate's bytes are requested before its stored-bit is known (almost every position
+      // in the window is stored): one memory round trip less on the search's dependent chain.
+      u32 len_spec = 0; int eq_spec = 0;
+      if (inwin) {
+        len_spec = br_match_len_c(d, q, cur, max_length, c0, c1);
+        if (len_spec < 4) len_spec = 0;
+        if (len_spec == max_length) eq_spec = (w.stale == (u32)br_ldg(d + q + max_length));
+      }
+#endif
       bool st = inwin && br_is_stored(w, q);
       u32 m = br_ballot(st);
       u32 rnk = (u32)br_popc(m & br_lanemask_lt());
@@ -298,12 +312,16 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
       collected += (u32)br_popc(m);
       // full match length of every taken candidate
       u32 len = 0; int eqmax = 0;
+#if BR_WALK_SPECLEN
+      if (take) { len = len_spec; eqmax = eq_spec; }
+#else
       if (take) {
         // H6: the first four bytes must agree, then the length counts on; H5: length >= 4.  Same thing.
         len = br_match_len_c(d, q, cur, max_length, c0, c1);
         if (len < 4) len = 0;
         if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + q + max_length));
       }
+#endif
       u32 score = len ? BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward) : 0;
       u32 pm = q & rmask;
       int last = -1;

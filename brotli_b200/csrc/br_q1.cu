@@ -134,7 +134,7 @@ static void run_threads(int threads, size_t count, const std::function<void(size
 
 extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const uint8_t* const* in, const size_t* in_n,
                                     const size_t* const* calls, const size_t* ncalls, int inputs_on_device,
-                                    uint8_t* const* out, size_t* out_n, int* ok, int threads) {
+                                    uint8_t* const* out, size_t* out_n, int* ok, int threads, int with_header, int end_op) {
   if (!j || lgwin < 10 || lgwin > 24 || count == 0 || count > (1u << 24)) return 0;
   std::vector<BrQ1Stream> streams; std::vector<BrQ1Frag> frags; std::vector<BrQ1Block> blocks;
   streams.reserve(count);
@@ -142,7 +142,7 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   u32 max_tb = 8;
   for (size_t s = 0; s < count; ++s) {
     if (in_n[s] > (1u << 28)) return 0;         // bit offsets of a stream are 32-bit
-    br_q1_plan_stream(lgwin, (u32)s, in_off, out_off, in_n[s], calls ? calls[s] : nullptr, calls ? ncalls[s] : 0, streams, frags, blocks);
+    br_q1_plan_stream(lgwin, (u32)s, in_off, out_off, in_n[s], calls ? calls[s] : nullptr, calls ? ncalls[s] : 0, streams, frags, blocks, with_header, end_op);
     in_off += (in_n[s] + 15 + 16) & ~(u64)15;   // >= 16 bytes of slack behind every stream (unaligned 8-byte loads)
     out_off += br_q1_stream_bound(frags, streams.back());
   }

@@ -33,9 +33,9 @@
 struct BrQ1Stream {
   u64 in_off, out_off;     // byte offsets of the stream in the batch input / output buffers (16-aligned)
   u32 size, first_frag, nfrags;
-  u32 hdr_lgwin;           // encode.c:673: max(lgwin, 18)
+  u32 hdr_lgwin;           // encode.c:673: max(lgwin, 18); 0 = no stream header (segment behind a FLUSH)
   u32 out_bytes;           // chain: size of the compressed stream
-  u32 pad;
+  u32 flush_end;           // the segment ends with a FLUSH: pad to a byte boundary (encode.c:1356)
 };
 struct BrQ1Frag {
   u32 stream, start, size; // start: offset in the stream
@@ -488,9 +488,11 @@ BR_DEV void br_q1_prep_block(const BrQ1& q, u32 bi, BrQ1Smem* sm) {
 BR_DEV void br_q1_chain_stream(const BrQ1& q, u32 si) {
   BrQ1Stream& st = q.streams[si];
   u32* out = q.out + (st.out_off >> 2);
-  // encode.c:203 EncodeWindowBits for lgwin >= 18
-  br_put_bits_at(out, 0, 4, (u64)(((st.hdr_lgwin - 17u) << 1) | 1u));
-  u32 ix = 4;
+  u32 ix = 0;
+  if (st.hdr_lgwin) {      // encode.c:203 EncodeWindowBits for lgwin >= 18
+    br_put_bits_at(out, 0, 4, (u64)(((st.hdr_lgwin - 17u) << 1) | 1u));
+    ix = 4;
+  }
   for (u32 f = st.first_frag; f < st.first_frag + st.nfrags; ++f) {
     BrQ1Frag& fr = q.frags[f];
     const u32 start_ix = ix;
@@ -508,6 +510,11 @@ BR_DEV void br_q1_chain_stream(const BrQ1& q, u32 si) {
     }
     fr.end_bit = ix;
     if (fr.is_last) { br_put_bits_at(out, ix, 2, 3); ix = (ix + 2u + 7u) & ~7u; }   // :641 ISLAST, ISEMPTY
+  }
+  if (st.flush_end && (ix & 7u)) {
+    // encode.c:1356 InjectBytePaddingBlock: ISLAST 0, MNIBBLES 11 (metadata), reserved 0, MSKIPBYTES 00
+    br_put_bits_at(out, ix, 6, 6);
+    ix = (ix + 6u + 7u) & ~7u;
   }
   st.out_bytes = (ix + 7u) >> 3;
 }

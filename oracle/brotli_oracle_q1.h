@@ -398,15 +398,18 @@ static void q1_compress_fragment(const uint8_t* in, size_t n, int is_last, uint3
    that brings `a` bytes is cut into fragments of at most 1 << lgwin bytes, each compressed with
    a freshly zeroed table (encode.c:156 GetHashTable); FINISH closes the stream after the last
    fragment of its call (an empty one if it brought no bytes).  call_sizes == NULL: one call. */
-int oracle_brotli_compress_q1(int lgwin, size_t n, const uint8_t* in, size_t ncalls, const size_t* call_sizes,
-                              size_t* out_n, uint8_t* out) {
+/* ops (nullable): per call 0 = PROCESS, 1 = FLUSH, 2 = FINISH; NULL = PROCESS ... PROCESS, FINISH.  A FLUSH
+   call compresses what it brought and then, if the stream is not byte aligned, appends the 6-bit empty
+   metadata block of encode.c:1356 InjectBytePaddingBlock. */
+int oracle_brotli_compress_q1_ops(int lgwin, size_t n, const uint8_t* in, size_t ncalls, const size_t* call_sizes,
+                                  const int* ops, size_t* out_n, uint8_t* out) {
   const size_t limit = (size_t)1 << lgwin;
   const size_t cap = *out_n;
   uint32_t* cmd_buf; uint8_t* lit_buf; int* table; uint8_t* buf;
   BitW w; size_t pos = 0, ci, one = n;
   int hdr_lgwin = lgwin < 18 ? 18 : lgwin;
   if (lgwin < 10 || lgwin > 24) return 0;
-  if (!call_sizes) { call_sizes = &one; ncalls = 1; }
+  if (!call_sizes) { call_sizes = &one; ncalls = 1; ops = NULL; }
   buf = (uint8_t*)calloc(2 * n + 1024 + 16 * (n / 1024 + ncalls + 4), 1);
   cmd_buf = (uint32_t*)malloc(4u << 17); lit_buf = (uint8_t*)malloc(1u << 17);
   table = (int*)malloc(sizeof(int) << 17);
@@ -414,17 +417,24 @@ int oracle_brotli_compress_q1(int lgwin, size_t n, const uint8_t* in, size_t nca
   wbits(&w, 4, (uint64_t)(((hdr_lgwin - 17) << 1) | 1));      /* encode.c:203 EncodeWindowBits, lgwin > 17 */
   for (ci = 0; ci < ncalls; ++ci) {
     size_t a = call_sizes[ci];
-    const int finish = ci + 1 == ncalls;
-    do {
-      size_t frag = a < limit ? a : limit, ts = 256;
-      while (ts < ((size_t)1 << 17) && ts < frag) ts <<= 1;       /* encode.c:148 HashTableSize */
-      memset(table, 0, ts * sizeof(int));
-      q1_compress_fragment(in + pos, frag, finish && frag == a, cmd_buf, lit_buf, table, ts, &w);
-      pos += frag; a -= frag;
-    } while (a != 0);
+    const int op = ops ? ops[ci] : (ci + 1 == ncalls ? 2 : 0);
+    if (a != 0 || op == 2) {
+      do {
+        size_t frag = a < limit ? a : limit, ts = 256;
+        while (ts < ((size_t)1 << 17) && ts < frag) ts <<= 1;       /* encode.c:148 HashTableSize */
+        memset(table, 0, ts * sizeof(int));
+        q1_compress_fragment(in + pos, frag, op == 2 && frag == a, cmd_buf, lit_buf, table, ts, &w);
+        pos += frag; a -= frag;
+      } while (a != 0);
+    }
+    if (op == 1 && (w.ix & 7) != 0) { wbits(&w, 6, 6); w.ix = (w.ix + 7) & ~(size_t)7; }
   }
   free(cmd_buf); free(lit_buf); free(table);
   { size_t bytes = (w.ix + 7) >> 3; int ok = bytes <= cap;
     if (ok) { memcpy(out, buf, bytes); *out_n = bytes; }
     free(buf); return ok; }
+}
+int oracle_brotli_compress_q1(int lgwin, size_t n, const uint8_t* in, size_t ncalls, const size_t* call_sizes,
+                              size_t* out_n, uint8_t* out) {
+  return oracle_brotli_compress_q1_ops(lgwin, n, in, ncalls, call_sizes, NULL, out_n, out);
 }

@@ -64,16 +64,19 @@ class Oracle:
         blob = open(TABLES, "rb").read()
         assert L.oracle_init(blob, len(blob)) == 1
 
-    def compress_q1_stream(self, data, lgwin, calls=None):
-        """The quality-1 stream for a sequence of CompressStream calls (sizes); None = one call."""
+    def compress_q1_stream(self, data, lgwin, calls=None, ops=None):
+        """The quality-1 stream for a sequence of CompressStream calls (sizes, and optionally their
+        operations: 0 PROCESS, 1 FLUSH, 2 FINISH); None = one FINISH call."""
         L = self.lib
-        L.oracle_brotli_compress_q1.argtypes = [C.c_int, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p,
-                                                C.POINTER(C.c_size_t), C.c_void_p]
+        L.oracle_brotli_compress_q1_ops.argtypes = [C.c_int, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                    C.POINTER(C.c_size_t), C.c_void_p]
         cap = 2 * len(data) + 100000
         out = C.create_string_buffer(cap)
         n = C.c_size_t(cap)
         arr = (C.c_size_t * len(calls))(*calls) if calls is not None else None
-        assert L.oracle_brotli_compress_q1(lgwin, len(data), data, len(calls) if calls is not None else 0, arr, C.byref(n), out) == 1
+        oarr = (C.c_int * len(ops))(*ops) if ops is not None else None
+        assert L.oracle_brotli_compress_q1_ops(lgwin, len(data), data, len(calls) if calls is not None else 0, arr, oarr,
+                                               C.byref(n), out) == 1
         return out.raw[:n.value]
 
     def compress(self, data, quality, lgwin):
@@ -122,5 +125,37 @@ def ref_compress_stream(ref, data, quality, lgwin, chunk, out_buf=1 << 19):
         if L.BrotliEncoderIsFinished(s):
             out += dst.raw[:out_buf - avail_out.value]
             break
+    L.BrotliEncoderDestroyInstance(s)
+    return bytes(out)
+
+
+def ref_stream_ops(ref, data, quality, lgwin, sizes, ops, out_buf=1 << 16):
+    """Drives the reference's CompressStream with an explicit list of (size, op) calls, draining the
+    output after each call the way encode.h:473 asks (repeat until no input and no more output)."""
+    L = ref.lib
+    L.BrotliEncoderCreateInstance.restype = C.c_void_p
+    L.BrotliEncoderCreateInstance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.BrotliEncoderSetParameter.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    L.BrotliEncoderDestroyInstance.argtypes = [C.c_void_p]
+    L.BrotliEncoderHasMoreOutput.argtypes = [C.c_void_p]
+    L.BrotliEncoderCompressStream.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.c_void_p]
+    s = L.BrotliEncoderCreateInstance(None, None, None)
+    L.BrotliEncoderSetParameter(s, 1, quality)
+    L.BrotliEncoderSetParameter(s, 2, lgwin)
+    src = C.create_string_buffer(data, max(1, len(data)))
+    dst = C.create_string_buffer(out_buf)
+    out = bytearray()
+    pos = 0
+    for size, op in zip(sizes, ops):
+        avail_in = C.c_size_t(size); next_in = C.c_void_p(C.addressof(src) + pos)
+        pos += size
+        while True:
+            avail_out = C.c_size_t(out_buf); next_out = C.c_void_p(C.addressof(dst))
+            assert L.BrotliEncoderCompressStream(s, op, C.byref(avail_in), C.byref(next_in), C.byref(avail_out),
+                                                 C.byref(next_out), None) == 1
+            out += dst.raw[:out_buf - avail_out.value]
+            if avail_in.value == 0 and not L.BrotliEncoderHasMoreOutput(s):
+                break
     L.BrotliEncoderDestroyInstance(s)
     return bytes(out)

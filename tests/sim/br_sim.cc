@@ -339,9 +339,10 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
 #ifdef BR_SIM_ENTROPY
 #include "../../brotli_b200/csrc/br_q1_plan.h"
 // One stream through the q1 device code with a one-lane warp and a one-thread CTA.
-extern "C" long sim_q1_compress(int lgwin, const u8* in, u32 n, const size_t* calls, size_t ncalls, u8* out, size_t out_cap) {
+extern "C" long sim_q1_compress_seg(int lgwin, const u8* in, u32 n, const size_t* calls, size_t ncalls, u8* out, size_t out_cap,
+                                    int with_header, int end_op) {
   std::vector<BrQ1Stream> streams; std::vector<BrQ1Frag> frags; std::vector<BrQ1Block> blocks;
-  br_q1_plan_stream(lgwin, 0, 0, 0, n, calls, ncalls, streams, frags, blocks);
+  br_q1_plan_stream(lgwin, 0, 0, 0, n, calls, ncalls, streams, frags, blocks, with_header, end_op);
   const size_t bound = br_q1_stream_bound(frags, streams[0]);
   std::vector<u8> din((size_t)n + 64, 0); memcpy(din.data(), in, n);
   std::vector<u32> dout(bound / 4 + 16, 0), cmds((size_t)n + 16), hdr(blocks.size() * BR_Q1_HDR_WORDS + 1, 0), counters(16, 0);
@@ -364,5 +365,8 @@ extern "C" long sim_q1_compress(int lgwin, const u8* in, u32 n, const size_t* ca
   if (sz > out_cap) return -1;
   memcpy(out, dout.data(), sz);
   return (long)sz;
+}
+extern "C" long sim_q1_compress(int lgwin, const u8* in, u32 n, const size_t* calls, size_t ncalls, u8* out, size_t out_cap) {
+  return sim_q1_compress_seg(lgwin, in, n, calls, ncalls, out, out_cap, 1, 2);
 }
 #endif

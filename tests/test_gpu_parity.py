@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from brotli_libs import REF_SO, Oracle, Ref, ref_compress_stream
+from brotli_libs import REF_SO, Oracle, Ref, ref_compress_stream, ref_stream_ops
 from golden_cases import make_case
 
 pytestmark = pytest.mark.gpu
@@ -199,3 +199,28 @@ def test_q1_cli_dropin(b200, tmp_path):
             subprocess.check_call([cli, "-q", "1", "-w", "22", "-f", "-o", str(dst), str(src)])
             outs.append(dst.read_bytes())
         assert outs[0] == outs[1] and len(outs[0]) > 0
+
+
+def test_q1_flush(b200):
+    """Compressor.flush() at quality 1 (go/cbrotli Writer.Flush, encoder_jni FLUSH): bytes delivered by each
+    flush are decodable so far and the whole stream equals the reference's for the same op sequence."""
+    from corpus import synth_web
+    ora = Oracle()
+    d = synth_web(900000, 61)
+    cases = [([0, 900000], [1, 2]), ([100000, 0, 800000, 0], [1, 1, 1, 2]), ([1, 2, 3, 899994], [1, 1, 0, 2]),
+             ([300000, 300000, 300000], [0, 1, 2]), ([450000, 450000, 0], [1, 1, 2])]
+    for sizes, ops in cases:
+        for w in (16, 22):
+            c = b200.Compressor(quality=1, lgwin=w)
+            out, o = b"", 0
+            for a, op in zip(sizes, ops):
+                piece = d[o:o + a]; o += a
+                if op == 0:
+                    out += c.process(piece)
+                elif op == 1:
+                    out += c._stream(piece, c._FLUSH)
+                else:
+                    out += c._stream(piece, c._FINISH)
+            assert out == ora.compress_q1_stream(d, w, sizes, ops), (sizes, ops, w)
+            if os.path.exists(REF_SO):
+                assert out == ref_stream_ops(Ref(), d, 1, w, sizes, ops)

@@ -26,6 +26,9 @@ def sim():
     L.sim_init(blob, len(blob), (1 << 22) + 2)
     L.sim_q1_compress.restype = C.c_long
     L.sim_q1_compress.argtypes = [C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.sim_q1_compress_seg.restype = C.c_long
+    L.sim_q1_compress_seg.argtypes = [C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                      C.c_int, C.c_int]
     return L
 
 
@@ -67,3 +70,35 @@ def test_sim_q1_call_patterns(sim):
             out = C.create_string_buffer(cap)
             r = sim.sim_q1_compress(w, d, len(d), arr, len(calls), out, cap)
             assert r >= 0 and out.raw[:r] == want, (calls, w)
+
+
+def test_sim_q1_flush_segments(sim):
+    """FLUSH at quality 1: the stream is a chain of byte-aligned segments (window bits only in the first,
+    byte padding behind every flushed one): device code per segment == oracle for the whole op sequence."""
+    from corpus import synth_web
+    d = synth_web(500000, 42)
+    ora = Oracle()
+    cases = [([0, 500000], [1, 2]), ([100000, 0, 400000, 0], [1, 1, 1, 2]), ([1, 2, 3, 499994], [1, 1, 0, 2]),
+             ([200000, 150000, 150000], [0, 1, 2]), ([250000, 250000, 0], [1, 1, 2])]
+    for sizes, ops in cases:
+        for w in (16, 22):
+            want = ora.compress_q1_stream(d, w, sizes, ops)
+            got, pos, seg_calls, seg_start, header = b"", 0, [], 0, 1
+            for a, op in zip(sizes, ops):
+                if a or op == 2:
+                    seg_calls.append(a)
+                pos += a
+                if op in (1, 2):
+                    piece = d[seg_start:pos]
+                    if op == 2 and not header and not piece:
+                        got += b"\x03"
+                    elif piece or header:
+                        arr = (C.c_size_t * max(1, len(seg_calls)))(*seg_calls)
+                        cap = 2 * len(piece) + 100000
+                        out = C.create_string_buffer(cap)
+                        r = sim.sim_q1_compress_seg(w, piece, len(piece), arr if seg_calls else None, len(seg_calls), out, cap, header, op)
+                        assert r >= 0
+                        got += out.raw[:r]
+                        header = 0
+                    seg_calls, seg_start = [], pos
+            assert got == want, (sizes, ops, w)
