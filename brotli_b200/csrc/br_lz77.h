@@ -73,8 +73,9 @@ BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
 #define BR_WALK_PREFETCH 0
 #endif
 
+// (measured: 64.1 vs 62.5 ms per 100 MB with it, and the zero / heavy-bucket cases get several times slower: off)
 #ifndef BR_WALK_SPECLEN
-#define BR_WALK_SPECLEN 1
+#define BR_WALK_SPECLEN 0
 #endif
 
 struct BrWalk {

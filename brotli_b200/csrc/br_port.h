@@ -34,6 +34,7 @@ BR_DEV int br_ctz64(u64 x) {   // x != 0
 }
 BR_DEV u32 br_lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 BR_DEV u32 br_match_any(u32 v) { return __match_any_sync(0xffffffffu, v); }
+BR_DEV void br_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 BR_DEV u32 br_atomic_or(u32* p, u32 v) { return atomicOr(p, v); }
 BR_DEV u32 br_atomic_and(u32* p, u32 v) { return atomicAnd(p, v); }
 BR_DEV u32 br_atomic_add(u32* p, u32 v) { return atomicAdd(p, v); }
@@ -80,6 +81,7 @@ BR_DEV int br_clz(u32 x) { return x ? __builtin_clz(x) : 32; }
 BR_DEV int br_ctz64(u64 x) { return __builtin_ctzll(x); }
 BR_DEV u32 br_lanemask_lt() { return 0; }
 BR_DEV u32 br_match_any(u32) { return 1u; }
+BR_DEV void br_prefetch_l2(const void*) {}
 BR_DEV u32 br_atomic_or(u32* p, u32 v) { u32 o = *p; *p = o | v; return o; }
 BR_DEV u32 br_atomic_and(u32* p, u32 v) { u32 o = *p; *p = o & v; return o; }
 BR_DEV u32 br_atomic_add(u32* p, u32 v) { u32 o = *p; *p = o + v; return o; }

@@ -17,7 +17,7 @@
 #include "br_q1_host.h"
 #include "br_q1_plan.h"
 
-__global__ void __launch_bounds__(128, 12) k_q1_parse(BrQ1 q) {
+__global__ void __launch_bounds__(128, 16) k_q1_parse(BrQ1 q) {
   const u32 slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int* table = q.tables + (size_t)slot * q.table_slot;
   for (;;) {
@@ -40,11 +40,23 @@ __global__ void __launch_bounds__(128) k_q1_emit(BrQ1 q) {
   __shared__ u32 scratch[8];
   br_q1_emit_block(q, blockIdx.x, scratch);
 }
-// dense offsets (16-aligned) of the compressed streams; one thread, the batch has <= ~10^6 streams
-__global__ void k_q1_offsets(BrQ1 q, u64* dense_off) {
-  u64 o = 0;
-  for (u32 s = 0; s < q.nstreams; ++s) { dense_off[s] = o; o += (q.streams[s].out_bytes + 15u) & ~15u; }
-  dense_off[q.nstreams] = o;
+// dense offsets (16-aligned) of the compressed streams: one CTA, each thread owns a contiguous run of streams
+__global__ void __launch_bounds__(1024) k_q1_offsets(BrQ1 q, u64* dense_off) {
+  __shared__ u64 part[1024];
+  const u32 per = (q.nstreams + blockDim.x - 1) / blockDim.x;
+  const u32 a = threadIdx.x * per, b = a + per < q.nstreams ? a + per : q.nstreams;
+  u64 sum = 0;
+  for (u32 s = a; s < b; ++s) sum += (q.streams[s].out_bytes + 15u) & ~15u;
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u64 o = 0;
+    for (u32 t = 0; t < blockDim.x; ++t) { const u64 v = part[t]; part[t] = o; o += v; }
+    dense_off[q.nstreams] = o;
+  }
+  __syncthreads();
+  u64 o = part[threadIdx.x];
+  for (u32 s = a; s < b; ++s) { dense_off[s] = o; o += (q.streams[s].out_bytes + 15u) & ~15u; }
 }
 __global__ void __launch_bounds__(256) k_q1_pack(BrQ1 q, const u64* dense_off, uint4* dense) {
   const u32 s = blockIdx.x;
@@ -89,7 +101,7 @@ struct BrQ1Job {
   Pinned h_in, h_out, h_off;
   u32 log2_n = 0;
   int sm_count = 0;
-  u32 warps_per_sm = 32, first_width = 32;   // tuning knobs (env BR_Q1_WARPS_PER_SM, BR_Q1_FIRST_WIDTH)
+  u32 warps_per_sm = 48, first_width = 32;   // tuning knobs (env BR_Q1_WARPS_PER_SM, BR_Q1_FIRST_WIDTH)
   BrQ1Stats stats = {};
 };
 
@@ -103,7 +115,7 @@ extern "C" BrQ1Job* br_q1_job_create(void) {
   }
   cudaDeviceGetAttribute(&j->sm_count, cudaDevAttrMultiProcessorCount, dev);
   for (auto& e : j->ev) cudaEventCreate(&e);
-  if (const char* e = getenv("BR_Q1_WARPS_PER_SM")) { int v = atoi(e); if (v >= 4 && v <= 48) j->warps_per_sm = (u32)v; }
+  if (const char* e = getenv("BR_Q1_WARPS_PER_SM")) { int v = atoi(e); if (v >= 4 && v <= 64) j->warps_per_sm = (u32)v; }
   if (const char* e = getenv("BR_Q1_FIRST_WIDTH")) { int v = atoi(e); if (v >= 1 && v <= 32) j->first_width = (u32)v; }
   // bit_cost.c:18 needs FastLog2 of sampled counts only (<= 2^17 / 43): the first 4096 entries
   u32 n = 0; const double* h = br_host_log2_table(&n);
@@ -196,7 +208,7 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   k_q1_chain<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(q);
   if (nbl) k_q1_emit<<<nbl, 128, 0, st>>>(q);
   cudaEventRecord(j->ev[3], st);
-  k_q1_offsets<<<1, 1, 0, st>>>(q, (u64*)j->dense_off.p);
+  k_q1_offsets<<<1, 1024, 0, st>>>(q, (u64*)j->dense_off.p);
   k_q1_pack<<<(unsigned)count, 256, 0, st>>>(q, (const u64*)j->dense_off.p, (uint4*)j->dense.p);
   cudaEventRecord(j->ev[4], st);
   // ---- results

@@ -150,6 +150,18 @@ BR_DEV u32 br_q1_refresh(const u8* d, u32 ip, u32 base, int* table, u32 shift, u
   return cand;
 }
 
+#ifndef BR_Q1_PREFETCH
+#define BR_Q1_PREFETCH 1
+#endif
+// Behind a copy that ends at ip: lane 0's slot is the one the refresh reads (:358), lanes 1.. are the
+// first probes of the trawl that follows if no copy starts at ip.  L2 prefetch hints only.
+BR_DEV void br_q1_prefetch_ahead(const u8* d, u32 ip, u32 ip_limit, const int* table, u32 shift, u32 mm) {
+#if BR_Q1_PREFETCH
+  const u32 pos = ip + (u32)br_lane();
+  if (pos <= ip_limit) br_prefetch_l2(table + br_q1_hash(br_ld64u(d, pos), shift, mm));
+#endif
+}
+
 // lanes copy n literal bytes
 BR_DEV void br_q1_copy_literals(const u8* d, u32 from, u8* to, u32 n) {
   for (u32 i = (u32)br_lane(); i < n; i += BR_WARP) to[i] = br_ldg(d + from + i);
@@ -183,6 +195,15 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
         const u32 nxt = pos + (m1 >> 5);
         const bool act = (u32)lane < width;
         const bool valid = act && nxt <= ip_limit;       // else the reference leaves for emit_remainder first (:283)
+#if BR_Q1_PREFETCH
+        {
+          // Table slots of the NEXT step's probes are pulled into L2 now: if this step finds nothing,
+          // the next one reads them at L2 instead of HBM latency.  A hint only: no value is consumed.
+          const u32 m2 = skip + width + (u32)lane;
+          const u32 pos2 = ip + (br_q1_skip_sum(m2) - br_q1_skip_sum(skip));
+          if (pos2 + (m2 >> 5) <= ip_limit) br_prefetch_l2(table + br_q1_hash(br_ld64u(d, pos2), shift, mm));
+        }
+#endif
         u64 v = 0; u32 h = 0xFFFFFFFFu - (u32)lane; u32 t = 0;
         if (valid) { v = br_ld64u(d, pos); h = br_q1_hash(v, shift, mm); t = (u32)table[h]; }
         const u32 peers = br_match_any(h);
@@ -233,6 +254,7 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
         last_distance = distance;
         ip += matched; next_emit = ip;
         if (ip >= ip_limit) break;
+        br_q1_prefetch_ahead(d, ip, ip_limit, table, shift, mm);
         u32 c0 = 0;
         if (lane == 0) c0 = br_q1_refresh(d, ip, base, table, shift, mm, true);
         cand = br_shfl(c0, 0);
@@ -247,6 +269,7 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
         ncmd += 2;
         ip += matched; next_emit = ip;
         if (ip >= ip_limit) { out = true; break; }
+        br_q1_prefetch_ahead(d, ip, ip_limit, table, shift, mm);
         u32 c0 = 0;
         if (lane == 0) c0 = br_q1_refresh(d, ip, base, table, shift, mm, false);
         cand = br_shfl(c0, 0);

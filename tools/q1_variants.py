@@ -8,7 +8,8 @@ total, count = 200_000_000, 10000
 src = synth_web(total)
 streams = [src[o:o + 65536] for o in [(i * 104729) % (total - 65536) for i in range(count)]]
 nbytes = sum(len(s) for s in streams)
-variants = [(32, 32)] if "--one" in sys.argv else [(32, 32), (48, 32), (32, 8), (48, 8), (48, 16), (48, 4), (24, 8)]
+libs = [a for a in sys.argv[1:] if a.endswith(".so")] or ["libbrotlienc_b200.so"]
+variants = [(48, 32)] if "--one" in sys.argv else [(48, 32), (64, 32)]
 base = None
 def run(w, f):
     global base
@@ -18,6 +19,10 @@ def run(w, f):
     if base is None: base = got
     print("warps/SM %2d first width %2d: parse %.1f ms code %.1f ms total %.1f ms  same bytes as first variant: %s" % (
         w, f, st["ms_parse"], st["ms_code"], st["ms_total"], got == base), flush=True)
-for w, f in variants:
-    os.environ["BR_Q1_WARPS_PER_SM"] = str(w); os.environ["BR_Q1_FIRST_WIDTH"] = str(f)
-    t = threading.Thread(target=run, args=(w, f)); t.start(); t.join()
+for so in libs:
+    brotli_b200._lib = None
+    brotli_b200.LIB_PATH = os.path.join(ROOT, "brotli_b200", so)
+    print(so, flush=True)
+    for w, f in variants:
+        os.environ["BR_Q1_WARPS_PER_SM"] = str(w); os.environ["BR_Q1_FIRST_WIDTH"] = str(f)
+        t = threading.Thread(target=run, args=(w, f)); t.start(); t.join()
