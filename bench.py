@@ -125,14 +125,37 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": round(value, 2), "unit": "MB/s", "cores": cores, "kind": kind,
                              "sample": "the full %d-byte stream per step, %d stream(s) on %d core(s) (ctypes releases the GIL)" % (WORKLOAD_BYTES, n_streams, cores)},
             "e2e": {"value": round(value, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_walk's first launch on this workload (profiles/r01f_summary.md)
 WALK_DRAM_GB = 27.68
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything any library prints on stdout (NCCL's version banner, ...) goes to stderr; the one JSON
+    line is written to the real stdout by _emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -272,7 +295,7 @@ def main():
                 "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_index", "ms_lz77", "ms_entropy", "ms_assemble", "ms_walk", "ms_encode")},
                 "lz77": {"iterations": int(st["lz77_iterations"]), "block_runs": int(st["block_runs"]), "blocks": int(st["blocks"]),
                          "metablocks": int(st["metablocks"])}}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

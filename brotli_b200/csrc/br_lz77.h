@@ -74,6 +74,10 @@ BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
 #endif
 
 // (measured: 64.1 vs 62.5 ms per 100 MB with it, and the zero / heavy-bucket cases get several times slower: off)
+// (measured: 39.2 vs 39.0 ms of k_walk per 100 MB with it: no gain, off)
+#ifndef BR_WALK_PF2
+#define BR_WALK_PF2 0
+#endif
 #ifndef BR_WALK_SPECLEN
 #define BR_WALK_SPECLEN 0
 #endif
@@ -252,6 +256,15 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
       lo = br_ldg(s.seg + key); hi = br_ldg(s.seg + key + 1);
       j = br_ldg(s.rank + cur);
     }
+#if BR_WALK_PF2
+    {
+      // The next search is almost always at cur + 1 (a literal step or the lazy re-search).  Its slice
+      // of S[] sits at a bucket-dependent place of a 4n-byte array, i.e. in HBM: pull it into L2 now.
+      // A hint only -- no value is consumed, so it cannot change the parse.
+      const u32 j1 = br_ldg(s.rank + cur + 1);
+      br_prefetch_l2(s.S + (j1 > (u32)lane ? j1 - 1u - (u32)lane : 0u));
+    }
+#endif
 #if BR_WALK_PREFETCH
     {
       const u32 k1 = br_hash_key_v(P, (c0 >> 8) | (c1 << 56));
