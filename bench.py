@@ -128,8 +128,8 @@ def run_reference(args, rank, world):
     _emit(line)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of k_walk's first launch on this workload (profiles/r01f_summary.md)
-WALK_DRAM_GB = 27.68
+# dram__bytes_read.sum + dram__bytes_write.sum of k_walk's first launch on this workload (profiles/r01l_summary.md)
+WALK_DRAM_GB = 30.61
 
 
 _REAL_STDOUT = None
@@ -288,7 +288,7 @@ def main():
                 "gpu_launches": int(st["launches"]) * args.steps,
                 "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 6), "traffic": WALK_DRAM_GB if kname == "k_walk" else None,
-                             "traffic_unit": "GB of DRAM read+write per launch (ncu --set full, first = dominant k_walk launch of this workload, profiles/r01f_summary.md)",
+                             "traffic_unit": "GB of DRAM read+write per launch (ncu --set full, first = dominant k_walk launch of this workload, profiles/r01l_summary.md)",
                              "algorithmic_gb_per_launch": round(per_launch / 1e9, 4),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"},
                 "cpu_baseline": cpu,

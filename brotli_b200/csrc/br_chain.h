@@ -8,6 +8,10 @@
 // later commit.
 #pragma once
 #include "br_cmd.h"
+#ifdef BR_SIM_DEBUG
+#include <stdio.h>
+static u32 br_sim_watch = 0xffffffffu;   // tests/sim: report commits that flip this position
+#endif
 
 // Compare and commit the stored-bits a walker just produced for chunk k (warp task).  The
 // walker owns the positions [start_pos, out_pos).  StitchToPreviousBlock of the FOLLOWING input
@@ -17,10 +21,27 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
   const BrBlockIn in = s.bin_used[k];
   const u32 a = in.start_pos, b = s.bout[k].out_pos;
   u32 diff = 0;
+  // Ranges of different runs must not overlap: where they do, one of the two runs is stale (it started
+  // from a guessed position, or a predecessor's last copy / ExtendLastCommand reaches into it), the later
+  // commit overwrites the earlier one, and two runs of the same parity in one launch even share their
+  // bits_cur bitmap.  The stale run is walked again anyway (its in-state changes); the other one is not --
+  // so every chunk whose latest range intersects mine is told to walk again.  Ranges of one input block
+  // are disjoint at the fixpoint, so this stops.
+  if (b > a) {
+    const u32 k0 = (k >> s.P.cpb_shift) << s.P.cpb_shift, k1 = br_min(k0 + (1u << s.P.cpb_shift), s.P.nblocks);
+    for (u32 c = k0 + (u32)br_lane(); c < k1; c += BR_WARP) {
+      if (c == k || !s.bout[c].valid) continue;
+      const u32 ca = s.bin_used[c].start_pos, cb = s.bout[c].out_pos;
+      if (ca < cb && ca < b && a < cb) br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
+    }
+  }
+  const u32* mine = s.bits_cur + (size_t)(k & 1u) * s.bits_words;
   if (b > a) {
     // stitch positions inside [a, b): the next block(s) starting at or shortly after blk_end
     u32 st_lo = 0, st_hi = 0;   // [st_lo, st_hi) of stitch-stored positions (at most one run here)
-    if (in.last && b == in.blk_end) {
+    // (any owner of one of the block's last three positions, not only the block's last chunk: a copy
+    // that runs to the block end makes an earlier chunk the owner)
+    if (b + 3 > in.blk_end) {
       for (u32 nb = k + 1; nb < s.P.nblocks; ++nb) {
         if (!s.bin[nb].first) continue;
         u32 np = s.bin[nb].blk_start, ne = s.bin[nb].blk_end;
@@ -34,7 +55,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
       u32 m = 0xffffffffu;
       if (x == w0) m &= 0xffffffffu << (a & 31);
       if (x == w1) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
-      u32 nv = s.bits_cur[x];
+      u32 nv = mine[x];
       for (u32 q = st_lo; q < st_hi; ++q) if ((q >> 5) == x) nv |= 1u << (q & 31);
       nv &= m;
       u32 ov = s.bits_latest[x] & m;
@@ -47,6 +68,11 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
         }
       }
       diff += (u32)br_popc(flips);
+#ifdef BR_SIM_DEBUG
+      if (br_sim_watch != 0xffffffffu && (br_sim_watch >> 5) == x && ((flips >> (br_sim_watch & 31)) & 1))
+        fprintf(stderr, "watch %u: epoch %u chunk %u range [%u,%u) flips it to %u\n", br_sim_watch, s.epoch, k, a, b,
+                (nv >> (br_sim_watch & 31)) & 1);
+#endif
       if (flips) {
         if (m == 0xffffffffu) s.bits_latest[x] = nv;
         else { br_atomic_and(s.bits_latest + x, ~m); br_atomic_or(s.bits_latest + x, nv); }
@@ -69,7 +95,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
               --j;
               const u32 pp = s.S[j];
               if (q - pp > s.P.max_backward || ++steps > 1024) { if (steps > 1024) B = V; break; }
-              if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5]) >> (pp & 31)) & 1) ++B;   // stored before or after this launch
+              if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5] | s.bits_cur[s.bits_words + (pp >> 5)]) >> (pp & 31)) & 1) ++B;   // stored before or after this launch
             }
           }
           const u32 q4 = br_ld32u(s.data, q);
@@ -85,7 +111,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
             if (pp - q > s.P.max_backward) break;
             const u32 before = cnt_e;
             if ((s.bits_prev[pp >> 5] >> (pp & 31)) & 1) ++cnt;
-            if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5]) >> (pp & 31)) & 1) ++cnt_e;
+            if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5] | s.bits_cur[s.bits_words + (pp >> 5)]) >> (pp & 31)) & 1) ++cnt_e;
             if (pp >= a && pp < b) continue;            // my own run is consistent with my own bits
             if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
             // q itself can only be chosen at pp if at least four bytes agree; and it can only push another

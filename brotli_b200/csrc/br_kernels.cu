@@ -459,7 +459,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   auto add = [&](size_t bytes) { need += (bytes + 255) & ~(size_t)255; };
   add((size_t)n + 64); add(2ull * n + 4); add(2ull * n + 4); add(4ull * n); add(2ull * n + 4); add(4ull * n); add(4ull * n);
   add(256ull * ntiles * 4); add(scan_tmp_words(256ull * ntiles) * 4);
-  add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
+  add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(2 * nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
   add(scan_tmp_words((size_t)n / 1024 + 8) * 4);
   add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
   for (int i = 0; i < 14; ++i) add(nb * 4ull + 64);
@@ -473,7 +473,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   u16* K2 = A.take<u16>((size_t)n + 2); u32* S = A.take<u32>(n); u32* rank = A.take<u32>(n);
   u32* hist = A.take<u32>(256ull * ntiles); u32* scan_tmp = A.take<u32>(scan_tmp_words(256ull * ntiles));
   u32* seg = A.take<u32>(P.nbuckets + 4);
-  u32* bits_latest = A.take<u32>(nwords); u32* bits_cur = A.take<u32>(nwords);
+  u32* bits_latest = A.take<u32>(nwords); u32* bits_cur = A.take<u32>(2 * (size_t)nwords);
   u32* srch_latest = A.take<u32>(nwords); u32* srch_cur = A.take<u32>(nwords); u32* bits_prev = A.take<u32>(nwords);
   u32* storedS = A.take<u32>(nwords + 64); u32* prefS = A.take<u32>((size_t)n / 1024 + 8);
   u32* scan_tmp2 = A.take<u32>(scan_tmp_words((size_t)n / 1024 + 8));
@@ -495,7 +495,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 
   CK(cudaMemcpyAsync(data, d_in, n, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(data + n, 0, 64, st));
-  s.data = data; s.S = S; s.rank = rank; s.seg = seg; s.bits_latest = bits_latest; s.bits_cur = bits_cur;
+  s.data = data; s.S = S; s.rank = rank; s.seg = seg; s.bits_latest = bits_latest; s.bits_cur = bits_cur; s.bits_words = (u32)nwords;
   s.storedS = storedS; s.prefS = prefS; s.bin = bin; s.bin_used = bin_used; s.bout = bout;
   s.cmd_blocks = cmd_blocks; s.cmd_stride = cmd_stride; s.dirty = dirty; s.changed_bits = changed_bits;
   s.changed_epoch = changed_epoch; s.epoch_changed = epoch_changed; s.epoch_suffix = epoch_suffix;
@@ -521,7 +521,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   CK(cudaMemsetAsync(force_unc, 0, (nb + 16) * 4, st));
   CK(cudaMemsetAsync(epoch_changed, 0, BR_MAX_EPOCHS * 4, st));
   CK(cudaMemsetAsync(counters, 0, 256, st));
-  CK(cudaMemsetAsync(bits_cur, 0, nwords * 4, st));
+  CK(cudaMemsetAsync(bits_cur, 0, 2 * (size_t)nwords * 4, st));
 
   // ---- position index: S, rank, seg
   k_hash_keys<<<(n + 255) / 256, 256, 0, st>>>(P, data, keys);
@@ -557,7 +557,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       if (n_dirty == 0) break;
       if (s.epoch + 2 >= BR_MAX_EPOCHS) { fprintf(stderr, "brotli_b200: LZ77 fixpoint did not converge\n"); return 0; }
       ++s.epoch; ++job->stats.lz77_iterations;
-      CK(cudaMemsetAsync(bits_cur, 0, nwords * 4, st));
+      CK(cudaMemsetAsync(bits_cur, 0, 2 * (size_t)nwords * 4, st));
       CK(cudaMemsetAsync(srch_cur, 0, nwords * 4, st));
       CK(cudaMemsetAsync(counters + 4, 0, 4, st));
       k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);

@@ -92,6 +92,7 @@ struct BrWalk {
   u32 min_wrap;
   u32 stale;       // the byte the reference finds just past the block end (see oracle)
   bool warming;    // warm-up (state refinement before the chunk proper): reads the snapshot, records nothing
+  u32* own;        // the bits_cur bitmap of this run (parity of the chunk index)
   u32 pf_pos, pf_lo, pf_hi, pf_j;   // prefetched index entry (bucket bounds, rank) of position pf_pos
 };
 
@@ -105,12 +106,12 @@ BR_DEV u32 br_ld_cur(const u32* p) {
 #endif
 }
 BR_DEV int br_own_get(const BrWalk& w, u32 q) {
-  return (br_ld_cur(w.s->bits_cur + (q >> 5)) >> (q & 31)) & 1;
+  return (br_ld_cur(w.own + (q >> 5)) >> (q & 31)) & 1;
 }
 BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b);
 BR_DEV void br_own_set(BrWalk& w, u32 q) {
   if (w.warming) return;   // warm-up: the snapshot is read, nothing is recorded
-  if (br_lane() == 0) br_atomic_or(w.s->bits_cur + (q >> 5), 1u << (q & 31));
+  if (br_lane() == 0) br_atomic_or(w.own + (q >> 5), 1u << (q & 31));
 #if BR_GPU
   __threadfence_block();   // the next search may consult this very bit (runs: cur and cur + 1 share a bucket)
 #endif
@@ -124,7 +125,7 @@ BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
     u32 m = 0xffffffffu;
     if (x == wa) m &= 0xffffffffu << (a & 31);
     if (x == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
-    br_atomic_or(w.s->bits_cur + x, m);
+    br_atomic_or(w.own + x, m);
   }
 #if BR_GPU
   __threadfence_block();
@@ -383,6 +384,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   const int lane = br_lane();
   BrWalk w;
   w.s = &s; w.d = s.data; w.p0 = in.start_pos; w.pend = in.blk_end;
+  w.own = s.bits_cur + (size_t)(b & 1u) * s.bits_words;
   w.dict_l = ((u64)in.dict_l_hi << 32) | in.dict_l_lo;
   w.dict_m = ((u64)in.dict_m_hi << 32) | in.dict_m_lo;
   w.dl = w.dm = w.gate_checks = w.gate_fail = 0;

@@ -107,7 +107,9 @@ struct BrStream {
   const u32* rank;       // rank[S[j]] = j
   const u32* seg;        // seg[key] = first index of bucket key in S; nbuckets + 2 entries
   u32* bits_latest;      // stored-position bitmap, latest run of every block
-  u32* bits_cur;         // written by the walkers of this iteration
+  u32* bits_cur;         // written by the walkers of this iteration: TWO bitmaps of bits_words words each; a run writes the
+                         // one of its chunk's parity, so the ranges of neighbouring chunks can overlap without mixing
+  u32 bits_words;
   const u32* bits_prev;  // copy of bits_latest taken before the commits of this iteration
   u32* srch_latest;      // positions FindLongestMatch was called on (latest run of their owner) ...
   u32* srch_cur;         // ... and in this iteration

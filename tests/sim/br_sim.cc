@@ -111,7 +111,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   m->bin = chunks; m->bin_used.resize(nb); m->bout.resize(nb);
   memset(m->bin_used.data(), 0, nb * sizeof(BrBlockIn));
   memset(m->bout.data(), 0, nb * sizeof(BrBlockOut));
-  m->bits_latest.assign(words, 0); m->bits_cur.assign(words, 0); m->srch_latest.assign(words, 0); m->srch_cur.assign(words, 0);
+  m->bits_latest.assign(words, 0); m->bits_cur.assign(2 * words, 0); m->srch_latest.assign(words, 0); m->srch_cur.assign(words, 0);
   // initial guess: everything stored except the unsearchable tail of each block
   for (u32 k = 0; k < nb; ++k)
     for (u32 p = m->bin[k].pos; p < m->bin[k].end && p + P.htl <= m->bin[k].blk_end; ++p) m->bits_latest[p >> 5] |= 1u << (p & 31);
@@ -127,7 +127,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   m->counters.assign(64, 0); m->hist.assign(256, 0); m->mbs.resize(nb + 1);
   s.cmd_stride = ch / 2 + 2;
   m->cmd_blocks.resize((size_t)nb * s.cmd_stride);
-  s.bits_latest = m->bits_latest.data(); s.bits_cur = m->bits_cur.data();
+  s.bits_latest = m->bits_latest.data(); s.bits_cur = m->bits_cur.data(); s.bits_words = (u32)m->bits_latest.size();
   s.srch_latest = m->srch_latest.data(); s.srch_cur = m->srch_cur.data();
   s.storedS = m->storedS.data(); s.prefS = m->prefS.data();
   s.bin = m->bin.data(); s.bin_used = m->bin_used.data(); s.bout = m->bout.data();
@@ -157,6 +157,9 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
 
 static void sim_lz77_fixpoint(SimStream& m) {
   BrStream& s = m.s; u32 nb = s.P.nblocks;
+#ifdef BR_SIM_DEBUG
+  if (getenv("BR_SIM_WATCH")) br_sim_watch = (u32)atoi(getenv("BR_SIM_WATCH"));
+#endif
   s.epoch = 0;
   for (;;) {
     br_chain(s);
@@ -172,6 +175,32 @@ static void sim_lz77_fixpoint(SimStream& m) {
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
     if (s.epoch >= BR_MAX_EPOCHS - 1) { fprintf(stderr, "sim: no fixpoint\n"); break; }
+  }
+  if (getenv("BR_SIM_VERIFY")) {
+    // Is the fixpoint self-consistent?  Re-walk every chunk from its final in-state against the final
+    // stored-bits and report the chunks whose bits or out-state come out differently.
+    ++s.epoch;
+    std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
+    std::vector<BrBlockOut> old(s.bout, s.bout + nb);
+    s.counters[4] = 0;
+    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; br_walk_one(s, k, s.bin[k], o); }
+    m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
+    for (u32 k = 0; k < nb; ++k) {
+      br_commit_bits(s, k);
+      const BrBlockOut& a = old[k]; const BrBlockOut& b = s.bout[k];
+      bool same = a.ncmd == b.ncmd && a.nlit == b.nlit && a.out_pos == b.out_pos && a.last_insert_len == b.last_insert_len &&
+                  !memcmp(a.dc, b.dc, sizeof(a.dc)) && a.apply_rh == b.apply_rh;
+      if (s.changed_bits[k] && getenv("BR_SIM_VERIFY")[0] == '2') {
+        u32 shown = 0;
+        for (u32 q = s.bin_used[k].start_pos; q < s.bout[k].out_pos && shown < 12; ++q) {
+          u32 o = (m.bits_prev[q >> 5] >> (q & 31)) & 1, n2 = (m.bits_latest[q >> 5] >> (q & 31)) & 1;
+          if (o != n2) { fprintf(stderr, "  pos %u: fixpoint %u rewalk %u\n", q, o, n2); ++shown; }
+        }
+      }
+      if (s.changed_bits[k] || !same)
+        fprintf(stderr, "verify: chunk %u [%u..%u) start %u: %u bits differ, out-state %s (ncmd %u/%u out_pos %u/%u)\n", k, s.bin[k].pos, s.bin[k].end,
+                s.bin[k].start_pos, s.changed_bits[k], same ? "same" : "DIFFERENT", a.ncmd, b.ncmd, a.out_pos, b.out_pos);
+    }
   }
   m.cmds_all.resize(s.counters[2] + 1);
   for (u32 k = 0; k < nb; ++k) br_compact_block(s, k, m.cmds_all.data(), m.block_mb.data());

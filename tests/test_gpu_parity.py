@@ -224,3 +224,18 @@ def test_q1_flush(b200):
             assert out == ora.compress_q1_stream(d, w, sizes, ops), (sizes, ops, w)
             if os.path.exists(REF_SO):
                 assert out == ref_stream_ops(Ref(), d, 1, w, sizes, ops)
+
+
+def test_fuzz_gpu(b200):
+    """Structured random inputs (tests/fuzz_cases.py) through the C ABI on the GPU, plus the regression inputs."""
+    from fuzz_cases import REGRESSIONS, cases
+    ora = Oracle()
+    todo = []
+    by_seed = {}
+    for seed, idx in REGRESSIONS:
+        by_seed.setdefault(seed, set()).add(idx)
+    for seed, idxs in by_seed.items():
+        todo += [(seed, i, d, q, w) for i, d, q, w in cases(seed, max(idxs) + 1) if i in idxs]
+    todo += [(31337, i, d, q, w) for i, d, q, w in cases(31337, 250)]
+    for seed, i, d, q, w in todo:
+        assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (seed, i, len(d), q, w)

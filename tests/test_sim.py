@@ -102,3 +102,36 @@ def test_sim_q1_flush_segments(sim):
                         header = 0
                     seg_calls, seg_start = [], pos
             assert got == want, (sizes, ops, w)
+
+
+def _fuzz_check(sim, d, q, w):
+    ora = Oracle()
+    cap = 2 * len(d) + 100000
+    out = C.create_string_buffer(cap)
+    if q == 1:
+        r = sim.sim_q1_compress(w, d, len(d), None, 0, out, cap)
+        return r >= 0 and out.raw[:r] == ora.compress_q1_stream(d, w)
+    if not d:
+        return True
+    st = np.zeros(8, np.uint32)
+    r = sim.sim_compress(q, w, d, len(d), out, cap, st.ctypes.data)
+    return r >= 0 and out.raw[:r] == ora.compress(d, q, w)
+
+
+def test_sim_fuzz_regressions(sim):
+    """Inputs found by fuzzing that broke the speculative parse (see tests/fuzz_cases.py)."""
+    from fuzz_cases import REGRESSIONS, cases
+    by_seed = {}
+    for seed, idx in REGRESSIONS:
+        by_seed.setdefault(seed, set()).add(idx)
+    for seed, idxs in by_seed.items():
+        for i, d, q, w in cases(seed, max(idxs) + 1):
+            if i in idxs:
+                assert _fuzz_check(sim, d, q, w), (seed, i, len(d), q, w)
+
+
+def test_sim_fuzz_sample(sim):
+    from fuzz_cases import cases
+    for i, d, q, w in cases(20250922, 120):
+        if len(d) <= 120000:
+            assert _fuzz_check(sim, d, q, w), (i, len(d), q, w)

@@ -24,3 +24,14 @@ t = time.time(); want = [ref.compress(s, 1, 22) for s in streams]; t_cpu = time.
 bad = sum(1 for a, b in zip(got, want) if a != b)
 print("reference: %.2fs on 1 core (%.1f MB/s); streams differing: %d of %d; parity %s" % (
     t_cpu, nbytes / t_cpu / 1e6, bad, count, bad == 0), flush=True)
+# the reference with one stream per host core (ctypes releases the GIL)
+import threading
+ncpu = os.cpu_count() or 1
+def work(k):
+    for i in range(k, count, ncpu):
+        ref.compress(streams[i], 1, 22)
+t = time.time()
+th = [threading.Thread(target=work, args=(k,)) for k in range(ncpu)]
+[x.start() for x in th]; [x.join() for x in th]
+t_all = time.time() - t
+print("reference on all %d host cores: %.2fs (%.1f MB/s)" % (ncpu, t_all, nbytes / t_all / 1e6), flush=True)
