@@ -11,6 +11,7 @@
 #ifdef BR_SIM_DEBUG
 #include <stdio.h>
 static u32 br_sim_watch = 0xffffffffu;   // tests/sim: report commits that flip this position
+static u64 br_sim_cnt[8];                // tests/sim: marks by source (0 successor, 1 overlap, 2 cap hits, 3 flips, 4 steps)
 #endif
 
 // Compare and commit the stored-bits a walker just produced for chunk k (warp task).  The
@@ -32,7 +33,12 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
     for (u32 c = k0 + (u32)br_lane(); c < k1; c += BR_WARP) {
       if (c == k || !s.bout[c].valid) continue;
       const u32 ca = s.bin_used[c].start_pos, cb = s.bout[c].out_pos;
-      if (ca < cb && ca < b && a < cb) br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
+      if (ca < cb && ca < b && a < cb) {
+        br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
+#ifdef BR_SIM_DEBUG
+        ++br_sim_cnt[1];
+#endif
+      }
     }
   }
   const u32* mine = s.bits_cur + (size_t)(k & 1u) * s.bits_words;
@@ -83,6 +89,9 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
           const u32 q = (x << 5) + (u32)br_ffs(flips) - 1u;
           flips &= flips - 1;
           const u32 jq = s.rank[q];
+#ifdef BR_SIM_DEBUG
+          ++br_sim_cnt[3];
+#endif
           const u16 key = s.skeys[jq];
           if (s.seg[key + 1] - s.seg[key] >= s.P.heavy_min) br_atomic_add(s.key_flips + key, 1);   // uint16 bucket counter may wrap
           const u32 V = 1u << s.P.block_bits;
@@ -103,7 +112,13 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
           // cnt_e: stored before OR after this launch -> upper bound of the view size in both snapshots
           u32 cnt = 0, cnt_e = 0, steps = 0;
           for (u32 j = jq + 1; j < s.P.n && s.skeys[j] == key && cnt < reach; ++j) {
-            if (++steps > 4096) {  // pathological bucket (long runs of unstored positions): give up precision,
+#ifdef BR_SIM_DEBUG
+            ++br_sim_cnt[4];
+#endif
+            if (++steps > s.P.step_cap) {
+#ifdef BR_SIM_DEBUG
+              ++br_sim_cnt[2];
+#endif  // pathological bucket (long runs of unstored positions): give up precision,
               br_atomic_max(&s.blk[in.blk].changed_epoch, (int)s.epoch);   // block-level window rule (br_chain_c)
               break;
             }
@@ -118,6 +133,9 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
             // candidate out of (or pull one into) pp's view if that view is full
             if (!(s.P.dbg_flags & 1) && br_ld32u(s.data, pp) != q4 && before + 1 + B < V) continue;
             u32 c = ((pp >> s.P.lgblock) << s.P.cpb_shift) + ((pp & ((1u << s.P.lgblock) - 1)) >> BR_CHUNK_BITS);
+#ifdef BR_SIM_DEBUG
+            ++br_sim_cnt[0];
+#endif
             br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
             if (c > 0) br_atomic_max(s.bitdep_epoch + c - 1, (int)s.epoch);   // its owner may be the chunk before
           }

@@ -28,6 +28,7 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->nbuckets = 1u << P->bucket_bits;
   P->cpb_shift = (u32)P->lgblock - BR_CHUNK_BITS;
   P->heavy_min = 65536;
-  P->dbg_flags = 1;   // the candidate-relevance filter stays off: it mis-validated one 200 MB case
+  P->step_cap = 4096;
+  P->dbg_flags = 1;   // the candidate-relevance filter stays off: it trims the marks of config 4 by 10 % only
   return 1;
 }

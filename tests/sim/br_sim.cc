@@ -87,6 +87,8 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   if (!br_derive_params(q, lgwin, n, n, &s.P)) { delete m; return nullptr; }
   BrParams& P = s.P;
   if (getenv("BR_SIM_HEAVY_MIN")) P.heavy_min = (u32)atoi(getenv("BR_SIM_HEAVY_MIN"));
+  if (getenv("BR_SIM_DBG_FLAGS")) P.dbg_flags = (u32)atoi(getenv("BR_SIM_DBG_FLAGS"));
+  if (getenv("BR_SIM_STEP_CAP")) P.step_cap = (u32)atoi(getenv("BR_SIM_STEP_CAP"));
   u32 bs = 1u << P.lgblock;
   const u32 ch = 1u << BR_CHUNK_BITS;
   std::vector<BrBlockIn> chunks;
@@ -164,7 +166,13 @@ static void sim_lz77_fixpoint(SimStream& m) {
   for (;;) {
     br_chain(s);
     if (getenv("BR_SIM_TRACE")) { u32 h[6] = {0}; u32 first = nb; for (u32 k = 0; k < nb; ++k) { h[s.dirty[k]]++; if (s.dirty[k] && first == nb) first = k; }
-      fprintf(stderr, "epoch %u dirty %u first %u: never %u state %u dict %u window %u wrap %u | flipped bits %u\n", s.epoch, s.counters[0], first, h[1], h[2], h[3], h[4], h[5], s.epoch_changed[s.epoch]); }
+      fprintf(stderr, "epoch %u dirty %u first %u: never %u state %u dict %u window %u wrap %u | flipped bits %u\n", s.epoch, s.counters[0], first, h[1], h[2], h[3], h[4], h[5], s.epoch_changed[s.epoch]);
+#ifdef BR_SIM_DEBUG
+      fprintf(stderr, "   last commit: flips %llu successor steps %llu marks %llu overlap marks %llu cap hits %llu\n", (unsigned long long)br_sim_cnt[3],
+              (unsigned long long)br_sim_cnt[4], (unsigned long long)br_sim_cnt[0], (unsigned long long)br_sim_cnt[1], (unsigned long long)br_sim_cnt[2]);
+      memset(br_sim_cnt, 0, sizeof(br_sim_cnt));
+#endif
+    }
     if (s.counters[0] == 0) break;
     ++s.epoch; ++m.iterations;
     sim_build_storedS(m);
