@@ -249,7 +249,7 @@ BR_DEV void br_chain_b(const BrStream& s) {
         if ((u32)e <= t_now) acc += s.epoch_changed[e];
         s.epoch_suffix[e] = acc;
       }
-      s.counters[0] = 0; s.counters[5] = 0;
+      s.counters[0] = 0; s.counters[5] = 0; s.counters[6] = 0xffffffffu;
       for (int i = 8; i < 16; ++i) s.counters[i] = 0;
     }
   }
@@ -420,7 +420,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     s.lil_in[k] = lil_true;
     s.block_mb[k] = W.mb;
     if (dirty) { br_atomic_add(s.counters + 0, 1); br_atomic_add(s.counters + 8 + (dirty < 6 ? dirty : 6), 1); }
-    if (dirty && !defer) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; }
+    if (dirty && !defer) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; br_atomic_min(s.counters + 6, k); }
     if (out.valid) {
       cmd_off += out.ncmd;
       if (!(dict_m < (dict_l >> 7))) { dict_l += edl; dict_m += edm; }

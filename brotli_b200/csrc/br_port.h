@@ -39,6 +39,7 @@ BR_DEV u32 br_atomic_or(u32* p, u32 v) { return atomicOr(p, v); }
 BR_DEV u32 br_atomic_and(u32* p, u32 v) { return atomicAnd(p, v); }
 BR_DEV u32 br_atomic_add(u32* p, u32 v) { return atomicAdd(p, v); }
 BR_DEV int br_atomic_max(int* p, int v) { return atomicMax(p, v); }
+BR_DEV u32 br_atomic_min(u32* p, u32 v) { return atomicMin(p, v); }
 // Bit-exact IEEE double ops: never contracted into FMA (the reference is built without
 // -march, so x86-64 emits separate mul/add).
 BR_DEV double br_dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -86,6 +87,7 @@ BR_DEV u32 br_atomic_or(u32* p, u32 v) { u32 o = *p; *p = o | v; return o; }
 BR_DEV u32 br_atomic_and(u32* p, u32 v) { u32 o = *p; *p = o & v; return o; }
 BR_DEV u32 br_atomic_add(u32* p, u32 v) { u32 o = *p; *p = o + v; return o; }
 BR_DEV int br_atomic_max(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+BR_DEV u32 br_atomic_min(u32* p, u32 v) { u32 o = *p; if (v < o) *p = v; return o; }
 BR_DEV double br_dmul(double a, double b) { volatile double r = a * b; return r; }
 BR_DEV double br_dadd(double a, double b) { volatile double r = a + b; return r; }
 BR_DEV double br_dsub(double a, double b) { volatile double r = a - b; return r; }
