@@ -2,7 +2,9 @@
  *
  * A plain-C, single-threaded CPU restatement of the google/brotli encoder hot
  * path for qualities 5..9 (bucket-ring hashers H5/H6 and their SIMD twins
- * H58/H68) and the greedy per-metablock entropy pipeline, for one-shot
+ * H58/H68) and the greedy per-metablock entropy pipeline, plus -- as groundwork
+ * for SURVEY.md section 8f rank 1 -- qualities 2..4 (single-slot / sweep hashers
+ * H2, H3, H4, H54, fast / trivial / context-free meta-block stores), for one-shot
  * BrotliEncoderCompress(quality, lgwin, GENERIC, n, ...) calls.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
@@ -190,6 +192,9 @@ typedef struct {
   size_t hash_type_len, store_lookahead;
   uint16_t* num;
   uint32_t* buckets;
+  /* qualities 2..4: hash_longest_match_quickly_inc.h (H2, H3, H4, H54): one position per slot */
+  int quick, qk_bits, qk_sweep_bits, qk_hash_len, qk_dict;
+  uint32_t* qk_table;
   size_t dict_lookups, dict_matches;
   size_t rmask;     /* ring buffer mask: quality.h:99 ComputeRbBits */
   const uint8_t* data;
@@ -226,8 +231,15 @@ static size_t hash_key(const Enc* e, size_t pos) {
   }
 }
 /* hash_longest_match64_inc.h:107 Store */
+static size_t quick_key(const Enc* e, size_t pos);
 static void hstore(Enc* e, size_t pos) {
-  size_t key = hash_key(e, pos);
+  size_t key;
+  if (e->quick) {   /* hash_longest_match_quickly_inc.h:96 Store */
+    const size_t off = pos & (size_t)(((1u << e->qk_sweep_bits) - 1u) << 3);
+    e->qk_table[(quick_key(e, pos) + off) & (((size_t)1 << e->qk_bits) - 1)] = (uint32_t)pos;
+    return;
+  }
+  key = hash_key(e, pos);
   size_t minor = e->num[key] & ((1u << e->block_bits) - 1);
   e->buckets[(key << e->block_bits) + minor] = (uint32_t)pos;
   ++e->num[key];
@@ -284,13 +296,13 @@ static int test_dict_item(size_t len, size_t word_idx, const uint8_t* data,
   out->score = score;
   return 1;
 }
-/* hash.h:179 SearchInStaticDictionary (shallow = false) */
-static void search_static_dict(Enc* e, const uint8_t* data, size_t max_length,
-    size_t max_backward, size_t max_distance, SR* out) {
+/* hash.h:179 SearchInStaticDictionary; shallow (the quickly hashers) probes one slot instead of two */
+static void search_static_dict_n(Enc* e, const uint8_t* data, size_t max_length,
+    size_t max_backward, size_t max_distance, SR* out, size_t probes) {
   size_t key, i;
   if (e->dict_matches < (e->dict_lookups >> 7)) return;
   key = ((load32(data) * 0x1E35A7BDu) >> (32 - 14)) << 1;
-  for (i = 0; i < 2; ++i, ++key) {
+  for (i = 0; i < probes; ++i, ++key) {
     e->dict_lookups++;
     if (g_hash_lengths[key] != 0) {
       if (test_dict_item(g_hash_lengths[key], g_hash_words[key], data,
@@ -299,11 +311,87 @@ static void search_static_dict(Enc* e, const uint8_t* data, size_t max_length,
     }
   }
 }
+static void search_static_dict(Enc* e, const uint8_t* data, size_t max_length,
+    size_t max_backward, size_t max_distance, SR* out) {
+  search_static_dict_n(e, data, max_length, max_backward, max_distance, out, 2);
+}
+
+/* hash_longest_match_quickly_inc.h:27 HashBytes: HASH_LEN bytes, kHashMul64, top BUCKET_BITS bits */
+static size_t quick_key(const Enc* e, size_t pos) {
+  uint8_t tmp[8] = {0};
+  size_t avail = e->n - pos; uint64_t v;
+  if (avail >= 8) v = load64(e->data + pos);
+  else { memcpy(tmp, e->data + pos, avail); v = load64(tmp); }
+  return (size_t)(((v << (64 - 8 * e->qk_hash_len)) * 0x1FE35A7BD3579BD3ull) >> (64 - e->qk_bits));
+}
+/* hash_longest_match_quickly_inc.h:147 FindLongestMatch: the last distance, then the BUCKET_SWEEP slots
+   key, key+8, ... (mod table size); the position is filed in the slot its own low bits select. */
+static void quick_find_longest_match(Enc* e, size_t cur, size_t max_length,
+    size_t max_backward, size_t dict_distance, size_t max_distance, SR* out) {
+  const uint8_t* data = e->data;
+  const size_t sweep = (size_t)1 << e->qk_sweep_bits, mask = ((size_t)1 << e->qk_bits) - 1;
+  const size_t best_len_in = out->len;
+  const size_t key = quick_key(e, cur);
+  const size_t min_score = out->score;
+  size_t best_score = out->score, best_len = best_len_in;
+  const size_t cached = (size_t)e->dist_cache[0];
+  size_t prev = cur - cached, i;
+  int compare_char = cur_byte(e, cur, best_len_in, max_length);
+  out->len_code_delta = 0;
+  if (prev < cur && cached <= max_backward) {
+    if (compare_char == data[prev + best_len]) {
+      const size_t len = match_len(data + prev, data + cur, max_length);
+      if (len >= 4) {
+        const size_t score = score_last(len);
+        if (best_score < score) {
+          out->len = len; out->distance = cached; out->score = score;
+          if (sweep == 1) { e->qk_table[key] = (uint32_t)cur; return; }
+          best_len = len; best_score = score;
+          compare_char = cur_byte(e, cur, len, max_length);
+        }
+      }
+    }
+  }
+  if (sweep == 1) {
+    size_t backward, len;
+    prev = e->qk_table[key];
+    e->qk_table[key] = (uint32_t)cur;
+    backward = cur - prev;
+    if (compare_char != data[prev + best_len_in]) return;
+    if (backward == 0 || backward > max_backward) return;
+    len = match_len(data + prev, data + cur, max_length);
+    if (len >= 4) {
+      const size_t score = score_normal(len, backward);
+      if (best_score < score) { out->len = len; out->distance = backward; out->score = score; return; }
+    }
+  } else {
+    for (i = 0; i < sweep; ++i) {
+      size_t backward, len;
+      prev = e->qk_table[(key + (i << 3)) & mask];
+      backward = cur - prev;
+      if (compare_char != data[prev + best_len]) continue;
+      if (backward == 0 || backward > max_backward) continue;
+      len = match_len(data + prev, data + cur, max_length);
+      if (len >= 4) {
+        const size_t score = score_normal(len, backward);
+        if (best_score < score) {
+          best_len = len; out->len = len;
+          compare_char = cur_byte(e, cur, len, max_length);
+          best_score = score; out->score = score; out->distance = backward;
+        }
+      }
+    }
+  }
+  if (e->qk_dict && min_score == out->score)
+    search_static_dict_n(e, data + cur, max_length, dict_distance, max_distance, out, 1);
+  if (sweep != 1) e->qk_table[(key + (cur & ((sweep - 1) << 3))) & mask] = (uint32_t)cur;
+}
 
 /* hash_longest_match64_inc.h:157 / hash_longest_match_inc.h:156 FindLongestMatch */
 static void find_longest_match(Enc* e, size_t cur, size_t max_length,
     size_t max_backward, size_t dict_distance, size_t max_distance, SR* out) {
   const uint8_t* data = e->data;
+  if (e->quick) { quick_find_longest_match(e, cur, max_length, max_backward, dict_distance, max_distance, out); return; }
   const size_t rmask = e->rmask;
   const size_t cur_m = cur & rmask;
   size_t min_score = out->score, best_score = out->score, best_len = out->len;
@@ -423,7 +511,8 @@ static void create_backward_references(Enc* e, size_t num_bytes, size_t position
       --max_length;
       for (;; --max_length) {
         SR sr2;
-        sr2.len = 0;  /* quality >= 5: MIN_QUALITY_FOR_EXTENSIVE_REFERENCE_SEARCH */
+        /* backward_references_inc.h:127 MIN_QUALITY_FOR_EXTENSIVE_REFERENCE_SEARCH */
+        sr2.len = e->quality < 5 ? (sr.len - 1 < max_length ? sr.len - 1 : max_length) : 0;
         sr2.len_code_delta = 0; sr2.distance = 0; sr2.score = kMinScore;
         max_distance = position + 1 < max_backward_limit ? position + 1 : max_backward_limit;
         dictionary_start = max_distance;
@@ -1305,6 +1394,8 @@ static void emit(Enc* e, const uint8_t* p, size_t n) {
   e->out_pos += n;
 }
 
+static void store_metablock_fast_trivial(Enc* e, size_t start_pos, size_t length, int is_last, BitW* w);
+
 /* encode.c:498 WriteMetaBlockInternal + tail of encode.c:985 EncodeData */
 static void write_metablock(Enc* e, size_t end_pos, int is_last) {
   const size_t bytes = end_pos - e->last_flush_pos;
@@ -1319,7 +1410,8 @@ static void write_metablock(Enc* e, size_t end_pos, int is_last) {
     memcpy(e->dist_cache, e->saved_dist_cache, 4 * sizeof(int));
     store_uncompressed(is_last, e->data, e->last_flush_pos, bytes, &w);
   } else {
-    store_compressed_metablock(e, e->last_flush_pos, bytes, is_last, &w);
+    if (e->quality < 4) store_metablock_fast_trivial(e, e->last_flush_pos, bytes, is_last, &w);   /* encode.c:543-556 */
+    else store_compressed_metablock(e, e->last_flush_pos, bytes, is_last, &w);
     if (bytes + 4 < (w.ix >> 3)) {
       memcpy(e->dist_cache, e->saved_dist_cache, 4 * sizeof(int));
       memset(storage, 0, 2 * bytes + 503 + 16);
@@ -1365,21 +1457,35 @@ static int oracle_compress_impl(int quality, int lgwin, size_t n, const uint8_t*
     size_t* out_n, uint8_t* out, void (*hook)(const Cmd*, size_t, size_t, size_t)) {
   Enc e; size_t pos = 0, block, max_mb;
   if (!g_blob) return 0;
-  if (quality < 5 || quality > 9 || lgwin < 17 || lgwin > 24) return 0;
+  if (quality < 2 || quality > 9 || lgwin > 24) return 0;
+  if (quality >= 5 ? lgwin < 17 : lgwin < 10) return 0;      /* lgwin <= 16 at quality 5+: H40..42, not restated */
   if (n == 0) { if (*out_n < 1) return 0; out[0] = 6; *out_n = 1; return 1; }
   memset(&e, 0, sizeof(e));
   e.quality = quality; e.lgwin = lgwin; e.size_hint = n; e.data = in; e.n = n;
   e.cmd_hook = hook;
-  e.lgblock = 16;
+  /* quality.h:75 ComputeLgBlock */
+  e.lgblock = quality < 4 ? 14 : 16;
   if (quality >= 9 && lgwin > 16) e.lgblock = lgwin < 18 ? lgwin : 18;
-  e.hash64 = (n >= (1u << 20) && lgwin >= 19);
-  e.block_bits = quality - 1;
-  e.bucket_bits = e.hash64 ? 15 : (quality < 7 ? 14 : 15);
-  e.ndist = quality < 7 ? 4 : quality < 9 ? 10 : 16;
-  e.hash_type_len = e.hash64 ? 8 : 4;
-  e.store_lookahead = e.hash_type_len;
-  e.num = (uint16_t*)calloc((size_t)1 << e.bucket_bits, 2);
-  e.buckets = (uint32_t*)calloc((size_t)1 << (e.bucket_bits + e.block_bits), 4);
+  if (quality < 5) {
+    /* quality.h:172 ChooseHasher: H2, H3, H4, and H54 for quality 4 on inputs >= 1 MiB (hash.h:251-338) */
+    e.quick = 1; e.qk_hash_len = 5;
+    if (quality == 2) { e.qk_bits = 16; e.qk_sweep_bits = 0; e.qk_dict = 1; }
+    else if (quality == 3) { e.qk_bits = 16; e.qk_sweep_bits = 1; e.qk_dict = 0; }
+    else if (n >= (1u << 20)) { e.qk_bits = 20; e.qk_sweep_bits = 2; e.qk_dict = 0; e.qk_hash_len = 7; }
+    else { e.qk_bits = 17; e.qk_sweep_bits = 2; e.qk_dict = 1; }
+    e.qk_table = (uint32_t*)calloc((size_t)1 << e.qk_bits, 4);
+    e.ndist = 1;
+    e.hash_type_len = 8; e.store_lookahead = 8;
+  } else {
+    e.hash64 = (n >= (1u << 20) && lgwin >= 19);
+    e.block_bits = quality - 1;
+    e.bucket_bits = e.hash64 ? 15 : (quality < 7 ? 14 : 15);
+    e.ndist = quality < 7 ? 4 : quality < 9 ? 10 : 16;
+    e.hash_type_len = e.hash64 ? 8 : 4;
+    e.store_lookahead = e.hash_type_len;
+    e.num = (uint16_t*)calloc((size_t)1 << e.bucket_bits, 2);
+    e.buckets = (uint32_t*)calloc((size_t)1 << (e.bucket_bits + e.block_bits), 4);
+  }
   { int rb = 1 + (lgwin > e.lgblock ? lgwin : e.lgblock);
     e.rmask = ((size_t)1 << rb) - 1;
     max_mb = (size_t)1 << (rb < 24 ? rb : 24); }
@@ -1388,8 +1494,10 @@ static int oracle_compress_impl(int quality, int lgwin, size_t n, const uint8_t*
   e.cmds = (Cmd*)malloc(sizeof(Cmd) * (max_mb / 2 + (1u << e.lgblock) + 64));
   e.out = out; e.out_cap = *out_n;
   /* encode.c:203 EncodeWindowBits */
-  if (lgwin == 17) { e.carry = 1; e.carry_bits = 7; }
-  else { e.carry = (uint8_t)(((lgwin - 17) << 1) | 1); e.carry_bits = 4; }
+  if (lgwin == 16) { e.carry = 0; e.carry_bits = 1; }
+  else if (lgwin == 17) { e.carry = 1; e.carry_bits = 7; }
+  else if (lgwin > 17) { e.carry = (uint8_t)(((lgwin - 17) << 1) | 1); e.carry_bits = 4; }
+  else { e.carry = (uint8_t)(((lgwin - 8) << 4) | 1); e.carry_bits = 7; }
   block = (size_t)1 << e.lgblock;
   while (pos < n) {
     size_t bytes = n - pos < block ? n - pos : block;
@@ -1402,7 +1510,9 @@ static int oracle_compress_impl(int quality, int lgwin, size_t n, const uint8_t*
     {
       const size_t processed = end - e.last_flush_pos;
       const int next_fits = processed + block <= max_mb;
-      if (!is_last && next_fits && e.num_literals < max_mb / 8 && e.num_cmds < max_mb / 8) {
+      /* encode.c:1152: below quality 4 at most MAX_NUM_DELAYED_SYMBOLS literals + commands are buffered */
+      const int should_flush = quality < 4 && e.num_literals + e.num_cmds >= 0x2FFF;
+      if (!is_last && !should_flush && next_fits && e.num_literals < max_mb / 8 && e.num_cmds < max_mb / 8) {
         pos = end; continue;
       }
     }
@@ -1414,13 +1524,77 @@ static int oracle_compress_impl(int quality, int lgwin, size_t n, const uint8_t*
     write_metablock(&e, end, is_last);
     pos = end;
   }
-  free(e.num); free(e.buckets); free(e.cmds);
+  free(e.num); free(e.buckets); free(e.qk_table); free(e.cmds);
   if (e.overflow) return 0;
   *out_n = e.out_pos;
   return 1;
 }
 
 #include "brotli_oracle_q1.h"
+
+/* brotli_bit_stream.c:1196 BrotliStoreMetaBlockTrivial (quality 3) and :1243 BrotliStoreMetaBlockFast
+   (quality 2): one code per category, no block splits, no contexts. */
+static void store_metablock_fast_trivial(Enc* e, size_t start_pos, size_t length, int is_last, BitW* w) {
+  const uint8_t* in = e->data;
+  const Cmd* cmds = e->cmds; const size_t ncmd = e->num_cmds;
+  uint32_t lit_histo[256], cmd_histo[704], dist_histo[140];
+  uint8_t lit_depth[256], cmd_depth[704], dist_depth[140];
+  uint16_t lit_bits[256], cmd_bits[704], dist_bits[140];
+  HTree* tree = (HTree*)malloc(sizeof(HTree) * (2 * 704 + 1));
+  size_t i, pos = start_pos, nlit = 0, ndist = 0;
+  memset(lit_histo, 0, sizeof(lit_histo)); memset(cmd_histo, 0, sizeof(cmd_histo)); memset(dist_histo, 0, sizeof(dist_histo));
+  memset(lit_depth, 0, sizeof(lit_depth)); memset(cmd_depth, 0, sizeof(cmd_depth)); memset(dist_depth, 0, sizeof(dist_depth));
+  memset(lit_bits, 0, sizeof(lit_bits)); memset(cmd_bits, 0, sizeof(cmd_bits)); memset(dist_bits, 0, sizeof(dist_bits));
+  for (i = 0; i < ncmd; ++i) {          /* :1133 BuildHistograms */
+    const Cmd c = cmds[i]; size_t j;
+    ++cmd_histo[c.cmd_prefix];
+    for (j = c.insert_len; j != 0; --j) { ++lit_histo[in[pos]]; ++pos; }
+    nlit += c.insert_len;
+    pos += cmd_copy_len(&c);
+    if (cmd_copy_len(&c) && c.cmd_prefix >= 128) { ++dist_histo[c.dist_prefix & 0x3FF]; ++ndist; }
+  }
+  /* :120 StoreCompressedMetaBlockHeader, then 13 zero bits: one block type per category, NPOSTFIX / NDIRECT 0,
+     context mode, trivial context maps */
+  wbits(w, 1, (uint64_t)is_last);
+  if (is_last) wbits(w, 1, 0);
+  store_mlen(length, w);
+  if (!is_last) wbits(w, 1, 0);
+  wbits(w, 13, 0);
+  if (e->quality == 3) {
+    build_and_store_tree(lit_histo, 256, 256, tree, lit_depth, lit_bits, w);
+    build_and_store_tree(cmd_histo, 704, 704, tree, cmd_depth, cmd_bits, w);
+    build_and_store_tree(dist_histo, 140, 64, tree, dist_depth, dist_bits, w);
+  } else if (ncmd <= 128) {
+    /* static command / distance codes of entropy_encode_static.h: depths 9 (symbols < 448) and 11, resp. 6;
+       their serialised forms (:524, :538) are what brotli_bit_stream.c:283 makes of those depths */
+    q1_build_and_store_tree_fast(lit_histo, nlit, 8, lit_depth, lit_bits, w);
+    for (i = 0; i < 704; ++i) cmd_depth[i] = i < 448 ? 9 : 11;
+    for (i = 0; i < 64; ++i) dist_depth[i] = 6;
+    depths_to_symbols(cmd_depth, 704, cmd_bits);
+    depths_to_symbols(dist_depth, 64, dist_bits);
+    wbits(w, 56, 0x0092624416307003ull); wbits(w, 3, 0);
+    wbits(w, 28, 0x0369DC03u);
+  } else {
+    q1_build_and_store_tree_fast(lit_histo, nlit, 8, lit_depth, lit_bits, w);
+    q1_build_and_store_tree_fast(cmd_histo, ncmd, 10, cmd_depth, cmd_bits, w);
+    q1_build_and_store_tree_fast(dist_histo, ndist, 6, dist_depth, dist_bits, w);
+  }
+  pos = start_pos;
+  for (i = 0; i < ncmd; ++i) {          /* :1159 StoreDataWithHuffmanCodes */
+    const Cmd c = cmds[i]; size_t j;
+    wbits(w, cmd_depth[c.cmd_prefix], cmd_bits[c.cmd_prefix]);
+    store_cmd_extra(&c, w);
+    for (j = c.insert_len; j != 0; --j) { wbits(w, lit_depth[in[pos]], lit_bits[in[pos]]); ++pos; }
+    pos += cmd_copy_len(&c);
+    if (cmd_copy_len(&c) && c.cmd_prefix >= 128) {
+      const size_t dc = c.dist_prefix & 0x3FF;
+      wbits(w, dist_depth[dc], dist_bits[dc]);
+      wbits(w, c.dist_prefix >> 10, c.dist_extra);
+    }
+  }
+  if (is_last) { w->ix = (w->ix + 7u) & ~(size_t)7u; w->buf[w->ix >> 3] = 0; }
+  free(tree);
+}
 
 int oracle_brotli_compress(int quality, int lgwin, size_t n, const uint8_t* in,
                            size_t* out_n, uint8_t* out) {

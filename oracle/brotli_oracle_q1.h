@@ -206,7 +206,7 @@ static void q1_write_run(uint32_t sym, size_t reps, const uint16_t* cl_bits, Bit
 /* brotli_bit_stream.c:404 BrotliBuildAndStoreHuffmanTreeFast */
 static void q1_build_and_store_tree_fast(const uint32_t* histo, size_t total, size_t max_bits,
                                          uint8_t* depth, uint16_t* bits, BitW* w) {
-  HTree tree[2 * 256 + 2];
+  HTree tree[2 * 704 + 2];
   size_t count = 0, symbols[4] = {0, 0, 0, 0}, length = 0, left = total, i;
   uint16_t cl_bits[18];
   while (left != 0) {

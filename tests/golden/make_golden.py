@@ -10,14 +10,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from brotli_libs import Ref
-from golden_cases import CASES, make_case
+from golden_cases import CASES, CASES_ORACLE_ONLY, make_case
 
 ref = Ref()
-out = []
-for c in CASES:
-    d = make_case(c)
-    comp = ref.compress(d, c["q"], c["lgwin"])
-    out.append(dict(c, in_sha256=hashlib.sha256(d).hexdigest(), out_len=len(comp),
-                    out_sha256=hashlib.sha256(comp).hexdigest()))
-    print(c, len(d), len(comp))
-json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1)
+for cases, name in ((CASES, "golden.json"), (CASES_ORACLE_ONLY, "golden_oracle_only.json")):
+    out = []
+    for c in cases:
+        d = make_case(c)
+        comp = ref.compress(d, c["q"], c["lgwin"])
+        out.append(dict(c, in_sha256=hashlib.sha256(d).hexdigest(), out_len=len(comp),
+                        out_sha256=hashlib.sha256(comp).hexdigest()))
+        print(c, len(d), len(comp))
+    json.dump(out, open(os.path.join(HERE, name), "w"), indent=1)

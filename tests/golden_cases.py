@@ -79,3 +79,24 @@ CASES = [
     dict(kind="mixed", n=2500000, seed=13, q=1, lgwin=22),
     dict(kind="text", n=5000000, seed=15, q=1, lgwin=20),     # five fragments
 ]
+
+
+# Qualities 2..4: restated in the oracle as groundwork, not built on the GPU yet.
+# Pinned in tests/golden/golden_oracle_only.json; only tests/test_oracle.py reads them.
+CASES_ORACLE_ONLY = [
+    dict(kind="text", n=1, seed=1, q=2, lgwin=22),
+    dict(kind="text", n=9, seed=1, q=3, lgwin=22),
+    dict(kind="text", n=1000, seed=3, q=4, lgwin=16),
+    dict(kind="web", n=65536, seed=16, q=2, lgwin=22),        # <= 128 commands per meta-block: static command code
+    dict(kind="web", n=65536, seed=16, q=3, lgwin=22),
+    dict(kind="web", n=65536, seed=16, q=4, lgwin=22),
+    dict(kind="text", n=300000, seed=5, q=2, lgwin=18),
+    dict(kind="text", n=300000, seed=5, q=3, lgwin=10),
+    dict(kind="text", n=300000, seed=5, q=4, lgwin=22),       # H4
+    dict(kind="text", n=1500000, seed=6, q=4, lgwin=22),      # H54 (>= 1 MiB)
+    dict(kind="binary", n=1500000, seed=9, q=2, lgwin=22),
+    dict(kind="binary", n=1500000, seed=9, q=3, lgwin=24),
+    dict(kind="zeros", n=400000, seed=0, q=2, lgwin=22),
+    dict(kind="random", n=300000, seed=10, q=3, lgwin=22),
+    dict(kind="mixed", n=2500000, seed=13, q=4, lgwin=20),
+]

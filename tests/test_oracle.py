@@ -10,7 +10,8 @@ from brotli_libs import REF_SO, Oracle, Ref, ref_compress_stream
 from golden_cases import make_case
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
-FAST = [g for g in GOLDEN if g["n"] <= 2_500_000]
+GOLDEN_ORACLE_ONLY = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_oracle_only.json")))
+FAST = [g for g in GOLDEN if g["n"] <= 2_500_000] + GOLDEN_ORACLE_ONLY
 
 
 @pytest.fixture(scope="module")
@@ -76,3 +77,19 @@ def test_q1_oracle_against_reference(oracle):
             calls.append(0)
         for w in (16, 22):
             assert oracle.compress_q1_stream(d, w, calls) == ref_compress_stream(ref, d, 1, w, chunk), (n, w)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built")
+def test_q234_oracle_against_reference(oracle):
+    """Qualities 2..4 (H2 / H3 / H4 / H54, fast / trivial / context-free meta-blocks): oracle groundwork for
+    SURVEY.md 8f rank 1, pinned against the reference over window sizes and hasher switches."""
+    from corpus import synth_binary, synth_web
+    ref = Ref()
+    base = synth_web(2_200_000, 71)
+    for n in (0, 1, 7, 8, 9, 100, 5000, 16384, 16385, 70000, 300000, (1 << 20) - 1, 1 << 20, 2_200_000):
+        for q in (2, 3, 4):
+            for w in (10, 16, 17, 22):
+                assert oracle.compress(base[:n], q, w) == ref.compress(base[:n], q, w), (n, q, w)
+    d = synth_binary(1_300_000, 72)
+    for q in (2, 3, 4):
+        assert oracle.compress(d, q, 24) == ref.compress(d, q, 24)
