@@ -40,3 +40,41 @@ def cases(seed, count):
 # (seed, index): inputs that exposed real bugs in the speculative parse (stitch-bit ownership when a copy runs
 # to the block end; stale overlapping walker ranges behind ExtendLastCommand)
 REGRESSIONS = [(1, 304), (4, 382), (7, 249), (7, 13), (6, 104), (5, 252), (5, 297)]
+
+
+def dict_cases(seed, count, tables_path):
+    """Texts made of words of the static dictionary (whole, tail-cut, upper-cased) between noise: exercises the
+    dictionary search, its cutoff transforms and the lookup gate (hash.h:140-202).  Yields (index, data, q, lgwin)."""
+    import struct
+    blob = open(tables_path, "rb").read()           # layout: oracle/gen_tables.c
+    size_bits = list(blob[8:40]); offsets = struct.unpack("<32I", blob[40:168]); dic = blob[168:168 + 122784]
+    rnd = random.Random(seed)
+
+    def word():
+        n = rnd.randint(4, 24)
+        i = rnd.randrange(1 << size_bits[n])
+        return dic[offsets[n] + n * i: offsets[n] + n * i + n]
+
+    for idx in range(count):
+        n = rnd.choice([rnd.randint(100, 5000), rnd.randint(5000, 100000)])
+        out = bytearray()
+        p_word = rnd.choice([0.9, 0.5, 0.1, 0.02])
+        sep = rnd.choice([b" ", b"", b"\n", None])
+        while len(out) < n:
+            r = rnd.random()
+            if r < p_word:
+                w = word()
+                t = rnd.random()
+                if t < 0.2:
+                    w = w[:max(1, len(w) - rnd.randint(1, 9))]
+                elif t < 0.3:
+                    w = w.upper()
+                out += w
+                out += sep if sep is not None else bytes([rnd.randrange(256)])
+            elif r < p_word + 0.05 and len(out) > 10:
+                d = rnd.randint(1, len(out))
+                for _ in range(rnd.randint(3, 60)):
+                    out.append(out[-d])
+            else:
+                out += bytes(rnd.randrange(256) for _ in range(rnd.randint(1, 30)))
+        yield idx, bytes(out[:n]), rnd.choice([5, 5, 6, 7, 9]), rnd.choice([17, 18, 22, 24])

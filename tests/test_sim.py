@@ -131,7 +131,9 @@ def test_sim_fuzz_regressions(sim):
 
 
 def test_sim_fuzz_sample(sim):
-    from fuzz_cases import cases
+    from fuzz_cases import cases, dict_cases
     for i, d, q, w in cases(20250922, 120):
         if len(d) <= 120000:
             assert _fuzz_check(sim, d, q, w), (i, len(d), q, w)
+    for i, d, q, w in dict_cases(20250923, 40, TABLES):
+        assert _fuzz_check(sim, d, q, w), ("dict", i, len(d), q, w)
