@@ -379,6 +379,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     }
   }
   bool prev_dirty = false;
+  u32 run_len = 0;
   for (u32 c = 0; c < B.nchunks; ++c) {
     const u32 k = B.first_chunk + c;
     BrBlockIn ni = s.bin[k];
@@ -412,7 +413,13 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     // From the third launch on, a chunk whose only problem is the state handed over by a dirty
     // predecessor is not scheduled: the predecessor's walker chases into it (br_walk_block), which
     // resolves a serial ripple in one launch instead of one launch per chunk.
-    const bool defer = dirty == 2 && prev_dirty && t_now >= 2;
+    bool defer = dirty == 2 && prev_dirty && t_now >= 2;
+    // Optional (BrParams::run_cap, off): once the iteration is past win_epoch launches, walk only the first
+    // run_cap chunks of every run of consecutive dirty chunks.  On data where each re-walk perturbs its
+    // successors again the front of such a run advances about one chunk per launch whatever is walked behind
+    // it, and -- unlike a window behind the first dirty chunk -- all runs keep advancing in parallel.
+    run_len = dirty ? run_len + 1 : 0;
+    if (dirty && s.P.run_cap && t_now >= s.P.win_epoch && run_len > s.P.run_cap) defer = true;
     prev_dirty = dirty != 0;
     s.bin[k] = ni;
     s.dirty[k] = defer ? 0u : dirty;

@@ -428,6 +428,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   if (getenv("BR_HEAVY_MIN")) P.heavy_min = (u32)strtoul(getenv("BR_HEAVY_MIN"), 0, 10);
   if (getenv("BR_DBG_FLAGS")) P.dbg_flags = (u32)strtoul(getenv("BR_DBG_FLAGS"), 0, 10);
   if (getenv("BR_STEP_CAP")) P.step_cap = (u32)strtoul(getenv("BR_STEP_CAP"), 0, 10);
+  if (getenv("BR_RUN_CAP")) P.run_cap = (u32)strtoul(getenv("BR_RUN_CAP"), 0, 10);
   if (getenv("BR_WIN_EPOCH")) P.win_epoch = (u32)strtoul(getenv("BR_WIN_EPOCH"), 0, 10);
   if (getenv("BR_WIN_CHUNKS")) P.win_chunks = (u32)strtoul(getenv("BR_WIN_CHUNKS"), 0, 10);
   const u32 bs = 1u << P.lgblock, ch = 1u << BR_CHUNK_BITS;

@@ -29,6 +29,7 @@ struct BrParams {
   u32 nbuckets;     // 1 << bucket_bits (+1 overflow bucket for the unhashable tail positions)
   u32 cpb_shift;    // lgblock - BR_CHUNK_BITS: chunks per full input block = 1 << cpb_shift
   u32 dbg_flags;    // bit 0: disable the candidate-relevance filter of the dependency marking (default: disabled)
+  u32 run_cap;      // from launch win_epoch on, walk only the first run_cap chunks of each run of dirty chunks (0 = off)
   u32 win_epoch, win_chunks;   // from launch win_epoch on, only dirty chunks within win_chunks of the first dirty one are walked
   u32 step_cap;     // successor-walk budget per flipped bit in the dependency marking; beyond it the block-level rule
   u32 heavy_min;    // buckets with at least this many positions take the counter-wrap path (65536; tests lower it)

@@ -89,6 +89,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   if (getenv("BR_SIM_HEAVY_MIN")) P.heavy_min = (u32)atoi(getenv("BR_SIM_HEAVY_MIN"));
   if (getenv("BR_SIM_DBG_FLAGS")) P.dbg_flags = (u32)atoi(getenv("BR_SIM_DBG_FLAGS"));
   if (getenv("BR_SIM_STEP_CAP")) P.step_cap = (u32)atoi(getenv("BR_SIM_STEP_CAP"));
+  if (getenv("BR_SIM_RUN_CAP")) P.run_cap = (u32)atoi(getenv("BR_SIM_RUN_CAP"));
   if (getenv("BR_SIM_WIN_EPOCH")) P.win_epoch = (u32)atoi(getenv("BR_SIM_WIN_EPOCH"));
   if (getenv("BR_SIM_WIN_CHUNKS")) P.win_chunks = (u32)atoi(getenv("BR_SIM_WIN_CHUNKS"));
   u32 bs = 1u << P.lgblock;
