@@ -69,9 +69,16 @@ def test_state_api_and_loud_failure(lib):
     if not brotli_b200.available():
         with pytest.raises(brotli_b200.error):
             brotli_b200.compress_oneshot(b"no gpu here " * 100, 5, 22)
+        with pytest.raises(brotli_b200.error):           # the quality-1 batch path has no CPU fallback either
+            brotli_b200.compress_oneshot(b"no gpu here " * 100, 1, 22)
+        with pytest.raises(brotli_b200.error):
+            brotli_b200.compress_batch([b"a" * 100, b"b" * 100], 1, 22)
     # parameters outside the implemented path are refused instead of silently changed
     out = C.create_string_buffer(4096)
     n = C.c_size_t(4096)
     assert lib.BrotliEncoderCompress(11, 22, 0, 100, b"x" * 100, C.byref(n), out) == 0
     n = C.c_size_t(4096)
     assert lib.BrotliEncoderCompress(5, 12, 0, 100, b"x" * 100, C.byref(n), out) == 0
+    for q in (0, 2, 3, 4, 10):                            # qualities without a GPU path: refused, never other bytes
+        n = C.c_size_t(4096)
+        assert lib.BrotliEncoderCompress(q, 22, 0, 100, b"x" * 100, C.byref(n), out) == 0
