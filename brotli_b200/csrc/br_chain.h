@@ -41,7 +41,8 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
       }
     }
   }
-  const u32* mine = s.bits_cur + (size_t)(k & 1u) * s.bits_words;
+  const u32* mine = s.bits_cur + (size_t)(s.bout[k].own_par & 1u) * s.bits_words;
+  const u32 my_head = s.bout[k].head;
   if (b > a) {
     // stitch positions inside [a, b): the next block(s) starting at or shortly after blk_end
     u32 st_lo = 0, st_hi = 0;   // [st_lo, st_hi) of stitch-stored positions (at most one run here)
@@ -94,23 +95,8 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
 #endif
           const u16 key = s.skeys[jq];
           if (s.seg[key + 1] - s.seg[key] >= s.P.heavy_min) br_atomic_add(s.key_flips + key, 1);   // uint16 bucket counter may wrap
-          const u32 V = 1u << s.P.block_bits;
-          // B: stored same-bucket positions older than q that a later search could still see (capped at V)
-          u32 B = 0;
-          {
-            const u32 lo = s.seg[key];
-            u32 steps = 0;
-            for (u32 j = jq; j > lo && B < V; ) {
-              --j;
-              const u32 pp = s.S[j];
-              if (q - pp > s.P.max_backward || ++steps > 1024) { if (steps > 1024) B = V; break; }
-              if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5] | s.bits_cur[s.bits_words + (pp >> 5)]) >> (pp & 31)) & 1) ++B;   // stored before or after this launch
-            }
-          }
-          const u32 q4 = br_ld32u(s.data, q);
-          // cnt: stored (snapshot the walkers read) strictly between q and pp -> is q inside pp's view;
-          // cnt_e: stored before OR after this launch -> upper bound of the view size in both snapshots
-          u32 cnt = 0, cnt_e = 0, steps = 0;
+          // cnt: stored (snapshot the walkers read) strictly between q and pp -> is q inside pp's view
+          u32 cnt = 0, steps = 0;
           for (u32 j = jq + 1; j < s.P.n && s.skeys[j] == key && cnt < reach; ++j) {
 #ifdef BR_SIM_DEBUG
             ++br_sim_cnt[4];
@@ -124,20 +110,20 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
             }
             const u32 pp = s.S[j];
             if (pp - q > s.P.max_backward) break;
-            const u32 before = cnt_e;
             if ((s.bits_prev[pp >> 5] >> (pp & 31)) & 1) ++cnt;
-            if (((s.bits_prev[pp >> 5] | s.bits_cur[pp >> 5] | s.bits_cur[s.bits_words + (pp >> 5)]) >> (pp & 31)) & 1) ++cnt_e;
             if (pp >= a && pp < b) continue;            // my own run is consistent with my own bits
             if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
-            // q itself can only be chosen at pp if at least four bytes agree; and it can only push another
-            // candidate out of (or pull one into) pp's view if that view is full
-            if (!(s.P.dbg_flags & 1) && br_ld32u(s.data, pp) != q4 && before + 1 + B < V) continue;
             u32 c = ((pp >> s.P.lgblock) << s.P.cpb_shift) + ((pp & ((1u << s.P.lgblock) - 1)) >> BR_CHUNK_BITS);
 #ifdef BR_SIM_DEBUG
             ++br_sim_cnt[0];
 #endif
-            br_atomic_max(s.bitdep_epoch + c, (int)s.epoch);
-            if (c > 0) br_atomic_max(s.bitdep_epoch + c - 1, (int)s.epoch);   // its owner may be the chunk before
+            // (its owner may be the chunk before.)  Not marked: this run itself, and the runs that the same walker
+            // made AFTER this one in this launch -- a sweep reads its own fresh bits (br_walk_block).
+            for (u32 xc = c > 0 ? c - 1 : 0; xc <= c; ++xc) {
+              if (xc == k) continue;
+              if (xc > k && s.bout[xc].valid && s.bout[xc].epoch == s.epoch && s.bout[xc].head == my_head) continue;
+              br_atomic_max(s.bitdep_epoch + xc, (int)s.epoch);
+            }
           }
         }
       }
@@ -242,12 +228,9 @@ BR_DEV void br_chain_b(const BrStream& s) {
     for (u32 k = (u32)lane; k <= P.nbuckets; k += BR_WARP) { u32 v = s.key_flips[k]; if (v > mx) mx = v; s.key_flips[k] = 0; }
     mx = br_warp_max(mx);
     if (lane == 0) {
-      if (t_now < BR_MAX_EPOCHS) s.epoch_changed[t_now] = mx;
-      u32 acc = 0;
-      s.epoch_suffix[BR_MAX_EPOCHS] = 0;
-      for (int e = BR_MAX_EPOCHS - 1; e >= 0; --e) {
-        if ((u32)e <= t_now) acc += s.epoch_changed[e];
-        s.epoch_suffix[e] = acc;
+      if (t_now <= P.max_epochs) {   // (the chain runs again for the same launch when a metablock falls back late)
+        if (s.counters[7] == t_now + 1) s.epoch_cum[t_now] += mx;
+        else { s.epoch_cum[t_now] = (t_now ? s.epoch_cum[t_now - 1] : 0u) + mx; s.counters[7] = t_now + 1; }
       }
       s.counters[0] = 0; s.counters[5] = 0; s.counters[6] = 0xffffffffu;
       for (int i = 8; i < 16; ++i) s.counters[i] = 0;
@@ -379,7 +362,6 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     }
   }
   bool prev_dirty = false;
-  u32 run_len = 0;
   for (u32 c = 0; c < B.nchunks; ++c) {
     const u32 k = B.first_chunk + c;
     BrBlockIn ni = s.bin[k];
@@ -406,7 +388,8 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
       if (!dirty && out.out_pos > ni.start_pos) {
         int seen = (int)out.epoch;
         if (s.bitdep_epoch[k] >= seen || ovf >= seen) dirty = 4;
-        u32 unseen = s.epoch_suffix[seen < BR_MAX_EPOCHS ? seen : BR_MAX_EPOCHS];
+        // flips in heavy buckets committed by launches >= seen (this run read the snapshot before launch `seen`)
+        u32 unseen = s.epoch_cum[t_now] - (seen > 0 ? s.epoch_cum[seen - 1] : 0u);
         if (!dirty && unseen > out.min_wrap_dist) dirty = 5;
       }
     }
@@ -414,15 +397,15 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     // predecessor is not scheduled: the predecessor's walker chases into it (br_walk_block), which
     // resolves a serial ripple in one launch instead of one launch per chunk.
     bool defer = dirty == 2 && prev_dirty && t_now >= 2;
-    // Optional (BrParams::run_cap, off): once the iteration is past win_epoch launches, walk only the first
-    // run_cap chunks of every run of consecutive dirty chunks.  On data where each re-walk perturbs its
-    // successors again the front of such a run advances about one chunk per launch whatever is walked behind
-    // it, and -- unlike a window behind the first dirty chunk -- all runs keep advancing in parallel.
-    run_len = dirty ? run_len + 1 : 0;
-    if (dirty && s.P.run_cap && t_now >= s.P.win_epoch && run_len > s.P.run_cap) defer = true;
+    // Sweep mode (from launch sweep_epoch on): only the head of every run of consecutive dirty chunks is scheduled
+    // and its walker sweeps the run.  On data where each re-walk perturbs its successors again (chaotic binary
+    // input: sparse-search phases, heavy buckets) re-walking all dirty chunks at once from the previous snapshot is
+    // a Jacobi iteration whose settled front advances one chunk per launch; the sweep is the sequential parse of
+    // the run, and all runs of the stream still advance in parallel.
+    if (dirty && prev_dirty && t_now >= s.P.sweep_epoch) defer = true;
     prev_dirty = dirty != 0;
     s.bin[k] = ni;
-    s.dirty[k] = defer ? 0u : dirty;
+    s.dirty[k] = defer ? (BR_DEFER | dirty) : dirty;
     s.cmd_off[k] = cmd_off;
     s.lil_in[k] = lil_true;
     s.block_mb[k] = W.mb;

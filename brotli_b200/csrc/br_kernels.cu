@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restr
 __global__ void __launch_bounds__(128, BR_WALK_MINB) k_walk(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.counters[5]) return;
-  br_walk_block(s, s.dirty_list[t]);
+  const u32 b = s.dirty_list[t];
+  br_walk_block(s, b, s.forced && b == s.counters[6]);
 }
 __global__ void k_commit(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -425,12 +426,15 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   BrStream s; memset(&s, 0, sizeof(s));
   if (!br_derive_params(quality, lgwin, size_hint, n, &s.P)) return 0;
   BrParams& P = s.P;
+#ifdef BR_DEBUG_KNOBS   // experiment switches: never in the release build (an environment variable must not change the bytes)
   if (getenv("BR_HEAVY_MIN")) P.heavy_min = (u32)strtoul(getenv("BR_HEAVY_MIN"), 0, 10);
-  if (getenv("BR_DBG_FLAGS")) P.dbg_flags = (u32)strtoul(getenv("BR_DBG_FLAGS"), 0, 10);
   if (getenv("BR_STEP_CAP")) P.step_cap = (u32)strtoul(getenv("BR_STEP_CAP"), 0, 10);
-  if (getenv("BR_RUN_CAP")) P.run_cap = (u32)strtoul(getenv("BR_RUN_CAP"), 0, 10);
-  if (getenv("BR_WIN_EPOCH")) P.win_epoch = (u32)strtoul(getenv("BR_WIN_EPOCH"), 0, 10);
-  if (getenv("BR_WIN_CHUNKS")) P.win_chunks = (u32)strtoul(getenv("BR_WIN_CHUNKS"), 0, 10);
+  if (getenv("BR_SWEEP_EPOCH")) P.sweep_epoch = (u32)strtoul(getenv("BR_SWEEP_EPOCH"), 0, 10);
+  if (getenv("BR_FORCE_EPOCH")) P.force_epoch = (u32)strtoul(getenv("BR_FORCE_EPOCH"), 0, 10);
+  const bool trace = getenv("BR_TRACE") != nullptr;
+#else
+  const bool trace = false;
+#endif
   const u32 bs = 1u << P.lgblock, ch = 1u << BR_CHUNK_BITS;
   // chunk / block tables (one-shot call: uniform input blocks of 1 << lgblock bytes)
   std::vector<BrBlockIn> hb; std::vector<BrBlk> hblk;
@@ -468,7 +472,10 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
   for (int i = 0; i < 14; ++i) add(nb * 4ull + 64);
   add(nblk * sizeof(BrBlk)); add(nblk * sizeof(BrBlkIn)); add((P.nbuckets + 8) * 4ull);
-  add(BR_MAX_EPOCHS * 8 + 64); add((nb + 1) * sizeof(BrMetaBlock)); add(4096);
+  // Launch bound: in forced mode every launch finalises at least one input block (at most two launches per block with
+  // the conservative block-level re-marks), and a late uncompressed fallback restarts the count at most once per metablock.
+  P.max_epochs = 4 * nb + 4096;
+  add(((size_t)P.max_epochs + 2) * 4 + 64); add((nb + 1) * sizeof(BrMetaBlock)); add(4096);
   need += 1 << 20;
   if (!job->arena.reserve(need)) return 0;
   BrArena& A = job->arena;
@@ -492,7 +499,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   int* bitdep_epoch = A.take<int>(nb + 16);
   BrBlk* d_blk = A.take<BrBlk>(nblk); BrBlkIn* d_blkin = A.take<BrBlkIn>(nblk);
   u32* key_flips = A.take<u32>(P.nbuckets + 8);
-  u32* epoch_changed = A.take<u32>(BR_MAX_EPOCHS); u32* epoch_suffix = A.take<u32>(BR_MAX_EPOCHS + 1);
+  u32* epoch_cum = A.take<u32>((size_t)P.max_epochs + 2);
   BrMetaBlock* mbs = A.take<BrMetaBlock>(nb + 1);
   u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256);
   if (!hist_scratch) return 0;
@@ -502,7 +509,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   s.data = data; s.S = S; s.rank = rank; s.seg = seg; s.bits_latest = bits_latest; s.bits_cur = bits_cur; s.bits_words = (u32)nwords;
   s.storedS = storedS; s.prefS = prefS; s.bin = bin; s.bin_used = bin_used; s.bout = bout;
   s.cmd_blocks = cmd_blocks; s.cmd_stride = cmd_stride; s.dirty = dirty; s.changed_bits = changed_bits;
-  s.changed_epoch = changed_epoch; s.epoch_changed = epoch_changed; s.epoch_suffix = epoch_suffix;
+  s.changed_epoch = changed_epoch; s.epoch_cum = epoch_cum;
   s.ext_total = ext_total; s.cmd_off = cmd_off; s.mbs = mbs; s.force_unc = force_unc;
   s.counters = counters; s.hist_scratch = hist_scratch;
   s.srch_latest = srch_latest; s.srch_cur = srch_cur; s.bits_prev = bits_prev; s.bitdep_epoch = bitdep_epoch; s.skeys = K2;
@@ -523,7 +530,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   CK(cudaMemsetAsync(srch_latest, 0, nwords * 4, st));
   CK(cudaMemsetAsync(key_flips, 0, (P.nbuckets + 8) * 4, st));
   CK(cudaMemsetAsync(force_unc, 0, (nb + 16) * 4, st));
-  CK(cudaMemsetAsync(epoch_changed, 0, BR_MAX_EPOCHS * 4, st));
+  CK(cudaMemsetAsync(epoch_cum, 0, 64, st));
   CK(cudaMemsetAsync(counters, 0, 256, st));
   CK(cudaMemsetAsync(bits_cur, 0, 2 * (size_t)nwords * 4, st));
 
@@ -548,6 +555,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   const u8* final_out = nullptr; size_t final_size = 0;
   for (;;) {   // rounds: repeated only when a metablock needs the late uncompressed fallback
     ++rounds;
+    const u32 round_epoch0 = s.epoch;
     for (;;) {
       k_chain_a<<<(nblk + 31) / 32, 32, 0, st>>>(s);
       k_chain_b<<<1, 32, 0, st>>>(s);
@@ -556,11 +564,12 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       CK(cudaStreamSynchronize(st));
       u32 n_dirty = hp[0], n_sched = hp[5]; n_mbs = hp[1]; total_cmds = hp[2];
       job->stats.block_runs += hp[4];
-      if (getenv("BR_TRACE")) fprintf(stderr, "epoch %u: dirty %u sched %u ran %u | never %u state %u dict %u bits %u wrap %u\n", s.epoch, hp[0], hp[5], hp[4], hp[9], hp[10], hp[11], hp[12], hp[13]), fprintf(stderr, "   chain_b: phase0 %u kcyc, blocks %u kcyc, slow-dict blocks %u\n", hp[20], hp[21], hp[22]);
+      if (trace) fprintf(stderr, "epoch %u: dirty %u sched %u ran %u | never %u state %u dict %u bits %u wrap %u\n", s.epoch, hp[0], hp[5], hp[4], hp[9], hp[10], hp[11], hp[12], hp[13]), fprintf(stderr, "   chain_b: phase0 %u kcyc, blocks %u kcyc, slow-dict blocks %u\n", hp[20], hp[21], hp[22]);
       if (walk_pending) { float wms; cudaEventElapsedTime(&wms, ev[6], ev[7]); job->stats.ms_walk += wms; walk_pending = false; }
       if (n_dirty == 0) break;
-      if (s.epoch + 2 >= BR_MAX_EPOCHS) { fprintf(stderr, "brotli_b200: LZ77 fixpoint did not converge\n"); return 0; }
+      if (s.epoch + 2 >= P.max_epochs) { fprintf(stderr, "brotli_b200: internal error: launch bound exceeded\n"); return 0; }
       ++s.epoch; ++job->stats.lz77_iterations;
+      s.forced = s.epoch - round_epoch0 >= P.force_epoch ? 1u : 0u;
       CK(cudaMemsetAsync(bits_cur, 0, 2 * (size_t)nwords * 4, st));
       CK(cudaMemsetAsync(srch_cur, 0, nwords * 4, st));
       CK(cudaMemsetAsync(counters + 4, 0, 4, st));
@@ -651,7 +660,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       u32 idx = hp[18] - 1, one = 1;
       CK(cudaMemcpyAsync(force_unc + idx, &one, 4, cudaMemcpyHostToDevice, st));
       CK(cudaStreamSynchronize(st));
-      if (rounds > 256) return 0;
+      if (rounds > (int)nblk + 8) return 0;   // (every round stores one more metablock raw)
       continue;
     }
     k_assemble_copy<<<dim3(64, n_mbs), 256, 0, st>>>(s, desc, outbits, out);

@@ -379,12 +379,15 @@ BR_DEV u32 br_compute_distance_code(u32 distance, u32 max_distance, const int* d
 // One chunk (see br_types.h).  The walker resumes the parse of its input block at
 // in.start_pos with the carried state and leaves when the position reaches the chunk end
 // (the last chunk of a block runs to the block end like the reference loop).
-BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOut& o) {
+// `head` is the first chunk of the sweep this run belongs to (== b when the walker starts here), `sweep_p0` the
+// first position the sweep owns (0xffffffff on entry for the head, which sets it): a walker that continues into the
+// chunks behind its own keeps writing the head's bitmap and reads its own fresh bits from sweep_p0 on.
+BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOut& o, u32 head, u32& sweep_p0) {
   const BrParams& P = s.P;
   const int lane = br_lane();
   BrWalk w;
-  w.s = &s; w.d = s.data; w.p0 = in.start_pos; w.pend = in.blk_end;
-  w.own = s.bits_cur + (size_t)(b & 1u) * s.bits_words;
+  w.s = &s; w.d = s.data; w.p0 = head == b ? in.start_pos : sweep_p0; w.pend = in.blk_end;
+  w.own = s.bits_cur + (size_t)(head & 1u) * s.bits_words;
   w.dict_l = ((u64)in.dict_l_hi << 32) | in.dict_l_lo;
   w.dict_m = ((u64)in.dict_m_hi << 32) | in.dict_m_lo;
   w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
@@ -530,7 +533,9 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     o.ext_len = ext; o.dl = w.dl; o.dm = w.dm;
     o.gate_checks = w.gate_checks; o.gate_fail = w.gate_fail;
     o.min_wrap_dist = w.min_wrap; o.valid = 1; o.epoch = s.epoch;
+    o.head = head; o.own_par = head & 1u;
   }
+  if (head == b) sweep_p0 = used.start_pos;
   if (lane == 0) {
     s.bout[b] = o;
     s.bin_used[b] = used;
@@ -540,34 +545,43 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   br_syncwarp();
 }
 
-// Walk chunk b, then CHASE: while the state this walker leaves differs from what the next chunk
-// of the same input block consumed on its latest run -- and nobody else runs that chunk in this
-// launch -- keep going.  This resolves, inside one launch, the ripples that otherwise cost one
-// launch per chunk (e.g. a distance-cache change flowing through match-free data).
-BR_DEV void br_walk_block(const BrStream& s, u32 b) {
-  // Optional scheduling window (BrParams::win_chunks, off by default): from launch win_epoch on, walk only
-  // the dirty chunks within win_chunks of the first dirty one.  On data where every re-walk perturbs its
-  // successors again this removes most of the wasted walks (sim: 125 k -> 18 k
-  // runs on a 3 MB sample) but needs more launches than the 40 ms a launch costs at 200 MB can pay for.
-  if (s.epoch >= s.P.win_epoch && s.P.win_chunks && b - s.counters[6] > s.P.win_chunks) return;
+// Walk chunk b, then go on into the chunks behind it (same input block) while
+//   * the next chunk is dirty but was left to this walker (BR_DEFER: the chain schedules only the head of a run of
+//     consecutive dirty chunks once the iteration is in sweep mode), or
+//   * the state this walker leaves differs from what the next chunk consumed on its latest run (CHASE),
+// and nobody else runs that chunk in this launch.  The walker sees its own fresh stored-bits from the sweep's first
+// position on, so a sweep over a run of dirty chunks is the sequential parse of that run: serial ripples (a
+// distance-cache change flowing through match-free data, stored-bits that keep perturbing the next chunk on chaotic
+// binary data) cost one launch, not one launch per chunk.
+BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
   BrBlockIn in = s.bin[b];
+  const u32 head = b;
+  u32 sweep_p0 = 0xffffffffu;
   for (;;) {
     BrBlockOut o;
-    br_walk_one(s, b, in, o);
+    br_walk_one(s, b, in, o, head, sweep_p0);
     if (in.last) return;
     const u32 nb = b + 1;
-    if (s.dirty[nb] != 0 || !s.bout[nb].valid) return;
-    const BrBlockIn u = s.bin_used[nb];
-    const u64 dl = (((u64)in.dict_l_hi << 32) | in.dict_l_lo) + o.dl, dm = (((u64)in.dict_m_hi << 32) | in.dict_m_lo) + o.dm;   // (a closed gate reports dl = dm = 0)
-    bool same = u.start_pos == o.out_pos && u.apply_rh == o.apply_rh && u.store_end == o.store_end && u.ext_dist == 0 &&
-                u.dc[0] == o.dc[0] && u.dc[1] == o.dc[1] && u.dc[2] == o.dc[2] && u.dc[3] == o.dc[3];
-    if (same) {
-      const BrBlockOut uo = s.bout[nb];
-      const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
-      u32 edl, edm;
-      if (ul != dl || um != dm) same = br_dict_gate_valid(dl, dm, uo.dl, uo.dm, uo.gate_checks, uo.gate_fail, &edl, &edm) != 0;
+    const u32 df = s.dirty[nb];
+    bool go = to_block_end;
+    if (!go) {
+      if (df != 0 && !(df & BR_DEFER)) return;   // scheduled: another walker runs it in this launch
+      go = (df & BR_DEFER) != 0;
     }
-    if (same) return;
+    const u64 dl = (((u64)in.dict_l_hi << 32) | in.dict_l_lo) + o.dl, dm = (((u64)in.dict_m_hi << 32) | in.dict_m_lo) + o.dm;   // (a closed gate reports dl = dm = 0)
+    if (!go) {
+      if (!s.bout[nb].valid) return;
+      const BrBlockIn u = s.bin_used[nb];
+      bool same = u.start_pos == o.out_pos && u.apply_rh == o.apply_rh && u.store_end == o.store_end && u.ext_dist == 0 &&
+                  u.dc[0] == o.dc[0] && u.dc[1] == o.dc[1] && u.dc[2] == o.dc[2] && u.dc[3] == o.dc[3];
+      if (same) {
+        const BrBlockOut uo = s.bout[nb];
+        const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
+        u32 edl, edm;
+        if (ul != dl || um != dm) same = br_dict_gate_valid(dl, dm, uo.dl, uo.dm, uo.gate_checks, uo.gate_fail, &edl, &edm) != 0;
+      }
+      if (same) return;
+    }
     BrBlockIn ni = s.bin[nb];
     ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0; ni.warm = 0;
     for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];

@@ -29,8 +29,7 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->cpb_shift = (u32)P->lgblock - BR_CHUNK_BITS;
   P->heavy_min = 65536;
   P->step_cap = 4096;
-  P->run_cap = 0;
-  P->win_epoch = 8; P->win_chunks = 0;   // scheduling window off: on config 4 it trades cheaper launches for more than 1024 of them
-  P->dbg_flags = 1;   // the candidate-relevance filter stays off: it trims the marks of config 4 by 10 % only
+  P->sweep_epoch = 3;    // text / web input settles in 3 launches; what is still dirty then is swept run by run
+  P->force_epoch = 64;
   return 1;
 }

@@ -28,9 +28,11 @@ struct BrParams {
   u32 nblocks;      // number of chunks (speculation units); input blocks are groups of them
   u32 nbuckets;     // 1 << bucket_bits (+1 overflow bucket for the unhashable tail positions)
   u32 cpb_shift;    // lgblock - BR_CHUNK_BITS: chunks per full input block = 1 << cpb_shift
-  u32 dbg_flags;    // bit 0: disable the candidate-relevance filter of the dependency marking (default: disabled)
-  u32 run_cap;      // from launch win_epoch on, walk only the first run_cap chunks of each run of dirty chunks (0 = off)
-  u32 win_epoch, win_chunks;   // from launch win_epoch on, only dirty chunks within win_chunks of the first dirty one are walked
+  u32 sweep_epoch;  // from this launch on: only the HEAD of every run of consecutive dirty chunks is scheduled; its walker
+                    // sweeps the run serially, seeing its own fresh stored-bits (Gauss-Seidel inside a run, Jacobi across runs)
+  u32 force_epoch;  // from this launch on the first scheduled walker also runs to the end of its input block whatever the
+                    // flags say: every launch then finalises at least one block, which bounds the number of launches
+  u32 max_epochs;   // size of the per-launch arrays (a bound no input reaches: see br_kernels.cu)
   u32 step_cap;     // successor-walk budget per flipped bit in the dependency marking; beyond it the block-level rule
   u32 heavy_min;    // buckets with at least this many positions take the counter-wrap path (65536; tests lower it)
 };
@@ -68,6 +70,8 @@ struct BrBlockOut {
   u32 min_wrap_dist;     // see br_lz77.h (bucket counter wrap sensitivity)
   u32 valid;
   u32 epoch;             // walker launch that produced this record
+  u32 head;              // first chunk of the sweep (one warp walking consecutive chunks) this run belongs to
+  u32 own_par;           // which of the two bits_cur bitmaps the run wrote (the parity of the sweep's head)
 };
 
 // Per reference input block (one EncodeData call): static layout, aggregates over its chunks and
@@ -100,7 +104,9 @@ struct BrMetaBlock {
   u32 scratch_off;
 };
 
-#define BR_MAX_EPOCHS 1024
+// BrStream::dirty[] values: 0 clean; reason (1..5) = scheduled for the next walker launch; BR_DEFER | reason = dirty but
+// left to the walker of the chunk before it (sweep / chase)
+#define BR_DEFER 0x100u
 
 // Device-resident view of one stream (all pointers are device pointers).
 struct BrStream {
@@ -128,9 +134,10 @@ struct BrStream {
   int* changed_epoch;    // [nblocks] last walker launch whose commit changed this chunk's bits (-1: never)
   int* bitdep_epoch;     // [nblocks] last launch that changed a stored-bit this chunk's searches may consult
   const u16* skeys;      // bucket key of S[j]
-  u32* epoch_changed;    // [BR_MAX_EPOCHS] total changed bits committed per walker launch
-  u32* epoch_suffix;     // [BR_MAX_EPOCHS + 1] suffix sums of the above (chain scratch)
+  u32* epoch_cum;        // [max_epochs + 1] epoch_cum[t] = sum over launches <= t of the largest number of stored-bit flips
+                         // any single heavy bucket saw in that launch (bucket counter wrap rule)
   u32 epoch;             // current walker launch number (1-based)
+  u32 forced;            // this launch: the first scheduled walker runs to the end of its input block (BrParams::force_epoch)
   u32* ext_total;        // [nblocks] bytes added to the chunk's last command by ExtendLastCommand
   u32* lil_in;           // [nblocks] true pending-literal count at the chunk start (added to its first command)
   BrBlk* blk;            // [nblk] reference input blocks
@@ -143,7 +150,7 @@ struct BrStream {
   u32* cmd_off;          // [nblocks] offset of the block's commands in the compacted array
   BrMetaBlock* mbs;      // [max_mbs]
   u32* force_unc;        // [max_mbs] late fallback: store this metablock uncompressed
-  u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags, 4 chunks walked this launch, 5 chunks scheduled, 6 last launch whose bit tracking overflowed (+1), 8.. dirty reasons
+  u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags, 4 chunks walked this launch, 5 chunks scheduled, 6 first scheduled chunk, 7 last launch entered in epoch_cum (+1), 8.. dirty reasons
   u32* hist_scratch;     // [256]
   // tables
   const u8* dict;        // RFC 7932 dictionary

@@ -36,7 +36,7 @@ struct SimStream {
   BrStream s;
   std::vector<u8> data;
   std::vector<u32> S, rank, seg, bits_latest, bits_cur, bits_prev, srch_latest, srch_cur, storedS, prefS, dirty, changed_bits,
-      epoch_changed, epoch_suffix, ext_total, lil_in, cmd_off, force_unc, counters, hist, block_mb;
+      epoch_cum, ext_total, lil_in, cmd_off, force_unc, counters, hist, block_mb;
   std::vector<int> changed_epoch, bitdep_epoch;
   std::vector<u16> skeys;
   std::vector<BrBlockIn> bin, bin_used;
@@ -87,11 +87,9 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   if (!br_derive_params(q, lgwin, n, n, &s.P)) { delete m; return nullptr; }
   BrParams& P = s.P;
   if (getenv("BR_SIM_HEAVY_MIN")) P.heavy_min = (u32)atoi(getenv("BR_SIM_HEAVY_MIN"));
-  if (getenv("BR_SIM_DBG_FLAGS")) P.dbg_flags = (u32)atoi(getenv("BR_SIM_DBG_FLAGS"));
   if (getenv("BR_SIM_STEP_CAP")) P.step_cap = (u32)atoi(getenv("BR_SIM_STEP_CAP"));
-  if (getenv("BR_SIM_RUN_CAP")) P.run_cap = (u32)atoi(getenv("BR_SIM_RUN_CAP"));
-  if (getenv("BR_SIM_WIN_EPOCH")) P.win_epoch = (u32)atoi(getenv("BR_SIM_WIN_EPOCH"));
-  if (getenv("BR_SIM_WIN_CHUNKS")) P.win_chunks = (u32)atoi(getenv("BR_SIM_WIN_CHUNKS"));
+  if (getenv("BR_SIM_SWEEP_EPOCH")) P.sweep_epoch = (u32)atoi(getenv("BR_SIM_SWEEP_EPOCH"));
+  if (getenv("BR_SIM_FORCE_EPOCH")) P.force_epoch = (u32)atoi(getenv("BR_SIM_FORCE_EPOCH"));
   u32 bs = 1u << P.lgblock;
   const u32 ch = 1u << BR_CHUNK_BITS;
   std::vector<BrBlockIn> chunks;
@@ -127,7 +125,8 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   }
   m->storedS.assign(words + 32, 0); m->prefS.assign(n / 1024 + 4, 0);
   m->dirty.assign(nb, 0); m->changed_bits.assign(nb, 0); m->changed_epoch.assign(nb, -1); m->bitdep_epoch.assign(nb + 1, -1);
-  m->epoch_changed.assign(BR_MAX_EPOCHS, 0); m->epoch_suffix.assign(BR_MAX_EPOCHS + 1, 0);
+  P.max_epochs = 4 * nb + 4096;
+  m->epoch_cum.assign(P.max_epochs + 2, 0);
   m->ext_total.assign(nb, 0); m->lil_in.assign(nb, 0); m->cmd_off.assign(nb, 0); m->force_unc.assign(nb + 1, 0);
   m->counters.assign(64, 0); m->hist.assign(256, 0); m->mbs.resize(nb + 1);
   s.cmd_stride = ch / 2 + 2;
@@ -138,7 +137,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   s.bin = m->bin.data(); s.bin_used = m->bin_used.data(); s.bout = m->bout.data();
   s.cmd_blocks = m->cmd_blocks.data(); s.dirty = m->dirty.data();
   s.changed_bits = m->changed_bits.data(); s.changed_epoch = m->changed_epoch.data(); s.bitdep_epoch = m->bitdep_epoch.data();
-  s.epoch_changed = m->epoch_changed.data(); s.epoch_suffix = m->epoch_suffix.data();
+  s.epoch_cum = m->epoch_cum.data();
   s.ext_total = m->ext_total.data(); s.lil_in = m->lil_in.data(); s.cmd_off = m->cmd_off.data();
   s.mbs = m->mbs.data(); s.force_unc = m->force_unc.data(); s.counters = m->counters.data();
   s.hist_scratch = m->hist.data();
@@ -168,8 +167,8 @@ static void sim_lz77_fixpoint(SimStream& m) {
   s.epoch = 0;
   for (;;) {
     br_chain(s);
-    if (getenv("BR_SIM_TRACE")) { u32 h[6] = {0}; u32 first = nb; for (u32 k = 0; k < nb; ++k) { h[s.dirty[k]]++; if (s.dirty[k] && first == nb) first = k; }
-      fprintf(stderr, "epoch %u dirty %u first %u: never %u state %u dict %u window %u wrap %u | flipped bits %u\n", s.epoch, s.counters[0], first, h[1], h[2], h[3], h[4], h[5], s.epoch_changed[s.epoch]);
+    if (getenv("BR_SIM_TRACE")) { u32 h[6] = {0}; u32 first = nb; for (u32 k = 0; k < nb; ++k) { h[s.dirty[k] & 7]++; if (s.dirty[k] && first == nb) first = k; }
+      fprintf(stderr, "epoch %u dirty %u first %u: never %u state %u dict %u window %u wrap %u | flipped bits %u\n", s.epoch, s.counters[0], first, h[1], h[2], h[3], h[4], h[5], s.epoch_cum[s.epoch] - (s.epoch ? s.epoch_cum[s.epoch - 1] : 0));
 #ifdef BR_SIM_DEBUG
       fprintf(stderr, "   last commit: flips %llu successor steps %llu marks %llu overlap marks %llu cap hits %llu\n", (unsigned long long)br_sim_cnt[3],
               (unsigned long long)br_sim_cnt[4], (unsigned long long)br_sim_cnt[0], (unsigned long long)br_sim_cnt[1], (unsigned long long)br_sim_cnt[2]);
@@ -181,11 +180,12 @@ static void sim_lz77_fixpoint(SimStream& m) {
     sim_build_storedS(m);
     std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
     s.counters[4] = 0;
-    { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) br_walk_block(s, k); }
+    s.forced = s.epoch >= s.P.force_epoch;
+    { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) br_walk_block(s, k, s.forced && k == s.counters[6]); }
     m.block_runs += s.counters[4];
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
-    if (s.epoch >= BR_MAX_EPOCHS - 1) { fprintf(stderr, "sim: no fixpoint\n"); break; }
+    if (s.epoch + 2 >= s.P.max_epochs) { fprintf(stderr, "sim: no fixpoint\n"); break; }
   }
   if (getenv("BR_SIM_VERIFY")) {
     // Is the fixpoint self-consistent?  Re-walk every chunk from its final in-state against the final
@@ -194,7 +194,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
     std::vector<BrBlockOut> old(s.bout, s.bout + nb);
     s.counters[4] = 0;
-    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; br_walk_one(s, k, s.bin[k], o); }
+    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; br_walk_one(s, k, s.bin[k], o, k, sp0); }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 k = 0; k < nb; ++k) {
       br_commit_bits(s, k);
