@@ -1,20 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- encoder input MB/s of the Brotli hot path on B200 (BASELINE.json metric).
+"""bench.py -- encoder input MB/s of the Brotli hot path on B200 (BASELINE.json metric "q5/q9").
 
-A "step" = one pass of the hot path over one batch: at N GPUs every rank compresses its own
-100 000 000-byte enwik8-shaped synthetic text stream (configs[1] of BASELINE.json: quality 5,
-lgwin 22, one-shot, bit-exact to the reference).  Independent streams share nothing, so the
-path shards across GPUs without a data-path collective (weak scaling); the compressed shards are
-gathered to rank 0 over NCCL at the end of every step (variable-size gather).
+One JSON line.  The HEADLINE keys (value / e2e / roofline / cpu_baseline) are BASELINE.json configs[1]:
+every rank compresses its own 100 000 000-byte enwik8-shaped text stream at quality 5, lgwin 22
+(independent streams shard without a data-path collective: weak scaling; the compressed shards are
+gathered to rank 0 over NCCL inside every step).  "sub_results" carries the other configs of the
+metric, each with its own value / e2e / roofline / cpu_baseline / bit_exact:
 
-  value : whole-job input MB/s with the input already resident in HBM (BrotliB200CompressDevice)
-  e2e   : same metric through the reference-facing C ABI call BrotliEncoderCompress with pinned
-          HOST buffers: H2D of the input and D2H of the compressed bytes inside the timed region
-  --impl reference : the reference's own CPU encoder (oracle/_ref, built from /root/reference by
-          oracle/Makefile; falls back to the oracle port) timed on the host cores for the same config
+  c4  200 MB Silesia-shaped binary mix, QUALITY 9, lgwin 24 -- the q9 half of the metric (one stream per
+      GPU; a single stream does not shard: replicas at N > 1)
+  c3  1 GiB synthetic web mix, quality 5, lgwin 22, cut into N shards: rank i compresses bytes
+      [i * 2^30 / N, (i + 1) * 2^30 / N) as its own stream (strong scaling)
+  c5  10 000 x 64 KiB independent streams (slices of the c3 mix), quality 1, lgwin 22, stream j on
+      GPU j mod N (strong scaling), one device batch per rank
+
+Per config:  value = whole-job input MB/s, inputs resident in HBM, shards gathered to rank 0 in the step;
+e2e = the same from HOST buffers: H2D of the inputs and D2H of the compressed bytes inside the timed region
+(N = 1: through the reference-facing C ABI call BrotliEncoderCompress / BrotliB200CompressBatch with pinned
+buffers, and again with pageable ones = "e2e_pageable"; N > 1: pinned H2D, device call, NCCL gather to rank 0,
+D2H of all shards on rank 0).  Parity ("bit_exact") is checked outside the timed region against the unmodified
+reference (oracle/_ref) run on the box's CPU on the same bytes, by every rank for its own shard.
+
+  --impl reference : the reference's own CPU encoder (oracle/_ref; falls back to the oracle port) timed on
+                     the host cores on the same configs; rank 0 only.
+  --configs c2,c4  : subset (the headline c2 always runs).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -26,9 +39,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-QUALITY, LGWIN = 5, 22
-WORKLOAD_BYTES = 100_000_000
-WORKLOAD = "100 MB enwik8-shaped synthetic text (tests/corpus.py synth_text, seed 20250922+rank), quality 5, lgwin 22, one stream per GPU"
+C2_BYTES, C3_BYTES, C4_BYTES = 100_000_000, 1 << 30, 200_000_000
+C5_COUNT, C5_SIZE = 10_000, 65536
+WORKLOADS = {
+    "c2": "100 MB enwik8-shaped synthetic text (tests/corpus.py synth_text, seed 20250922+rank), quality 5, lgwin 22, one stream per GPU",
+    "c3": "1 GiB synthetic web mix (synth_web, seed 20250923) cut into N shards of 2^30/N bytes, quality 5, lgwin 22, shard i on GPU i",
+    "c4": "200 MB Silesia-shaped binary mix (synth_binary, seed 20250924), quality 9, lgwin 24, one stream per GPU (replicas at N > 1)",
+    "c5": "10 000 x 64 KiB streams (slices of the c3 mix at offsets i*104729 mod (2^30-65536)), quality 1, lgwin 22, stream j on GPU j mod N",
+}
+QL = {"c2": (5, 22), "c3": (5, 22), "c4": (9, 24), "c5": (1, 22)}
+METRIC = "encoder input MB/s (bit-exact)"
 
 
 def log(*a):
@@ -68,68 +88,124 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_input(rank, nbytes=WORKLOAD_BYTES):
-    from corpus import synth_text
+# ------------------------------------------------------------------------------------------ inputs
+_WEB = None
+
+
+def web_mix():
+    global _WEB
+    if _WEB is None:
+        from corpus import synth_web
+        t = time.time()
+        _WEB = synth_web(C3_BYTES)
+        log("generated the %d-byte web mix in %.1fs" % (len(_WEB), time.time() - t))
+    return _WEB
+
+
+def c5_offsets():
+    return [(i * 104729) % (C3_BYTES - C5_SIZE) for i in range(C5_COUNT)]
+
+
+def make_stream_input(cfg, rank, world):
+    from brotli_b200.shard import shard_range
+    from corpus import synth_binary, synth_text
     t = time.time()
-    d = synth_text(nbytes, seed=20250922 + rank)
-    log("rank %d: generated %d bytes in %.1fs" % (rank, len(d), time.time() - t))
+    if cfg == "c2":
+        d = synth_text(C2_BYTES, seed=20250922 + rank)
+    elif cfg == "c4":
+        d = synth_binary(C4_BYTES)
+    else:
+        lo, hi = shard_range(C3_BYTES, rank, world)
+        d = web_mix()[lo:hi]
+    log("rank %d: %s input %d bytes ready in %.1fs" % (rank, cfg, len(d), time.time() - t))
     return d
 
 
 def ref_lib():
-    """The reference CPU encoder for the baseline arm: oracle/_ref if it was built, else the port."""
+    """The reference CPU encoder: oracle/_ref if it was built (kind "reference"), else the oracle port."""
     from brotli_libs import REF_SO, Oracle, Ref
     if os.path.exists(REF_SO):
         return "reference", Ref()
     return "port", Oracle()
 
 
-def cpu_time_one(lib, data):
-    t = time.time()
-    out = lib.compress(data, QUALITY, LGWIN)
-    return time.time() - t, len(out)
+def run_threads(n, fn):
+    th = [threading.Thread(target=fn, args=(i,)) for i in range(n)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
 
 
-def run_reference(args, rank, world):
+# ------------------------------------------------------------------------------------------ reference arm
+def reference_config(cfg, lib, n_gpus, steps, warmup):
+    """Times the reference on the host cores for one config; returns (value MB/s, ms_per_step, cores, sample)."""
+    q, w = QL[cfg]
+    ncpu = os.cpu_count() or 1
+    if cfg in ("c2", "c4"):
+        # one stream cannot use more than one core (single-threaded per BrotliEncoderState); N replicas -> N cores
+        d0 = make_stream_input(cfg, 0, 1)
+        datas = [d0] * n_gpus
+        cores = min(n_gpus, ncpu)
+        units = len(d0) * n_gpus
+        sample = "the whole %d-byte stream per step, %d stream(s) on %d core(s)" % (len(d0), n_gpus, cores)
+        def step():
+            run_threads(n_gpus, lambda i: lib.compress(datas[i], q, w))
+    elif cfg == "c3":
+        from brotli_b200.shard import shard_range
+        web = web_mix()
+        shards = [web[slice(*shard_range(C3_BYTES, r, n_gpus))] for r in range(n_gpus)]
+        cores = min(n_gpus, ncpu)
+        units = C3_BYTES
+        sample = "the whole 1 GiB mix per step, %d shard(s) on %d core(s)" % (n_gpus, cores)
+        def step():
+            run_threads(n_gpus, lambda i: lib.compress(shards[i], q, w))
+    else:
+        web = web_mix()
+        streams = [web[o:o + C5_SIZE] for o in c5_offsets()]
+        cores = ncpu
+        units = C5_COUNT * C5_SIZE
+        sample = "all 10 000 streams per step, dealt over %d host threads (ctypes releases the GIL)" % cores
+        def step():
+            def work(k):
+                for i in range(k, C5_COUNT, cores):
+                    lib.compress(streams[i], q, w)
+            run_threads(cores, work)
+    for _ in range(warmup):
+        step()
+    t0 = time.time()
+    for _ in range(steps):
+        step()
+    dt = time.time() - t0
+    return units * steps / dt / 1e6, 1e3 * dt / steps, cores, sample
+
+
+def run_reference(args, rank):
     if rank != 0:
         return
     kind, lib = ref_lib()
-    data = make_input(0)
-    # one stream cannot use more than one core in the reference (single-threaded per state);
-    # with N > 1 shards the host runs one encoder per shard on separate cores.
-    n_streams = args.gpus
-    cores = min(n_streams, os.cpu_count() or 1)
-    datas = [data] if n_streams == 1 else [data] * n_streams   # same shape per shard; content reuse keeps setup short
-    def step():
-        if n_streams == 1:
-            return cpu_time_one(lib, datas[0])[0]
-        th, res = [], [0.0] * n_streams
-        t0 = time.time()
-        def work(i):
-            lib.compress(datas[i], QUALITY, LGWIN)
-        for i in range(n_streams):
-            x = threading.Thread(target=work, args=(i,)); x.start(); th.append(x)
-        for x in th:
-            x.join()
-        return time.time() - t0
-    for _ in range(args.warmup):
-        step()
-    times = [step() for _ in range(args.steps)]
-    total = sum(times)
-    value = n_streams * WORKLOAD_BYTES * args.steps / total / 1e6
-    line = {"impl": "reference", "metric": "encoder input MB/s (quality 5, lgwin 22, bit-exact)", "value": round(value, 2),
-            "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(1e3 * total / args.steps, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams": n_streams},
-            "cpu_baseline": {"value": round(value, 2), "unit": "MB/s", "cores": cores, "kind": kind,
-                             "sample": "the full %d-byte stream per step, %d stream(s) on %d core(s) (ctypes releases the GIL)" % (WORKLOAD_BYTES, n_streams, cores)},
-            "e2e": {"value": round(value, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    v, ms, cores, sample = reference_config("c2", lib, args.gpus, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": "MB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS["c2"], "quality": 5, "lgwin": 22},
+            "cpu_baseline": {"value": round(v, 2), "unit": "MB/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": round(v, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host_cores": os.cpu_count(), "sub_results": {}}
+    for cfg in args.configs:
+        if cfg == "c2":
+            continue
+        v, ms, cores, sample = reference_config(cfg, lib, args.gpus, 1, 0)
+        line["sub_results"][cfg] = {"workload": WORKLOADS[cfg], "quality": QL[cfg][0], "lgwin": QL[cfg][1],
+                                    "value": round(v, 2), "unit": "MB/s", "ms_per_step": round(ms, 2), "steps": 1,
+                                    "cpu_baseline": {"value": round(v, 2), "unit": "MB/s", "cores": cores, "kind": kind, "sample": sample},
+                                    "e2e": {"value": round(v, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of k_walk's first launch on this workload (profiles/r01l_summary.md)
-WALK_DRAM_GB = 30.61
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu captures
+# (profiles/): k_walk's first launch on c2, k_q1_parse on c5.  None where no capture of that config exists.
+TRAFFIC_GB = {"c2": 30.61, "c5": 114.0}
 
 
 _REAL_STDOUT = None
@@ -154,6 +230,254 @@ def _emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+# ------------------------------------------------------------------------------------------ GPU arm
+class Ctx(object):
+    pass
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        v = json.load(open(p)).get("hbm_gbs")
+        if v:
+            return float(v), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6550.0, "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def bench_stream(ctx, cfg, steps, warmup, extra_warm=True):
+    """One single-stream config (c2, c4, or this rank's c3 shard)."""
+    import torch
+    import torch.distributed as dist
+    import brotli_b200
+    from brotli_b200.shard import ShardGather
+    L, world, rank = ctx.L, ctx.world, ctx.rank
+    q, w = QL[cfg]
+    data = make_stream_input(cfg, rank, world)
+    n = len(data)
+    h_page = torch.frombuffer(bytearray(data), dtype=torch.uint8)          # pageable host copy
+    h_in = h_page.pin_memory()
+    d_in = h_in.cuda()
+    cap = L.BrotliEncoderMaxCompressedSize(n) + 64
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    gather = ShardGather(cap, "cuda") if world > 1 else None
+    h_all = torch.empty((world, gather.cap), dtype=torch.uint8).pin_memory() if (world > 1 and rank == 0) else None
+    res = {"sizes": None}
+
+    def step_device():
+        sz = C.c_size_t(cap)
+        assert L.BrotliB200CompressDevice(q, w, n, d_in.data_ptr(), C.byref(sz), d_out.data_ptr()), "BrotliB200CompressDevice failed"
+        if gather:
+            gather.gather(d_out, sz.value)
+        return sz.value
+
+    def step_e2e_c_abi(hin, hout):
+        sz = C.c_size_t(cap)
+        assert L.BrotliEncoderCompress(q, w, 0, n, hin.data_ptr(), C.byref(sz), hout.data_ptr()), "BrotliEncoderCompress failed"
+        return sz.value
+
+    def step_e2e_multi():
+        d_in.copy_(h_in, non_blocking=True)
+        sz = C.c_size_t(cap)
+        assert L.BrotliB200CompressDevice(q, w, n, d_in.data_ptr(), C.byref(sz), d_out.data_ptr())
+        parts = gather.gather(d_out, sz.value)
+        if rank == 0:
+            for r, p in enumerate(parts):
+                h_all[r, :p.numel()].copy_(p, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            res["sizes"] = list(gather.sizes)
+        return sz.value
+
+    for _ in range(warmup):
+        step_device()
+    dt, outs = ctx.timed(step_device, steps)
+    st = brotli_b200.last_stats()
+    out_size = outs[-1]
+    if world == 1:
+        if extra_warm:
+            step_e2e_c_abi(h_in, h_out)
+        dt_e2e, outs2 = ctx.timed(lambda: step_e2e_c_abi(h_in, h_out), steps)
+        h_pout = torch.zeros(cap, dtype=torch.uint8)
+        if extra_warm:
+            step_e2e_c_abi(h_page, h_pout)
+        dt_page, _ = ctx.timed(lambda: step_e2e_c_abi(h_page, h_pout), max(1, steps // 2))
+        dt_page *= steps / max(1, steps // 2)
+        got = bytes(h_out[:out_size].numpy().tobytes())
+        d2h = out_size
+    else:
+        if extra_warm:
+            step_e2e_multi()
+        dt_e2e, outs2 = ctx.timed(step_e2e_multi, steps)
+        dt_page = None
+        h_mine = torch.empty(out_size, dtype=torch.uint8)
+        h_mine.copy_(d_out[:out_size])
+        got = bytes(h_mine.numpy().tobytes())
+        d2h = sum(res["sizes"]) if rank == 0 else 0
+    assert outs2[-1] == out_size
+
+    # ---- parity of this very run against the reference, outside the timed region: every rank checks its own shard;
+    # rank 0 also checks that the gathered copies are the bytes the ranks produced
+    kind, lib = ref_lib()
+    t1 = time.time(); want = lib.compress(data, q, w); t_cpu = time.time() - t1
+    ok = (got == want)
+    if world > 1:
+        digs = [None] * world
+        dist.all_gather_object(digs, hashlib.sha256(got).hexdigest())
+        if rank == 0:
+            for r in range(world):
+                ok = ok and hashlib.sha256(bytes(h_all[r, :res["sizes"][r]].numpy().tobytes())).hexdigest() == digs[r]
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    total_in = ctx.sum_over_ranks(n)
+    total_out = ctx.sum_over_ranks(out_size)
+    walk_ms = st["ms_walk"]
+    r = {"workload": WORKLOADS[cfg], "quality": q, "lgwin": w, "steps": steps, "warmup": warmup,
+         "scaling": "strong" if cfg == "c3" else "weak",
+         "input_bytes": total_in, "compressed_bytes": total_out, "bit_exact": ok,
+         "value": round(total_in * steps / dt / 1e6, 2), "unit": "MB/s", "ms_per_step": round(1e3 * dt / steps, 2),
+         "e2e": {"value": round(total_in * steps / dt_e2e / 1e6, 2), "unit": "MB/s",
+                 "h2d_bytes_per_step": total_in, "d2h_bytes_per_step": d2h if world > 1 else out_size,
+                 "path": "BrotliEncoderCompress(host in, host out), pinned buffers" if world == 1 else
+                         "pinned H2D + BrotliB200CompressDevice + NCCL gather to rank 0 + D2H of all shards on rank 0"},
+         "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_index", "ms_lz77", "ms_entropy", "ms_assemble", "ms_walk", "ms_encode")},
+         "lz77": {"walk_launches": int(st["lz77_iterations"]), "chunk_walks": int(st["block_runs"]), "chunks": int(st["blocks"]),
+                  "metablocks": int(st["metablocks"])},
+         "gpu_launches": int(st["launches"]) * steps}
+    if dt_page is not None:
+        r["e2e_pageable"] = {"value": round(total_in * steps / dt_page / 1e6, 2), "unit": "MB/s",
+                             "path": "BrotliEncoderCompress with pageable (malloc) host buffers, as a drop-in caller passes them"}
+    # roofline of the dominant kernel, k_walk: algorithmic bytes (SURVEY.md 8d: 1 byte read + 1/ratio written per input
+    # byte) of the chunks its launches walked / their summed duration (CUDA events on the job's stream)
+    peak, src = hbm_peak()
+    if walk_ms > 0:
+        algo = st["walk_bytes"] * (1.0 + out_size / float(n))
+        ach = algo / (walk_ms / 1e3) / 1e9
+        r["roofline"] = {"bound": "hbm", "kernel": "k_walk", "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
+                         "frac": round(ach / peak, 6), "traffic": TRAFFIC_GB.get(cfg),
+                         "traffic_unit": "GB of DRAM read+write per launch (ncu --set full, profiles/)",
+                         "algorithmic_gb": round(algo / 1e9, 4), "kernel_ms": round(walk_ms, 2),
+                         "launches": int(st["walk_launches"]), "peak_source": src}
+    if world == 1:
+        r["cpu_baseline"] = {"value": round(n / t_cpu / 1e6, 2), "unit": "MB/s", "cores": 1, "kind": kind,
+                             "sample": "the whole %d-byte stream once, 1 thread (the reference encoder is single-threaded per stream)" % n}
+    del d_in, d_out, h_in, h_out
+    torch.cuda.empty_cache()
+    return r
+
+
+def bench_c5(ctx, steps, warmup):
+    """10 000 x 64 KiB at quality 1: stream j on GPU j mod N, one device batch per rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import brotli_b200
+    from brotli_b200.shard import ShardGather, streams_of_rank
+    L, world, rank = ctx.L, ctx.world, ctx.rank
+    q, w = QL["c5"]
+    web = web_mix()
+    offs = c5_offsets()
+    mine = streams_of_rank(C5_COUNT, rank, world)
+    cnt = len(mine)
+    packed = np.empty(cnt * C5_SIZE, np.uint8)
+    for k, j in enumerate(mine):
+        packed[k * C5_SIZE:(k + 1) * C5_SIZE] = np.frombuffer(web, np.uint8, C5_SIZE, offs[j])
+    h_in = torch.from_numpy(packed).pin_memory()
+    d_in = h_in.cuda()
+    nbytes = cnt * C5_SIZE
+    cap = nbytes + 64 * cnt + 4096
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    in_off = (C.c_uint64 * cnt)(*[k * C5_SIZE for k in range(cnt)])
+    in_sz = (C.c_size_t * cnt)(*([C5_SIZE] * cnt))
+    out_off = (C.c_uint64 * (cnt + 1))()
+    out_sz = (C.c_size_t * cnt)()
+    gather = ShardGather(cap, "cuda") if world > 1 else None
+    h_all = torch.empty((world, gather.cap if gather else cap), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    kern_ms = [0.0]
+    res = {}
+
+    def step_device():
+        good = L.BrotliB200CompressBatchDevice(q, w, cnt, d_in.data_ptr(), in_off, in_sz, d_out.data_ptr(), cap, out_off, out_sz)
+        assert good == cnt, "BrotliB200CompressBatchDevice: %d of %d" % (good, cnt)
+        dense = int(out_off[cnt])
+        if gather:
+            gather.gather(d_out, dense)
+        return dense
+
+    def step_e2e():
+        d_in.copy_(h_in, non_blocking=True)
+        dense = step_device_nogather()
+        if gather:
+            parts = gather.gather(d_out, dense)
+        else:
+            parts = [d_out[:dense]]
+        if rank == 0:
+            for r, p in enumerate(parts):
+                h_all[r, :p.numel()].copy_(p, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            res["sizes"] = [int(p.numel()) for p in parts]
+        return dense
+
+    def step_device_nogather():
+        good = L.BrotliB200CompressBatchDevice(q, w, cnt, d_in.data_ptr(), in_off, in_sz, d_out.data_ptr(), cap, out_off, out_sz)
+        assert good == cnt
+        return int(out_off[cnt])
+
+    for _ in range(warmup):
+        step_device()
+    dt, outs = ctx.timed(step_device, steps)
+    st = brotli_b200.last_stats_q1()
+    dense = outs[-1]
+    step_e2e()
+    dt_e2e, _ = ctx.timed(step_e2e, steps)
+    out_total = sum(int(out_sz[k]) for k in range(cnt))
+    # the reference-facing host batch call (pageable per-stream buffers, as a caller passes them)
+    streams = [web[offs[j]:offs[j] + C5_SIZE] for j in mine]
+    t0 = time.time(); got = brotli_b200.compress_batch(streams, q, w, threads=16); t_host_call = time.time() - t0
+    # parity: every stream of this rank against the reference; rank 0's device copy against the host-call bytes
+    kind, lib = ref_lib()
+    ncpu = max(1, (os.cpu_count() or 1) // world)
+    want = [None] * cnt
+    t1 = time.time()
+    def work(k):
+        for i in range(k, cnt, ncpu):
+            want[i] = lib.compress(streams[i], q, w)
+    run_threads(ncpu, work)
+    t_cpu_all = time.time() - t1
+    ok = all(a == b for a, b in zip(got, want))
+    h_dense = torch.empty(dense, dtype=torch.uint8); h_dense.copy_(d_out[:dense])
+    hd = h_dense.numpy()
+    ok = ok and all(bytes(hd[int(out_off[k]):int(out_off[k]) + int(out_sz[k])].tobytes()) == want[k] for k in range(cnt))
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    total_in = ctx.sum_over_ranks(nbytes)
+    total_out = ctx.sum_over_ranks(out_total)
+    peak, src = hbm_peak()
+    parse_ms = st["ms_parse"]
+    algo = nbytes + out_total
+    ach = algo / (parse_ms / 1e3) / 1e9 if parse_ms > 0 else 0.0
+    r = {"workload": WORKLOADS["c5"], "quality": q, "lgwin": w, "steps": steps, "warmup": warmup, "scaling": "strong",
+         "streams": C5_COUNT, "input_bytes": total_in, "compressed_bytes": total_out, "bit_exact": ok,
+         "value": round(total_in * steps / dt / 1e6, 2), "unit": "MB/s", "ms_per_step": round(1e3 * dt / steps, 2),
+         "e2e": {"value": round(total_in * steps / dt_e2e / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": total_in,
+                 "d2h_bytes_per_step": sum(res["sizes"]) if rank == 0 else 0,
+                 "path": "pinned H2D of the packed streams + BrotliB200CompressBatchDevice + NCCL gather to rank 0 + D2H on rank 0"},
+         "e2e_pageable": {"value": round(nbytes * world / t_host_call / 1e6, 2), "unit": "MB/s",
+                          "path": "BrotliB200CompressBatch(host pointer arrays, pageable per-stream buffers) incl. ctypes marshalling, one call per rank"},
+         "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_h2d", "ms_parse", "ms_code", "ms_pack", "ms_d2h")},
+         "roofline": {"bound": "hbm", "kernel": "k_q1_parse", "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
+                      "frac": round(ach / peak, 6), "traffic": TRAFFIC_GB.get("c5") if world == 1 else None,
+                      "traffic_unit": "GB of DRAM read+write per launch (ncu --set full, profiles/)",
+                      "algorithmic_gb": round(algo / 1e9, 4), "kernel_ms": round(parse_ms, 2), "launches": 1, "peak_source": src},
+         "gpu_launches": int(st["launches"]) * steps}
+    if world == 1:
+        r["cpu_baseline"] = {"value": round(nbytes / t_cpu_all / 1e6, 2), "unit": "MB/s", "cores": ncpu, "kind": kind,
+                             "sample": "all 10 000 streams once, dealt over %d host threads" % ncpu}
+    return r
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -161,13 +485,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--bytes", type=int, default=WORKLOAD_BYTES, help=argparse.SUPPRESS)
+    ap.add_argument("--configs", default="c2,c4,c3,c5")
     args = ap.parse_args()
+    args.configs = [c for c in args.configs.split(",") if c in WORKLOADS]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
@@ -178,43 +503,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    L = brotli_b200.lib()
-    data = make_input(rank, args.bytes)
-    n = len(data)
-    h_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
-    d_in = h_in.cuda()
-    cap = L.BrotliEncoderMaxCompressedSize(n) + 64
-    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
-
-    def gather_to_rank0(nbytes):
-        """variable-size gather of the compressed shards (NCCL): sizes, then payloads."""
-        if world == 1:
-            return
-        sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
-        mine = torch.tensor([nbytes], dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(sizes, mine)
-        if rank == 0:
-            sz = sizes.tolist()
-            bufs = [torch.empty(int(s), dtype=torch.uint8, device="cuda") for s in sz]
-            reqs = [dist.irecv(bufs[r], src=r) for r in range(1, world)]
-            for q in reqs:
-                q.wait()
-        else:
-            dist.send(d_out[:nbytes], dst=0)
-
-    def step_device():
-        sz = C.c_size_t(cap)
-        ok = L.BrotliB200CompressDevice(QUALITY, LGWIN, n, d_in.data_ptr(), C.byref(sz), d_out.data_ptr())
-        assert ok, "BrotliB200CompressDevice failed"
-        gather_to_rank0(sz.value)
-        return sz.value
-
-    def step_e2e():
-        sz = C.c_size_t(cap)
-        ok = L.BrotliEncoderCompress(QUALITY, LGWIN, 0, n, h_in.data_ptr(), C.byref(sz), h_out.data_ptr())
-        assert ok, "BrotliEncoderCompress failed"
-        return sz.value
+    ctx = Ctx()
+    ctx.L, ctx.rank, ctx.world = brotli_b200.lib(), rank, world
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,6 +513,7 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """barrier + synchronize on both sides; max over ranks."""
         barrier()
         t0 = time.perf_counter()
         outs = [fn() for _ in range(steps)]
@@ -234,67 +525,42 @@ def main():
             dt = float(t.item())
         return dt, outs
 
-    for _ in range(args.warmup):
-        out_size = step_device()
+    def sum_over_ranks(v):
+        if world == 1:
+            return int(v)
+        t = torch.tensor([int(v)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
+    ctx.timed, ctx.sum_over_ranks = timed, sum_over_ranks
     sampler = ClockSampler(local_rank)
     sampler.start()
-    dt, outs = timed(step_device, args.steps)
-    st = brotli_b200.last_stats()
+    head = bench_stream(ctx, "c2", args.steps, args.warmup)
     sampler.stop_flag = True
-    out_size = outs[-1]
-    step_e2e()
-    dt_e2e, outs2 = timed(step_e2e, args.steps)
-    assert outs2[-1] == out_size
-
-    # parity of this very run against the reference, outside the timed region (rank 0)
-    parity = None
-    cpu = None
+    sub = {}
+    for cfg in args.configs:
+        t0 = time.time()
+        if cfg == "c4":
+            sub[cfg] = bench_stream(ctx, "c4", 1, 1, extra_warm=False)
+        elif cfg == "c3":
+            sub[cfg] = bench_stream(ctx, "c3", 3, 1, extra_warm=False)
+        elif cfg == "c5":
+            sub[cfg] = bench_c5(ctx, 5, 2)
+        if cfg in sub:
+            log("rank %d: %s done in %.1fs" % (rank, cfg, time.time() - t0))
     if rank == 0:
-        kind, lib = ref_lib()
-        t_cpu, ref_size = cpu_time_one(lib, data)
-        want = lib.compress(data, QUALITY, LGWIN) if False else None
-        got = bytes(h_out[:out_size].numpy().tobytes())
-        t1 = time.time(); want = lib.compress(data, QUALITY, LGWIN); t_cpu2 = time.time() - t1
-        parity = (got == want)
-        t_best = min(t_cpu, t_cpu2)
-        cpu = {"value": round(n / t_best / 1e6, 2), "unit": "MB/s", "cores": 1, "kind": kind,
-               "sample": "the whole %d-byte stream, best of 2 runs, 1 thread (the reference encoder is single-threaded per stream)" % n}
-
-    if rank == 0:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak = json.load(f).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        value = world * n * args.steps / dt / 1e6
-        e2e = world * n * args.steps / dt_e2e / 1e6
-        # dominant kernel of the step: bytes it must move / its duration
-        walk_ms, enc_ms = st["ms_walk"], st["ms_encode"]
-        if walk_ms >= enc_ms:
-            kname = "k_walk"
-            algo = st["walk_bytes"] + 16.0 * st["total_cmds"] * st["walk_launches"] / max(1.0, st["lz77_iterations"])
-            per_launch = algo / max(1.0, st["walk_launches"])
-            dur = walk_ms / max(1.0, st["walk_launches"]) / 1e3
-        else:
-            kname = "k_encode_mb"
-            per_launch = n + 16.0 * st["total_cmds"] + out_size
-            dur = enc_ms / 1e3
-        achieved = per_launch / dur / 1e9
-        line = {"metric": "encoder input MB/s (quality 5, lgwin 22, bit-exact)", "value": round(value, 2), "unit": "MB/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": round(1e3 * dt / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+        line = {"metric": METRIC, "value": head["value"], "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "input_bytes_per_gpu": n, "l2": "input (100 MB) and index (~3.5 GB) exceed the 126 MB L2",
-                           "bit_exact_vs_reference": parity, "compressed_bytes": out_size},
-                "clocks": sampler.summary(),
-                "e2e": {"value": round(e2e, 2), "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": out_size},
-                "gpu_launches": int(st["launches"]) * args.steps,
-                "roofline": {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
-                             "frac": round(achieved / peak, 6), "traffic": WALK_DRAM_GB if kname == "k_walk" else None,
-                             "traffic_unit": "GB of DRAM read+write per launch (ncu --set full, first = dominant k_walk launch of this workload, profiles/r01l_summary.md)",
-                             "algorithmic_gb_per_launch": round(per_launch / 1e9, 4),
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"},
-                "cpu_baseline": cpu,
-                "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_index", "ms_lz77", "ms_entropy", "ms_assemble", "ms_walk", "ms_encode")},
-                "lz77": {"iterations": int(st["lz77_iterations"]), "block_runs": int(st["block_runs"]), "blocks": int(st["blocks"]),
-                         "metablocks": int(st["metablocks"])}}
+                "config": {"workload": WORKLOADS["c2"], "quality": 5, "lgwin": 22, "input_bytes_per_gpu": C2_BYTES,
+                           "l2": "input (100 MB) and index (~3.5 GB) exceed the 126 MB L2",
+                           "bit_exact_vs_reference": head["bit_exact"], "compressed_bytes": head["compressed_bytes"]},
+                "clocks": sampler.summary(), "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+                "roofline": head.get("roofline"), "cpu_baseline": head.get("cpu_baseline"),
+                "stages_ms": head["stages_ms"], "lz77": head["lz77"], "host_cores": os.cpu_count(),
+                "sub_results": sub}
+        if "e2e_pageable" in head:
+            line["e2e_pageable"] = head["e2e_pageable"]
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -54,6 +54,9 @@ def lib():
         L.BrotliB200CompressBatch.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_int]
         L.BrotliB200CompressBatch.restype = C.c_size_t
+        L.BrotliB200CompressBatchDevice.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.BrotliB200CompressBatchDevice.restype = C.c_size_t
         L.BrotliB200LastStats.argtypes = [C.POINTER(C.c_double)]
         L.BrotliB200LastStatsQ1.argtypes = [C.POINTER(C.c_double)]
         L.BrotliB200Available.restype = C.c_int

@@ -151,7 +151,7 @@ int compress_host_q1(const Params& p0, const uint8_t* in, size_t n, const std::v
   const uint8_t* ins[1] = {in}; size_t in_n[1] = {n};
   const size_t* cl[1] = {calls ? calls->data() : nullptr}; size_t ncl[1] = {calls ? calls->size() : 0};
   uint8_t* outs[1] = {out_vec->data()}; size_t out_n[1] = {cap}; int ok[1] = {0};
-  if (!br_q1_compress_batch(tls.q1, p.lgwin, 1, ins, in_n, calls ? cl : nullptr, calls ? ncl : nullptr, 0, outs, out_n, ok, 1, with_header, end_op))
+  if (!br_q1_compress_batch(tls.q1, p.lgwin, 1, ins, in_n, calls ? cl : nullptr, calls ? ncl : nullptr, nullptr, outs, out_n, ok, 1, with_header, end_op))
     return 0;
   record_q1_stats();
   out_vec->resize(out_n[0]);
@@ -253,7 +253,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
     int w = lgwin < 10 ? 10 : lgwin;
     std::vector<int> ok(count, 0);
     std::vector<size_t> caps(encoded_sizes, encoded_sizes + count);
-    br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, 0, outputs, encoded_sizes, ok.data(), threads, 1, 2);
+    br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, nullptr, outputs, encoded_sizes, ok.data(), threads, 1, 2);
     record_q1_stats();
     size_t good = 0;
     for (size_t i = 0; i < count; ++i) {
@@ -288,6 +288,26 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
   size_t ok = 0;
   for (int t = 0; t < threads; ++t) { th[(size_t)t].join(); ok += okc[(size_t)t]; }
   return ok;
+}
+
+size_t BrotliB200CompressBatchDevice(int quality, int lgwin, size_t count, const void* d_inputs, const uint64_t* input_offsets,
+    const size_t* input_sizes, void* d_encoded, size_t encoded_capacity, uint64_t* encoded_offsets, size_t* encoded_sizes) {
+  Params p; p.quality = quality; p.lgwin = lgwin;
+  if (quality != 1 || !count || !supported(p) || !ensure_q1()) return 0;   /* quality 5..9: one stream per BrotliB200CompressDevice call */
+  for (size_t i = 0; i < count; ++i) if (input_sizes[i] == 0) return 0;
+  BrQ1Packed pk; pk.d_in = (const uint8_t*)d_inputs; pk.in_off = input_offsets; pk.d_out = (uint8_t*)d_encoded;
+  pk.out_cap = encoded_capacity; pk.out_off = encoded_offsets;
+  std::vector<int> ok(count, 0);
+  int w = lgwin < 10 ? 10 : lgwin > 24 ? 24 : lgwin;
+  if (!br_q1_compress_batch(tls.q1, w, count, nullptr, input_sizes, nullptr, nullptr, &pk, nullptr, encoded_sizes, ok.data(), 1, 1, 2)) return 0;
+  record_q1_stats();
+  size_t good = 0;
+  for (size_t i = 0; i < count; ++i) {
+    /* encode.c:1345: a stream above BrotliEncoderMaxCompressedSize is replaced by the raw stream in the one-shot
+       wrapper; that rewrite needs the host copy of the input, so such a stream is reported as failed here */
+    if (encoded_sizes[i] <= BrotliEncoderMaxCompressedSize(input_sizes[i])) ++good; else encoded_sizes[i] = 0;
+  }
+  return good;
 }
 
 BrotliEncoderState* BrotliEncoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque) {

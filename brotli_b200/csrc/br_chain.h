@@ -402,15 +402,14 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     // input: sparse-search phases, heavy buckets) re-walking all dirty chunks at once from the previous snapshot is
     // a Jacobi iteration whose settled front advances one chunk per launch; the sweep is the sequential parse of
     // the run, and all runs of the stream still advance in parallel.
-    if (dirty && prev_dirty && t_now >= s.P.sweep_epoch) defer = true;
+    const bool defer_sweep = dirty && prev_dirty && t_now >= s.P.sweep_epoch;
     prev_dirty = dirty != 0;
     s.bin[k] = ni;
-    s.dirty[k] = defer ? (BR_DEFER | dirty) : dirty;
+    s.dirty[k] = defer_sweep ? (BR_DEFER_SWEEP | dirty) : defer ? (BR_DEFER_STATE | dirty) : dirty;   // br_chain_d schedules
     s.cmd_off[k] = cmd_off;
     s.lil_in[k] = lil_true;
     s.block_mb[k] = W.mb;
     if (dirty) { br_atomic_add(s.counters + 0, 1); br_atomic_add(s.counters + 8 + (dirty < 6 ? dirty : 6), 1); }
-    if (dirty && !defer) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; br_atomic_min(s.counters + 6, k); }
     if (out.valid) {
       cmd_off += out.ncmd;
       if (!(dict_m < (dict_l >> 7))) { dict_l += edl; dict_m += edm; }
@@ -418,11 +417,29 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
   }
 }
 
+// Scheduling (thread per chunk, after br_chain_c has flagged every chunk): builds the list of walkers of the next launch.
+//   * VERIFY launch: in sweep mode, when far more chunks are dirty than the last launch walked, most of them were only
+//     marked by the conservative dependency rule of br_commit_bits (a flipped stored-bit marks every searched position of
+//     its bucket within the ring's reach, i.e. megabytes of input).  Sweeping them serially run by run would cost a full
+//     serial launch for chunks that come out unchanged; instead every dirty chunk is walked on its own, in parallel, from
+//     the snapshot: unchanged ones are clean afterwards, the others flip bits and are swept in the next launch.
+BR_DEV void br_chain_d(const BrStream& s, u32 k) {
+  u32 d = s.dirty[k];
+  if (!d) return;
+  const u32 t_now = s.epoch;
+  const bool sweep_mode = t_now >= s.P.sweep_epoch;
+  const bool verify = sweep_mode && s.counters[4] != 0 && s.counters[0] > 4u * s.counters[4] && s.counters[0] > 64u;
+  if (verify && (d & BR_DEFER_SWEEP)) d &= ~BR_DEFER_SWEEP;
+  s.dirty[k] = d;
+  if (!(d & BR_DEFER)) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; br_atomic_min(s.counters + 6, k); }
+}
+
 // sequential driver for the CPU sim / single-thread use
 BR_DEV void br_chain(const BrStream& s) {
   for (u32 bi = 0; bi < s.nblk; ++bi) br_chain_a(s, bi);
   br_chain_b(s);
   for (u32 bi = 0; bi < s.nblk; ++bi) br_chain_c(s, bi);
+  for (u32 k = 0; k < s.P.nblocks; ++k) br_chain_d(s, k);
 }
 
 // Gather one chunk's commands into the stream-wide compacted array, applying the

@@ -359,104 +359,6 @@ BR_DEV void br_store_mlen(u32 length, BrBitW& w) {
 // ------------------------------------------------------------------ greedy block splitter
 struct BrSplit { u32 num_types, num_blocks; u8* types; u32* lengths; };
 
-// metablock_inc.h:14 BlockSplitter and metablock.c:463 ContextBlockSplitter in one: every block
-// type owns num_contexts histograms.  The histogram being filled (`cur`) lives in shared
-// memory; finished block types live in `H` (global scratch).
-struct BrSplitter {
-  u32 alphabet, num_contexts, max_block_types, min_block_size;
-  double split_threshold;
-  u32 num_blocks;
-  BrSplit split;
-  u32* cur;            // [num_contexts][alphabet]   (shared memory)
-  u32* H;              // [max_types * num_contexts][alphabet]
-  u32 target_block_size, block_size, last_ix[2];
-  double last_entropy[2 * 13];
-  u32 merge_last_count;
-  u32* combined;       // [2 * num_contexts][alphabet]
-  double* ent;         // scratch [3 * num_contexts]
-};
-
-BR_DEV void br_splitter_init(BrSplitter& s, u32 alphabet, u32 num_contexts, u32 min_block_size,
-                             double thr, u8* types, u32* lengths, u32* cur, u32* H, u32* combined, double* ent) {
-  s.alphabet = alphabet; s.num_contexts = num_contexts; s.max_block_types = 256 / num_contexts;
-  s.min_block_size = min_block_size; s.split_threshold = thr; s.num_blocks = 0;
-  s.split.types = types; s.split.lengths = lengths; s.split.num_types = 0; s.split.num_blocks = 0;
-  s.target_block_size = min_block_size; s.block_size = 0;
-  s.last_ix[0] = s.last_ix[1] = 0; s.merge_last_count = 0;
-  s.cur = cur; s.H = H; s.combined = combined; s.ent = ent;
-  for (u32 i = (u32)br_lane(); i < num_contexts * alphabet; i += BR_WARP) cur[i] = 0;
-  br_syncwarp();
-}
-// metablock_inc.h:86 BlockSplitterFinishBlock / metablock.c:524 ContextBlockSplitterFinishBlock
-BR_DEV void br_splitter_finish_block(const BrStream& st, BrSplitter& s, int is_final) {
-  const u32 nc = s.num_contexts, A = s.alphabet, NA = nc * A;
-  double* last_entropy = s.last_entropy;
-  u32* H = s.H;
-  const int lane = br_lane();
-  br_syncwarp();
-  if (s.block_size < s.min_block_size) s.block_size = s.min_block_size;
-  if (s.num_blocks == 0) {
-    if (lane == 0) { s.split.lengths[0] = s.block_size; s.split.types[0] = 0; }
-    for (u32 t = (u32)lane; t < nc; t += BR_WARP) s.ent[t] = br_bits_entropy(st, s.cur + t * A, A);
-    br_syncwarp();
-    for (u32 i = 0; i < nc; ++i) { last_entropy[i] = s.ent[i]; last_entropy[nc + i] = last_entropy[i]; }
-    for (u32 x = (u32)lane; x < NA; x += BR_WARP) { H[x] = s.cur[x]; s.cur[x] = 0; }
-    ++s.num_blocks; ++s.split.num_types;
-    s.block_size = 0;
-  } else if (s.block_size > 0) {
-    for (u32 x = (u32)lane; x < 2 * NA; x += BR_WARP) {
-      u32 j = x / NA, r = x - j * NA;
-      s.combined[x] = s.cur[r] + H[s.last_ix[j] * A + r];
-    }
-    br_syncwarp();
-    // 3 * nc independent entropy sums, each strictly sequential inside
-    for (u32 t = (u32)lane; t < 3 * nc; t += BR_WARP) {
-      const u32* src = t < nc ? s.cur + t * A : s.combined + (t - nc) * A;
-      s.ent[t] = br_bits_entropy(st, src, A);
-    }
-    br_syncwarp();
-    double diff[2] = {0.0, 0.0};
-    for (u32 i = 0; i < nc; ++i)
-      for (u32 j = 0; j < 2; ++j) {
-        u32 jx = j * nc + i;
-        diff[j] = br_dadd(diff[j], br_dsub(br_dsub(s.ent[nc + jx], s.ent[i]), last_entropy[jx]));
-      }
-    if (s.split.num_types < s.max_block_types && diff[0] > s.split_threshold && diff[1] > s.split_threshold) {
-      if (lane == 0) { s.split.lengths[s.num_blocks] = s.block_size; s.split.types[s.num_blocks] = (u8)s.split.num_types; }
-      s.last_ix[1] = s.last_ix[0];
-      s.last_ix[0] = s.split.num_types * nc;
-      for (u32 i = 0; i < nc; ++i) { last_entropy[nc + i] = last_entropy[i]; last_entropy[i] = s.ent[i]; }
-      for (u32 x = (u32)lane; x < NA; x += BR_WARP) { H[s.last_ix[0] * A + x] = s.cur[x]; s.cur[x] = 0; }
-      ++s.num_blocks; ++s.split.num_types;
-      s.block_size = 0; s.merge_last_count = 0; s.target_block_size = s.min_block_size;
-    } else if (diff[1] < br_dsub(diff[0], 20.0)) {
-      if (lane == 0) { s.split.lengths[s.num_blocks] = s.block_size; s.split.types[s.num_blocks] = s.split.types[s.num_blocks - 2]; }
-      u32 t = s.last_ix[0]; s.last_ix[0] = s.last_ix[1]; s.last_ix[1] = t;
-      for (u32 x = (u32)lane; x < NA; x += BR_WARP) { H[s.last_ix[0] * A + x] = s.combined[NA + x]; s.cur[x] = 0; }
-      for (u32 i = 0; i < nc; ++i) { last_entropy[nc + i] = last_entropy[i]; last_entropy[i] = s.ent[2 * nc + i]; }
-      ++s.num_blocks;
-      s.block_size = 0; s.merge_last_count = 0; s.target_block_size = s.min_block_size;
-    } else {
-      if (lane == 0) s.split.lengths[s.num_blocks - 1] += s.block_size;
-      for (u32 x = (u32)lane; x < NA; x += BR_WARP) { H[s.last_ix[0] * A + x] = s.combined[x]; s.cur[x] = 0; }
-      for (u32 i = 0; i < nc; ++i) {
-        last_entropy[i] = s.ent[nc + i];
-        if (s.split.num_types == 1) last_entropy[nc + i] = last_entropy[i];
-      }
-      s.block_size = 0;
-      if (++s.merge_last_count > 1) s.target_block_size += s.min_block_size;
-    }
-  }
-  br_syncwarp();
-  if (is_final) s.split.num_blocks = s.num_blocks;
-}
-// one symbol (warp-uniform call)
-BR_DEV void br_splitter_add(const BrStream& st, BrSplitter& s, u32 symbol) {
-  if (br_lane() == 0) ++s.cur[symbol];
-  ++s.block_size;
-  if (s.block_size == s.target_block_size) br_splitter_finish_block(st, s, 0);
-}
-
 #define BR_CTX_UTF8(st, p1, p2) ((u32)(br_ldg((st).ctx_lut + 1024 + (p1)) | br_ldg((st).ctx_lut + 1280 + (p2))))
 
 BR_DEV u32 br_static_ctx_map(int which, u32 ctx) {
@@ -575,10 +477,6 @@ struct BrMbMem {
 };
 // variable part follows: literal split (types, lengths), command split, distance split
 BR_HD u32 br_align8(u32 x) { return (x + 7u) & ~7u; }
-BR_HD u32 br_mb_scratch_bytes(u32 nlit, u32 ncmd) {
-  u32 lb = nlit / 512 + 2, cb = ncmd / 1024 + 2, db = ncmd / 512 + 2;
-  return br_align8((u32)sizeof(BrMbMem)) + br_align8(lb) + lb * 4 + br_align8(cb) + cb * 4 + br_align8(db) + db * 4;
-}
 
 // brotli_bit_stream.c:879 BlockEncoder state (warp-uniform registers)
 struct BrBlockEnc {
@@ -628,23 +526,6 @@ BR_DEV void br_block_enc_init(BrBlockEnc& b, u32 hist_len, const BrSplit& s, BrB
   b.num_blocks = s.num_blocks; b.last_type = 1; b.second_last_type = 0; b.code = code;
   b.block_ix = 0; b.block_len = s.num_blocks == 0 ? 0 : s.lengths[0]; b.entropy_ix = 0;
   b.depths = 0; b.bits = 0;
-}
-// advance to the next block of the split if the current one is exhausted (StoreSymbol prologue)
-BR_DEV void br_block_enc_switch(BrBlockEnc& b, u32 ctx_shift, BrBitW& w) {
-  if (b.block_len == 0) {
-    u32 ix = ++b.block_ix;
-    u32 bl = b.lengths[ix], bt = b.types[ix];
-    b.block_len = bl;
-    b.entropy_ix = ctx_shift ? (bt << ctx_shift) : bt * b.hist_len;
-    br_store_block_switch(b, bl, bt, 0, w);
-  }
-}
-// brotli_bit_stream.c:879 StoreSymbol
-BR_DEV void br_store_symbol(BrBlockEnc& b, u32 symbol, BrBitW& w) {
-  br_block_enc_switch(b, 0, w);
-  --b.block_len;
-  u32 ix = b.entropy_ix + symbol;
-  br_put_bits(w, br_ldg(b.depths + ix), br_ldg(b.bits + ix));
 }
 // brotli_bit_stream.c:794 StoreTrivialContextMap (lane-0 section)
 BR_DEV void br_store_trivial_context_map(u32 num_types, u32 context_bits, BrMbScratch* sc, BrBitW& w) {
@@ -735,158 +616,4 @@ BR_DEV void br_encode_context_map(const u32* cmap, u32 cmap_size, u32 num_cluste
     }
     br_put_bits(w, 1, 1);
   BR_LANE0_END(w)
-}
-
-// Adds the literals [pos, pos + n) to the literal splitter, honouring block boundaries.
-BR_DEV void br_add_literal_run(const BrStream& st, BrSplitter& ls, int which, u32 pos, u32 n) {
-  const int lane = br_lane();
-  while (n) {
-    u32 take = br_min(n, ls.target_block_size - ls.block_size);
-    for (u32 base = 0; base < take; base += BR_WARP) {
-      u32 i = base + (u32)lane;
-      if (i < take) {
-        u32 p = pos + i;
-        u32 lit = st.data[p];
-        u32 c = 0;
-        if (which != 1) c = br_static_ctx_map(which, BR_CTX_UTF8(st, br_data_or_zero(st, p, 1), br_data_or_zero(st, p, 2)));
-        br_atomic_add(ls.cur + c * 256 + lit, 1);
-      }
-    }
-    ls.block_size += take; pos += take; n -= take;
-    if (ls.block_size == ls.target_block_size) br_splitter_finish_block(st, ls, 0);
-  }
-}
-
-// The whole compressed metablock.  `smem`: 4096 u32 of shared memory for the histograms
-// being filled.  Output bits go to `out` starting at bit 0; returns the number of bits.
-BR_DEV u32 br_encode_metablock(const BrStream& st, const BrMetaBlock& mb, const BrCmd* cmds_all,
-                               u8* scratch, u32* out, u32* smem) {
-  const int lane = br_lane();
-  BrMbMem* M = (BrMbMem*)scratch;
-  BrMbScratch* sc = &M->sc;
-  const BrCmd* cmds = cmds_all + mb.cmd_off;
-  const u32 ncmd = mb.ncmd, nlit = mb.nlit, length = mb.end - mb.start;
-  // variable part of the scratch
-  u32 lb = nlit / 512 + 2, cb = ncmd / 1024 + 2, db = ncmd / 512 + 2;
-  u8* vp = scratch + br_align8((u32)sizeof(BrMbMem));
-  u8* lit_types = vp; vp += br_align8(lb); u32* lit_lengths = (u32*)vp; vp += lb * 4;
-  u8* cmd_types = vp; vp += br_align8(cb); u32* cmd_lengths = (u32*)vp; vp += cb * 4;
-  u8* dist_types = vp; vp += br_align8(db); u32* dist_lengths = (u32*)vp;
-
-  const u32 nctx = br_decide_context_modeling(st, mb.start, length, sc->rle_syms);
-  const int which = (int)nctx;  // 1, 2, 3 or 13 selects the static map (br_static_ctx_map)
-
-  BrSplitter ls, cs, ds;
-  br_splitter_init(ls, 256, nctx, 512, 400.0, lit_types, lit_lengths, smem, M->lit_H, M->lit_comb, sc->ent);
-  br_splitter_init(cs, 704, 1, 1024, 500.0, cmd_types, cmd_lengths, smem + 13 * 256, M->cmd_H, M->cmd_comb, sc->ent);
-  br_splitter_init(ds, 64, 1, 512, 100.0, dist_types, dist_lengths, smem + 13 * 256 + 704, M->dist_H, M->dist_comb, sc->ent);
-  // ---- pass 1: histograms + greedy splits (metablock.c:771)
-  {
-    u32 pos = mb.start;
-    for (u32 i = 0; i < ncmd; ++i) {
-      const BrCmd c = cmds[i];
-      br_splitter_add(st, cs, c.cmd_prefix);
-      br_add_literal_run(st, ls, which, pos, c.insert_len);
-      pos += c.insert_len + br_cmd_copy_len(c);
-      if (br_cmd_copy_len(c) && c.cmd_prefix >= 128) br_splitter_add(st, ds, c.dist_prefix & 0x3FF);
-    }
-  }
-  br_splitter_finish_block(st, ls, 1);
-  br_splitter_finish_block(st, cs, 1);
-  br_splitter_finish_block(st, ds, 1);
-  const u32 n_lit_histo = ls.split.num_types * nctx, n_cmd_histo = cs.split.num_types, n_dist_histo = ds.split.num_types;
-  // metablock.c:677 MapStaticContexts
-  u32 cmap_size = 0;
-  if (nctx > 1) {
-    cmap_size = ls.split.num_types << 6;
-    for (u32 x = (u32)lane; x < cmap_size; x += BR_WARP)
-      M->cmap[x] = (x >> 6) * nctx + br_static_ctx_map(which, x & 63);
-  }
-  // metablock.c:841 BrotliOptimizeHistograms: independent per histogram -> one lane each
-  {
-    u32 total = n_lit_histo + n_cmd_histo + n_dist_histo;
-    for (u32 t = (u32)lane; t < total; t += BR_WARP) {
-      u8 good[704];
-      if (t < n_lit_histo) br_optimize_counts_for_rle(256, M->lit_H + t * 256, good);
-      else if (t < n_lit_histo + n_cmd_histo) br_optimize_counts_for_rle(704, M->cmd_H + (t - n_lit_histo) * 704, good);
-      else br_optimize_counts_for_rle(64, M->dist_H + (t - n_lit_histo - n_cmd_histo) * 64, good);
-    }
-  }
-  br_syncwarp();
-  // ---- header (brotli_bit_stream.c:120)
-  BrBitW w; w.out = out; w.ix = 0;
-  br_put_bits(w, 1, (u64)mb.is_last);
-  if (mb.is_last) br_put_bits(w, 1, 0);
-  br_store_mlen(length, w);
-  if (!mb.is_last) br_put_bits(w, 1, 0);
-  BrBlockEnc le, ce, de;
-  br_block_enc_init(le, 256, ls.split, &M->code[0]);
-  br_block_enc_init(ce, 704, cs.split, &M->code[1]);
-  br_block_enc_init(de, 64, ds.split, &M->code[2]);
-  br_build_and_store_block_split_code(le, sc, w);
-  br_build_and_store_block_split_code(ce, sc, w);
-  br_build_and_store_block_split_code(de, sc, w);
-  br_put_bits(w, 2, 0);  // NPOSTFIX
-  br_put_bits(w, 4, 0);  // NDIRECT >> NPOSTFIX
-  for (u32 i = 0; i < ls.split.num_types; ++i) br_put_bits(w, 2, 2);  // CONTEXT_UTF8
-  if (cmap_size == 0) br_store_trivial_context_map(n_lit_histo, 6, sc, w);
-  else br_encode_context_map(M->cmap, cmap_size, n_lit_histo, sc, w);
-  br_store_trivial_context_map(n_dist_histo, 2, sc, w);
-  // ---- prefix codes (block_encoder_inc.h:8)
-  BR_LANE0_BEGIN
-    for (u32 i = 0; i < n_lit_histo; ++i)
-      br_build_and_store_tree(M->lit_H + i * 256, 256, 256, sc, M->lit_depth + i * 256, M->lit_bits + i * 256, w);
-    for (u32 i = 0; i < n_cmd_histo; ++i)
-      br_build_and_store_tree(M->cmd_H + i * 704, 704, 704, sc, M->cmd_depth + i * 704, M->cmd_bits + i * 704, w);
-    for (u32 i = 0; i < n_dist_histo; ++i)
-      br_build_and_store_tree(M->dist_H + i * 64, 64, 64, sc, M->dist_depth + i * 64, M->dist_bits + i * 64, w);
-  BR_LANE0_END(w)
-#if BR_GPU
-  __threadfence_block();
-#endif
-  le.depths = M->lit_depth; le.bits = M->lit_bits;
-  ce.depths = M->cmd_depth; ce.bits = M->cmd_bits;
-  de.depths = M->dist_depth; de.bits = M->dist_bits;
-  // ---- pass 2: symbols (brotli_bit_stream.c:1062)
-  {
-    u32 pos = mb.start;
-    for (u32 i = 0; i < ncmd; ++i) {
-      const BrCmd c = cmds[i];
-      br_store_symbol(ce, c.cmd_prefix, w);
-      {  // brotli_bit_stream.c:82 StoreCommandExtra
-        u32 clc = br_cmd_copy_len_code(c);
-        u32 ic = br_ins_code(c.insert_len), cc = br_copy_code(clc);
-        u32 insn = br_ins_extra(ic);
-        u64 insv = c.insert_len - br_ins_base(ic), copyv = clc - br_copy_base(cc);
-        br_put_bits(w, insn + br_copy_extra(cc), (copyv << insn) | insv);
-      }
-      u32 n = c.insert_len;
-      while (n) {
-        br_block_enc_switch(le, cmap_size ? 6 : 0, w);
-        u32 take = br_min(n, le.block_len);
-        for (u32 base = 0; base < take; base += BR_WARP) {
-          u32 k = base + (u32)lane, nb = 0, bits = 0;
-          if (k < take) {
-            u32 p = pos + k, lit = st.data[p], hix;
-            if (cmap_size) {
-              u32 ctx = BR_CTX_UTF8(st, br_data_or_zero(st, p, 1), br_data_or_zero(st, p, 2));
-              hix = M->cmap[le.entropy_ix + ctx] * 256 + lit;
-            } else hix = le.entropy_ix + lit;
-            nb = M->lit_depth[hix]; bits = M->lit_bits[hix];
-          }
-          u32 tot, off = br_warp_excl_scan(nb, &tot);
-          if (nb) br_put_bits_at(w.out, w.ix + off, nb, bits);
-          w.ix += tot;
-        }
-        le.block_len -= take; pos += take; n -= take;
-      }
-      u32 cl = br_cmd_copy_len(c);
-      pos += cl;
-      if (cl && c.cmd_prefix >= 128) {
-        br_store_symbol(de, c.dist_prefix & 0x3FF, w);
-        br_put_bits(w, c.dist_prefix >> 10, c.dist_extra);
-      }
-    }
-  }
-  return w.ix;  // byte alignment of the last metablock happens at stream assembly
 }

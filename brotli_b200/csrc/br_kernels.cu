@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "br_params.h"
 #include "br_lz77.h"
@@ -169,14 +170,15 @@ __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restr
 }
 
 // ---------------------------------------------------------------------------- warp-task kernels
-#ifndef BR_WALK_MINB
-#define BR_WALK_MINB 8
-#endif
-__global__ void __launch_bounds__(128, BR_WALK_MINB) k_walk(BrStream s) {
+// G = bucket-ring rows fetched together (br_lz77.h): 1 for the 16/32-entry rings of quality 5-6 (throughput bound,
+// 8 CTAs per SM), 4 for the 64/128-entry rings of quality 7-8 and 8 (the whole 256-entry ring) at quality 9 (more
+// registers, fewer resident warps).
+template <int G>
+__global__ void __launch_bounds__(128, G == 1 ? 8 : G == 4 ? 5 : 4) k_walk(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.counters[5]) return;
   const u32 b = s.dirty_list[t];
-  br_walk_block(s, b, s.forced && b == s.counters[6]);
+  br_walk_block<G>(s, b, s.forced && b == s.counters[6]);
 }
 __global__ void k_commit(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -191,6 +193,10 @@ __global__ void __launch_bounds__(32) k_chain_b(BrStream s) { br_chain_b(s); }
 __global__ void k_chain_c(BrStream s) {
   u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
   if (bi < s.nblk) br_chain_c(s, bi);
+}
+__global__ void k_chain_d(BrStream s) {
+  u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < s.P.nblocks) br_chain_d(s, k);
 }
 __global__ void k_compact(BrStream s, BrCmd* cmds_all, const u32* __restrict__ block_mb) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -352,22 +358,30 @@ struct BrDeviceTables {
   u32 log2tab_n = 0;
 };
 static BrDeviceTables g_tables[16];
+static std::mutex g_tables_mu;
 
 extern "C" const unsigned char br_tables_blob[];
 extern "C" const unsigned int br_tables_blob_len;
 extern "C" const double* br_host_log2_table(u32* n);   // br_host.cc
 
+// Per-device constant tables, uploaded once.  Jobs of several host threads (BrotliB200CompressBatch) come here
+// concurrently: the init is serialised, the uploads are synchronous copies that have completed before `device` is
+// published, so kernels on any (non-blocking) stream launched afterwards see the finished tables.
 static BrDeviceTables* get_tables() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  std::lock_guard<std::mutex> lock(g_tables_mu);
   BrDeviceTables& t = g_tables[dev];
   if (t.device == dev) return &t;
-  if (cudaMalloc(&t.blob, br_tables_blob_len) != cudaSuccess) return nullptr;
-  cudaMemcpy(t.blob, br_tables_blob, br_tables_blob_len, cudaMemcpyHostToDevice);
+  u8* blob = nullptr; double* l2 = nullptr;
   u32 n = 0; const double* h = br_host_log2_table(&n);
-  if (cudaMalloc(&t.log2tab, (size_t)n * 8) != cudaSuccess) return nullptr;
-  cudaMemcpy(t.log2tab, h, (size_t)n * 8, cudaMemcpyHostToDevice);
-  t.log2tab_n = n;
+  if (cudaMalloc(&blob, br_tables_blob_len) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMalloc(&l2, (size_t)n * 8) != cudaSuccess) { cudaGetLastError(); cudaFree(blob); return nullptr; }
+  if (cudaMemcpy(blob, br_tables_blob, br_tables_blob_len, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(l2, h, (size_t)n * 8, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError(); cudaFree(blob); cudaFree(l2); return nullptr;
+  }
+  t.blob = blob; t.log2tab = l2; t.log2tab_n = n;
   t.device = dev;
   return &t;
 }
@@ -395,18 +409,22 @@ struct BrJob {
   cudaStream_t st = nullptr;
   BrArena arena, arena2;     // arena2: metablock scratch / bit buffers / output (sized after LZ77)
   u32* h_pinned = nullptr;    // small pinned readback area
+  cudaEvent_t ev[10] = {};    // stage timers, created once per job
   BrJobStats stats;
 };
 
+extern "C" void br_job_destroy(BrJob* j);
 extern "C" BrJob* br_job_create(void) {
   BrJob* j = new BrJob();
   if (cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking) != cudaSuccess) { delete j; return nullptr; }
   if (cudaMallocHost(&j->h_pinned, 4096) != cudaSuccess) { cudaStreamDestroy(j->st); delete j; return nullptr; }
+  for (auto& e : j->ev) if (cudaEventCreate(&e) != cudaSuccess) { br_job_destroy(j); return nullptr; }
   return j;
 }
 extern "C" void br_job_destroy(BrJob* j) {
   if (!j) return;
   j->arena.release(); j->arena2.release();
+  for (auto& e : j->ev) if (e) cudaEventDestroy(e);
   if (j->h_pinned) cudaFreeHost(j->h_pinned);
   if (j->st) cudaStreamDestroy(j->st);
   delete j;
@@ -456,8 +474,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   P.nblocks = nb;
   cudaStream_t st = job->st;
   memset(&job->stats, 0, sizeof(job->stats));
-  cudaEvent_t ev[10];
-  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEvent_t* ev = job->ev;
   cudaEventRecord(ev[0], st);
 
   const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
@@ -560,12 +577,16 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       k_chain_a<<<(nblk + 31) / 32, 32, 0, st>>>(s);
       k_chain_b<<<1, 32, 0, st>>>(s);
       k_chain_c<<<(nblk + 31) / 32, 32, 0, st>>>(s);
+      k_chain_d<<<(nb + 255) / 256, 256, 0, st>>>(s);
       CK(cudaMemcpyAsync(hp, counters, 128, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       u32 n_dirty = hp[0], n_sched = hp[5]; n_mbs = hp[1]; total_cmds = hp[2];
       job->stats.block_runs += hp[4];
-      if (trace) fprintf(stderr, "epoch %u: dirty %u sched %u ran %u | never %u state %u dict %u bits %u wrap %u\n", s.epoch, hp[0], hp[5], hp[4], hp[9], hp[10], hp[11], hp[12], hp[13]), fprintf(stderr, "   chain_b: phase0 %u kcyc, blocks %u kcyc, slow-dict blocks %u\n", hp[20], hp[21], hp[22]);
-      if (walk_pending) { float wms; cudaEventElapsedTime(&wms, ev[6], ev[7]); job->stats.ms_walk += wms; walk_pending = false; }
+      if (trace) fprintf(stderr, "epoch %u: dirty %u sched %u ran %u longest sweep %u | never %u state %u dict %u bits %u wrap %u\n", s.epoch, hp[0], hp[5], hp[4], hp[16], hp[9], hp[10], hp[11], hp[12], hp[13]);
+      if (walk_pending) {
+        float wms; cudaEventElapsedTime(&wms, ev[6], ev[7]); job->stats.ms_walk += wms; walk_pending = false;
+        if (trace) fprintf(stderr, "   walk launch %u: %.2f ms\n", s.epoch, wms);
+      }
       if (n_dirty == 0) break;
       if (s.epoch + 2 >= P.max_epochs) { fprintf(stderr, "brotli_b200: internal error: launch bound exceeded\n"); return 0; }
       ++s.epoch; ++job->stats.lz77_iterations;
@@ -573,10 +594,13 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       CK(cudaMemsetAsync(bits_cur, 0, 2 * (size_t)nwords * 4, st));
       CK(cudaMemsetAsync(srch_cur, 0, nwords * 4, st));
       CK(cudaMemsetAsync(counters + 4, 0, 4, st));
+      CK(cudaMemsetAsync(counters + 16, 0, 4, st));
       k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
       scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
       cudaEventRecord(ev[6], st);
-      k_walk<<<(n_sched + 3) / 4, 128, 0, st>>>(s);
+      if (P.block_bits >= 8) k_walk<8><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
+      else if (P.block_bits >= 6) k_walk<4><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
+      else k_walk<1><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
       cudaEventRecord(ev[7], st);
       walk_pending = true; ++job->stats.walk_launches; job->stats.launches += 6;
       job->stats.walk_bytes += (u64)n_sched * ch;
@@ -678,7 +702,6 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   cudaEventElapsedTime(&ms, ev[0], ev[4]); job->stats.ms_total = ms;
   cudaEventElapsedTime(&ms, ev[8], ev[9]); job->stats.ms_encode = ms;
   job->stats.total_cmds = total_cmds; job->stats.launches += 12;
-  for (auto& e : ev) cudaEventDestroy(e);
   job->stats.nblocks = nb; job->stats.n_metablocks = n_mbs; job->stats.rounds = (u32)rounds;
   job->stats.out_bytes = final_size; job->stats.in_bytes = n;
   *d_out = final_out; *out_size = final_size;

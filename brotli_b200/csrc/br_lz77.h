@@ -23,6 +23,12 @@
 #include "br_cmd.h"
 
 struct BrSR { u32 len, distance, score; int delta; };
+#ifdef BR_SIM_DEBUG
+static u64 br_sim_w[12];   // tests/sim: 0 searches, 1 ring rows, 2 heavy-path searches, 3 heavy own-scan rows, 4 countS calls, 5 own_set, 6 set_range, 7 dict searches, 8 ring groups, 9 candidates taken, 10 match_len beyond 16 bytes
+#define BR_W(i, n) (br_sim_w[i] += (n))
+#else
+#define BR_W(i, n)
+#endif
 
 #define BR_SCORE_BASE 1920u  /* hash.h:102: 30 * 8 * sizeof(size_t) */
 #define BR_MIN_SCORE (BR_SCORE_BASE + 100u)
@@ -54,6 +60,21 @@ BR_DEV u32 br_match_len_c(const u8* d, u32 a, u32 b, u32 limit, u64 c0, u64 c1) 
   return br_match_len(d, a, b, limit);
 }
 
+// Same, with the first 8 bytes at `a` (the candidate) already loaded as well.
+BR_DEV u32 br_match_len_d0(const u8* d, u32 a, u32 b, u32 limit, u64 c0, u64 c1, u64 a0) {
+  if (limit >= 8) {
+    u64 x = a0 ^ c0;
+    if (x) return (u32)(br_ctz64(x) >> 3);
+    if (limit >= 16) {
+      x = br_ld64u(d, a + 8) ^ c1;
+      if (x) return 8u + (u32)(br_ctz64(x) >> 3);
+      return 16u + br_match_len(d, a + 16, b + 16, limit - 16);
+    }
+    return 8u + br_match_len(d, a + 8, b + 8, limit - 8);
+  }
+  return br_match_len(d, a, b, limit);
+}
+
 // hash_longest_match64_inc.h:23 / hash_longest_match_inc.h:23 HashBytes
 BR_DEV u32 br_hash_key(const BrParams& P, const u8* d, u32 pos) {
   if (P.hash64) {
@@ -68,20 +89,6 @@ BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
   if (P.hash64) return (u32)((v * (0x1FE35A7BD3579BD3ull << 24)) >> (64 - 15));
   return ((u32)v * 0x1E35A7BDu) >> (32 - P.bucket_bits);
 }
-// (measured: no gain on B200 -- 63.6 vs 62.4 ms per 100 MB -- so it stays off; kept for the record)
-#ifndef BR_WALK_PREFETCH
-#define BR_WALK_PREFETCH 0
-#endif
-
-// (measured: 64.1 vs 62.5 ms per 100 MB with it, and the zero / heavy-bucket cases get several times slower: off)
-// (measured: 39.2 vs 39.0 ms of k_walk per 100 MB with it: no gain, off)
-#ifndef BR_WALK_PF2
-#define BR_WALK_PF2 0
-#endif
-#ifndef BR_WALK_SPECLEN
-#define BR_WALK_SPECLEN 0
-#endif
-
 struct BrWalk {
   const BrStream* s;
   const u8* d;
@@ -92,8 +99,8 @@ struct BrWalk {
   u32 min_wrap;
   u32 stale;       // the byte the reference finds just past the block end (see oracle)
   bool warming;    // warm-up (state refinement before the chunk proper): reads the snapshot, records nothing
-  u32* own;        // the bits_cur bitmap of this run (parity of the chunk index)
-  u32 pf_pos, pf_lo, pf_hi, pf_j;   // prefetched index entry (bucket bounds, rank) of position pf_pos
+  u32* own;        // the bits_cur bitmap of this run (parity of the sweep's head chunk)
+  bool fence_due;  // own bits were written since the last fence (see br_own_sync)
 };
 
 // Stored-bits of the walker's own range [p0, ...) live in bits_cur (global): written with
@@ -108,16 +115,27 @@ BR_DEV u32 br_ld_cur(const u32* p) {
 BR_DEV int br_own_get(const BrWalk& w, u32 q) {
   return (br_ld_cur(w.own + (q >> 5)) >> (q & 31)) & 1;
 }
-BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b);
+// Writers (lane 0, or one lane per word) and readers (any lane) of the own bits are different threads of the warp:
+// a fence + warp barrier must lie between a write and the next read.  The fence is not paid at the write -- it
+// would wait for the atomic's round trip to L2 on every search -- but right before the next read, several memory
+// round trips later, when the atomic has long been performed.
+BR_DEV void br_own_sync(BrWalk& w) {
+  if (w.fence_due) {
+#if BR_GPU
+    __threadfence_block();
+#endif
+    w.fence_due = false;
+    br_syncwarp();
+  }
+}
 BR_DEV void br_own_set(BrWalk& w, u32 q) {
+  BR_W(5, 1);
   if (w.warming) return;   // warm-up: the snapshot is read, nothing is recorded
   if (br_lane() == 0) br_atomic_or(w.own + (q >> 5), 1u << (q & 31));
-#if BR_GPU
-  __threadfence_block();   // the next search may consult this very bit (runs: cur and cur + 1 share a bucket)
-#endif
-  br_syncwarp();
+  w.fence_due = true;      // (runs: cur and cur + 1 share a bucket, so the next search may consult this very bit)
 }
 BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
+  BR_W(6, 1);
   if (a >= b) return;
   if (w.warming) return;
   u32 wa = a >> 5, wb = (b - 1) >> 5;
@@ -127,10 +145,7 @@ BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
     if (x == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
     br_atomic_or(w.own + x, m);
   }
-#if BR_GPU
-  __threadfence_block();
-#endif
-  br_syncwarp();
+  w.fence_due = true;
 }
 BR_DEV int br_is_stored(const BrWalk& w, u32 q) {
   if (q >= w.p0) return br_own_get(w, q);
@@ -138,6 +153,7 @@ BR_DEV int br_is_stored(const BrWalk& w, u32 q) {
 }
 // Number of stored positions (latest snapshot) among S[a .. b).
 BR_DEV u32 br_countS_upto(const BrStream& s, u32 x) {
+  BR_W(4, 1);
   u32 base = br_ldg(s.prefS + (x >> 10));
   u32 w0 = (x >> 10) << 5, w1 = x >> 5, acc = 0;
   for (u32 wi = w0 + (u32)br_lane(); wi < w1; wi += BR_WARP) acc += (u32)br_popc(br_ldg(s.storedS + wi));
@@ -170,6 +186,7 @@ BR_DEV int br_test_dict_item(const BrWalk& w, u32 len, u32 word_idx, u32 cur, u3
 // hash.h:179 SearchInStaticDictionary (warp-uniform)
 BR_DEV void br_search_static_dict(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, BrSR& out) {
   const BrStream& s = *w.s;
+  BR_W(7, 1);
   ++w.gate_checks;
   if (w.dict_m < (w.dict_l >> 7)) { ++w.gate_fail; return; }
   u32 key = ((br_ld32u(w.d, cur) * 0x1E35A7BDu) >> (32 - 14)) << 1;
@@ -191,6 +208,14 @@ BR_DEV void br_search_static_dict(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
 // best_len, or -- only when best_len already equals max_length -- when the byte just past the
 // block end compares equal (w.stale).  Candidates that pass it by coincidence with a shorter
 // length can never beat the running score, so they are dropped here without side effects.
+//
+// G = rows (32 candidates each) of the bucket's slice of S that are fetched TOGETHER.  A deep bucket ring
+// (quality 7-9: 64-256 entries) is several rows; fetching row by row puts three dependent memory round trips
+// (S row -> stored bits -> candidate bytes) on the search's critical path PER ROW.  With G > 1 the G rows are
+// loaded back to back, then their stored bits and the first 8 bytes of every candidate (speculatively, before the
+// stored bit is known), and only then the rows are folded in order: three round trips per G rows.  This is what a
+// latency-bound walker (a sweep, br_walk_block) needs; the fold itself is unchanged.
+template <int G>
 BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_backward,
                                   u32 dict_distance, BrSR& out) {
   const BrStream& s = *w.s;
@@ -202,23 +227,50 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   const u32 min_score = out.score;
   u32 best_score = out.score, best_len = out.len;
   out.len = 0; out.delta = 0;
+  BR_W(0, 1);
   bool brk = false;
   // the bytes at the search position, shared by every candidate comparison below
   const u64 c0 = br_ld64u(d, cur), c1 = br_ld64u(d, cur + 8);
+  // Load order = latency plan.  (1) the index entry of `cur` (bucket bounds, rank) and the first bytes of the
+  // distance-cache candidates are requested together; (2) the first G rows of the bucket's slice of S go out as soon
+  // as the rank is there, and the distance-cache fold runs while they are in flight; (3) stored bits + candidate
+  // bytes; (4) fold.  Three dependent round trips per search instead of one per step.
+  const u32 key = br_hash_key_v(P, c0);
+  const u32 lo = br_ldg(s.seg + key), hi = br_ldg(s.seg + key + 1);
+  const u32 j = br_ldg(s.rank + cur);
   // ---- distance cache probes: lane k owns candidate k (hash.h:80 PrepareDistanceCache layout)
-  for (int base = 0; base < P.ndist && !brk; base += BR_WARP) {
-    const int k = base + lane;
+  constexpr int ND = (16 + BR_WARP - 1) / BR_WARP;
+  u32 dback[ND]; u64 da0[ND]; bool dvalid[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    const int k = i * BR_WARP + lane;
     int back_i = 0;
     if (k < 4) back_i = k == 0 ? w.dc[0] : k == 1 ? w.dc[1] : k == 2 ? w.dc[2] : w.dc[3];
     else if (k < 16) {   // dc[4..15] = last -1, +1, -2, +2, -3, +3; second last likewise (hash.h:83-97)
       int mag = (int)((0xE79u >> (2 * ((k - 4) >> 1))) & 3u);
       back_i = (k < 10 ? w.dc[0] : w.dc[1]) + ((k & 1) ? mag : -mag);
     }
-    const bool valid = (k < P.ndist) && back_i > 0 && (u32)back_i <= max_backward;
-    const u32 back = (u32)back_i;
+    dvalid[i] = (k < P.ndist) && back_i > 0 && (u32)back_i <= max_backward;
+    dback[i] = (u32)back_i;
+    da0[i] = dvalid[i] ? br_ld64u(d, cur - (u32)back_i) : 0;
+  }
+  // first G rows of the bucket ring (consumed by the loop further down)
+  u32 q[G]; bool has[G];
+#pragma unroll
+  for (int r = 0; r < G; ++r) {
+    const u32 jr = j > (u32)(r * BR_WARP) ? j - (u32)(r * BR_WARP) : 0u;
+    has[r] = jr >= lo + 1 + (u32)lane;
+    q[r] = has[r] ? br_ldg(s.S + (jr - 1 - (u32)lane)) : 0;
+  }
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    if (i * BR_WARP >= P.ndist || brk) break;
+    const int k = i * BR_WARP + lane;
+    const bool valid = dvalid[i];
+    const u32 back = dback[i];
     u32 len = 0; int eqmax = 0;
     if (valid) {
-      len = br_match_len_c(d, cur - back, cur, max_length, c0, c1);
+      len = br_match_len_d0(d, cur - back, cur, max_length, c0, c1, da0[i]);
       if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + (cur - back) + max_length));
     }
     u32 score = 135u * len + BR_SCORE_BASE + 15u;
@@ -244,43 +296,16 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   if (best_len < 3) best_len = 3;
   // ---- bucket ring
   {
-    // Index entry of `cur`: bucket bounds and the position's rank.  Most searches follow each
-    // other at consecutive positions, so the entry of cur + 1 is requested now and consumed by the
-    // next call: its latency hides behind this search's gather chain.
-    u32 lo, hi, j;
-#if BR_WALK_PREFETCH
-    if (w.pf_pos == cur) { lo = w.pf_lo; hi = w.pf_hi; j = w.pf_j; }
-    else
-#endif
-    {
-      const u32 key = br_hash_key_v(P, c0);
-      lo = br_ldg(s.seg + key); hi = br_ldg(s.seg + key + 1);
-      j = br_ldg(s.rank + cur);
-    }
-#if BR_WALK_PF2
-    {
-      // The next search is almost always at cur + 1 (a literal step or the lazy re-search).  Its slice
-      // of S[] sits at a bucket-dependent place of a 4n-byte array, i.e. in HBM: pull it into L2 now.
-      // A hint only -- no value is consumed, so it cannot change the parse.
-      const u32 j1 = br_ldg(s.rank + cur + 1);
-      br_prefetch_l2(s.S + (j1 > (u32)lane ? j1 - 1u - (u32)lane : 0u));
-    }
-#endif
-#if BR_WALK_PREFETCH
-    {
-      const u32 k1 = br_hash_key_v(P, (c0 >> 8) | (c1 << 56));
-      w.pf_lo = br_ldg(s.seg + k1); w.pf_hi = br_ldg(s.seg + k1 + 1);
-      w.pf_j = br_ldg(s.rank + cur + 1);
-      w.pf_pos = cur + 1;
-    }
-#endif
     const u32 block_size = 1u << P.block_bits;
     u32 V = block_size;
     if (hi - lo >= P.heavy_min) {
       // The reference's per-bucket counter is a uint16 (hash_longest_match64_inc.h:52): after
       // 65536 insertions it wraps and the ring looks empty again.  c = insertions so far.
       u32 own_cnt = 0, jj = j, n_own = 0;
+      BR_W(2, 1);
+      br_own_sync(w);
       while (jj > lo) {
+        BR_W(3, 1);
         u32 idx = jj - 1 - (u32)lane;
         bool has = (jj >= lo + 1 + (u32)lane);
         u32 q = has ? br_ldg(s.S + idx) : 0;
@@ -303,57 +328,69 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
     }
     u32 collected = 0, jj = j;
     bool done = false;
+    br_own_sync(w);
     while (!done && collected < V && jj > lo) {
-      u32 idx = jj - 1 - (u32)lane;
-      bool has = (jj >= lo + 1 + (u32)lane);
-      u32 q = has ? br_ldg(s.S + idx) : 0;
-      u32 backward = cur - q;
-      bool inwin = has && backward <= max_backward;
-#if BR_WALK_SPECLEN
-      // The candidate's bytes are requested before its stored-bit is known (almost every position
-      // in the window is stored): one memory round trip less on the search's dependent chain.
-      u32 len_spec = 0; int eq_spec = 0;
-      if (inwin) {
-        len_spec = br_match_len_c(d, q, cur, max_length, c0, c1);
-        if (len_spec < 4) len_spec = 0;
-        if (len_spec == max_length) eq_spec = (w.stale == (u32)br_ldg(d + q + max_length));
+      u64 d0[G]; bool inwin[G], st[G];
+      BR_W(8, 1);
+      // ---- fetch: G rows of S (the first G are already here), then their stored bits and (G > 1) the candidates' first bytes
+      if (jj != j) {
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+          const u32 jr = jj > (u32)(r * BR_WARP) ? jj - (u32)(r * BR_WARP) : 0u;
+          has[r] = jr >= lo + 1 + (u32)lane;
+          q[r] = has[r] ? br_ldg(s.S + (jr - 1 - (u32)lane)) : 0;
+        }
       }
-#endif
-      bool st = inwin && br_is_stored(w, q);
-      u32 m = br_ballot(st);
-      u32 rnk = (u32)br_popc(m & br_lanemask_lt());
-      bool take = st && (collected + rnk < V);
-      if (br_ballot(has && !inwin) != 0 || br_ballot(!has) != 0) done = true;
-      collected += (u32)br_popc(m);
-      // full match length of every taken candidate
-      u32 len = 0; int eqmax = 0;
-#if BR_WALK_SPECLEN
-      if (take) { len = len_spec; eqmax = eq_spec; }
-#else
-      if (take) {
-        // H6: the first four bytes must agree, then the length counts on; H5: length >= 4.  Same thing.
-        len = br_match_len_c(d, q, cur, max_length, c0, c1);
-        if (len < 4) len = 0;
-        if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + q + max_length));
+#pragma unroll
+      for (int r = 0; r < G; ++r) {
+        inwin[r] = has[r] && cur - q[r] <= max_backward;
+        st[r] = inwin[r] && br_is_stored(w, q[r]);
       }
-#endif
-      u32 score = len ? BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward) : 0;
-      u32 pm = q & rmask;
-      int last = -1;
-      for (;;) {
-        if (cur_m + best_len > rmask) { done = true; break; }
-        bool ok = take && len != 0 && lane > last && !(pm + best_len > rmask) &&
-                  (len > best_len || (len == best_len && best_len == max_length && eqmax)) &&
-                  score > best_score;
-        u32 mm = br_ballot(ok);
-        if (!mm) break;
-        int f = br_ffs(mm) - 1;
-        best_len = br_shfl(len, f);
-        best_score = br_shfl(score, f);
-        out.len = best_len; out.distance = br_shfl(backward, f); out.score = best_score;
-        last = f;
+      if (G > 1) {
+#pragma unroll
+        for (int r = 0; r < G; ++r) d0[r] = inwin[r] ? br_ld64u(d, q[r]) : 0;
       }
-      jj = jj > BR_WARP ? jj - BR_WARP : 0;
+      // ---- fold, row by row, newest first
+#pragma unroll
+      for (int r = 0; r < G; ++r) {
+        if (r > 0) {
+          const u32 jr = jj > (u32)(r * BR_WARP) ? jj - (u32)(r * BR_WARP) : 0u;
+          if (done || collected >= V || jr <= lo) break;
+        }
+        const u32 backward = cur - q[r];
+        BR_W(1, 1);
+        const u32 m = br_ballot(st[r]);
+        const u32 rnk = (u32)br_popc(m & br_lanemask_lt());
+        const bool take = st[r] && (collected + rnk < V);
+        if (br_ballot(has[r] && !inwin[r]) != 0 || br_ballot(!has[r]) != 0) done = true;
+        collected += (u32)br_popc(m);
+        // full match length of every taken candidate
+        // (H6: the first four bytes must agree, then the length counts on; H5: length >= 4.  Same thing.)
+        u32 len = 0; int eqmax = 0;
+        if (take) {
+          BR_W(9, 1);
+          len = G > 1 ? br_match_len_d0(d, q[r], cur, max_length, c0, c1, d0[r]) : br_match_len_c(d, q[r], cur, max_length, c0, c1);
+          if (len < 4) len = 0;
+          if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + q[r] + max_length));
+        }
+        const u32 score = len ? BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward) : 0;
+        const u32 pm = q[r] & rmask;
+        int last = -1;
+        for (;;) {
+          if (cur_m + best_len > rmask) { done = true; break; }
+          bool ok = take && len != 0 && lane > last && !(pm + best_len > rmask) &&
+                    (len > best_len || (len == best_len && best_len == max_length && eqmax)) &&
+                    score > best_score;
+          u32 mm = br_ballot(ok);
+          if (!mm) break;
+          int f = br_ffs(mm) - 1;
+          best_len = br_shfl(len, f);
+          best_score = br_shfl(score, f);
+          out.len = best_len; out.distance = br_shfl(backward, f); out.score = best_score;
+          last = f;
+        }
+      }
+      jj = jj > (u32)(G * BR_WARP) ? jj - (u32)(G * BR_WARP) : 0;
     }
     br_own_set(w, cur);  // the insertion at hash_longest_match64_inc.h:268
     if (!w.warming && br_lane() == 0) br_atomic_or(s.srch_cur + (cur >> 5), 1u << (cur & 31));
@@ -382,6 +419,7 @@ BR_DEV u32 br_compute_distance_code(u32 distance, u32 max_distance, const int* d
 // `head` is the first chunk of the sweep this run belongs to (== b when the walker starts here), `sweep_p0` the
 // first position the sweep owns (0xffffffff on entry for the head, which sets it): a walker that continues into the
 // chunks behind its own keeps writing the head's bitmap and reads its own fresh bits from sweep_p0 on.
+template <int G>
 BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOut& o, u32 head, u32& sweep_p0) {
   const BrParams& P = s.P;
   const int lane = br_lane();
@@ -392,7 +430,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   w.dict_m = ((u64)in.dict_m_hi << 32) | in.dict_m_lo;
   w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
   w.min_wrap = 0xffffffffu;
-  w.pf_pos = 0xffffffffu; w.pf_lo = w.pf_hi = w.pf_j = 0;
+  w.fence_due = false;
   w.stale = in.blk_end <= P.rmask ? 0u : (u32)s.data[in.blk_end - (P.rmask + 1)];
   for (int i = 0; i < 4; ++i) w.dc[i] = in.dc[i];
   const u32 pos_end = in.blk_end;
@@ -462,7 +500,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
       const u32 sp = position + (have ? 1u : 0u);
       const u32 md = br_min(sp, P.max_backward);
       BrSR cur; cur.len = 0; cur.delta = 0; cur.distance = 0; cur.score = BR_MIN_SCORE;
-      br_find_longest_match(w, sp, max_length, md, md, cur);
+      br_find_longest_match<G>(w, sp, max_length, md, md, cur);
       if (!have) {
         sr = cur;
         if (!(sr.score > BR_MIN_SCORE)) break;
@@ -522,6 +560,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     w.dict_l = dict_l0; w.dict_m = dict_m0; w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
     w.min_wrap = 0xffffffffu;
   }
+  br_own_sync(w);   // a sweep's next chunk starts with a fresh BrWalk: nothing may stay pending
   if (in.last) {
     insert_length += pos_end - position;
     position = pos_end;
@@ -553,15 +592,20 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
 // position on, so a sweep over a run of dirty chunks is the sequential parse of that run: serial ripples (a
 // distance-cache change flowing through match-free data, stored-bits that keep perturbing the next chunk on chaotic
 // binary data) cost one launch, not one launch per chunk.
+template <int G>
 BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
   BrBlockIn in = s.bin[b];
   const u32 head = b;
   u32 sweep_p0 = 0xffffffffu;
   for (;;) {
     BrBlockOut o;
-    br_walk_one(s, b, in, o, head, sweep_p0);
-    if (in.last) return;
+    br_walk_one<G>(s, b, in, o, head, sweep_p0);
+    if (br_lane() == 0) br_atomic_max((int*)s.counters + 16, (int)(b - head + 1));   // longest sweep of this launch (diagnostic)
+    if (in.last) return;   // (a sweep ends with its input block: what happens between two blocks is the chain's business)
     const u32 nb = b + 1;
+    BrBlockIn ni = s.bin[nb];
+    ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0; ni.warm = 0;
+    for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];
     const u32 df = s.dirty[nb];
     bool go = to_block_end;
     if (!go) {
@@ -572,8 +616,8 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
     if (!go) {
       if (!s.bout[nb].valid) return;
       const BrBlockIn u = s.bin_used[nb];
-      bool same = u.start_pos == o.out_pos && u.apply_rh == o.apply_rh && u.store_end == o.store_end && u.ext_dist == 0 &&
-                  u.dc[0] == o.dc[0] && u.dc[1] == o.dc[1] && u.dc[2] == o.dc[2] && u.dc[3] == o.dc[3];
+      bool same = u.start_pos == ni.start_pos && u.apply_rh == ni.apply_rh && u.store_end == ni.store_end && u.ext_dist == ni.ext_dist &&
+                  u.dc[0] == ni.dc[0] && u.dc[1] == ni.dc[1] && u.dc[2] == ni.dc[2] && u.dc[3] == ni.dc[3];
       if (same) {
         const BrBlockOut uo = s.bout[nb];
         const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
@@ -582,9 +626,6 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
       }
       if (same) return;
     }
-    BrBlockIn ni = s.bin[nb];
-    ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0; ni.warm = 0;
-    for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];
     ni.dict_l_lo = (u32)dl; ni.dict_l_hi = (u32)(dl >> 32); ni.dict_m_lo = (u32)dm; ni.dict_m_hi = (u32)(dm >> 32);
     in = ni; b = nb;
   }

@@ -66,6 +66,21 @@ __global__ void __launch_bounds__(256) k_q1_pack(BrQ1 q, const u64* dense_off, u
   for (u32 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+// device-resident batch: copy stream s from the caller's packed buffer to the pipeline's layout (16-byte aligned starts)
+__global__ void __launch_bounds__(256) k_q1_gather(BrQ1 q, const u8* __restrict__ src, const u64* __restrict__ src_off, u8* dst) {
+  const u32 s = blockIdx.x;
+  const u8* a = src + src_off[s];
+  u8* b = dst + q.streams[s].in_off;
+  const u32 n = q.streams[s].size;
+  if ((((size_t)a) & 15u) == 0) {
+    const u32 nv = n >> 4;
+    for (u32 i = threadIdx.x; i < nv; i += blockDim.x) ((uint4*)b)[i] = ((const uint4*)a)[i];
+    for (u32 i = (nv << 4) + threadIdx.x; i < n; i += blockDim.x) b[i] = a[i];
+  } else {
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) b[i] = a[i];
+  }
+}
+
 // ------------------------------------------------------------------ host
 namespace {
 struct Arena {
@@ -107,6 +122,7 @@ struct BrQ1Job {
 
 extern "C" const double* br_host_log2_table(u32* n);   // br_host.cc
 
+extern "C" void br_q1_job_destroy(BrQ1Job* j);
 extern "C" BrQ1Job* br_q1_job_create(void) {
   BrQ1Job* j = new BrQ1Job();
   int dev = 0;
@@ -121,7 +137,10 @@ extern "C" BrQ1Job* br_q1_job_create(void) {
   u32 n = 0; const double* h = br_host_log2_table(&n);
   j->log2_n = n < 4096 ? n : 4096;
   if (!j->log2.need((size_t)j->log2_n * 8)) { delete j; return nullptr; }
-  cudaMemcpy(j->log2.p, h, (size_t)j->log2_n * 8, cudaMemcpyHostToDevice);
+  // (a pageable-source cudaMemcpy may return before the DMA lands; the job's stream is non-blocking, so wait here)
+  if (cudaMemcpy(j->log2.p, h, (size_t)j->log2_n * 8, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError(); br_q1_job_destroy(j); return nullptr;
+  }
   return j;
 }
 extern "C" void br_q1_job_destroy(BrQ1Job* j) {
@@ -145,8 +164,9 @@ static void run_threads(int threads, size_t count, const std::function<void(size
 }
 
 extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const uint8_t* const* in, const size_t* in_n,
-                                    const size_t* const* calls, const size_t* ncalls, int inputs_on_device,
+                                    const size_t* const* calls, const size_t* ncalls, const BrQ1Packed* packed,
                                     uint8_t* const* out, size_t* out_n, int* ok, int threads, int with_header, int end_op) {
+  const bool inputs_on_device = packed != nullptr;
   if (!j || lgwin < 10 || lgwin > 24 || count == 0 || count > (1u << 24)) return 0;
   std::vector<BrQ1Stream> streams; std::vector<BrQ1Frag> frags; std::vector<BrQ1Block> blocks;
   streams.reserve(count);
@@ -177,8 +197,9 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   cudaEventRecord(j->ev[0], st);
   // ---- inputs
   if (inputs_on_device) {
-    for (size_t s = 0; s < count; ++s)
-      if (in_n[s]) cudaMemcpyAsync((u8*)j->in.p + streams[s].in_off, in[s], in_n[s], cudaMemcpyDeviceToDevice, st);
+    // the packed offsets ride in dense_off (rewritten by k_q1_offsets later, after the gather)
+    cudaMemcpyAsync(j->dense_off.p, packed->in_off, count * 8, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(j->in.p, 0, total_in + 64, st);
   } else {
     if (!j->h_in.need(total_in + 64)) return 0;
     u8* hp = (u8*)j->h_in.p;
@@ -192,7 +213,6 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   if (nbl) cudaMemcpyAsync(j->blocks.p, blocks.data(), (size_t)nbl * sizeof(BrQ1Block), cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(j->counters.p, 0, 64, st);
   cudaMemsetAsync(j->out.p, 0, total_out + 64, st);
-  cudaEventRecord(j->ev[1], st);
 
   BrQ1 q; memset(&q, 0, sizeof(q));
   q.in = (const u8*)j->in.p; q.out = (u32*)j->out.p; q.cmds = (u32*)j->cmds.p; q.lits = (u8*)j->lits.p;
@@ -202,6 +222,8 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   q.log2tab = (const double*)j->log2.p; q.log2tab_n = j->log2_n;
   q.first_width = j->first_width;
 
+  if (inputs_on_device) k_q1_gather<<<(unsigned)count, 256, 0, st>>>(q, packed->d_in, (const u64*)j->dense_off.p, (u8*)j->in.p);
+  cudaEventRecord(j->ev[1], st);
   if (nfr) k_q1_parse<<<nwarps / 4, 128, 0, st>>>(q);
   cudaEventRecord(j->ev[2], st);
   if (nbl) k_q1_prep<<<nbl, 128, 0, st>>>(q);
@@ -221,14 +243,13 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   const u64 dense_bytes = h_off[count];
   size_t good = 0;
   if (inputs_on_device) {
-    // device-resident variant: outputs are device pointers too
-    for (size_t s = 0; s < count; ++s) {
-      const size_t sz = h_streams[s].out_bytes;
-      ok[s] = sz <= out_n[s];
-      if (ok[s]) { cudaMemcpyAsync(out[s], (const u8*)j->dense.p + h_off[s], sz, cudaMemcpyDeviceToDevice, st); out_n[s] = sz; ++good; }
-    }
+    // device-resident variant: the dense packing goes to the caller's device buffer, offsets and sizes to the host
+    if (dense_bytes > packed->out_cap) return 0;
+    cudaMemcpyAsync(packed->d_out, j->dense.p, dense_bytes, cudaMemcpyDeviceToDevice, st);
     cudaEventRecord(j->ev[5], st);
-    cudaStreamSynchronize(st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 0;
+    for (size_t s = 0; s < count; ++s) { packed->out_off[s] = h_off[s]; out_n[s] = h_streams[s].out_bytes; ok[s] = 1; ++good; }
+    packed->out_off[count] = dense_bytes;
   } else {
     if (!j->h_out.need(dense_bytes + 64)) return 0;
     cudaMemcpyAsync(j->h_out.p, j->dense.p, dense_bytes, cudaMemcpyDeviceToHost, st);

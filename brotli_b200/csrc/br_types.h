@@ -104,9 +104,12 @@ struct BrMetaBlock {
   u32 scratch_off;
 };
 
-// BrStream::dirty[] values: 0 clean; reason (1..5) = scheduled for the next walker launch; BR_DEFER | reason = dirty but
-// left to the walker of the chunk before it (sweep / chase)
-#define BR_DEFER 0x100u
+// BrStream::dirty[] values: 0 clean; reason (1..5) = scheduled for the next walker launch; with a BR_DEFER_* bit the
+// chunk is dirty but left to the walker of the chunk before it: BR_DEFER_STATE = only its in-state is off (chase),
+// BR_DEFER_SWEEP = sweep mode (the chain schedules only the head of a run of consecutive dirty chunks).
+#define BR_DEFER_STATE 0x100u
+#define BR_DEFER_SWEEP 0x200u
+#define BR_DEFER (BR_DEFER_STATE | BR_DEFER_SWEEP)
 
 // Device-resident view of one stream (all pointers are device pointers).
 struct BrStream {

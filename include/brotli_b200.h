@@ -86,6 +86,13 @@ BROTLI_B200_API BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, siz
  * only parallelises the host-side packing.  encoded_sizes[i]: in = capacity of outputs[i], out = bytes written.
  * Returns the number of streams compressed successfully. */
 BROTLI_B200_API size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8_t* const* inputs, const size_t* input_sizes, uint8_t* const* outputs, size_t* encoded_sizes, int threads);
+/* Quality 1, device resident: `count` non-empty streams sit in ONE device buffer, stream i at d_inputs + input_offsets[i]
+ * (host array), input_sizes[i] bytes (host array).  The compressed streams are packed into d_encoded (device), stream i at
+ * d_encoded + encoded_offsets[i] (host array of count + 1 entries, 16-byte aligned starts, last = bytes used),
+ * encoded_sizes[i] bytes (host array; 0 = that stream must go through the host call: it compressed to more than
+ * BrotliEncoderMaxCompressedSize).  Bytes equal BrotliEncoderCompress(1, lgwin, GENERIC, ...) per stream.
+ * Returns the number of streams compressed. */
+BROTLI_B200_API size_t BrotliB200CompressBatchDevice(int quality, int lgwin, size_t count, const void* d_inputs, const uint64_t* input_offsets, const size_t* input_sizes, void* d_encoded, size_t encoded_capacity, uint64_t* encoded_offsets, size_t* encoded_sizes);
 /* Timings (milliseconds, CUDA events) and counters of the calling thread's last compress call.
  * out[0..15]: total, index (hash+sort), lz77, entropy, assemble, lz77 iterations, block runs,
  * blocks, metablocks, kernel launches, summed k_walk ms, k_encode_mb ms, k_walk launches,

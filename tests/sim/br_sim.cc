@@ -49,6 +49,7 @@ struct SimStream {
   std::vector<u32> dirty_list, ran_list;
   int iterations = 0;
   u64 block_runs = 0;
+  double model_cost = 0;
 };
 
 static void sim_build_sorted(SimStream& m) {
@@ -179,10 +180,21 @@ static void sim_lz77_fixpoint(SimStream& m) {
     ++s.epoch; ++m.iterations;
     sim_build_storedS(m);
     std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
-    s.counters[4] = 0;
+    s.counters[4] = 0; s.counters[16] = 0;
     s.forced = s.epoch >= s.P.force_epoch;
-    { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) br_walk_block(s, k, s.forced && k == s.counters[6]); }
+    { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
+      if (s.P.block_bits >= 8) br_walk_block<8>(s, k, f); else if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
     m.block_runs += s.counters[4];
+#ifdef BR_SIM_DEBUG
+    if (getenv("BR_SIM_TRACE")) { fprintf(stderr, "   work: searches %llu rows %llu groups %llu taken %llu | heavy %llu own-scan rows %llu countS %llu | own_set %llu set_range %llu dict %llu\n",
+      (unsigned long long)br_sim_w[0], (unsigned long long)br_sim_w[1], (unsigned long long)br_sim_w[8], (unsigned long long)br_sim_w[9], (unsigned long long)br_sim_w[2], (unsigned long long)br_sim_w[3],
+      (unsigned long long)br_sim_w[4], (unsigned long long)br_sim_w[5], (unsigned long long)br_sim_w[6], (unsigned long long)br_sim_w[7]); memset(br_sim_w, 0, sizeof(br_sim_w)); }
+#endif
+    { // cost model of a launch on the GPU, in chunk-walk times: the longest sweep (serial) or the whole work over ~2000 resident warps
+      double c = (double)s.counters[16] > s.counters[4] / 2000.0 ? (double)s.counters[16] : s.counters[4] / 2000.0;
+      m.model_cost += c;
+      if (getenv("BR_SIM_TRACE")) fprintf(stderr, "   launch %u: sched %u ran %u longest sweep %u  (model cost %.1f, total %.1f)\n", s.epoch, s.counters[5], s.counters[4], s.counters[16], c, m.model_cost);
+    }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
     if (s.epoch + 2 >= s.P.max_epochs) { fprintf(stderr, "sim: no fixpoint\n"); break; }
@@ -194,7 +206,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
     std::vector<BrBlockOut> old(s.bout, s.bout + nb);
     s.counters[4] = 0;
-    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; br_walk_one(s, k, s.bin[k], o, k, sp0); }
+    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; br_walk_one<1>(s, k, s.bin[k], o, k, sp0); }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 k = 0; k < nb; ++k) {
       br_commit_bits(s, k);
@@ -327,9 +339,8 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
     u32 nm = s.counters[1];
     res.clear();
     u64 bit = 0;
-    const bool use_v2 = getenv("BR_SIM_V1") == nullptr;
     SimEnt E;
-    if (use_v2) sim_entropy2(*m, E);
+    sim_entropy2(*m, E);
     if (lgwin == 17) put_bits_host(res, bit, 7, 1); else put_bits_host(res, bit, 4, ((lgwin - 17) << 1) | 1);
     bool redo = false;
     for (u32 i = 0; i < nm && !redo; ++i) {
@@ -337,13 +348,9 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
       u32 bytes = mb.end - mb.start;
       bool compressed = mb.compress != 0;
       if (compressed) {
-        std::vector<u8> scratch(br_mb_scratch_bytes(mb.nlit, mb.ncmd) + 64);
         std::vector<u32> obuf((2 * (size_t)bytes + 503) / 4 + 8, 0);
-        u32 bits;
-        if (use_v2) {
-          bits = s.mbs[i].out_bits;
-          memcpy(obuf.data(), E.outbits.data() + E.out_off[i], ((size_t)bits + 31) / 32 * 4);
-        } else bits = br_encode_metablock(s, mb, m->cmds_all.data(), scratch.data(), obuf.data(), smem.data());
+        const u32 bits = s.mbs[i].out_bits;
+        memcpy(obuf.data(), E.outbits.data() + E.out_off[i], ((size_t)bits + 31) / 32 * 4);
         u64 storage_ix = (bit & 7) + bits;
         if (mb.is_last) storage_ix = (storage_ix + 7) & ~7ull;
         if ((u64)bytes + 4 < (storage_ix >> 3)) {
@@ -367,7 +374,7 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
     if (!redo) { res.resize((bit + 7) >> 3, 0); break; }
     if (rounds > 64) { delete m; return -4; }
   }
-  stats[0] = (u32)m->iterations; stats[1] = (u32)m->block_runs; stats[2] = s.P.nblocks; stats[3] = (u32)rounds;
+  stats[0] = (u32)m->iterations; stats[1] = (u32)m->block_runs; stats[2] = s.P.nblocks; stats[3] = (u32)rounds; stats[4] = (u32)m->model_cost;
   delete m;
   if (res.size() > out_cap) return -3;
   memcpy(out, res.data(), res.size());

@@ -25,5 +25,5 @@ cap = len(d) + len(d) // 2 + 4096
 out = C.create_string_buffer(cap); st = np.zeros(8, np.uint32)
 t = time.time(); r = L.sim_compress(q, w, d, len(d), out, cap, st.ctypes.data); t = time.time() - t
 want = Oracle().compress(d, q, w)
-print("sim: %d bytes, %d launches, %d chunk walks for %d chunks, rounds %d, %.1fs; parity %s" % (
-    r, st[0], st[1], st[2], st[3], t, out.raw[:r] == want))
+print("sim: %d bytes, %d launches, %d chunk walks for %d chunks, rounds %d, serial-cost model %d chunk-times, %.1fs; parity %s" % (
+    r, st[0], st[1], st[2], st[3], st[4], t, out.raw[:r] == want))
