@@ -361,7 +361,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
       if (ce > ovf) ovf = ce;
     }
   }
-  bool prev_dirty = false;
+  bool prev_dirty = false, sweeping = false;
   for (u32 c = 0; c < B.nchunks; ++c) {
     const u32 k = B.first_chunk + c;
     BrBlockIn ni = s.bin[k];
@@ -397,12 +397,26 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     // predecessor is not scheduled: the predecessor's walker chases into it (br_walk_block), which
     // resolves a serial ripple in one launch instead of one launch per chunk.
     bool defer = dirty == 2 && prev_dirty && t_now >= 2;
-    // Sweep mode (from launch sweep_epoch on): only the head of every run of consecutive dirty chunks is scheduled
-    // and its walker sweeps the run.  On data where each re-walk perturbs its successors again (chaotic binary
-    // input: sparse-search phases, heavy buckets) re-walking all dirty chunks at once from the previous snapshot is
-    // a Jacobi iteration whose settled front advances one chunk per launch; the sweep is the sequential parse of
-    // the run, and all runs of the stream still advance in parallel.
-    const bool defer_sweep = dirty && prev_dirty && t_now >= s.P.sweep_epoch;
+    // Sweep mode (from launch sweep_epoch on).  Two kinds of dirt need opposite treatment:
+    //  * STATE (reason 2, 3): the parse really arrives here in another state (position phase of the sparse search on
+    //    incompressible data, distance cache).  Everything behind it in the input block is suspect, and only a walker
+    //    that carries the true state can settle it: the chunk becomes the head of a SWEEP and every later dirty chunk of
+    //    the block is left to that walker (it walks on while chunks are deferred or its out-state differs from what the
+    //    next chunk consumed).  Scheduling those later chunks on their own would stop the sweep in front of each of them
+    //    and the settled front would advance one chunk per launch.
+    //  * BITS only (reason 4, 5): a stored-bit this chunk may have consulted flipped.  The marking rule is conservative
+    //    (br_commit_bits: megabytes of input behind every flip), most such chunks come out unchanged, and they are
+    //    independent of each other: each is walked on its own, all in parallel.
+    // Safety net for inputs whose stored-bits truly chase each other from chunk to chunk: after sweep_epoch + 9 launches
+    // every third launch sweeps every run of dirty chunks whatever the reason.
+    const bool sweep_mode = t_now >= s.P.sweep_epoch;
+    const bool full_sweep = sweep_mode && t_now >= s.P.sweep_epoch + 9 && (t_now - s.P.sweep_epoch) % 3 == 0;
+    bool defer_sweep = false;
+    if (sweep_mode && dirty) {
+      if (sweeping || (full_sweep && prev_dirty)) defer_sweep = true;
+      else if (dirty == 2 || dirty == 3) sweeping = true;   // head of a sweep
+    }
+    if (full_sweep && !dirty) sweeping = false;
     prev_dirty = dirty != 0;
     s.bin[k] = ni;
     s.dirty[k] = defer_sweep ? (BR_DEFER_SWEEP | dirty) : defer ? (BR_DEFER_STATE | dirty) : dirty;   // br_chain_d schedules

@@ -608,6 +608,18 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       k_commit<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s);
     }
     cudaEventRecord(ev[2], st);
+#ifdef BR_DEBUG_KNOBS
+    if (trace) {   // the slowest chunk walks of the final state, and a per-megabyte profile
+      std::vector<BrBlockOut> hb2(nb);
+      cudaMemcpyAsync(hb2.data(), bout, nb * sizeof(BrBlockOut), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
+      const u32 per = (1u << 20) >> BR_CHUNK_BITS;
+      for (u32 a = 0; a < nb; a += per) {
+        unsigned long long cyc = 0, se = 0, ro = 0; u32 mx = 0;
+        for (u32 k = a; k < a + per && k < nb; ++k) { cyc += hb2[k].dbg_kcycles; se += hb2[k].dbg_searches; ro += hb2[k].dbg_rows; if (hb2[k].dbg_kcycles > mx) mx = hb2[k].dbg_kcycles; }
+        fprintf(stderr, "MiB %4u: %7.2f Mcycles per chunk (max %7.2f)  searches/chunk %5llu rows/search %5.1f\n", a / per, cyc / 1024.0 / per, mx / 1024.0, se / per, se ? (double)ro / se : 0.0);
+      }
+    }
+#endif
     // ---- entropy stage
     std::vector<BrMetaBlock> hm(n_mbs);
     CK(cudaMemcpyAsync(hm.data(), mbs, n_mbs * sizeof(BrMetaBlock), cudaMemcpyDeviceToHost, st));

@@ -101,6 +101,9 @@ struct BrWalk {
   bool warming;    // warm-up (state refinement before the chunk proper): reads the snapshot, records nothing
   u32* own;        // the bits_cur bitmap of this run (parity of the sweep's head chunk)
   bool fence_due;  // own bits were written since the last fence (see br_own_sync)
+#ifdef BR_DEBUG_KNOBS
+  u32 dbg_searches, dbg_rows, dbg_mlsteps;
+#endif
 };
 
 // Stored-bits of the walker's own range [p0, ...) live in bits_cur (global): written with
@@ -228,6 +231,9 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   u32 best_score = out.score, best_len = out.len;
   out.len = 0; out.delta = 0;
   BR_W(0, 1);
+#ifdef BR_DEBUG_KNOBS
+  ++w.dbg_searches;
+#endif
   bool brk = false;
   // the bytes at the search position, shared by every candidate comparison below
   const u64 c0 = br_ld64u(d, cur), c1 = br_ld64u(d, cur + 8);
@@ -359,6 +365,9 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
         }
         const u32 backward = cur - q[r];
         BR_W(1, 1);
+#ifdef BR_DEBUG_KNOBS
+        ++w.dbg_rows;
+#endif
         const u32 m = br_ballot(st[r]);
         const u32 rnk = (u32)br_popc(m & br_lanemask_lt());
         const bool take = st[r] && (collected + rnk < V);
@@ -431,6 +440,10 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
   w.min_wrap = 0xffffffffu;
   w.fence_due = false;
+#ifdef BR_DEBUG_KNOBS
+  w.dbg_searches = w.dbg_rows = w.dbg_mlsteps = 0;
+  const long long dbg_t0 = clock64();
+#endif
   w.stale = in.blk_end <= P.rmask ? 0u : (u32)s.data[in.blk_end - (P.rmask + 1)];
   for (int i = 0; i < 4; ++i) w.dc[i] = in.dc[i];
   const u32 pos_end = in.blk_end;
@@ -573,6 +586,9 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     o.gate_checks = w.gate_checks; o.gate_fail = w.gate_fail;
     o.min_wrap_dist = w.min_wrap; o.valid = 1; o.epoch = s.epoch;
     o.head = head; o.own_par = head & 1u;
+#ifdef BR_DEBUG_KNOBS
+    o.dbg_kcycles = (u32)((clock64() - dbg_t0) >> 10); o.dbg_searches = w.dbg_searches; o.dbg_rows = w.dbg_rows; o.dbg_mlsteps = w.dbg_mlsteps;
+#endif
   }
   if (head == b) sweep_p0 = used.start_pos;
   if (lane == 0) {

@@ -72,6 +72,9 @@ struct BrBlockOut {
   u32 epoch;             // walker launch that produced this record
   u32 head;              // first chunk of the sweep (one warp walking consecutive chunks) this run belongs to
   u32 own_par;           // which of the two bits_cur bitmaps the run wrote (the parity of the sweep's head)
+#ifdef BR_DEBUG_KNOBS
+  u32 dbg_kcycles, dbg_searches, dbg_rows, dbg_mlsteps;   // profile of the latest run (debug build)
+#endif
 };
 
 // Per reference input block (one EncodeData call): static layout, aggregates over its chunks and

@@ -31,6 +31,24 @@ def test_golden(b200, g):
     assert hashlib.sha256(out).hexdigest() == g["out_sha256"]
 
 
+FIXDIR = os.path.join(os.path.dirname(__file__), "golden", "fixtures")
+FIXTURES = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fixtures.json")))
+
+
+@pytest.mark.parametrize("g", FIXTURES, ids=lambda g: "%s-q%d-w%d" % (g["label"], g["q"], g["lgwin"]))
+def test_reference_fixtures(b200, g):
+    """The CUDA path on the reference's own tests/testdata files (real text, binary AST, map tiles, repeats, noise,
+    a one-byte file ...), against digests of the compiled reference.  alice29.txt[:65536] at quality 5 / lgwin 22 is
+    BASELINE.json config C1: 24 091 bytes."""
+    d = open(os.path.join(FIXDIR, g["file"]), "rb").read()[:g["n"]]
+    assert hashlib.sha256(d).hexdigest() == g["in_sha256"]
+    out = b200.compress_oneshot(d, g["q"], g["lgwin"])
+    assert len(out) == g["out_len"]
+    assert hashlib.sha256(out).hexdigest() == g["out_sha256"]
+    if g["label"] == "alice29.txt[:65536]" and g["q"] == 5:
+        assert len(out) == 24091
+
+
 def test_against_oracle_all_qualities(b200):
     ora = Oracle()
     from corpus import synth_text, synth_web

@@ -14,9 +14,29 @@ GOLDEN_ORACLE_ONLY = json.load(open(os.path.join(os.path.dirname(__file__), "gol
 FAST = [g for g in GOLDEN if g["n"] <= 2_500_000] + GOLDEN_ORACLE_ONLY
 
 
+FIXDIR = os.path.join(os.path.dirname(__file__), "golden", "fixtures")
+FIXTURES = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fixtures.json")))
+
+
+def fixture_bytes(g):
+    """The reference's own test files (byte copies under tests/golden/fixtures, see make_fixture_golden.py)."""
+    d = open(os.path.join(FIXDIR, g["file"]), "rb").read()
+    return d[:g["n"]]
+
+
 @pytest.fixture(scope="module")
 def oracle():
     return Oracle()
+
+
+@pytest.mark.parametrize("g", FIXTURES, ids=lambda g: "%s-q%d-w%d" % (g["label"], g["q"], g["lgwin"]))
+def test_oracle_on_reference_fixtures(oracle, g):
+    """The oracle on the reference's tests/testdata files, against digests of the compiled reference; includes
+    BASELINE.json config C1 = alice29.txt[:65536] at quality 5, lgwin 22 (24 091 bytes)."""
+    d = fixture_bytes(g)
+    assert hashlib.sha256(d).hexdigest() == g["in_sha256"]
+    out = oracle.compress(d, g["q"], g["lgwin"])
+    assert len(out) == g["out_len"] and hashlib.sha256(out).hexdigest() == g["out_sha256"]
 
 
 @pytest.mark.parametrize("g", FAST, ids=lambda g: "%s-%d-q%d-w%d" % (g["kind"], g["n"], g["q"], g["lgwin"]))

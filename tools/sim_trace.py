@@ -14,6 +14,11 @@ elif kind == "web": d = synth_web(n, seed)
 elif kind == "walk":
     rs = np.random.RandomState(seed & 0x7fffffff)
     d = np.cumsum(rs.normal(0, 50, size=n // 4).astype(np.int64)).astype(np.int32).tobytes()
+elif kind == "soup":   # the opcode soup of synth_binary: 64 patterns of 2-9 bytes in random order
+    import random
+    rs = np.random.RandomState(seed & 0x7fffffff); rng = random.Random(seed)
+    pats = [bytes(rs.randint(0, 256, size=rng.randint(2, 9), dtype=np.uint8)) for _ in range(64)]
+    d = b"".join(rng.choice(pats) for _ in range(n // 5))[:n]
 else:
     d = np.random.RandomState(seed & 0x7fffffff).randint(0, 256, size=n, dtype=np.uint8).tobytes()
 L = C.CDLL(os.environ.get("SIM_SO", os.path.join(ROOT, "tests", "sim", "libbrsim.so")))
