@@ -232,7 +232,7 @@ BR_DEV void br_chain_b(const BrStream& s) {
         if (s.counters[7] == t_now + 1) s.epoch_cum[t_now] += mx;
         else { s.epoch_cum[t_now] = (t_now ? s.epoch_cum[t_now - 1] : 0u) + mx; s.counters[7] = t_now + 1; }
       }
-      s.counters[0] = 0; s.counters[5] = 0; s.counters[6] = 0xffffffffu;
+      s.counters[0] = 0; s.counters[5] = 0; s.counters[6] = 0xffffffffu; s.counters[17] = 0; s.counters[18] = 0;
       for (int i = 8; i < 16; ++i) s.counters[i] = 0;
     }
   }
@@ -362,6 +362,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     }
   }
   bool prev_dirty = false, sweeping = false;
+  u32 blk_state_dirty = 0;
   for (u32 c = 0; c < B.nchunks; ++c) {
     const u32 k = B.first_chunk + c;
     BrBlockIn ni = s.bin[k];
@@ -411,15 +412,16 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     // every third launch sweeps every run of dirty chunks whatever the reason.
     const bool sweep_mode = t_now >= s.P.sweep_epoch;
     const bool full_sweep = sweep_mode && t_now >= s.P.sweep_epoch + 9 && (t_now - s.P.sweep_epoch) % 3 == 0;
-    bool defer_sweep = false;
+    u32 defer_sweep = 0;
     if (sweep_mode && dirty) {
-      if (sweeping || (full_sweep && prev_dirty)) defer_sweep = true;
-      else if (dirty == 2 || dirty == 3) sweeping = true;   // head of a sweep
+      if (full_sweep && prev_dirty) defer_sweep = BR_DEFER_FULL;
+      else if (dirty == 2 || dirty == 3) sweeping = true;   // head of a sweep (or chased by the walker of the chunk before it: `defer`)
+      else if (sweeping) defer_sweep = BR_DEFER_SWEEP;
     }
-    if (full_sweep && !dirty) sweeping = false;
+    if (sweep_mode && !full_sweep && (dirty == 2 || dirty == 3)) blk_state_dirty = 1;
     prev_dirty = dirty != 0;
     s.bin[k] = ni;
-    s.dirty[k] = defer_sweep ? (BR_DEFER_SWEEP | dirty) : defer ? (BR_DEFER_STATE | dirty) : dirty;   // br_chain_d schedules
+    s.dirty[k] = defer_sweep ? (defer_sweep | dirty) : defer ? (BR_DEFER_STATE | dirty) : dirty;   // br_chain_d schedules
     s.cmd_off[k] = cmd_off;
     s.lil_in[k] = lil_true;
     s.block_mb[k] = W.mb;
@@ -429,6 +431,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
       if (!(dict_m < (dict_l >> 7))) { dict_l += edl; dict_m += edm; }
     }
   }
+  s.blk[bi].state_dirty = blk_state_dirty;
 }
 
 // Scheduling (thread per chunk, after br_chain_c has flagged every chunk): builds the list of walkers of the next launch.
@@ -443,9 +446,29 @@ BR_DEV void br_chain_d(const BrStream& s, u32 k) {
   const u32 t_now = s.epoch;
   const bool sweep_mode = t_now >= s.P.sweep_epoch;
   const bool verify = sweep_mode && s.counters[4] != 0 && s.counters[0] > 4u * s.counters[4] && s.counters[0] > 64u;
-  if (verify && (d & BR_DEFER_SWEEP)) d &= ~BR_DEFER_SWEEP;
+  if (verify) d &= ~(BR_DEFER_SWEEP | BR_DEFER_FULL);
+  else if (sweep_mode && ((t_now - s.P.sweep_epoch) & 1u) == 0 && (d == 4 || d == 5) && s.bout[k].valid) {
+    // a sweep that starts in an earlier block of this group of sweep_blocks blocks may arrive here (br_walk_block crosses
+    // block boundaries): leave the chunk to it, like the chunks behind a state-dirty chunk of its own block.  Every
+    // second launch only: a sweep that stops early (its state fell in step again) leaves these chunks unwalked, and
+    // they must not wait behind ever new sweeps of the blocks before them.
+    const u32 bi = s.bin[k].blk, g0 = bi & ~(s.P.sweep_blocks - 1u);
+    for (u32 j = g0; j < bi; ++j) if (s.blk[j].state_dirty) { d |= BR_DEFER_SWEEP; break; }
+  }
   s.dirty[k] = d;
-  if (!(d & BR_DEFER)) { u32 slot = br_atomic_add(s.counters + 5, 1); s.dirty_list[slot] = k; br_atomic_min(s.counters + 6, k); }
+  if (!(d & BR_DEFER)) {
+    // Sweep heads (state-dirty chunks) go to the FRONT of the list, the rest is filled from the back: CTAs start in list
+    // order, so the long serial sweeps begin with the launch instead of trailing behind thousands of one-chunk walkers.
+    if (sweep_mode && (d == 2 || d == 3)) { u32 slot = br_atomic_add(s.counters + 17, 1); s.dirty_list[slot] = k; }
+    else { u32 slot = br_atomic_add(s.counters + 18, 1); s.dirty_list[s.P.nblocks - 1u - slot] = k; }
+    br_atomic_add(s.counters + 5, 1);
+    br_atomic_min(s.counters + 6, k);
+  }
+}
+// entry t of the schedule built above (t < counters[5])
+BR_DEV u32 br_sched_entry(const BrStream& s, u32 t) {
+  const u32 nfront = s.counters[17];
+  return t < nfront ? s.dirty_list[t] : s.dirty_list[s.P.nblocks - 1u - (t - nfront)];
 }
 
 // sequential driver for the CPU sim / single-thread use

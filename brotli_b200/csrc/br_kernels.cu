@@ -177,7 +177,7 @@ template <int G>
 __global__ void __launch_bounds__(128, G == 1 ? 8 : G == 4 ? 5 : 4) k_walk(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.counters[5]) return;
-  const u32 b = s.dirty_list[t];
+  const u32 b = br_sched_entry(s, t);
   br_walk_block<G>(s, b, s.forced && b == s.counters[6]);
 }
 __global__ void k_commit(BrStream s) {

@@ -600,14 +600,61 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   br_syncwarp();
 }
 
-// Walk chunk b, then go on into the chunks behind it (same input block) while
-//   * the next chunk is dirty but was left to this walker (BR_DEFER: the chain schedules only the head of a run of
-//     consecutive dirty chunks once the iteration is in sweep mode), or
-//   * the state this walker leaves differs from what the next chunk consumed on its latest run (CHASE),
-// and nobody else runs that chunk in this launch.  The walker sees its own fresh stored-bits from the sweep's first
-// position on, so a sweep over a run of dirty chunks is the sequential parse of that run: serial ripples (a
-// distance-cache change flowing through match-free data, stored-bits that keep perturbing the next chunk on chaotic
-// binary data) cost one launch, not one launch per chunk.
+// A sweep that reaches the end of its input block goes on into the next one.  What EncodeData does between two blocks
+// (encode.c:985: StitchToPreviousBlock, ExtendLastCommand eligibility, merge-or-flush) is the chain's business, but
+// the walker can PREDICT the in-state of the next block's first chunk from its own out-state and the metablock layout
+// of the last chain run; the chain verifies it like any other in-state (a wrong prediction leaves that chunk dirty).
+// Returns false at a boundary the walker cannot see through (metablock stored raw: distance cache restored; a block
+// swallowed whole by ExtendLastCommand; chunk records it cannot trust).
+BR_DEV bool br_predict_next_block(const BrStream& s, u32 b, const BrBlockIn& in, const BrBlockOut& o, BrBlockIn& ni) {
+  const BrParams& P = s.P;
+  const u32 nb = b + 1;
+  ni = s.bin[nb];
+  const bool flush = s.block_mb[nb] != s.block_mb[b];   // (layout of the last chain run)
+  if (flush && !s.mbs[s.block_mb[b]].compress) return false;
+  // (lane 0 reads what lane 0 wrote -- this sweep's own chunk records and commands -- and broadcasts the verdict)
+  u32 ext_dist = 0, fail = 0;
+  if (!flush && br_lane() == 0) {
+    // pending literals behind the block's last command, and that command
+    u32 lil = 0, c = b;
+    const u32 first = s.blk[in.blk].first_chunk;
+    bool found = false;
+    for (;;) {
+      const BrBlockOut oc = c == b ? o : s.bout[c];
+      if (!oc.valid) { fail = 1; break; }
+      lil += oc.last_insert_len;
+      if (oc.ncmd > 0) { found = true; break; }
+      if (c == first) break;
+      --c;
+    }
+    if (!fail && !found && lil == 0) fail = 1;   // no command and nothing pending: swallowed by ExtendLastCommand
+    if (!fail && found && lil == 0) {
+      const BrCmd lc = s.cmd_blocks[(size_t)c * s.cmd_stride + (c == b ? o.ncmd : s.bout[c].ncmd) - 1];
+      const u32 dcode = br_cmd_restore_dcode(lc.dist_prefix, lc.dist_extra);
+      const int cmd_dist = o.dc[0];
+      if (dcode < 16 || (cmd_dist > 0 && dcode - 15 == (u32)cmd_dist)) {
+        const u32 lpp = in.blk_end - (lc.copy_len & 0x1FFFFFF);
+        const u32 maxd = br_min(lpp, P.max_backward);
+        if (cmd_dist > 0 && (u32)cmd_dist <= maxd) ext_dist = (u32)cmd_dist;
+      }
+    }
+  }
+  ext_dist = br_shfl(ext_dist, 0); fail = br_shfl(fail, 0);
+  if (fail) return false;
+  ni.start_pos = ni.blk_start; ni.ext_dist = ext_dist; ni.apply_rh = 0; ni.store_end = 0; ni.warm = 0;
+  for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];
+  return true;
+}
+
+// Walk chunk b, then go on into the chunks behind it (same input block) while nobody else runs the next chunk in this
+// launch and
+//   * the state this walker leaves differs from what the next chunk consumed on its latest run (CHASE; the chain leaves
+//     such chunks to this walker: BR_DEFER_STATE, BR_DEFER_SWEEP), or
+//   * the next chunk was handed to this walker unconditionally (BR_DEFER_FULL, full-sweep launches).
+// The walker sees its own fresh stored-bits from the sweep's first position on, so a sweep over consecutive chunks is
+// the sequential parse of that stretch: serial ripples (the position phase of the sparse search running through
+// incompressible data, a distance-cache change flowing through match-free data) cost one launch per input block, not
+// one launch per chunk.
 template <int G>
 BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
   BrBlockIn in = s.bin[b];
@@ -617,20 +664,27 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
     BrBlockOut o;
     br_walk_one<G>(s, b, in, o, head, sweep_p0);
     if (br_lane() == 0) br_atomic_max((int*)s.counters + 16, (int)(b - head + 1));   // longest sweep of this launch (diagnostic)
-    if (in.last) return;   // (a sweep ends with its input block: what happens between two blocks is the chain's business)
     const u32 nb = b + 1;
-    BrBlockIn ni = s.bin[nb];
-    ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0; ni.warm = 0;
-    for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];
+    BrBlockIn ni;
+    if (in.last) {
+      // block boundary: crossed by the sweeps of a sweep-mode launch, inside a group of sweep_blocks blocks
+      const bool full_sweep = s.epoch > s.P.sweep_epoch + 9 && (s.epoch - 1 - s.P.sweep_epoch) % 3 == 0;   // (as br_chain_c decided it)
+      if (to_block_end || in.is_last || s.epoch <= s.P.sweep_epoch || full_sweep || ((in.blk + 1) & (s.P.sweep_blocks - 1u)) == 0) return;
+      if (!br_predict_next_block(s, b, in, o, ni)) return;
+    } else {
+      ni = s.bin[nb];
+      ni.start_pos = o.out_pos; ni.apply_rh = o.apply_rh; ni.store_end = o.store_end; ni.ext_dist = 0; ni.warm = 0;
+      for (int i = 0; i < 4; ++i) ni.dc[i] = o.dc[i];
+    }
     const u32 df = s.dirty[nb];
     bool go = to_block_end;
     if (!go) {
       if (df != 0 && !(df & BR_DEFER)) return;   // scheduled: another walker runs it in this launch
-      go = (df & BR_DEFER) != 0;
+      go = (df & BR_DEFER_FULL) != 0;   // (BR_DEFER_STATE / BR_DEFER_SWEEP: only if the state differs, below)
     }
     const u64 dl = (((u64)in.dict_l_hi << 32) | in.dict_l_lo) + o.dl, dm = (((u64)in.dict_m_hi << 32) | in.dict_m_lo) + o.dm;   // (a closed gate reports dl = dm = 0)
+    if (!go && !s.bout[nb].valid) { if (!(df & BR_DEFER)) return; go = true; }   // (a deferred chunk that never ran)
     if (!go) {
-      if (!s.bout[nb].valid) return;
       const BrBlockIn u = s.bin_used[nb];
       bool same = u.start_pos == ni.start_pos && u.apply_rh == ni.apply_rh && u.store_end == ni.store_end && u.ext_dist == ni.ext_dist &&
                   u.dc[0] == ni.dc[0] && u.dc[1] == ni.dc[1] && u.dc[2] == ni.dc[2] && u.dc[3] == ni.dc[3];
@@ -643,6 +697,17 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
       if (same) return;
     }
     ni.dict_l_lo = (u32)dl; ni.dict_l_hi = (u32)(dl >> 32); ni.dict_m_lo = (u32)dm; ni.dict_m_hi = (u32)(dm >> 32);
+    if (in.last && ni.blk_end - ni.blk_start >= s.P.htl - 1 && ni.blk_start >= 3) {
+      // StitchToPreviousBlock (hash_longest_match64_inc.h:127) of the block the sweep enters: the last three positions of
+      // the block it leaves.  br_commit_bits adds them for their owner; the sweep reads its own bitmap from sweep_p0 on.
+      u32* own = s.bits_cur + (size_t)(head & 1u) * s.bits_words;
+      if (br_lane() == 0)
+        for (u32 q = ni.blk_start - 3; q < ni.blk_start; ++q) if (q >= sweep_p0) br_atomic_or(own + (q >> 5), 1u << (q & 31));
+#if BR_GPU
+      __threadfence_block();
+#endif
+      br_syncwarp();
+    }
     in = ni; b = nb;
   }
 }

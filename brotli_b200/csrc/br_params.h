@@ -31,5 +31,6 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->step_cap = 4096;
   P->sweep_epoch = 3;    // text / web input settles in 3 launches; what is still dirty then is swept run by run
   P->force_epoch = 64;
+  P->sweep_blocks = P->lgblock >= 18 ? 8 : 32;   // sweeps are at most 2 MiB of input long
   return 1;
 }

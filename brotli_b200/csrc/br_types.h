@@ -32,6 +32,7 @@ struct BrParams {
                     // sweeps the run serially, seeing its own fresh stored-bits (Gauss-Seidel inside a run, Jacobi across runs)
   u32 force_epoch;  // from this launch on the first scheduled walker also runs to the end of its input block whatever the
                     // flags say: every launch then finalises at least one block, which bounds the number of launches
+  u32 sweep_blocks; // power of two: a sweep crosses input-block boundaries except into blocks whose index is a multiple of this
   u32 max_epochs;   // size of the per-launch arrays (a bound no input reaches: see br_kernels.cu)
   u32 step_cap;     // successor-walk budget per flipped bit in the dependency marking; beyond it the block-level rule
   u32 heavy_min;    // buckets with at least this many positions take the counter-wrap path (65536; tests lower it)
@@ -86,6 +87,7 @@ struct BrBlk {
   int out_dc[4];
   u32 lc_copy_len, lc_dist_prefix, lc_dist_extra;   // the block's last command
   int changed_epoch;
+  u32 state_dirty;   // br_chain_c: the block holds a chunk whose in-state is off (a sweep starts in it)
 };
 // What the block-to-block recurrence derives for an input block (br_chain_b -> br_chain_c).
 struct BrBlkIn {
@@ -108,11 +110,15 @@ struct BrMetaBlock {
 };
 
 // BrStream::dirty[] values: 0 clean; reason (1..5) = scheduled for the next walker launch; with a BR_DEFER_* bit the
-// chunk is dirty but left to the walker of the chunk before it: BR_DEFER_STATE = only its in-state is off (chase),
-// BR_DEFER_SWEEP = sweep mode (the chain schedules only the head of a run of consecutive dirty chunks).
+// chunk is dirty but left to the walker of the chunk before it (br_walk_block):
+//   BR_DEFER_STATE  its in-state is off and the chunk before it is walked anyway (chase);
+//   BR_DEFER_SWEEP  it lies behind a state-dirty chunk of its input block: the sweep that starts there walks it if it
+//                   arrives with another state than the chunk consumed, otherwise the chunk is scheduled next time;
+//   BR_DEFER_FULL   full sweep: the walker of the run's head walks it whatever the state.
 #define BR_DEFER_STATE 0x100u
 #define BR_DEFER_SWEEP 0x200u
-#define BR_DEFER (BR_DEFER_STATE | BR_DEFER_SWEEP)
+#define BR_DEFER_FULL 0x400u
+#define BR_DEFER (BR_DEFER_STATE | BR_DEFER_SWEEP | BR_DEFER_FULL)
 
 // Device-resident view of one stream (all pointers are device pointers).
 struct BrStream {

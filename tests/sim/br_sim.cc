@@ -90,6 +90,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
   if (getenv("BR_SIM_HEAVY_MIN")) P.heavy_min = (u32)atoi(getenv("BR_SIM_HEAVY_MIN"));
   if (getenv("BR_SIM_STEP_CAP")) P.step_cap = (u32)atoi(getenv("BR_SIM_STEP_CAP"));
   if (getenv("BR_SIM_SWEEP_EPOCH")) P.sweep_epoch = (u32)atoi(getenv("BR_SIM_SWEEP_EPOCH"));
+  if (getenv("BR_SIM_SWEEP_BLOCKS")) P.sweep_blocks = (u32)atoi(getenv("BR_SIM_SWEEP_BLOCKS"));
   if (getenv("BR_SIM_FORCE_EPOCH")) P.force_epoch = (u32)atoi(getenv("BR_SIM_FORCE_EPOCH"));
   u32 bs = 1u << P.lgblock;
   const u32 ch = 1u << BR_CHUNK_BITS;
@@ -182,7 +183,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
     s.counters[4] = 0; s.counters[16] = 0;
     s.forced = s.epoch >= s.P.force_epoch;
-    { u32 nd = s.counters[5]; std::vector<u32> dl(s.dirty_list, s.dirty_list + nd); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
+    { u32 nd = s.counters[5]; std::vector<u32> dl(nd); for (u32 t = 0; t < nd; ++t) dl[t] = br_sched_entry(s, t); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
       if (s.P.block_bits >= 8) br_walk_block<8>(s, k, f); else if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
     m.block_runs += s.counters[4];
 #ifdef BR_SIM_DEBUG
