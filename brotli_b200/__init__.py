@@ -132,7 +132,8 @@ class Compressor(object):
         if not self._s:
             raise error("BrotliEncoderCreateInstance failed")
         for param, val in ((0, mode), (1, quality), (2, lgwin), (3, lgblock)):
-            L.BrotliEncoderSetParameter(self._s, param, val)
+            if not L.BrotliEncoderSetParameter(self._s, param, val):   # python/_brotli.c:432 raises as well
+                raise error("BrotliEncoderSetParameter(%d, %d) failed" % (param, val))
 
     def __del__(self):
         if getattr(self, "_s", None):
@@ -159,6 +160,10 @@ class Compressor(object):
             if avail_in.value == 0:
                 break
         return b"".join(out)
+
+    def emit_metadata(self, payload):
+        """BROTLI_OPERATION_EMIT_METADATA (encode.h:127): a metadata block with `payload` (<= 16 MiB) at the current position."""
+        return self._stream(payload, 3)
 
     def process(self, string):
         return self._stream(string, self._PROCESS)

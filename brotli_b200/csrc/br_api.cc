@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <new>
 #include <thread>
 #include <vector>
 #include "../../include/brotli_b200.h"
@@ -114,7 +115,7 @@ size_t make_uncompressed_stream(const uint8_t* input, size_t input_size, uint8_t
 
 // host buffer -> device -> pipeline -> host vector / buffer.  Returns 0 on failure.
 int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap,
-                  size_t* out_n, std::vector<uint8_t>* out_vec) {
+                  size_t* out_n, std::vector<uint8_t>* out_vec, const BrCuts* cuts = nullptr) {
   if (!supported(p) || n == 0 || n > (1u << 30)) return 0;
   if (!ensure_job()) return 0;
   if (tls.d_in_cap < n) {
@@ -127,7 +128,7 @@ int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t
   if (cudaMemcpyAsync(tls.d_in, in, n, cudaMemcpyHostToDevice, st) != cudaSuccess) return 0;
   const uint8_t* d_out = nullptr; size_t sz = 0;
   int q = p.quality, w = p.lgwin > 24 ? 24 : p.lgwin;
-  if (!br_job_compress_device(tls.job, q, w, size_hint, tls.d_in, (uint32_t)n, &d_out, &sz)) return 0;
+  if (!br_job_compress_device(tls.job, q, w, size_hint, tls.d_in, (uint32_t)n, &d_out, &sz, cuts)) return 0;
   record_stats();
   if (out_vec) { out_vec->resize(sz); out = out_vec->data(); out_cap = sz; }
   if (sz > out_cap) return 0;
@@ -160,16 +161,126 @@ int compress_host_q1(const Params& p0, const uint8_t* in, size_t n, const std::v
 
 }  // namespace
 
+// Buffers of an encoder instance come from the caller's allocator pair when one was given (encode.h:295-306).
+template <class T> struct BrAlloc {
+  typedef T value_type;
+  brotli_alloc_func af = nullptr; brotli_free_func ff = nullptr; void* opaque = nullptr;
+  BrAlloc() {}
+  BrAlloc(brotli_alloc_func a, brotli_free_func f, void* o) : af(a), ff(f), opaque(o) {}
+  template <class U> BrAlloc(const BrAlloc<U>& o) : af(o.af), ff(o.ff), opaque(o.opaque) {}
+  T* allocate(size_t n) {
+    void* p = af ? af(opaque, n * sizeof(T)) : malloc(n * sizeof(T));
+    if (!p) throw std::bad_alloc();
+    return (T*)p;
+  }
+  void deallocate(T* p, size_t) { if (ff) ff(opaque, p); else free(p); }
+  template <class U> bool operator==(const BrAlloc<U>& o) const { return af == o.af && ff == o.ff && opaque == o.opaque; }
+  template <class U> bool operator!=(const BrAlloc<U>& o) const { return !(*this == o); }
+};
+typedef std::vector<uint8_t, BrAlloc<uint8_t>> ByteVec;
+
+// A FLUSH (kind 1) or EMIT_METADATA (kind 2) operation at input position pos (quality 5..9).
+struct StreamEvent { uint32_t pos; int kind; std::vector<uint8_t> meta; };
+
 struct BrotliEncoderStateStruct {
   brotli_alloc_func alloc_func; brotli_free_func free_func; void* opaque;
   Params params;
   bool initialized = false, finished = false, compressed = false, hint_fixed = false;
   bool q1_header_done = false;   // quality 1: a FLUSH already delivered the window bits
-  std::vector<uint8_t> input, output;
+  ByteVec input, output;
   std::vector<size_t> calls;     // quality 1: bytes brought by each CompressStream call (encode.c:1425 cuts fragments per call)
+  std::vector<StreamEvent> events;   // quality 5..9: the FLUSH / EMIT_METADATA operations so far
+  size_t wire_sent = 0;          // quality 5..9: bytes of the stream already handed to `output`
   size_t out_pos = 0;
   uint64_t total_out = 0;
+  BrotliEncoderStateStruct(brotli_alloc_func a, brotli_free_func f, void* o)
+      : alloc_func(a), free_func(f), opaque(o), input(BrAlloc<uint8_t>(a, f, o)), output(BrAlloc<uint8_t>(a, f, o)) {}
 };
+
+namespace {
+// LSB-first bit writer over a byte vector (c/enc/write_bits.h:33)
+struct BitOut {
+  std::vector<uint8_t>& v; uint32_t pb;   // pb: bits used in the last byte (0 = byte aligned)
+  void put(uint32_t n, uint64_t bits) {
+    for (uint32_t i = 0; i < n; ++i) {
+      if (pb == 0) v.push_back(0);
+      if ((bits >> i) & 1) v.back() |= (uint8_t)(1u << pb);
+      pb = (pb + 1) & 7;
+    }
+  }
+  void align() { pb = 0; }
+};
+// encode.c:1228 WriteMetadataHeader + the body (encode.c:1584)
+void put_metadata(BitOut& w, const std::vector<uint8_t>& meta) {
+  const size_t size = meta.size();
+  w.put(1, 0); w.put(2, 3); w.put(1, 0);
+  if (size == 0) w.put(2, 0);
+  else {
+    uint32_t nbits = size == 1 ? 1 : (32u - (uint32_t)__builtin_clz((uint32_t)size - 1));
+    uint32_t nbytes = (nbits + 7) / 8;
+    w.put(2, nbytes); w.put(8 * nbytes, size - 1);
+  }
+  w.align();
+  w.v.insert(w.v.end(), meta.begin(), meta.end());
+}
+int lgblock_of(const Params& p) { return (p.quality >= 9 && p.lgwin > 16) ? (p.lgwin < 18 ? p.lgwin : 18) : 16; }
+
+// The whole stream for the operations seen so far (quality 5..9): the device compresses the accumulated input cut at the
+// positions of the FLUSH / EMIT_METADATA operations (br_kernels.cu k_assemble_scan pads behind a FLUSH); metadata blocks and
+// everything that happens before the first input byte are spliced in here.  Every call reproduces the bytes of the call
+// before as a prefix: the parse is causal, and each cut ends on a byte boundary.
+int build_wire(BrotliEncoderState* s, bool is_final, bool finish_empty, std::vector<uint8_t>& W) {
+  const size_t n = s->input.size();
+  const int lgwin = s->params.lgwin > 24 ? 24 : s->params.lgwin;
+  W.clear();
+  BitOut w{W, 0};
+  size_t e = 0;
+  const std::vector<StreamEvent>& ev = s->events;
+  const bool lead = !ev.empty() && ev[0].pos == 0;
+  if (lead || n == 0) {
+    if (lgwin == 17) w.put(7, 1); else w.put(4, (uint64_t)(((lgwin - 17) << 1) | 1));   // encode.c:670 window bits
+    for (; e < ev.size() && ev[e].pos == 0; ++e) {
+      if (ev[e].kind == 1) { if (w.pb) { w.put(6, 6); w.align(); } }   // encode.c:1356 InjectBytePaddingBlock
+      else put_metadata(w, ev[e].meta);
+    }
+  }
+  if (n == 0) {
+    if (is_final) { w.put(2, 3); w.align(); }   // encode.c:1006: ISLAST + ISEMPTY
+    return 1;
+  }
+  std::vector<uint32_t> cut_pos, cut_kind;
+  for (size_t i = e; i < ev.size(); ++i)
+    if (cut_pos.empty() || cut_pos.back() != ev[i].pos) { cut_pos.push_back(ev[i].pos); cut_kind.push_back((uint32_t)ev[i].kind); }
+  const bool cut_at_end = !cut_pos.empty() && cut_pos.back() == n;
+  std::vector<uint64_t> end_bit(cut_pos.size() + 1, 0);
+  BrCuts c; c.pos = cut_pos.data(); c.kind = cut_kind.data(); c.n = (uint32_t)cut_pos.size();
+  c.is_final = (is_final && !cut_at_end) ? 1 : 0; c.with_header = lead ? 0 : 1;
+  c.finish_empty = (c.is_final && finish_empty) ? 1 : 0; c.end_bit = end_bit.data();
+  if (!c.is_final && !cut_at_end) return 0;   // (callers only build the wire at a cut or at FINISH)
+  std::vector<uint8_t> D;
+  size_t got = 0;
+  if (!compress_host(s->params, s->params.size_hint, s->input.data(), n, nullptr, 0, &got, &D, &c)) return 0;
+  size_t from = 0;
+  for (size_t i = 0; i < cut_pos.size(); ++i) {
+    const uint64_t eb = end_bit[i];
+    size_t upto, next;
+    if (cut_kind[i] == 1) { next = (size_t)(((eb & 7) ? eb + 6 : eb) + 7) >> 3; upto = next; }   // the device wrote the padding block
+    else { upto = (size_t)((eb + 7) >> 3); next = upto; }
+    W.insert(W.end(), D.begin() + (long)from, D.begin() + (long)upto);
+    w.pb = cut_kind[i] == 2 ? (uint32_t)(eb & 7) : 0;
+    bool first = true;
+    for (; e < ev.size() && ev[e].pos == cut_pos[i]; ++e, first = false) {
+      if (ev[e].kind == 2) put_metadata(w, ev[e].meta);   // (a FLUSH on a byte boundary emits nothing)
+      else if (!first) {}
+    }
+    w.align();
+    from = next;
+  }
+  W.insert(W.end(), D.begin() + (long)from, D.end());
+  if (is_final && cut_at_end) W.push_back(3);   // encode.c:520: empty last metablock on a byte boundary
+  return 1;
+}
+}  // namespace
 
 extern "C" {
 
@@ -233,7 +344,7 @@ BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, size_t input_size, 
   if (!supported(p) || input_size == 0 || input_size > (1u << 30) || !ensure_job()) return BROTLI_FALSE;
   const uint8_t* d_out = nullptr; size_t sz = 0;
   if (!br_job_compress_device(tls.job, quality, lgwin, (uint32_t)input_size, (const uint8_t*)d_input,
-                              (uint32_t)input_size, &d_out, &sz)) return BROTLI_FALSE;
+                              (uint32_t)input_size, &d_out, &sz, nullptr)) return BROTLI_FALSE;
   record_stats();
   if (sz > *encoded_size) return BROTLI_FALSE;
   cudaStream_t st = (cudaStream_t)br_job_stream(tls.job);
@@ -312,12 +423,16 @@ size_t BrotliB200CompressBatchDevice(int quality, int lgwin, size_t count, const
 
 BrotliEncoderState* BrotliEncoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque) {
   if ((alloc_func == nullptr) != (free_func == nullptr)) return nullptr;   /* encode.h:295 */
-  BrotliEncoderState* s = new (std::nothrow) BrotliEncoderState();
-  if (!s) return nullptr;
-  s->alloc_func = alloc_func; s->free_func = free_func; s->opaque = opaque;
-  return s;
+  void* mem = alloc_func ? alloc_func(opaque, sizeof(BrotliEncoderState)) : malloc(sizeof(BrotliEncoderState));
+  if (!mem) return nullptr;
+  return new (mem) BrotliEncoderState(alloc_func, free_func, opaque);
 }
-void BrotliEncoderDestroyInstance(BrotliEncoderState* state) { delete state; }
+void BrotliEncoderDestroyInstance(BrotliEncoderState* state) {
+  if (!state) return;
+  brotli_free_func ff = state->free_func; void* opaque = state->opaque;
+  state->~BrotliEncoderStateStruct();
+  if (ff) ff(opaque, state); else free(state);
+}
 
 BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* s, BrotliEncoderParameter p, uint32_t value) {
   if (s->initialized) return BROTLI_FALSE;   /* encode.c:63 */
@@ -360,16 +475,28 @@ static void push_output(BrotliEncoderState* s, size_t* available_out, uint8_t** 
   if (total_out) *total_out = (size_t)s->total_out;
 }
 
-/* encode.c:1634.  Input is accumulated on the host until FINISH, then the whole stream goes
-   through the GPU pipeline in one piece -- the bytes equal the reference's for the same call
-   sequence (the size hint is frozen when the reference would have
-   frozen it, at its first EncodeData call).  FLUSH and EMIT_METADATA are not implemented yet:
-   they fail instead of silently behaving differently. */
+/* encode.c:1634.  Quality 5..9: the input is accumulated on the host; every FLUSH / EMIT_METADATA / FINISH sends the
+   whole stream so far through the GPU pipeline, cut where those operations happened (build_wire), and hands out the bytes
+   that are new.  The bytes equal the reference's for the same call sequence (the size hint is frozen
+   when the reference would have frozen it, at its first EncodeData call).  Cost: a stream with k flushes is compressed k
+   times, and host memory grows with the stream (at most 1 GiB, then PROCESS fails) -- the reference's bounded-memory
+   streaming needs the pipeline to resume from a saved window, which it does not do yet.
+   Quality 1 (encode.c:1425): every call compresses its own fragments; FLUSH is cheap. */
+static BROTLI_BOOL compress_stream_impl(BrotliEncoderState* s, BrotliEncoderOperation op, size_t* available_in,
+    const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out);
 BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOperation op, size_t* available_in,
     const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out) {
+  try { return compress_stream_impl(s, op, available_in, next_in, available_out, next_out, total_out); }
+  catch (const std::bad_alloc&) { return BROTLI_FALSE; }   /* the reference reports allocation failure the same way */
+}
+static BROTLI_BOOL compress_stream_impl(BrotliEncoderState* s, BrotliEncoderOperation op, size_t* available_in,
+    const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out) {
   s->initialized = true;
-  if (op == BROTLI_OPERATION_EMIT_METADATA) return BROTLI_FALSE;
-  if (op == BROTLI_OPERATION_FLUSH && s->params.quality == 1 && supported(s->params) && !s->compressed) {
+  const bool q1 = s->params.quality == 1;
+  if (!supported(s->params)) return BROTLI_FALSE;
+  if (op == BROTLI_OPERATION_EMIT_METADATA && q1) return BROTLI_FALSE;   /* not built for the fragment coder */
+  if (s->compressed && (*available_in != 0 || op == BROTLI_OPERATION_EMIT_METADATA)) return BROTLI_FALSE;   /* input after finish */
+  if (op == BROTLI_OPERATION_FLUSH && q1 && !s->compressed) {
     /* Quality 1 (encode.c:1425): the fragments of this call are compressed now, then the stream is padded
        to a byte boundary (encode.c:1356), so everything delivered so far is decodable. */
     if (*available_in) {
@@ -389,28 +516,57 @@ BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOper
     push_output(s, available_out, next_out, total_out);
     return BROTLI_TRUE;
   }
-  if (op == BROTLI_OPERATION_FLUSH) {
-    if (*available_in == 0 && s->input.empty()) { push_output(s, available_out, next_out, total_out); return BROTLI_TRUE; }
-    return BROTLI_FALSE;
+  if (!q1 && !s->compressed) {
+    /* ---- quality 5..9 */
+    if (op == BROTLI_OPERATION_EMIT_METADATA) {
+      if (*available_in > (1u << 24)) return BROTLI_FALSE;   /* encode.c:1552 */
+    } else if (*available_in) {
+      if (s->input.size() + *available_in > ((size_t)1 << 30)) return BROTLI_FALSE;   /* positions are 32-bit in the pipeline */
+      s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
+    }
+    const bool finish_without_input = op == BROTLI_OPERATION_FINISH && *available_in == 0;
+    if (!s->hint_fixed) {
+      /* encode.c:1619 UpdateSizeHint runs at the first EncodeData: when the first input block (1 << lgblock) is full
+         or the operation is not PROCESS. */
+      if (op != BROTLI_OPERATION_PROCESS || s->input.size() >= ((size_t)1 << lgblock_of(s->params))) {
+        /* (an estimate of zero -- an operation before any input -- is taken again at the next EncodeData) */
+        if (s->params.size_hint == 0) s->params.size_hint = (uint32_t)s->input.size();
+        s->hint_fixed = s->params.size_hint != 0;
+      }
+    }
+    if (op == BROTLI_OPERATION_EMIT_METADATA) {
+      StreamEvent e; e.pos = (uint32_t)s->input.size(); e.kind = 2; e.meta.assign(*next_in, *next_in + *available_in);
+      s->events.push_back(std::move(e));
+    } else if (op == BROTLI_OPERATION_FLUSH) {
+      StreamEvent e; e.pos = (uint32_t)s->input.size(); e.kind = 1;
+      s->events.push_back(std::move(e));
+    }
+    if (op != BROTLI_OPERATION_EMIT_METADATA) *next_in += *available_in;
+    else *next_in += *available_in;
+    *available_in = 0;
+    if (op != BROTLI_OPERATION_PROCESS) {
+      const size_t last_cut = s->events.empty() ? 0 : s->events.back().pos;
+      const size_t bs = (size_t)1 << lgblock_of(s->params);
+      /* FINISH without input right behind a full input block: that block was already encoded as a non-last one */
+      const bool finish_empty = finish_without_input && s->input.size() > last_cut && (s->input.size() - last_cut) % bs == 0;
+      std::vector<uint8_t> W;
+      if (!build_wire(s, op == BROTLI_OPERATION_FINISH, finish_empty, W)) return BROTLI_FALSE;
+      if (W.size() < s->wire_sent) return BROTLI_FALSE;
+      s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
+      s->output.insert(s->output.end(), W.begin() + (long)s->wire_sent, W.end());
+      s->wire_sent = W.size();
+      if (op == BROTLI_OPERATION_FINISH) { s->compressed = true; ByteVec(s->input.get_allocator()).swap(s->input); }
+    }
+    push_output(s, available_out, next_out, total_out);
+    if (s->compressed && s->out_pos == s->output.size()) s->finished = true;
+    return BROTLI_TRUE;
   }
-  if (s->compressed && *available_in != 0) return BROTLI_FALSE;   /* input after finish */
-  if (!supported(s->params)) return BROTLI_FALSE;
+  /* ---- quality 1, PROCESS / FINISH */
   if (!s->compressed && (*available_in || op == BROTLI_OPERATION_FINISH)) s->calls.push_back(*available_in);
   if (*available_in) {
+    if (s->input.size() + *available_in > ((size_t)1 << 28)) return BROTLI_FALSE;   /* bit offsets of a stream are 32-bit */
     s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
     *next_in += *available_in; *available_in = 0;
-  }
-  if (!s->hint_fixed) {
-    /* encode.c:1619 UpdateSizeHint runs at the first EncodeData: when the first input block
-       (1 << lgblock) is full or the operation is not PROCESS. */
-    size_t lgblock = (s->params.quality >= 9 && s->params.lgwin > 16) ? (s->params.lgwin < 18 ? s->params.lgwin : 18) : 16;
-    if (op != BROTLI_OPERATION_PROCESS || s->input.size() >= ((size_t)1 << lgblock)) {
-      if (s->params.size_hint == 0) {
-        size_t t = s->input.size();
-        s->params.size_hint = t >= (1u << 30) ? (1u << 30) : (uint32_t)t;
-      }
-      s->hint_fixed = true;
-    }
   }
   if (op == BROTLI_OPERATION_FINISH && !s->compressed && s->q1_header_done) {
     /* quality 1 behind a FLUSH: the last segment has no window bits */
@@ -420,26 +576,23 @@ BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* s, BrotliEncoderOper
     s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
     s->output.insert(s->output.end(), seg.begin(), seg.end());
     s->compressed = true;
-    std::vector<uint8_t>().swap(s->input);
+    ByteVec(s->input.get_allocator()).swap(s->input);
   }
   if (op == BROTLI_OPERATION_FINISH && !s->compressed) {
+    std::vector<uint8_t> seg;
     if (s->input.empty()) {
       /* encode.c:1006: empty stream = window bits + ISLAST + ISEMPTY */
       int lgwin = s->params.lgwin > 24 ? 24 : s->params.lgwin;
-      if (s->params.quality == 1 && lgwin < 18) lgwin = 18;      /* encode.c:673 */
-      uint32_t bits = lgwin == 17 ? 1u : (uint32_t)(((lgwin - 17) << 1) | 1), nb = lgwin == 17 ? 7 : 4;
+      if (lgwin < 18) lgwin = 18;      /* encode.c:673 */
+      uint32_t bits = (uint32_t)(((lgwin - 17) << 1) | 1), nb = 4;
       bits |= 3u << nb; nb += 2;
-      s->output.assign((nb + 7) / 8, 0);
-      for (uint32_t i = 0; i < (nb + 7) / 8; ++i) s->output[i] = (uint8_t)(bits >> (8 * i));
-    } else {
-      size_t got = 0;
-      if (s->params.quality == 1) {
-        if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &s->output)) return BROTLI_FALSE;
-      } else if (!compress_host(s->params, s->params.size_hint, s->input.data(), s->input.size(), nullptr, 0, &got, &s->output))
-        return BROTLI_FALSE;
-    }
+      seg.assign((nb + 7) / 8, 0);
+      for (uint32_t i = 0; i < (nb + 7) / 8; ++i) seg[i] = (uint8_t)(bits >> (8 * i));
+    } else if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &seg)) return BROTLI_FALSE;
+    s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
+    s->output.insert(s->output.end(), seg.begin(), seg.end());
     s->compressed = true;
-    std::vector<uint8_t>().swap(s->input);
+    ByteVec(s->input.get_allocator()).swap(s->input);
   }
   push_output(s, available_out, next_out, total_out);
   if (s->compressed && s->out_pos == s->output.size()) s->finished = true;

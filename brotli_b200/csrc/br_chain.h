@@ -14,6 +14,14 @@ static u32 br_sim_watch = 0xffffffffu;   // tests/sim: report commits that flip 
 static u64 br_sim_cnt[8];                // tests/sim: marks by source (0 successor, 1 overlap, 2 cap hits, 3 flips, 4 steps)
 #endif
 
+// Chunk whose nominal slice holds position p.  Input blocks are at most 1 << lgblock bytes long but need not be aligned
+// (a FLUSH cuts one short): slot_blk gives the block at the aligned position below p, a short scan finds p's block.
+BR_DEV u32 br_chunk_of(const BrStream& s, u32 p) {
+  u32 b = s.slot_blk[p >> s.P.lgblock];
+  while (p >= s.blk[b].end) ++b;
+  return s.blk[b].first_chunk + ((p - s.blk[b].start) >> BR_CHUNK_BITS);
+}
+
 // Compare and commit the stored-bits a walker just produced for chunk k (warp task).  The
 // walker owns the positions [start_pos, out_pos).  StitchToPreviousBlock of the FOLLOWING input
 // block (hash_longest_match64_inc.h:127) stores the last three positions of a block after its
@@ -29,7 +37,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
   // so every chunk whose latest range intersects mine is told to walk again.  Ranges of one input block
   // are disjoint at the fixpoint, so this stops.
   if (b > a) {
-    const u32 k0 = (k >> s.P.cpb_shift) << s.P.cpb_shift, k1 = br_min(k0 + (1u << s.P.cpb_shift), s.P.nblocks);
+    const u32 k0 = s.blk[in.blk].first_chunk, k1 = k0 + s.blk[in.blk].nchunks;
     for (u32 c = k0 + (u32)br_lane(); c < k1; c += BR_WARP) {
       if (c == k || !s.bout[c].valid) continue;
       const u32 ca = s.bin_used[c].start_pos, cb = s.bout[c].out_pos;
@@ -113,7 +121,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
             if ((s.bits_prev[pp >> 5] >> (pp & 31)) & 1) ++cnt;
             if (pp >= a && pp < b) continue;            // my own run is consistent with my own bits
             if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
-            u32 c = ((pp >> s.P.lgblock) << s.P.cpb_shift) + ((pp & ((1u << s.P.lgblock) - 1)) >> BR_CHUNK_BITS);
+            u32 c = br_chunk_of(s, pp);
 #ifdef BR_SIM_DEBUG
             ++br_sim_cnt[0];
 #endif
@@ -305,12 +313,16 @@ BR_DEV void br_chain_b(const BrStream& s) {
       }
     }
     cmd_total += B.ncmd;
+    bool closes_stream = false, empty_last = false;
     // merge-or-flush (encode.c:1141)
     const u32 end = B.end;
     {
       const u32 processed = end - last_flush_pos;
       const bool next_fits = processed + blocksize <= P.max_mb;
-      if (!B.is_last && !B.force_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) continue;
+      if (!B.is_last && !B.force_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) {
+        if (!(P.finish_empty && bi + 1 == nblk)) continue;
+        closes_stream = true;    // merged, and the FINISH call that brought nothing flushes it as the last metablock
+      } else if (P.finish_empty && bi + 1 == nblk) empty_last = true;
     }
     u32 tail = 0;
     if (last_insert_len > 0) { tail = last_insert_len; ++num_cmds; num_lits += tail; last_insert_len = 0; ++cmd_total; }
@@ -324,10 +336,10 @@ BR_DEV void br_chain_b(const BrStream& s) {
       m.start = last_flush_pos; m.end = end;
       m.first_block = first_blk_chunk; m.last_block = B.first_chunk + B.nchunks - 1;
       m.cmd_off = first_blk_cmd_base; m.ncmd = num_cmds; m.nlit = num_lits;
-      m.is_last = B.is_last; m.compress = (u32)compress;
+      m.is_last = (B.is_last || closes_stream) ? 1u : 0u; m.compress = (u32)compress;
       m.prev_byte = last_flush_pos > 0 ? s.data[last_flush_pos - 1] : 0;
       m.prev_byte2 = last_flush_pos > 1 ? s.data[last_flush_pos - 2] : 0;
-      m.pad0 = m.pad1 = 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
+      m.flushed = (u8)B.force_flush; m.empty_last = empty_last ? 1 : 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
       s.mbs[n_mbs] = m;
     }
     br_syncwarp();

@@ -134,24 +134,28 @@ static void scan_exclusive(u32* a, u32 n, u32* tmp, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------- stored bits
 // Initial speculation: every hashable position of a block is stored (true for > 99.8 % of
-// text positions).
+// text positions).  One CTA per input block (blocks cut by a FLUSH are irregular); words shared
+// by two blocks are ORed into a zeroed bitmap.
 __global__ void k_init_bits(BrStream s) {
-  u32 wi = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 nwords = (s.P.n + 31) / 32;
-  if (wi >= nwords) return;
-  u32 bs = 1u << s.P.lgblock, v = 0;
-  for (u32 b = 0; b < 32; ++b) {
-    u32 p = wi * 32 + b;
-    if (p >= s.P.n) break;
-    u32 blk_end = (p / bs + 1) * bs; if (blk_end > s.P.n) blk_end = s.P.n;   // uniform blocks (one-shot)
-    if (p + s.P.htl <= blk_end) v |= 1u << b;
-    // StitchToPreviousBlock of the next block stores the last three positions of this one
-    if (blk_end < s.P.n && p + 3 >= blk_end) {
-      u32 nxt = s.P.n - blk_end < bs ? s.P.n - blk_end : bs;
-      if (nxt >= s.P.htl - 1) v |= 1u << b;
-    }
+  const BrBlk B = s.blk[blockIdx.x];
+  const u32 htl = s.P.htl;
+  // positions of this block that the parse stores: those with a full hash load inside the block ...
+  u32 lo = B.start, hi = B.end - B.start >= htl ? B.end - htl + 1 : B.start;
+  // ... and the last three, stored by StitchToPreviousBlock of the next block (hash_longest_match64_inc.h:127)
+  u32 s_lo = 0, s_hi = 0;
+  if (blockIdx.x + 1 < s.nblk) {
+    const BrBlk N = s.blk[blockIdx.x + 1];
+    if (N.end - N.start >= htl - 1 && N.start >= 3) { s_lo = N.start - 3 > B.start ? N.start - 3 : B.start; s_hi = N.start; }
   }
-  s.bits_latest[wi] = v;
+  const u32 w0 = B.start >> 5, w1 = (B.end - 1) >> 5;
+  for (u32 wi = w0 + threadIdx.x; wi <= w1; wi += blockDim.x) {
+    u32 v = 0;
+    for (u32 b = 0; b < 32; ++b) {
+      const u32 p = wi * 32 + b;
+      if ((p >= lo && p < hi) || (p >= s_lo && p < s_hi)) v |= 1u << b;
+    }
+    if (v) atomicOr(s.bits_latest + wi, v);
+  }
 }
 // bits_latest permuted into S order + per-1024 popcounts
 __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restrict__ storedS, u32* __restrict__ blockcnt) {
@@ -281,13 +285,22 @@ __global__ void k_emit_lit(BrStream s, BrEnt e) {
 
 // ---------------------------------------------------------------------------- stream assembly
 struct BrCopyDesc { u64 dst_bit; u64 src_off; u32 nbits; u32 kind; };  // kind 0: bit copy from outbits, 1: raw bytes from input
-// res[0..1]: total bytes (u64), res[2]: first metablock that needs the late fallback (+1), 0 if none
-__global__ void k_assemble_scan(BrStream s, const u64* __restrict__ out_off, u32* out, BrCopyDesc* desc, u32* res) {
+// res[0..1]: total bytes (u64), res[2]: first metablock that needs the late fallback (+1), 0 if none, res[3]: cuts seen.
+// with_header: the stream starts here (window bits); 0 when the caller already sent them (a FLUSH / EMIT_METADATA before any
+// input).  cut_kind[i] says what ended the i-th flushed metablock: 1 = FLUSH (encode.c:1356 InjectBytePaddingBlock: an empty
+// metadata block pads to a byte boundary unless the stream stands on one), 2 = EMIT_METADATA (encode.c:1549: no padding
+// block -- the caller merges its metadata header into the pending bits -- and the next metablock starts on the next byte
+// boundary).  cut_end_bit[i] receives the bit position where that metablock ended (before any padding).
+__global__ void k_assemble_scan(BrStream s, const u64* __restrict__ out_off, u32* out, BrCopyDesc* desc, u32* res,
+                                int with_header, const u32* __restrict__ cut_kind, u64* cut_end_bit) {
   if (threadIdx.x != 0) return;
   u64 bit = 0;
+  u32 ncut = 0;
   const int lgwin = s.P.lgwin;
-  if (lgwin == 17) { br_put_bits_at(out, 0, 7, 1); bit = 7; }
-  else { br_put_bits_at(out, 0, 4, (u64)(((lgwin - 17) << 1) | 1)); bit = 4; }
+  if (with_header) {
+    if (lgwin == 17) { br_put_bits_at(out, 0, 7, 1); bit = 7; }
+    else { br_put_bits_at(out, 0, 4, (u64)(((lgwin - 17) << 1) | 1)); bit = 4; }
+  }
   u32 nm = s.counters[1], fallback = 0;
   for (u32 i = 0; i < nm; ++i) {
     BrMetaBlock mb = s.mbs[i];
@@ -315,9 +328,16 @@ __global__ void k_assemble_scan(BrStream s, const u64* __restrict__ out_off, u32
       if (mb.is_last) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 2, 3); bit += 2; bit = (bit + 7) & ~7ull; }
     }
     desc[i] = d;
+    if (mb.empty_last) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 2, 3); bit += 2; bit = (bit + 7) & ~7ull; }   // encode.c:520
+    if (mb.flushed && !mb.is_last) {
+      cut_end_bit[ncut] = bit;
+      if (cut_kind[ncut] == 1 && (bit & 7)) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 6, 6); bit += 6; }
+      bit = (bit + 7) & ~7ull;
+      ++ncut;
+    }
   }
   u64 total = (bit + 7) >> 3;
-  res[0] = (u32)total; res[1] = (u32)(total >> 32); res[2] = fallback;
+  res[0] = (u32)total; res[1] = (u32)(total >> 32); res[2] = fallback; res[3] = ncut;
 }
 // grid.y = metablock, grid.x strides over its words / bytes
 __global__ void k_assemble_copy(BrStream s, const BrCopyDesc* __restrict__ desc, const u32* __restrict__ outbits, u32* out) {
@@ -437,8 +457,9 @@ static size_t scan_tmp_words(size_t n) { return n / SCAN_CHUNK + n / SCAN_CHUNK 
 // Compress one stream whose input already sits in device memory (d_in, n bytes).  The
 // compressed bytes are left in device memory (*d_out, *out_size; valid until the next call on
 // this job).  Returns 1 on success, 0 on failure (unsupported parameters, CUDA error).
+// `cuts` (nullable): the stream is cut by FLUSH / EMIT_METADATA operations (br_pipeline.h BrCuts).
 extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 size_hint,
-                                      const u8* d_in, u32 n, const u8** d_out, size_t* out_size) {
+                                      const u8* d_in, u32 n, const u8** d_out, size_t* out_size, const BrCuts* cuts) {
   BrDeviceTables* T = get_tables();
   if (!T || n == 0) return 0;
   BrStream s; memset(&s, 0, sizeof(s));
@@ -453,23 +474,18 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 #else
   const bool trace = false;
 #endif
-  const u32 bs = 1u << P.lgblock, ch = 1u << BR_CHUNK_BITS;
-  // chunk / block tables (one-shot call: uniform input blocks of 1 << lgblock bytes)
+  const u32 ch = 1u << BR_CHUNK_BITS;
+  // chunk / block tables: the reference's input blocks (1 << lgblock bytes, shorter where a FLUSH cut the input)
   std::vector<BrBlockIn> hb; std::vector<BrBlk> hblk;
-  for (u64 bstart = 0; bstart < n; bstart += bs) {
-    u32 bend = (u32)(bstart + bs < n ? bstart + bs : n);
-    BrBlk B; memset(&B, 0, sizeof(B));
-    B.start = (u32)bstart; B.end = bend; B.is_last = (bend == n); B.changed_epoch = -1;
-    B.first_chunk = (u32)hb.size();
-    for (u64 c = bstart; c < bend; c += ch) {
-      BrBlockIn ci; memset(&ci, 0, sizeof(ci));
-      ci.pos = (u32)c; ci.end = (u32)(c + ch < bend ? c + ch : bend); ci.blk_start = (u32)bstart; ci.blk_end = bend;
-      ci.first = (c == bstart); ci.last = (ci.end == bend); ci.is_last = B.is_last; ci.blk = (u32)hblk.size();
-      hb.push_back(ci);
-    }
-    B.nchunks = (u32)hb.size() - B.first_chunk;
-    hblk.push_back(B);
-  }
+  const u32 ncuts = cuts ? cuts->n : 0;
+  const bool is_final = cuts ? cuts->is_final != 0 : true;
+  const int with_header = cuts ? cuts->with_header : 1;
+  P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
+  if (!is_final && (ncuts == 0 || cuts->pos[ncuts - 1] != n)) return 0;   // an unfinished stream ends at a cut
+  if (P.finish_empty && (!is_final || (ncuts && cuts->pos[ncuts - 1] == n))) return 0;
+  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, ncuts, is_final && !P.finish_empty, hb, hblk);
+  std::vector<u32> h_slot(((size_t)n >> P.lgblock) + 2, 0);
+  { u32 b = 0; for (size_t i = 0; i < h_slot.size(); ++i) { const u64 p = (u64)i << P.lgblock; while (b + 1 < hblk.size() && hblk[b].end <= p) ++b; h_slot[i] = b; } }
   const u32 nb = (u32)hb.size(), nblk = (u32)hblk.size();
   P.nblocks = nb;
   cudaStream_t st = job->st;
@@ -489,6 +505,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
   for (int i = 0; i < 14; ++i) add(nb * 4ull + 64);
   add(nblk * sizeof(BrBlk)); add(nblk * sizeof(BrBlkIn)); add((P.nbuckets + 8) * 4ull);
+  add(h_slot.size() * 4); add((ncuts + 2) * 4ull); add((ncuts + 2) * 8ull);
   // Launch bound: in forced mode every launch finalises at least one input block (at most two launches per block with
   // the conservative block-level re-marks), and a late uncompressed fallback restarts the count at most once per metablock.
   P.max_epochs = 4 * nb + 4096;
@@ -516,6 +533,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   int* bitdep_epoch = A.take<int>(nb + 16);
   BrBlk* d_blk = A.take<BrBlk>(nblk); BrBlkIn* d_blkin = A.take<BrBlkIn>(nblk);
   u32* key_flips = A.take<u32>(P.nbuckets + 8);
+  u32* slot_blk = A.take<u32>(h_slot.size()); u32* d_cut_kind = A.take<u32>(ncuts + 2); u64* d_cut_end = A.take<u64>(ncuts + 2);
   u32* epoch_cum = A.take<u32>((size_t)P.max_epochs + 2);
   BrMetaBlock* mbs = A.take<BrMetaBlock>(nb + 1);
   u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256);
@@ -538,6 +556,9 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 
   CK(cudaMemcpyAsync(bin, hb.data(), nb * sizeof(BrBlockIn), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_blk, hblk.data(), nblk * sizeof(BrBlk), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(slot_blk, h_slot.data(), h_slot.size() * 4, cudaMemcpyHostToDevice, st));
+  if (ncuts) CK(cudaMemcpyAsync(d_cut_kind, cuts->kind, ncuts * 4, cudaMemcpyHostToDevice, st));
+  s.slot_blk = slot_blk;
   CK(cudaStreamSynchronize(st));
   CK(cudaMemsetAsync(bout, 0, nb * sizeof(BrBlockOut), st));
   CK(cudaMemsetAsync(bin_used, 0, nb * sizeof(BrBlockIn), st));
@@ -561,7 +582,8 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   k_radix_scatter<8, true><<<ntiles, 256, 0, st>>>(K1, V1, n, hist, ntiles, K2, S);
   k_rank<<<(n + 255) / 256, 256, 0, st>>>(S, n, rank);
   k_seg<<<(n + 1 + 255) / 256, 256, 0, st>>>(K2, n, P.nbuckets, seg);
-  k_init_bits<<<(u32)((nwords + 255) / 256), 256, 0, st>>>(s);
+  CK(cudaMemsetAsync(bits_latest, 0, nwords * 4, st));
+  k_init_bits<<<nblk, 256, 0, st>>>(s);
   cudaEventRecord(ev[1], st);
 
   // ---- LZ77 fixpoint
@@ -688,7 +710,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     cudaEventRecord(ev[9], st);
     cudaEventRecord(ev[3], st);
     ++job->stats.encode_launches; job->stats.launches += 24;
-    k_assemble_scan<<<1, 32, 0, st>>>(s, d_ooff, out, desc, res);
+    k_assemble_scan<<<1, 32, 0, st>>>(s, d_ooff, out, desc, res, with_header, d_cut_kind, d_cut_end);
     CK(cudaMemcpyAsync(hp + 16, res, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (hp[18]) {   // encode.c:604: the coded metablock is larger than the input -> store it raw and
@@ -716,6 +738,10 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   job->stats.total_cmds = total_cmds; job->stats.launches += 12;
   job->stats.nblocks = nb; job->stats.n_metablocks = n_mbs; job->stats.rounds = (u32)rounds;
   job->stats.out_bytes = final_size; job->stats.in_bytes = n;
+  if (cuts && cuts->end_bit && ncuts) {
+    CK(cudaMemcpyAsync(cuts->end_bit, d_cut_end, ncuts * 8ull, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   *d_out = final_out; *out_size = final_size;
   return 1;
 }

@@ -669,7 +669,7 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
     if (in.last) {
       // block boundary: crossed by the sweeps of a sweep-mode launch, inside a group of sweep_blocks blocks
       const bool full_sweep = s.epoch > s.P.sweep_epoch + 9 && (s.epoch - 1 - s.P.sweep_epoch) % 3 == 0;   // (as br_chain_c decided it)
-      if (to_block_end || in.is_last || s.epoch <= s.P.sweep_epoch || full_sweep || ((in.blk + 1) & (s.P.sweep_blocks - 1u)) == 0) return;
+      if (to_block_end || in.is_last || nb >= s.P.nblocks || s.epoch <= s.P.sweep_epoch || full_sweep || ((in.blk + 1) & (s.P.sweep_blocks - 1u)) == 0) return;
       if (!br_predict_next_block(s, b, in, o, ni)) return;
     } else {
       ni = s.bin[nb];

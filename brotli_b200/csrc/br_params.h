@@ -2,6 +2,7 @@
 // ChooseHasher / ComputeRbBits / MaxMetablockSize (c/enc/quality.h:59-225) decide for a
 // given (quality, lgwin, size_hint).  Host only.
 #pragma once
+#include <vector>
 #include "br_types.h"
 
 // Returns 0 if the combination is outside what this library implements (the BrotliEncoder*
@@ -33,4 +34,35 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->force_epoch = 64;
   P->sweep_blocks = P->lgblock >= 18 ? 8 : 32;   // sweeps are at most 2 MiB of input long
   return 1;
+}
+
+// The reference's input blocks (one EncodeData call each, c/enc/encode.c:1665-1719) and their 2 KiB chunks for a stream
+// of n bytes.  `cuts` (sorted, each in (0, n]) are the positions where a FLUSH / EMIT_METADATA operation ended the input
+// of a CompressStream call: the running block ends there with force_flush set (encode.c:1700) and the next one starts
+// with a full 1 << lgblock budget again (encode.c:1016 UpdateLastProcessedPos).  is_final: FINISH has been seen (the
+// last block carries is_last); otherwise the stream simply stops behind its last block.
+static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u32 ncuts, bool is_final,
+                                   std::vector<BrBlockIn>& chunks, std::vector<BrBlk>& blks) {
+  const u32 bs = 1u << P.lgblock, ch = 1u << BR_CHUNK_BITS;
+  u32 ci = 0;
+  u64 bstart = 0;
+  while (bstart < n) {
+    while (ci < ncuts && cuts[ci] <= bstart) ++ci;
+    u64 bend = bstart + bs < n ? bstart + bs : n;
+    bool forced = false;
+    if (ci < ncuts && cuts[ci] <= bend) { bend = cuts[ci]; forced = true; }
+    BrBlk B; memset(&B, 0, sizeof(B));
+    B.start = (u32)bstart; B.end = (u32)bend; B.is_last = (is_final && bend == n) ? 1u : 0u;
+    B.force_flush = forced && !B.is_last ? 1u : 0u; B.changed_epoch = -1;
+    B.first_chunk = (u32)chunks.size();
+    for (u64 c = bstart; c < bend; c += ch) {
+      BrBlockIn k; memset(&k, 0, sizeof(k));
+      k.pos = (u32)c; k.end = (u32)(c + ch < bend ? c + ch : bend); k.blk_start = (u32)bstart; k.blk_end = (u32)bend;
+      k.first = (c == bstart); k.last = (k.end == bend); k.is_last = B.is_last; k.force_flush = B.force_flush; k.blk = (u32)blks.size();
+      chunks.push_back(k);
+    }
+    B.nchunks = (u32)chunks.size() - B.first_chunk;
+    blks.push_back(B);
+    bstart = bend;
+  }
 }

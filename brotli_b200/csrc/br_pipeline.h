@@ -11,12 +11,18 @@ struct BrJobStats {
   uint32_t lz77_iterations, nblocks, n_metablocks, rounds, launches;
   uint64_t block_runs, in_bytes, out_bytes;
 };
+// A stream cut by FLUSH / EMIT_METADATA operations (c/enc/encode.c:1634): pos[i] (sorted, in (0, n]) = input position where
+// the i-th such operation ended the input, kind[i] = 1 FLUSH, 2 EMIT_METADATA.  is_final = 0: FINISH has not been seen, the
+// stream ends behind the cut at n.  with_header = 0: the window bits were already sent.  end_bit (host, nullable) receives
+// the bit position in the output where the metablock in front of each cut ended.
+// finish_empty: FINISH came without input right behind a full input block (BrParams::finish_empty).
+struct BrCuts { const uint32_t* pos; const uint32_t* kind; uint32_t n; int is_final; int with_header; int finish_empty; uint64_t* end_bit; };
 extern "C" {
 BrJob* br_job_create(void);
 void br_job_destroy(BrJob*);
 const BrJobStats* br_job_stats(const BrJob*);
 void* br_job_stream(BrJob*);
 int br_job_compress_device(BrJob* job, int quality, int lgwin, uint32_t size_hint,
-                           const uint8_t* d_in, uint32_t n, const uint8_t** d_out, size_t* out_size);
+                           const uint8_t* d_in, uint32_t n, const uint8_t** d_out, size_t* out_size, const BrCuts* cuts);
 int br_debug_sort(int quality, int lgwin, const uint8_t* h_in, uint32_t n, uint32_t* h_S, uint32_t* h_seg);
 }

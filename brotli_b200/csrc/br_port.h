@@ -18,6 +18,7 @@ typedef uint64_t u64;
 #if defined(__CUDACC__) && !defined(BR_SIM)
 #define BR_GPU 1
 #define BR_DEV __device__ __forceinline__
+#define BR_DEV_M __device__ __forceinline__   /* for static member functions */
 #define BR_HD __host__ __device__ __forceinline__
 #define BR_DEV_NOINLINE __device__ __noinline__
 #define BR_WARP 32
@@ -69,6 +70,7 @@ BR_DEV u32 br_warp_max(u32 v) {
 #else
 #define BR_GPU 0
 #define BR_DEV static inline
+#define BR_DEV_M inline
 #define BR_HD static inline
 #define BR_DEV_NOINLINE static
 #define BR_WARP 1

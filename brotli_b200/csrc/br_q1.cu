@@ -28,6 +28,64 @@ __global__ void __launch_bounds__(128, 16) k_q1_parse(BrQ1 q) {
     br_q1_parse_fragment(q, f, table);
   }
 }
+// ---- on-chip variant: fragments of at most 64 KiB (BASELINE config 5 is 10 000 of them)
+// One warp per CTA, one CTA per SM.  Shared memory: the 2^16-entry hash table as u16 positions (128 KiB) and the
+// fragment's input (<= 64 KiB + slack), fetched by ONE TMA bulk copy (cp.async.bulk, completion on an mbarrier) while
+// the warp zeroes the table.  Every probe of the trawl loop -- input bytes, table slot, candidate bytes -- is then a
+// shared-memory access: no DRAM sector per probe, no table memset in HBM.
+#define BR_Q1_SHM_TABLE (1u << 16)
+#define BR_Q1_SHM_INPUT (65536u + 64u)
+#define BR_Q1_SHM_BYTES (BR_Q1_SHM_TABLE * 2u + BR_Q1_SHM_INPUT + 16u)
+__device__ __forceinline__ u32 br_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(32, 1) k_q1_parse_shm(BrQ1 q) {
+  extern __shared__ __align__(128) u8 shm[];
+  u16* table = (u16*)shm;
+  u8* buf = shm + BR_Q1_SHM_TABLE * 2u;
+  unsigned long long* bar = (unsigned long long*)(buf + BR_Q1_SHM_INPUT);
+  const u32 lane = threadIdx.x;
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(br_smem_addr(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  u32 phase = 0;
+  for (;;) {
+    u32 f = 0;
+    if (lane == 0) f = atomicAdd(q.counters, 1u);
+    f = __shfl_sync(0xffffffffu, f, 0);
+    if (f >= q.nfrags) return;
+    const BrQ1Frag fr = q.frags[f];
+    const BrQ1Stream& st = q.streams[fr.stream];
+    // input bytes [fr.start & ~15, fr.start + fr.size + 16) rounded up to 16: behind every stream lie >= 16 bytes of slack
+    const u32 a0 = fr.start & ~15u;
+    u32 nbytes = (fr.start - a0) + fr.size + 16u;
+    nbytes = (nbytes + 15u) & ~15u;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous fragment's reads are done (generic proxy)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(br_smem_addr(bar)), "r"(nbytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(br_smem_addr(buf)), "l"(q.in + st.in_off + a0), "r"(nbytes), "r"(br_smem_addr(bar)) : "memory");
+    }
+    // zero the table while the copy is in flight (encode.c:156 GetHashTable)
+    {
+      uint4* t4 = (uint4*)table;
+      const u32 n4 = (2u << fr.table_bits) >> 4;
+      for (u32 i = lane; i < n4; i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+      if (n4 == 0) for (u32 i = lane; i < (1u << fr.table_bits); i += 32) table[i] = 0;
+    }
+    {
+      u32 ok = 0;
+      do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(br_smem_addr(bar)), "r"(phase) : "memory");
+      } while (!ok);
+      phase ^= 1u;
+    }
+    __syncwarp();
+    br_q1_parse_fragment_shm(q, f, table, buf);
+    __syncwarp();
+  }
+}
 __global__ void __launch_bounds__(128) k_q1_prep(BrQ1 q) {
   __shared__ BrQ1Smem sm;
   br_q1_prep_block(q, blockIdx.x, &sm);
@@ -116,7 +174,9 @@ struct BrQ1Job {
   Pinned h_in, h_out, h_off;
   u32 log2_n = 0;
   int sm_count = 0;
-  u32 warps_per_sm = 48, first_width = 32;   // tuning knobs (env BR_Q1_WARPS_PER_SM, BR_Q1_FIRST_WIDTH)
+  u32 warps_per_sm = 16, first_width = 32;   // tuning knobs (env BR_Q1_WARPS_PER_SM, BR_Q1_FIRST_WIDTH); 16: r02l sweep
+  bool shm_ok = false;        // the device grants k_q1_parse_shm its shared memory
+  int kernel_choice = 0;      // 0 / 1 global-memory tables, 2 on-chip tables whenever the fragments fit (env BR_Q1_KERNEL)
   BrQ1Stats stats = {};
 };
 
@@ -131,6 +191,9 @@ extern "C" BrQ1Job* br_q1_job_create(void) {
   }
   cudaDeviceGetAttribute(&j->sm_count, cudaDevAttrMultiProcessorCount, dev);
   for (auto& e : j->ev) cudaEventCreate(&e);
+  j->shm_ok = cudaFuncSetAttribute(k_q1_parse_shm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BR_Q1_SHM_BYTES) == cudaSuccess;
+  if (!j->shm_ok) cudaGetLastError();
+  if (const char* e = getenv("BR_Q1_KERNEL")) j->kernel_choice = atoi(e);
   if (const char* e = getenv("BR_Q1_WARPS_PER_SM")) { int v = atoi(e); if (v >= 4 && v <= 64) j->warps_per_sm = (u32)v; }
   if (const char* e = getenv("BR_Q1_FIRST_WIDTH")) { int v = atoi(e); if (v >= 1 && v <= 32) j->first_width = (u32)v; }
   // bit_cost.c:18 needs FastLog2 of sampled counts only (<= 2^17 / 43): the first 4096 entries
@@ -224,7 +287,20 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
 
   if (inputs_on_device) k_q1_gather<<<(unsigned)count, 256, 0, st>>>(q, packed->d_in, (const u64*)j->dense_off.p, (u8*)j->in.p);
   cudaEventRecord(j->ev[1], st);
-  if (nfr) k_q1_parse<<<nwarps / 4, 128, 0, st>>>(q);
+  u32 max_frag = 0;
+  for (auto& f : frags) if (f.size > max_frag) max_frag = f.size;
+  // table and input on chip when every fragment fits (<= 64 KiB) and there are enough of them to fill the SMs
+  // The on-chip variant is bit-exact but measured 4.3x SLOWER on BASELINE config 5 (profiles/r02l_q1_variants.log: parse
+  // 265 ms against 58-61 ms): with the 128 KiB table only ONE warp fits an SM, every instruction latency of its
+  // dependent probe chain is exposed, and 148 latency-bound warps lose to 16-48 warps per SM that hide each other's
+  // HBM round trips.  It stays selectable (BR_Q1_KERNEL=2) for the record; the default is the global-table kernel.
+  const bool on_chip = j->shm_ok && max_frag <= 65536u && j->kernel_choice == 2;
+  if (nfr) {
+    if (on_chip) {
+      u32 ctas = nfr < (u32)j->sm_count ? nfr : (u32)j->sm_count;
+      k_q1_parse_shm<<<ctas, 32, BR_Q1_SHM_BYTES, st>>>(q);
+    } else k_q1_parse<<<nwarps / 4, 128, 0, st>>>(q);
+  }
   cudaEventRecord(j->ev[2], st);
   if (nbl) k_q1_prep<<<nbl, 128, 0, st>>>(q);
   k_q1_chain<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(q);

@@ -79,16 +79,46 @@ struct BrQ1Smem {          // shared memory of one prep CTA
 };
 
 // ------------------------------------------------------------------ parse
+// Where the fragment's input bytes and its hash table live:
+//   BrQ1Glob  both in global memory (any fragment size; the table is a per-warp slot of 2^17 ints)
+//   BrQ1Shm   both in SHARED memory: fragments of at most 64 KiB (positions fit 16 bits, so the 2^16-entry table the
+//             reference uses for them is 128 KiB) with the input staged next to it by one TMA bulk copy (br_q1.cu)
+struct BrQ1Glob {
+  typedef int TT;
+  static BR_DEV_M u64 ld64(const u8* d, u32 pos) { return br_ld64u(d, pos); }
+  static BR_DEV_M u8 ld8(const u8* p) { return br_ldg(p); }
+  static BR_DEV_M void prefetch(const void* p) { br_prefetch_l2(p); }
+};
+struct BrQ1Shm {
+  typedef u16 TT;
+  static BR_DEV_M u64 ld64(const u8* d, u32 pos) {   // d is 4-byte aligned (see br_q1_parse_fragment_shm)
+    const u32* w = (const u32*)d;
+    const u32 i = pos >> 2, sh = (pos & 3u) * 8u;
+    const u32 a = w[i], b = w[i + 1], c = w[i + 2];
+#if BR_GPU
+    const u32 lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+#else
+    const u64 t = ((u64)b << 32) | a, t2 = ((u64)c << 32) | b;
+    const u32 lo = (u32)(t >> sh), hi = (u32)(t2 >> sh);
+#endif
+    return ((u64)hi << 32) | lo;
+  }
+  static BR_DEV_M u8 ld8(const u8* p) { return *p; }
+  static BR_DEV_M void prefetch(const void*) {}
+};
+
 // :32 Hash / :39 HashBytesAtOffset; v = the 8 bytes at the position
 BR_DEV u32 br_q1_hash(u64 v, u32 shift, u32 mm) {
   return (u32)(((v << ((8u - mm) * 8u)) * 0x1E35A7BDull) >> shift);
 }
 // :47 IsMatch with the bytes at the first position already loaded
+template <class M>
 BR_DEV bool br_q1_is_match(const u8* d, u64 va, u32 b, u32 mm) {
-  u64 x = va ^ br_ld64u(d, b);
+  u64 x = va ^ M::ld64(d, b);
   return mm == 4 ? (u32)x == 0 : (x & 0xFFFFFFFFFFFFull) == 0;
 }
 // find_match_length.h:20 over the whole warp: lane l compares bytes [8l, 8l+8) of each 8*BR_WARP step
+template <class M>
 BR_DEV u32 br_q1_match_len(const u8* d, u32 a, u32 b, u32 limit) {
   const u32 lane = (u32)br_lane();
   u32 done = 0;
@@ -97,7 +127,7 @@ BR_DEV u32 br_q1_match_len(const u8* d, u32 a, u32 b, u32 limit) {
     const u32 n = off < limit ? br_min(8u, limit - off) : 0u;
     u32 eq = 0;
     if (n) {
-      u64 x = br_ld64u(d, a + off) ^ br_ld64u(d, b + off);
+      u64 x = M::ld64(d, a + off) ^ M::ld64(d, b + off);
       if (n < 8) x |= 1ull << (8u * n);
       eq = x ? (u32)br_ctz64(x) >> 3 : 8u;
     }
@@ -127,26 +157,28 @@ BR_DEV u32 br_q1_word_extra_bits(u32 code) {   // :460 kNumExtraBits
 // :334 / :401 table refresh behind a copy that ends at ip (lane 0); returns the candidate for ip.
 // `first`: the variant behind the first copy of a run, whose min_match == 4 form files ip-1 under
 // the hash of ip-3 (:339 uses offset 0 twice).
-BR_DEV u32 br_q1_refresh(const u8* d, u32 ip, u32 base, int* table, u32 shift, u32 mm, bool first) {
+template <class M>
+BR_DEV u32 br_q1_refresh(const u8* d, u32 ip, u32 base, typename M::TT* table, u32 shift, u32 mm, bool first) {
+  typedef typename M::TT TT;
   u32 cur;
   if (mm == 4) {
-    const u64 v = br_ld64u(d, ip - 3);
+    const u64 v = M::ld64(d, ip - 3);
     cur = br_q1_hash(v >> 24, shift, 4);
-    table[br_q1_hash(v, shift, 4)] = (int)(ip - 3 - base);
-    table[br_q1_hash(v >> 8, shift, 4)] = (int)(ip - 2 - base);
-    table[br_q1_hash(first ? v : v >> 16, shift, 4)] = (int)(ip - 1 - base);
+    table[br_q1_hash(v, shift, 4)] = (TT)(ip - 3 - base);
+    table[br_q1_hash(v >> 8, shift, 4)] = (TT)(ip - 2 - base);
+    table[br_q1_hash(first ? v : v >> 16, shift, 4)] = (TT)(ip - 1 - base);
   } else {
-    u64 v = br_ld64u(d, ip - 5);
-    table[br_q1_hash(v, shift, 6)] = (int)(ip - 5 - base);
-    table[br_q1_hash(v >> 8, shift, 6)] = (int)(ip - 4 - base);
-    table[br_q1_hash(v >> 16, shift, 6)] = (int)(ip - 3 - base);
-    v = br_ld64u(d, ip - 2);
+    u64 v = M::ld64(d, ip - 5);
+    table[br_q1_hash(v, shift, 6)] = (TT)(ip - 5 - base);
+    table[br_q1_hash(v >> 8, shift, 6)] = (TT)(ip - 4 - base);
+    table[br_q1_hash(v >> 16, shift, 6)] = (TT)(ip - 3 - base);
+    v = M::ld64(d, ip - 2);
     cur = br_q1_hash(v >> 16, shift, 6);
-    table[br_q1_hash(v, shift, 6)] = (int)(ip - 2 - base);
-    table[br_q1_hash(v >> 8, shift, 6)] = (int)(ip - 1 - base);
+    table[br_q1_hash(v, shift, 6)] = (TT)(ip - 2 - base);
+    table[br_q1_hash(v >> 8, shift, 6)] = (TT)(ip - 1 - base);
   }
   const u32 cand = base + (u32)table[cur];
-  table[cur] = (int)(ip - base);
+  table[cur] = (TT)(ip - base);
   return cand;
 }
 
@@ -155,20 +187,24 @@ BR_DEV u32 br_q1_refresh(const u8* d, u32 ip, u32 base, int* table, u32 shift, u
 #endif
 // Behind a copy that ends at ip: lane 0's slot is the one the refresh reads (:358), lanes 1.. are the
 // first probes of the trawl that follows if no copy starts at ip.  L2 prefetch hints only.
-BR_DEV void br_q1_prefetch_ahead(const u8* d, u32 ip, u32 ip_limit, const int* table, u32 shift, u32 mm) {
+template <class M>
+BR_DEV void br_q1_prefetch_ahead(const u8* d, u32 ip, u32 ip_limit, const typename M::TT* table, u32 shift, u32 mm) {
 #if BR_Q1_PREFETCH
   const u32 pos = ip + (u32)br_lane();
-  if (pos <= ip_limit) br_prefetch_l2(table + br_q1_hash(br_ld64u(d, pos), shift, mm));
+  if (pos <= ip_limit) M::prefetch(table + br_q1_hash(M::ld64(d, pos), shift, mm));
 #endif
 }
 
 // lanes copy n literal bytes
+template <class M>
 BR_DEV void br_q1_copy_literals(const u8* d, u32 from, u8* to, u32 n) {
-  for (u32 i = (u32)br_lane(); i < n; i += BR_WARP) to[i] = br_ldg(d + from + i);
+  for (u32 i = (u32)br_lane(); i < n; i += BR_WARP) to[i] = M::ld8(d + from + i);
 }
 
 // :228 CreateCommands for one block; warp-uniform.
-BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u32 bi, int* table, u64 in_off) {
+template <class M>
+BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u32 bi, typename M::TT* table, u64 in_off) {
+  typedef typename M::TT TT;
   const int lane = br_lane();
   BrQ1Block& blk = q.blocks[bi];
   const u32 start = blk.start, ip_end = start + blk.size, base = fr.start;
@@ -201,11 +237,11 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
           // the next one reads them at L2 instead of HBM latency.  A hint only: no value is consumed.
           const u32 m2 = skip + width + (u32)lane;
           const u32 pos2 = ip + (br_q1_skip_sum(m2) - br_q1_skip_sum(skip));
-          if (pos2 + (m2 >> 5) <= ip_limit) br_prefetch_l2(table + br_q1_hash(br_ld64u(d, pos2), shift, mm));
+          if (pos2 + (m2 >> 5) <= ip_limit) M::prefetch(table + br_q1_hash(M::ld64(d, pos2), shift, mm));
         }
 #endif
         u64 v = 0; u32 h = 0xFFFFFFFFu - (u32)lane; u32 t = 0;
-        if (valid) { v = br_ld64u(d, pos); h = br_q1_hash(v, shift, mm); t = (u32)table[h]; }
+        if (valid) { v = M::ld64(d, pos); h = br_q1_hash(v, shift, mm); t = (u32)table[h]; }
         const u32 peers = br_match_any(h);
         const u32 earlier = peers & br_lanemask_lt();
         const int src = earlier ? 31 - br_clz(earlier) : lane;
@@ -213,8 +249,8 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
         const u32 ctab = earlier ? ppos : base + t;
         bool m_last = false, m_tab = false;
         if (valid) {
-          if (last_distance) m_last = br_q1_is_match(d, v, pos - last_distance, mm);
-          if (!m_last) m_tab = br_q1_is_match(d, v, ctab, mm) && pos - ctab <= BR_Q1_MAX_DISTANCE;
+          if (last_distance) m_last = br_q1_is_match<M>(d, v, pos - last_distance, mm);
+          if (!m_last) m_tab = br_q1_is_match<M>(d, v, ctab, mm) && pos - ctab <= BR_Q1_MAX_DISTANCE;
         }
         const u32 hits = br_ballot(valid && (m_last || m_tab));
         const u32 inval = br_ballot(act && !valid);
@@ -222,7 +258,7 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
         const int lim = hits ? br_ffs(hits) - 1 : inval ? br_ffs(inval) - 2 : (int)width - 1;
         const u32 upto = lim >= 31 ? 0xFFFFFFFFu : ((1u << (lim + 1)) - 1u);
         const u32 mine = peers & upto;
-        if (valid && lane <= lim && 31 - br_clz(mine) == lane) table[h] = (int)(pos - base);
+        if (valid && lane <= lim && 31 - br_clz(mine) == lane) table[h] = (TT)(pos - base);
         br_syncwarp();
         if (hits) {
           const int f = br_ffs(hits) - 1;
@@ -238,9 +274,9 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
       if (!hit) break;
       // ---- first copy of the run, with its literals (:309-360)
       {
-        const u32 matched = mm + br_q1_match_len(d, cand + mm, ip + mm, ip_end - ip - mm);
+        const u32 matched = mm + br_q1_match_len<M>(d, cand + mm, ip + mm, ip_end - ip - mm);
         const u32 distance = ip - cand, insert = ip - next_emit;
-        br_q1_copy_literals(d, next_emit, lw + nlit, insert);
+        br_q1_copy_literals<M>(d, next_emit, lw + nlit, insert);
         nlit += insert;
         const u32 m2 = matched - 2u, cc = br_copy_code(m2), cx = (m2 - br_copy_base(cc)) << 8;
         if (lane == 0) {
@@ -254,24 +290,24 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
         last_distance = distance;
         ip += matched; next_emit = ip;
         if (ip >= ip_limit) break;
-        br_q1_prefetch_ahead(d, ip, ip_limit, table, shift, mm);
+        br_q1_prefetch_ahead<M>(d, ip, ip_limit, table, shift, mm);
         u32 c0 = 0;
-        if (lane == 0) c0 = br_q1_refresh(d, ip, base, table, shift, mm, true);
+        if (lane == 0) c0 = br_q1_refresh<M>(d, ip, base, table, shift, mm, true);
         cand = br_shfl(c0, 0);
         br_syncwarp();
       }
       // ---- further copies that start right here (:377-440)
       bool out = false;
-      while (ip - cand <= BR_Q1_MAX_DISTANCE && br_q1_is_match(d, br_ld64u(d, ip), cand, mm)) {
-        const u32 matched = mm + br_q1_match_len(d, cand + mm, ip + mm, ip_end - ip - mm);
+      while (ip - cand <= BR_Q1_MAX_DISTANCE && br_q1_is_match<M>(d, M::ld64(d, ip), cand, mm)) {
+        const u32 matched = mm + br_q1_match_len<M>(d, cand + mm, ip + mm, ip_end - ip - mm);
         last_distance = ip - cand;
         if (lane == 0) { cw[ncmd] = br_q1_copy_word(matched); cw[ncmd + 1] = br_q1_distance_word(last_distance); }
         ncmd += 2;
         ip += matched; next_emit = ip;
         if (ip >= ip_limit) { out = true; break; }
-        br_q1_prefetch_ahead(d, ip, ip_limit, table, shift, mm);
+        br_q1_prefetch_ahead<M>(d, ip, ip_limit, table, shift, mm);
         u32 c0 = 0;
-        if (lane == 0) c0 = br_q1_refresh(d, ip, base, table, shift, mm, false);
+        if (lane == 0) c0 = br_q1_refresh<M>(d, ip, base, table, shift, mm, false);
         cand = br_shfl(c0, 0);
         br_syncwarp();
       }
@@ -281,7 +317,7 @@ BR_DEV void br_q1_parse_block(const BrQ1& q, const u8* d, const BrQ1Frag& fr, u3
   }
   if (next_emit < ip_end) {                  // :444 emit_remainder
     const u32 insert = ip_end - next_emit;
-    br_q1_copy_literals(d, next_emit, lw + nlit, insert);
+    br_q1_copy_literals<M>(d, next_emit, lw + nlit, insert);
     if (lane == 0) cw[ncmd] = br_q1_insert_word(insert);
     ++ncmd; nlit += insert;
   }
@@ -295,7 +331,15 @@ BR_DEV void br_q1_parse_fragment(const BrQ1& q, u32 fi, int* table) {
   const BrQ1Stream& st = q.streams[fr.stream];
   for (u32 i = (u32)br_lane(); i < (1u << fr.table_bits); i += BR_WARP) table[i] = 0;
   br_syncwarp();
-  for (u32 b = 0; b < fr.nblocks; ++b) br_q1_parse_block(q, q.in + st.in_off, fr, fr.first_block + b, table, st.in_off);
+  for (u32 b = 0; b < fr.nblocks; ++b) br_q1_parse_block<BrQ1Glob>(q, q.in + st.in_off, fr, fr.first_block + b, table, st.in_off);
+}
+// The same with table and input on chip.  `buf` holds the bytes [fr.start & ~15, ...) of the stream (16-byte aligned
+// copy: see k_q1_parse_shm), so buf - (fr.start & ~15) is a 4-byte aligned base that is indexed by stream positions.
+BR_DEV void br_q1_parse_fragment_shm(const BrQ1& q, u32 fi, u16* table, const u8* buf) {
+  const BrQ1Frag fr = q.frags[fi];
+  const BrQ1Stream& st = q.streams[fr.stream];
+  const u8* d = buf - (fr.start & ~15u);
+  for (u32 b = 0; b < fr.nblocks; ++b) br_q1_parse_block<BrQ1Shm>(q, d, fr, fr.first_block + b, table, st.in_off);
 }
 
 // ------------------------------------------------------------------ prep

@@ -32,6 +32,8 @@ struct BrParams {
                     // sweeps the run serially, seeing its own fresh stored-bits (Gauss-Seidel inside a run, Jacobi across runs)
   u32 force_epoch;  // from this launch on the first scheduled walker also runs to the end of its input block whatever the
                     // flags say: every launch then finalises at least one block, which bounds the number of launches
+  u32 finish_empty; // FINISH arrived without input right behind a full input block: that block was encoded as a non-last one
+                    // (encode.c:1700), the stream is closed by whatever is still pending or by an empty last metablock
   u32 sweep_blocks; // power of two: a sweep crosses input-block boundaries except into blocks whose index is a multiple of this
   u32 max_epochs;   // size of the per-launch arrays (a bound no input reaches: see br_kernels.cu)
   u32 step_cap;     // successor-walk budget per flipped bit in the dependency marking; beyond it the block-level rule
@@ -103,7 +105,9 @@ struct BrMetaBlock {
   u32 nlit;
   u32 is_last;
   u32 compress;          // 0: stored uncompressed (ShouldCompress said no or late fallback)
-  u8 prev_byte, prev_byte2, pad0, pad1;
+  u8 prev_byte, prev_byte2;
+  u8 flushed;            // the metablock ends at a FLUSH / EMIT_METADATA cut (BrBlk::force_flush)
+  u8 empty_last;         // an empty last metablock (ISLAST, ISLASTEMPTY) follows this one (BrParams::finish_empty)
   u32 tail_insert;       // insert-only command appended at flush (0 if none)
   u32 out_bits;          // bits produced by the compressed encoder (relative, from bit 0)
   u32 scratch_off;
@@ -152,6 +156,8 @@ struct BrStream {
   u32 forced;            // this launch: the first scheduled walker runs to the end of its input block (BrParams::force_epoch)
   u32* ext_total;        // [nblocks] bytes added to the chunk's last command by ExtendLastCommand
   u32* lil_in;           // [nblocks] true pending-literal count at the chunk start (added to its first command)
+  const u32* slot_blk;   // [(n >> lgblock) + 1] index of the input block that holds position i << lgblock (streams cut by FLUSH
+                         // have irregular blocks; see br_chunk_of)
   BrBlk* blk;            // [nblk] reference input blocks
   BrBlkIn* blkin;        // [nblk]
   u32* key_flips;        // [nbuckets + 1] stored-bit flips per heavy bucket in the current launch

@@ -46,7 +46,7 @@ struct SimStream {
   std::vector<BrBlk> blks;
   std::vector<BrBlkIn> blkin;
   std::vector<u32> key_flips;
-  std::vector<u32> dirty_list, ran_list;
+  std::vector<u32> dirty_list, ran_list, slot_blk;
   int iterations = 0;
   u64 block_runs = 0;
   double model_cost = 0;
@@ -81,34 +81,25 @@ static void sim_build_storedS(SimStream& m) {
   }
 }
 
-static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n) {
+struct SimCuts { const u32* pos; const u32* kind; u32 n; int is_final; int with_header; int finish_empty; u64* end_bit; u32 size_hint; };
+static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts* cuts = nullptr) {
   SimStream* m = new SimStream();
   BrStream& s = m->s;
   memset(&s, 0, sizeof(s));
-  if (!br_derive_params(q, lgwin, n, n, &s.P)) { delete m; return nullptr; }
+  if (!br_derive_params(q, lgwin, cuts ? cuts->size_hint : n, n, &s.P)) { delete m; return nullptr; }
   BrParams& P = s.P;
   if (getenv("BR_SIM_HEAVY_MIN")) P.heavy_min = (u32)atoi(getenv("BR_SIM_HEAVY_MIN"));
   if (getenv("BR_SIM_STEP_CAP")) P.step_cap = (u32)atoi(getenv("BR_SIM_STEP_CAP"));
   if (getenv("BR_SIM_SWEEP_EPOCH")) P.sweep_epoch = (u32)atoi(getenv("BR_SIM_SWEEP_EPOCH"));
   if (getenv("BR_SIM_SWEEP_BLOCKS")) P.sweep_blocks = (u32)atoi(getenv("BR_SIM_SWEEP_BLOCKS"));
   if (getenv("BR_SIM_FORCE_EPOCH")) P.force_epoch = (u32)atoi(getenv("BR_SIM_FORCE_EPOCH"));
-  u32 bs = 1u << P.lgblock;
   const u32 ch = 1u << BR_CHUNK_BITS;
   std::vector<BrBlockIn> chunks;
-  for (u32 bstart = 0; bstart < n; bstart += bs) {
-    u32 bend = std::min(n, bstart + bs);
-    for (u32 c = bstart; c < bend; c += ch) {
-      BrBlockIn ci; memset(&ci, 0, sizeof(ci));
-      ci.pos = c; ci.end = std::min(bend, c + ch); ci.blk_start = bstart; ci.blk_end = bend;
-      ci.first = (c == bstart); ci.last = (ci.end == bend); ci.is_last = (bend == n);
-      ci.blk = (u32)m->blks.size();
-      chunks.push_back(ci);
-    }
-    BrBlk B; memset(&B, 0, sizeof(B));
-    B.start = bstart; B.end = bend; B.is_last = (bend == n); B.changed_epoch = -1;
-    B.nchunks = (bend - bstart + ch - 1) / ch; B.first_chunk = (u32)chunks.size() - B.nchunks;
-    m->blks.push_back(B);
-  }
+  P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
+  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, cuts ? cuts->n : 0, cuts ? (cuts->is_final != 0 && !cuts->finish_empty) : true, chunks, m->blks);
+  m->slot_blk.assign(((size_t)n >> P.lgblock) + 2, 0);
+  { u32 bb = 0; for (size_t i = 0; i < m->slot_blk.size(); ++i) { const u64 pp = (u64)i << P.lgblock; while (bb + 1 < m->blks.size() && m->blks[bb].end <= pp) ++bb; m->slot_blk[i] = bb; } }
+  s.slot_blk = m->slot_blk.data();
   P.nblocks = (u32)chunks.size();
   m->data.assign(in, in + n); m->data.resize(n + 64, 0);
   s.data = m->data.data();
@@ -325,10 +316,10 @@ static void sim_entropy2(SimStream& m, SimEnt& E) {
   for (u32 o = 0; o < e.total_lits; ++o) br_emit_lit(s, e, o);
 }
 
-// Full pipeline; returns compressed size or negative error.
-extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, size_t out_cap, u32* stats) {
+// Full pipeline; returns compressed size or negative error.  cuts: see br_pipeline.h BrCuts.
+static long sim_compress_impl(int q, int lgwin, const u8* in, u32 n, u8* out, size_t out_cap, u32* stats, const SimCuts* cuts) {
   if (n == 0) { if (out_cap < 1) return -3; out[0] = 6; return 1; }
-  SimStream* m = sim_setup(q, lgwin, in, n);
+  SimStream* m = sim_setup(q, lgwin, in, n, cuts);
   if (!m) return -1;
   BrStream& s = m->s;
   std::vector<u8> res;
@@ -342,8 +333,9 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
     u64 bit = 0;
     SimEnt E;
     sim_entropy2(*m, E);
-    if (lgwin == 17) put_bits_host(res, bit, 7, 1); else put_bits_host(res, bit, 4, ((lgwin - 17) << 1) | 1);
+    if (!cuts || cuts->with_header) { if (lgwin == 17) put_bits_host(res, bit, 7, 1); else put_bits_host(res, bit, 4, ((lgwin - 17) << 1) | 1); }
     bool redo = false;
+    u32 ncut = 0;
     for (u32 i = 0; i < nm && !redo; ++i) {
       BrMetaBlock mb = s.mbs[i];
       u32 bytes = mb.end - mb.start;
@@ -371,6 +363,13 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
         bit += (u64)bytes * 8;
         if (mb.is_last) { put_bits_host(res, bit, 2, 3); bit = (bit + 7) & ~7ull; }
       }
+      if (mb.empty_last) { put_bits_host(res, bit, 2, 3); bit = (bit + 7) & ~7ull; }
+      if (mb.flushed && !mb.is_last) {   // k_assemble_scan's cut handling
+        if (cuts->end_bit) cuts->end_bit[ncut] = bit;
+        if (cuts->kind[ncut] == 1 && (bit & 7)) put_bits_host(res, bit, 6, 6);
+        bit = (bit + 7) & ~7ull;
+        ++ncut;
+      }
     }
     if (!redo) { res.resize((bit + 7) >> 3, 0); break; }
     if (rounds > 64) { delete m; return -4; }
@@ -380,6 +379,14 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
   if (res.size() > out_cap) return -3;
   memcpy(out, res.data(), res.size());
   return (long)res.size();
+}
+extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, size_t out_cap, u32* stats) {
+  return sim_compress_impl(q, lgwin, in, n, out, out_cap, stats, nullptr);
+}
+extern "C" long sim_compress_cuts(int q, int lgwin, u32 size_hint, const u8* in, u32 n, const u32* cut_pos, const u32* cut_kind, u32 ncuts,
+                                  int is_final, int with_header, int finish_empty, u64* end_bit, u8* out, size_t out_cap, u32* stats) {
+  SimCuts c; c.pos = cut_pos; c.kind = cut_kind; c.n = ncuts; c.is_final = is_final; c.with_header = with_header; c.finish_empty = finish_empty; c.end_bit = end_bit; c.size_hint = size_hint;
+  return sim_compress_impl(q, lgwin, in, n, out, out_cap, stats, &c);
 }
 #endif
 
@@ -402,7 +409,18 @@ extern "C" long sim_q1_compress_seg(int lgwin, const u8* in, u32 n, const size_t
   q.streams = streams.data(); q.frags = frags.data(); q.blocks = blocks.data(); q.codes = codes.data(); q.hdr = hdr.data();
   q.tables = table.data(); q.table_slot = 1u << 17; q.nstreams = 1; q.nfrags = (u32)frags.size(); q.nblocks = (u32)blocks.size();
   q.first_width = 8; q.counters = counters.data(); q.log2tab = g_t.log2tab.data(); q.log2tab_n = (u32)std::min<size_t>(g_t.log2tab.size(), 4096);
-  for (u32 f = 0; f < q.nfrags; ++f) br_q1_parse_fragment(q, f, table.data());
+  for (u32 f = 0; f < q.nfrags; ++f) {
+    if (getenv("BR_SIM_Q1_SHM") && frags[f].size <= 65536) {
+      // the on-chip variant (u16 table, input copy aligned like the TMA destination of k_q1_parse_shm)
+      std::vector<u16> t16((size_t)1 << 16, 0);
+      const u32 a0 = frags[f].start & ~15u;
+      std::vector<u8> buf((size_t)65536 + 128, 0);
+      size_t nb = (size_t)(frags[f].start - a0) + frags[f].size + 16;
+      if (a0 + nb > din.size()) nb = din.size() - a0;
+      memcpy(buf.data(), din.data() + a0, nb);
+      br_q1_parse_fragment_shm(q, f, t16.data(), buf.data());
+    } else br_q1_parse_fragment(q, f, table.data());
+  }
   BrQ1Smem* sm = new BrQ1Smem();
   for (u32 b = 0; b < q.nblocks; ++b) br_q1_prep_block(q, b, sm);
   delete sm;

