@@ -458,7 +458,7 @@ BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* s, BrotliEncoderParame
   }
 }
 
-BrotliEncoderPreparedDictionary* BrotliEncoderPrepareDictionary(int, size_t, const uint8_t*, int,
+BrotliEncoderPreparedDictionary* BrotliEncoderPrepareDictionary(BrotliSharedDictionaryType, size_t, const uint8_t*, int,
     brotli_alloc_func, brotli_free_func, void*) { return nullptr; }
 void BrotliEncoderDestroyPreparedDictionary(BrotliEncoderPreparedDictionary*) {}
 BROTLI_BOOL BrotliEncoderAttachPreparedDictionary(BrotliEncoderState*, const BrotliEncoderPreparedDictionary*) {

@@ -16,64 +16,23 @@
  */
 #ifndef BROTLI_B200_H_
 #define BROTLI_B200_H_
-#include <stddef.h>
-#include <stdint.h>
+/* The reference API itself -- the 13 BROTLI_ENC_API functions of c/include/brotli/encode.h (SetParameter :289,
+ * CreateInstance :306, DestroyInstance :314, PrepareDictionary :343, DestroyPreparedDictionary :348,
+ * AttachPreparedDictionary :361, MaxCompressedSize :375, Compress :405, CompressStream :473, IsFinished :486,
+ * HasMoreOutput :495, TakeOutput :526, Version :542) -- is declared in include/brotli/encode.h of this repository with the
+ * reference's own types (no re-definition here, so this header mixes with <brotli/encode.h> and <brotli/decode.h>).
+ *
+ * Limits of the implemented path (everything else returns BROTLI_FALSE / NULL, never other bytes):
+ *   quality 1 (lgwin 10..24) and quality 5..9 (lgwin 17..24), modes GENERIC / TEXT, default LGBLOCK / NPOSTFIX / NDIRECT,
+ *   no dictionaries, no LARGE_WINDOW, no STREAM_OFFSET; one stream <= 1 GiB (quality 1: 256 MiB) -- BrotliEncoderCompressStream
+ *   fails on the PROCESS call that crosses it.  FLUSH, FINISH and (quality 5..9) EMIT_METADATA follow encode.h:93-157; at
+ *   quality 5..9 the stream so far is kept in host memory and recompressed at every FLUSH (see csrc/br_api.cc). */
+#include <brotli/encode.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define BROTLI_BOOL int              /* c/include/brotli/types.h:49 */
-#define BROTLI_TRUE 1
-#define BROTLI_FALSE 0
-typedef void* (*brotli_alloc_func)(void* opaque, size_t size);   /* types.h:73 */
-typedef void (*brotli_free_func)(void* opaque, void* address);   /* types.h:81 */
-
-typedef enum BrotliEncoderMode {     /* encode.h:45 */
-  BROTLI_MODE_GENERIC = 0, BROTLI_MODE_TEXT = 1, BROTLI_MODE_FONT = 2
-} BrotliEncoderMode;
-typedef enum BrotliEncoderOperation {  /* encode.h:93 */
-  BROTLI_OPERATION_PROCESS = 0, BROTLI_OPERATION_FLUSH = 1,
-  BROTLI_OPERATION_FINISH = 2, BROTLI_OPERATION_EMIT_METADATA = 3
-} BrotliEncoderOperation;
-typedef enum BrotliEncoderParameter {  /* encode.h:160 */
-  BROTLI_PARAM_MODE = 0, BROTLI_PARAM_QUALITY = 1, BROTLI_PARAM_LGWIN = 2,
-  BROTLI_PARAM_LGBLOCK = 3, BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING = 4,
-  BROTLI_PARAM_SIZE_HINT = 5, BROTLI_PARAM_LARGE_WINDOW = 6, BROTLI_PARAM_NPOSTFIX = 7,
-  BROTLI_PARAM_NDIRECT = 8, BROTLI_PARAM_STREAM_OFFSET = 9, BROTLI_PARAM_BASE64_MODE = 10,
-  BROTLI_PARAM_MAX_BASE64_REGIONS = 11, BROTLI_PARAM_SIMD_HASHER = 12
-} BrotliEncoderParameter;
-
-typedef struct BrotliEncoderStateStruct BrotliEncoderState;                 /* encode.h:271 */
-typedef struct BrotliEncoderPreparedDictionaryStruct BrotliEncoderPreparedDictionary;
-
-#define BROTLI_B200_API __attribute__((visibility("default")))
-
-/* encode.h:289 */
-BROTLI_B200_API BROTLI_BOOL BrotliEncoderSetParameter(BrotliEncoderState* state, BrotliEncoderParameter param, uint32_t value);
-/* encode.h:306 */
-BROTLI_B200_API BrotliEncoderState* BrotliEncoderCreateInstance(brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque);
-/* encode.h:314 */
-BROTLI_B200_API void BrotliEncoderDestroyInstance(BrotliEncoderState* state);
-/* encode.h:343 -- custom dictionaries are outside the implemented path: returns NULL */
-BROTLI_B200_API BrotliEncoderPreparedDictionary* BrotliEncoderPrepareDictionary(int type, size_t data_size, const uint8_t* data, int quality, brotli_alloc_func alloc_func, brotli_free_func free_func, void* opaque);
-/* encode.h:348 */
-BROTLI_B200_API void BrotliEncoderDestroyPreparedDictionary(BrotliEncoderPreparedDictionary* dictionary);
-/* encode.h:361 -- returns BROTLI_FALSE */
-BROTLI_B200_API BROTLI_BOOL BrotliEncoderAttachPreparedDictionary(BrotliEncoderState* state, const BrotliEncoderPreparedDictionary* dictionary);
-/* encode.h:375 */
-BROTLI_B200_API size_t BrotliEncoderMaxCompressedSize(size_t input_size);
-/* encode.h:405 -- one-shot; the bytes equal the reference's for the same arguments */
-BROTLI_B200_API BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode, size_t input_size, const uint8_t* input_buffer, size_t* encoded_size, uint8_t* encoded_buffer);
-/* encode.h:473 */
-BROTLI_B200_API BROTLI_BOOL BrotliEncoderCompressStream(BrotliEncoderState* state, BrotliEncoderOperation op, size_t* available_in, const uint8_t** next_in, size_t* available_out, uint8_t** next_out, size_t* total_out);
-/* encode.h:486 */
-BROTLI_B200_API BROTLI_BOOL BrotliEncoderIsFinished(BrotliEncoderState* state);
-/* encode.h:495 */
-BROTLI_B200_API BROTLI_BOOL BrotliEncoderHasMoreOutput(BrotliEncoderState* state);
-/* encode.h:526 */
-BROTLI_B200_API const uint8_t* BrotliEncoderTakeOutput(BrotliEncoderState* state, size_t* size);
-/* encode.h:542 */
-BROTLI_B200_API uint32_t BrotliEncoderVersion(void);
+#define BROTLI_B200_API BROTLI_ENC_API
 
 /* ---- B200 extensions (not in the reference API) ------------------------------------ */
 /* Same as BrotliEncoderCompress but input and output live in DEVICE memory of the current

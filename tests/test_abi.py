@@ -20,9 +20,15 @@ def lib():
     return C.CDLL(SO, mode=os.RTLD_LOCAL)
 
 
+ENCODE_H = os.path.join(ROOT, "include", "brotli", "encode.h")
+
+
 def declared_symbols():
-    text = open(HEADER).read()
-    return sorted(set(re.findall(r"BROTLI_B200_API[^;(]*?\b(Brotli\w+)\s*\(", text)))
+    """Every function the public headers declare: the reference API (include/brotli/encode.h) and the B200 extensions."""
+    names = set()
+    for path, macro in ((HEADER, "BROTLI_B200_API"), (ENCODE_H, "BROTLI_ENC_API")):
+        names |= set(re.findall(macro + r"[^;(]*?\b(Brotli\w+)\s*\(", open(path).read()))
+    return sorted(names)
 
 
 def test_header_declares_reference_api():
@@ -82,3 +88,31 @@ def test_state_api_and_loud_failure(lib):
     for q in (0, 2, 3, 4, 10):                            # qualities without a GPU path: refused, never other bytes
         n = C.c_size_t(4096)
         assert lib.BrotliEncoderCompress(q, 22, 0, 100, b"x" * 100, C.byref(n), out) == 0
+
+
+def test_pkgconfig_dropin_layout(tmp_path):
+    """packaging/install_dropin.sh lays the library out under the reference's names (libbrotlienc.so.1, libbrotlienc.pc,
+    brotli/encode.h): a C99 program built the way go/cbrotli/cgo.go:10 or a USE_SYSTEM_BROTLI python build would (pkg-config
+    libbrotlienc) links against it and runs the host-only entry points."""
+    import shutil
+    import subprocess
+    if not (shutil.which("pkg-config") and shutil.which("gcc")):
+        pytest.skip("pkg-config / gcc not available")
+    if not os.path.exists(SO):
+        import __graft_entry__
+        __graft_entry__.build_product()
+    prefix = tmp_path / "prefix"
+    subprocess.check_call([os.path.join(ROOT, "packaging", "install_dropin.sh"), str(prefix)])
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include <brotli/encode.h>\n#include <brotli_b200.h>\n'
+                   'int main(void) { BrotliEncoderState* s = BrotliEncoderCreateInstance(0, 0, 0);\n'
+                   '  int ok = s && BrotliEncoderSetParameter(s, BROTLI_PARAM_QUALITY, 5); BrotliEncoderDestroyInstance(s);\n'
+                   '  printf("%u %zu %d\\n", BrotliEncoderVersion(), BrotliEncoderMaxCompressedSize(1 << 20), ok); return 0; }\n')
+    env = dict(os.environ, PKG_CONFIG_PATH=str(prefix / "lib" / "pkgconfig"))
+    flags = subprocess.check_output(["pkg-config", "--cflags", "--libs", "libbrotlienc"], env=env, text=True).split()
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)] + flags)
+    out = subprocess.check_output([str(exe)], env=dict(os.environ, LD_LIBRARY_PATH=str(prefix / "lib")), text=True)
+    assert out.split() == ["16785408", str((1 << 20) + 2 + 4 * 64 + 3 + 1), "1"]
+    needed = subprocess.check_output(["readelf", "-d", str(exe)], text=True)
+    assert "libbrotlienc.so.1" in needed

@@ -227,6 +227,23 @@ def test_cli_dropin(b200, tmp_path):
     assert outs[0] == outs[1] and len(outs[0]) > 0
 
 
+def test_cli_dropin_stdin(b200, tmp_path):
+    """The same CLI reading a PIPE: no size hint (c/tools/brotli.c:1448-1452), 512 KiB PROCESS calls, an input that is an
+    exact multiple of the read size (FINISH arrives without input behind a full block), quality 5 and 9."""
+    import subprocess
+    from brotli_libs import ROOT
+    cli_ref = os.path.join(ROOT, "oracle", "_ref", "brotli_cli_ref")
+    cli_b200 = os.path.join(ROOT, "oracle", "_ref", "brotli_cli_b200")
+    if not (os.path.exists(cli_ref) and os.path.exists(cli_b200)):
+        pytest.skip("CLI binaries were not built (oracle/Makefile ref)")
+    from corpus import synth_web
+    for n, q, w in ((3 * 524288, 5, 22), (2_500_001, 9, 24), (700_000, 6, 18)):
+        data = synth_web(n, 78)
+        outs = [subprocess.run([cli, "-q", str(q), "-w", str(w), "-c"], input=data, stdout=subprocess.PIPE, check=True).stdout
+                for cli in (cli_ref, cli_b200)]
+        assert outs[0] == outs[1] and len(outs[0]) > 0, (n, q, w)
+
+
 def test_q1_oneshot_against_oracle(b200):
     """Quality 1 through BrotliEncoderCompress: every hash-table size / min_match, block and fragment
     boundaries, raw meta-blocks, the raw-stream rule."""
