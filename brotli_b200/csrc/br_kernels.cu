@@ -177,8 +177,14 @@ __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restr
 // G = bucket-ring rows fetched together (br_lz77.h): 1 for the 16/32-entry rings of quality 5-6 (throughput bound,
 // 8 CTAs per SM), 4 for the 64/128-entry rings of quality 7-8 and 8 (the whole 256-entry ring) at quality 9 (more
 // registers, fewer resident warps).
+#ifndef BR_WALK1_MINB
+#define BR_WALK1_MINB 8
+#endif
+#ifndef BR_WALK_G_SMALL
+#define BR_WALK_G_SMALL 1   /* rows fetched together for the 16/32-entry rings */
+#endif
 template <int G>
-__global__ void __launch_bounds__(128, G == 1 ? 8 : G == 4 ? 5 : 4) k_walk(BrStream s) {
+__global__ void __launch_bounds__(128, G <= 2 ? BR_WALK1_MINB : G == 4 ? 5 : 4) k_walk(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.counters[5]) return;
   const u32 b = br_sched_entry(s, t);
@@ -622,7 +628,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       cudaEventRecord(ev[6], st);
       if (P.block_bits >= 8) k_walk<8><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
       else if (P.block_bits >= 6) k_walk<4><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
-      else k_walk<1><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
+      else k_walk<BR_WALK_G_SMALL><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
       cudaEventRecord(ev[7], st);
       walk_pending = true; ++job->stats.walk_launches; job->stats.launches += 6;
       job->stats.walk_bytes += (u64)n_sched * ch;

@@ -207,6 +207,39 @@ def test_full_size_properties(b200):
     assert out == ref.compress(d, 5, 22)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_q9_ring_wrap_and_nonsettling_inputs(b200):
+    """Quality 9 / lgwin 24 beyond the 32 MiB ring buffer of the reference (BASELINE config C4's path: H6, 256-entry
+    rings, 256 KiB input blocks), on the Silesia-shaped binary mix, and inputs whose parse never settles by itself --
+    uniform noise (the sparse search's position phase runs through the whole input) and int32 random walks.  The
+    encoder must never fail (encode.c:1340-1353) and must equal the reference run on the box."""
+    import numpy as np
+    from corpus import synth_binary
+    ref = Ref()
+    cases = [("binary mix 48 MiB", synth_binary(48 << 20, 91), 9, 24),
+             ("uniform noise 24 MiB", np.random.RandomState(92).randint(0, 256, 24 << 20, dtype=np.uint8).tobytes(), 9, 24),
+             ("uniform noise 16 MiB q5", np.random.RandomState(93).randint(0, 256, 16 << 20, dtype=np.uint8).tobytes(), 5, 22),
+             ("random walk 64 MiB", np.cumsum(np.random.RandomState(94).normal(0, 50, (64 << 20) // 4).astype(np.int64)).astype(np.int32).tobytes(), 9, 24)]
+    for name, d, q, w in cases:
+        out = b200.compress_oneshot(d, q, w)
+        assert out == ref.compress(d, q, w), name
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_config3_slice_and_config5_streams(b200):
+    """BASELINE config C3 (web mix, quality 5, lgwin 22) on a 256 MiB slice, and config C5 on 1000 of its 64 KiB streams
+    (quality 1, one device batch), each against the reference run on the box."""
+    from corpus import synth_web
+    ref = Ref()
+    web = synth_web(256 << 20)
+    out = b200.compress_oneshot(web, 5, 22)
+    assert out == ref.compress(web, 5, 22)
+    streams = [web[o:o + 65536] for o in [(i * 104729) % (len(web) - 65536) for i in range(1000)]]
+    got = b200.compress_batch(streams, 1, 22)
+    for i, s in enumerate(streams):
+        assert got[i] == ref.compress(s, 1, 22), i
+
+
 def test_cli_dropin(b200, tmp_path):
     """The reference's own CLI (c/tools/brotli.c, unmodified) linked against this library instead of
     libbrotlienc produces the same file as the CLI linked against the reference encoder."""
