@@ -13,7 +13,9 @@
 #include "br_cmd.h"
 
 // ------------------------------------------------------------------ bit writer
-struct BrBitW { u32* out; u32 ix; };
+// per_thread = 0: the cursor is warp-uniform and lane 0 writes; 1: the writer belongs to ONE thread (parallel tree
+// storing in br_prep_codes).  out = nullptr: count bits only.
+struct BrBitW { u32* out; u32 ix; u32 per_thread; };
 // LSB-first append (write_bits.h:33).  The buffer is pre-zeroed and every write is an atomic
 // OR (RED at L2), so lane-0 serial writes and lane-parallel writes can interleave freely.
 BR_DEV void br_put_bits_at(u32* out, u32 ix, u32 n, u64 bits) {  // n <= 56
@@ -26,7 +28,7 @@ BR_DEV void br_put_bits_at(u32* out, u32 ix, u32 n, u64 bits) {  // n <= 56
 }
 // warp-uniform call: lane 0 writes, every lane advances its copy of the cursor
 BR_DEV void br_put_bits(BrBitW& w, u32 n, u64 bits) {
-  if (br_lane() == 0) br_put_bits_at(w.out, w.ix, n, bits);
+  if (w.out && (w.per_thread || br_lane() == 0)) br_put_bits_at(w.out, w.ix, n, bits);
   w.ix += n;
 }
 // Serial sections run on lane 0 only; afterwards the cursor is re-broadcast.
@@ -245,6 +247,10 @@ struct BrMbScratch {
   u32 rle_syms[256 * 64];    // context map run-length symbols
 };
 
+// What one thread needs to store one prefix code (br_store_huffman_tree): the RLE-coded code lengths and the tree of
+// the 18-symbol code-length code.
+struct BrTreeSc { BrHTree tree[2 * 18 + 2]; u8 ht[704], hx[704]; };
+
 // brotli_bit_stream.c:165 + :283 BrotliStoreHuffmanTree
 template <class SC> BR_DEV void br_store_huffman_tree(const u8* depths, u32 num, SC* sc, BrBitW& w) {
   const u8 kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
@@ -296,7 +302,7 @@ BR_DEV void br_build_tree(const u32* histo, u32 histo_len, BrHTree* tree, u8* de
   br_depths_to_symbols(depth, histo_len, bits);
 }
 // Store (+ :242 StoreSimpleHuffmanTree / :283 BrotliStoreHuffmanTree)
-BR_DEV void br_store_tree(const u32* histo, u32 histo_len, u32 alphabet_size, BrMbScratch* sc,
+template <class SC> BR_DEV void br_store_tree(const u32* histo, u32 histo_len, u32 alphabet_size, SC* sc,
                           const u8* depth, BrBitW& w) {
   u32 count = 0, s4[4] = {0, 0, 0, 0}, max_bits = 0;
   for (u32 i = 0; i < histo_len; i++) {

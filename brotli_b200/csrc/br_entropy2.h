@@ -48,7 +48,7 @@ BR_HD u32 br_mb2_var_bytes(u32 nblk) { return br_align8(nblk * ((u32)sizeof(BrBl
 BR_HD u32 br_mb2_scratch_bytes(u32 nlit, u32 ncmd) {
   u32 lb = nlit / 512 + 2, cb = ncmd / 1024 + 2, db = ncmd / 512 + 2;
   return br_align8((u32)sizeof(BrMbMem)) + br_mb2_var_bytes(lb) + br_mb2_var_bytes(cb) + br_mb2_var_bytes(db) +
-         BR_PREP_THREADS * (u32)sizeof(BrHTree) * (2 * 704 + 2);
+         BR_PREP_THREADS * (u32)sizeof(BrHTree) * (2 * 704 + 2) + (3 * 256 + 8) * 4;   // + sizes / offsets of the stored codes
 }
 BR_DEV BrBlockInfo* br_mb2_blocks(u8* scratch, const BrMbAux& a, int cat) { return (BrBlockInfo*)(scratch + a.var_off[cat]); }
 BR_DEV u32* br_mb2_lengths(u8* scratch, const BrMbAux& a, int cat, u32 nblk) {
@@ -265,24 +265,36 @@ BR_DEV void br_prep_codes(const BrStream& st, const BrMetaBlock& mb, BrMbAux& a,
   BrMbMem* M = (BrMbMem*)scratch;
   const u32 nctx = a.which;
   const u32 nl = a.num_types[0] * nctx, ncm = a.num_types[1], nd = a.num_types[2];
-  BrHTree* trees = (BrHTree*)(scratch + br_mb2_scratch_bytes(mb.nlit, mb.ncmd) - BR_PREP_THREADS * (u32)sizeof(BrHTree) * (2 * 704 + 2));
+  BrHTree* trees = (BrHTree*)(scratch + br_mb2_scratch_bytes(mb.nlit, mb.ncmd) - BR_PREP_THREADS * (u32)sizeof(BrHTree) * (2 * 704 + 2) - (3 * 256 + 8) * 4);
   BrHTree* mytree = trees + (size_t)(tid % BR_PREP_THREADS) * (2 * 704 + 2);
+  // Every prefix code of the metablock is built by its own thread, which also measures how many bits its serialised form
+  // takes (brotli_bit_stream.c:349: the store, run against a counting writer).  Once the header in front of the codes is
+  // written the offsets are known and the same threads store their codes in parallel: all writes are atomic ORs.
+  u32* tree_bits = (u32*)(trees + (size_t)BR_PREP_THREADS * (2 * 704 + 2));   // [nl + ncm + nd] sizes, then bit offsets
+  const u32 ntrees = nl + ncm + nd;
+  const u32 stride = nt < BR_PREP_THREADS ? nt : BR_PREP_THREADS;
   if (tid < BR_PREP_THREADS) {
-    const u32 stride = nt < BR_PREP_THREADS ? nt : BR_PREP_THREADS;
-    for (u32 t = tid; t < nl + ncm + nd; t += stride) {
+    for (u32 t = tid; t < ntrees; t += stride) {
       u8 good[704];
+      const u32* H; u8* dep; u32 len;
       if (t < nl) {
+        H = M->lit_H + t * 256; dep = M->lit_depth + t * 256; len = 256;
         br_optimize_counts_for_rle(256, M->lit_H + t * 256, good);
-        br_build_tree(M->lit_H + t * 256, 256, mytree, M->lit_depth + t * 256, M->lit_bits + t * 256);
+        br_build_tree(H, 256, mytree, dep, M->lit_bits + t * 256);
       } else if (t < nl + ncm) {
         u32 x = t - nl;
+        H = M->cmd_H + x * 704; dep = M->cmd_depth + x * 704; len = 704;
         br_optimize_counts_for_rle(704, M->cmd_H + x * 704, good);
-        br_build_tree(M->cmd_H + x * 704, 704, mytree, M->cmd_depth + x * 704, M->cmd_bits + x * 704);
+        br_build_tree(H, 704, mytree, dep, M->cmd_bits + x * 704);
       } else {
         u32 x = t - nl - ncm;
+        H = M->dist_H + x * 64; dep = M->dist_depth + x * 64; len = 64;
         br_optimize_counts_for_rle(64, M->dist_H + x * 64, good);
-        br_build_tree(M->dist_H + x * 64, 64, mytree, M->dist_depth + x * 64, M->dist_bits + x * 64);
+        br_build_tree(H, 64, mytree, dep, M->dist_bits + x * 64);
       }
+      BrBitW cw; cw.out = nullptr; cw.ix = 0; cw.per_thread = 1;
+      br_store_tree(H, len, len, (BrTreeSc*)mytree, dep, cw);   // (the big tree is done: its memory is the store's scratch)
+      tree_bits[t] = cw.ix;
     }
   }
   // metablock.c:677 MapStaticContexts
@@ -292,12 +304,12 @@ BR_DEV void br_prep_codes(const BrStream& st, const BrMetaBlock& mb, BrMbAux& a,
   __threadfence_block();
 #endif
   br_cta_sync();
-  if (tid >= BR_WARP) return;
-  // ---- warp 0: header and codes, warp-uniform
   const int lane = br_lane();
   BrMbScratch* sc = &M->sc;
   const u32 cmap_size = nctx > 1 ? (a.num_types[0] << 6) : 0;
-  BrBitW w; w.out = out; w.ix = 0;
+  BrBitW w; w.out = out; w.ix = 0; w.per_thread = 0;
+  if (tid < BR_WARP) {
+  // ---- warp 0: header in front of the codes, warp-uniform
   br_put_bits(w, 1, (u64)mb.is_last);
   if (mb.is_last) br_put_bits(w, 1, 0);
   br_store_mlen(mb.end - mb.start, w);
@@ -317,11 +329,26 @@ BR_DEV void br_prep_codes(const BrStream& st, const BrMetaBlock& mb, BrMbAux& a,
   if (cmap_size == 0) br_store_trivial_context_map(nl, 6, sc, w);
   else br_encode_context_map(M->cmap, cmap_size, nl, sc, w);
   br_store_trivial_context_map(nd, 2, sc, w);
-  BR_LANE0_BEGIN
-    for (u32 i = 0; i < nl; ++i) br_store_tree(M->lit_H + i * 256, 256, 256, sc, M->lit_depth + i * 256, w);
-    for (u32 i = 0; i < ncm; ++i) br_store_tree(M->cmd_H + i * 704, 704, 704, sc, M->cmd_depth + i * 704, w);
-    for (u32 i = 0; i < nd; ++i) br_store_tree(M->dist_H + i * 64, 64, 64, sc, M->dist_depth + i * 64, w);
-  BR_LANE0_END(w)
+  if (lane == 0) {   // sizes -> bit offsets
+    u32 acc = w.ix;
+    for (u32 t = 0; t < ntrees; ++t) { const u32 v = tree_bits[t]; tree_bits[t] = acc; acc += v; }
+    tree_bits[ntrees] = acc;
+  }
+  }
+#if BR_GPU
+  __threadfence_block();
+#endif
+  br_cta_sync();
+  if (tid < BR_PREP_THREADS) {
+    for (u32 t = tid; t < ntrees; t += stride) {
+      BrBitW tw; tw.out = out; tw.ix = tree_bits[t]; tw.per_thread = 1;
+      if (t < nl) br_store_tree(M->lit_H + t * 256, 256, 256, (BrTreeSc*)mytree, M->lit_depth + t * 256, tw);
+      else if (t < nl + ncm) { const u32 x = t - nl; br_store_tree(M->cmd_H + x * 704, 704, 704, (BrTreeSc*)mytree, M->cmd_depth + x * 704, tw); }
+      else { const u32 x = t - nl - ncm; br_store_tree(M->dist_H + x * 64, 64, 64, (BrTreeSc*)mytree, M->dist_depth + x * 64, tw); }
+    }
+  }
+  if (tid >= BR_WARP) return;
+  w.ix = tree_bits[ntrees];
   // ---- block tables: start ordinal of every block and the block-switch bits that precede it
   for (int cat = 0; cat < 3; ++cat) {
     u32 nblk = br_mb2_nblk(cat, mb.nlit, mb.ncmd);

@@ -1,7 +1,7 @@
 // br_kernels.cu -- CUDA kernels (sm_100a) and the per-stream pipeline that drives them.
 //
 // Stage map (reference function -> kernel):
-//   hash keys / bucket rings (hash_longest_match64_inc.h Store*)  -> k_hash_keys, k_radix_*, k_rank, k_seg
+//   hash keys / bucket rings (hash_longest_match64_inc.h Store*)  -> k_hash_keys, k_radix_* (the last pass writes rank[]), k_seg
 //   CreateBackwardReferences + FindLongestMatch                   -> k_walk      (one warp per input block)
 //   EncodeData glue (encode.c:985)                                -> k_chain     (one warp per stream)
 //   BrotliBuildMetaBlockGreedy + BrotliStoreMetaBlock             -> k_encode_mb (one warp per metablock)
@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(256) k_radix_count(const u16* __restrict__ key
   hist[threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
 }
 // stable scatter: warp w of the CTA owns elements [w*512, w*512+512) of the tile, row by row
+// `inv` (nullable): the final pass also writes the inverse permutation inv[position] = index in the sorted order (BrStream::rank)
 template <int SHIFT, bool HAS_VALS>
 __global__ void __launch_bounds__(256) k_radix_scatter(const u16* __restrict__ keys, const u32* __restrict__ vals, u32 n,
-    const u32* __restrict__ hist_scanned, u32 ntiles, u16* __restrict__ out_keys, u32* __restrict__ out_vals) {
+    const u32* __restrict__ hist_scanned, u32 ntiles, u16* __restrict__ out_keys, u32* __restrict__ out_vals, u32* __restrict__ inv) {
   __shared__ u32 wcnt[8][256];
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (u32 i = threadIdx.x; i < 8 * 256; i += 256) (&wcnt[0][0])[i] = 0;
@@ -78,16 +79,14 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const u16* __restrict__ k
     if (j < n) {
       u32 dst = wcnt[warp][d] + rank;
       out_keys[dst] = (u16)k;
-      out_vals[dst] = HAS_VALS ? vals[j] : j;
+      const u32 v = HAS_VALS ? vals[j] : j;
+      out_vals[dst] = v;
+      if (inv) inv[v] = dst;
     }
     __syncwarp();
     if (d != 0xFFFFFFFFu && rank == 0) wcnt[warp][d] += __popc(m);
     __syncwarp();
   }
-}
-__global__ void k_rank(const u32* __restrict__ S, u32 n, u32* __restrict__ rank) {
-  u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) rank[S[j]] = j;
 }
 // seg[k] = first index in S whose key is >= k, for k in [0, nbuckets + 1]
 __global__ void k_seg(const u16* __restrict__ sorted_keys, u32 n, u32 nbuckets, u32* __restrict__ seg) {
@@ -582,11 +581,10 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   k_hash_keys<<<(n + 255) / 256, 256, 0, st>>>(P, data, keys);
   k_radix_count<0><<<ntiles, 256, 0, st>>>(keys, n, hist, ntiles);
   scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
-  k_radix_scatter<0, false><<<ntiles, 256, 0, st>>>(keys, nullptr, n, hist, ntiles, K1, V1);
+  k_radix_scatter<0, false><<<ntiles, 256, 0, st>>>(keys, nullptr, n, hist, ntiles, K1, V1, nullptr);
   k_radix_count<8><<<ntiles, 256, 0, st>>>(K1, n, hist, ntiles);
   scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
-  k_radix_scatter<8, true><<<ntiles, 256, 0, st>>>(K1, V1, n, hist, ntiles, K2, S);
-  k_rank<<<(n + 255) / 256, 256, 0, st>>>(S, n, rank);
+  k_radix_scatter<8, true><<<ntiles, 256, 0, st>>>(K1, V1, n, hist, ntiles, K2, S, rank);
   k_seg<<<(n + 1 + 255) / 256, 256, 0, st>>>(K2, n, P.nbuckets, seg);
   CK(cudaMemsetAsync(bits_latest, 0, nwords * 4, st));
   k_init_bits<<<nblk, 256, 0, st>>>(s);
@@ -766,10 +764,10 @@ extern "C" __attribute__((visibility("default"))) int br_debug_sort(int quality,
   k_hash_keys<<<(n + 255) / 256, 256>>>(P, data, keys);
   k_radix_count<0><<<ntiles, 256>>>(keys, n, hist, ntiles);
   scan_exclusive(hist, 256 * ntiles, tmp, 0);
-  k_radix_scatter<0, false><<<ntiles, 256>>>(keys, nullptr, n, hist, ntiles, K1, V1);
+  k_radix_scatter<0, false><<<ntiles, 256>>>(keys, nullptr, n, hist, ntiles, K1, V1, nullptr);
   k_radix_count<8><<<ntiles, 256>>>(K1, n, hist, ntiles);
   scan_exclusive(hist, 256 * ntiles, tmp, 0);
-  k_radix_scatter<8, true><<<ntiles, 256>>>(K1, V1, n, hist, ntiles, K2, S);
+  k_radix_scatter<8, true><<<ntiles, 256>>>(K1, V1, n, hist, ntiles, K2, S, nullptr);
   k_seg<<<(n + 1 + 255) / 256, 256>>>(K2, n, P.nbuckets, seg);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_S, S, 4ull * n, cudaMemcpyDeviceToHost));

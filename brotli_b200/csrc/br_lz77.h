@@ -89,6 +89,9 @@ BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
   if (P.hash64) return (u32)((v * (0x1FE35A7BD3579BD3ull << 24)) >> (64 - 15));
   return ((u32)v * 0x1E35A7BDu) >> (32 - P.bucket_bits);
 }
+#ifndef BR_WALK_SPEC1
+#define BR_WALK_SPEC1 0   /* G == 1: request the candidates' first bytes before their stored bit is known */
+#endif
 struct BrWalk {
   const BrStream* s;
   const u8* d;
@@ -352,7 +355,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
         inwin[r] = has[r] && cur - q[r] <= max_backward;
         st[r] = inwin[r] && br_is_stored(w, q[r]);
       }
-      if (G > 1) {
+      if (G > 1 || BR_WALK_SPEC1) {
 #pragma unroll
         for (int r = 0; r < G; ++r) d0[r] = inwin[r] ? br_ld64u(d, q[r]) : 0;
       }
@@ -378,7 +381,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
         u32 len = 0; int eqmax = 0;
         if (take) {
           BR_W(9, 1);
-          len = G > 1 ? br_match_len_d0(d, q[r], cur, max_length, c0, c1, d0[r]) : br_match_len_c(d, q[r], cur, max_length, c0, c1);
+          len = (G > 1 || BR_WALK_SPEC1) ? br_match_len_d0(d, q[r], cur, max_length, c0, c1, d0[r]) : br_match_len_c(d, q[r], cur, max_length, c0, c1);
           if (len < 4) len = 0;
           if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + q[r] + max_length));
         }

@@ -530,7 +530,7 @@ BR_DEV void br_q1_prep_block(const BrQ1& q, u32 bi, BrQ1Smem* sm) {
   for (u32 i = tid; i < ncmd; i += nt) br_smem_add(&sm->cmd_histo[cw[i] & 0xFFu], 1);
   br_cta_sync();
   if (tid == 0) {
-    BrBitW w; w.out = sm->hdr; w.ix = 0;
+    BrBitW w; w.out = sm->hdr; w.ix = 0; w.per_thread = 0;
     br_q1_put_mb_header(sm->hdr, 0, size, 0); w.ix = br_q1_mb_header_bits(size);
     br_put_bits(w, 13, 0);                       // :581 no block splits, no contexts
     for (u32 i = 0; i < 256; ++i) { sm->lit_depth[i] = 0; sm->lit_bits[i] = 0; }
