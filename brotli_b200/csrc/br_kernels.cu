@@ -174,10 +174,14 @@ __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restr
 
 // ---------------------------------------------------------------------------- warp-task kernels
 // G = bucket-ring rows fetched together (br_lz77.h): 1 for the 16/32-entry rings of quality 5-6 (throughput bound,
-// 8 CTAs per SM), 4 for the 64/128-entry rings of quality 7-8 and 8 (the whole 256-entry ring) at quality 9 (more
-// registers, fewer resident warps).
+// 8 CTAs per SM), 4 for the 64-256-entry rings of quality 7-9 (more registers, fewer resident warps).
 #ifndef BR_WALK1_MINB
 #define BR_WALK1_MINB 8
+#endif
+#ifndef BR_WALK_G_DEEP
+#define BR_WALK_G_DEEP 4    /* rows fetched together for the 256-entry rings of quality 9: 8 (the whole ring, 125 registers,
+                               16 warps per SM) walks one chunk faster, 4 (96 registers, 20 warps per SM) wins on the whole
+                               job -- config C4 5.37 s against 5.90 s (profiles/r02p_variants.log) */
 #endif
 #ifndef BR_WALK_G_SMALL
 #define BR_WALK_G_SMALL 1   /* rows fetched together for the 16/32-entry rings */
@@ -624,7 +628,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
       scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
       cudaEventRecord(ev[6], st);
-      if (P.block_bits >= 8) k_walk<8><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
+      if (P.block_bits >= 8) k_walk<BR_WALK_G_DEEP><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
       else if (P.block_bits >= 6) k_walk<4><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
       else k_walk<BR_WALK_G_SMALL><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
       cudaEventRecord(ev[7], st);

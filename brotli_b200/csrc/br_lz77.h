@@ -90,7 +90,8 @@ BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
   return ((u32)v * 0x1E35A7BDu) >> (32 - P.bucket_bits);
 }
 #ifndef BR_WALK_SPEC1
-#define BR_WALK_SPEC1 0   /* G == 1: request the candidates' first bytes before their stored bit is known */
+#define BR_WALK_SPEC1 0   /* G == 1: request the candidates' first bytes before their stored bit is known
+                             (measured: 33.2 against 32.7 ms of k_walk per 100 MB of text -- no gain, off) */
 #endif
 struct BrWalk {
   const BrStream* s;

@@ -175,7 +175,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     s.counters[4] = 0; s.counters[16] = 0;
     s.forced = s.epoch >= s.P.force_epoch;
     { u32 nd = s.counters[5]; std::vector<u32> dl(nd); for (u32 t = 0; t < nd; ++t) dl[t] = br_sched_entry(s, t); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
-      if (s.P.block_bits >= 8) br_walk_block<8>(s, k, f); else if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
+      if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
     m.block_runs += s.counters[4];
 #ifdef BR_SIM_DEBUG
     if (getenv("BR_SIM_TRACE")) { fprintf(stderr, "   work: searches %llu rows %llu groups %llu taken %llu | heavy %llu own-scan rows %llu countS %llu | own_set %llu set_range %llu dict %llu\n",
