@@ -19,7 +19,7 @@ static u64 br_sim_cnt[8];                // tests/sim: marks by source (0 succes
 BR_DEV u32 br_chunk_of(const BrStream& s, u32 p) {
   u32 b = s.slot_blk[p >> s.P.lgblock];
   while (p >= s.blk[b].end) ++b;
-  return s.blk[b].first_chunk + ((p - s.blk[b].start) >> BR_CHUNK_BITS);
+  return s.blk[b].first_chunk + ((p - s.blk[b].start) >> s.P.chunk_bits);
 }
 
 // Compare and commit the stored-bits a walker just produced for chunk k (warp task).  The

@@ -483,7 +483,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 #else
   const bool trace = false;
 #endif
-  const u32 ch = 1u << BR_CHUNK_BITS;
+  const u32 ch = 1u << P.chunk_bits;
   // chunk / block tables: the reference's input blocks (1 << lgblock bytes, shorter where a FLUSH cut the input)
   std::vector<BrBlockIn> hb; std::vector<BrBlk> hblk;
   const u32 ncuts = cuts ? cuts->n : 0;
@@ -642,7 +642,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     if (trace) {   // the slowest chunk walks of the final state, and a per-megabyte profile
       std::vector<BrBlockOut> hb2(nb);
       cudaMemcpyAsync(hb2.data(), bout, nb * sizeof(BrBlockOut), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
-      const u32 per = (1u << 20) >> BR_CHUNK_BITS;
+      const u32 per = (1u << 20) >> P.chunk_bits;
       for (u32 a = 0; a < nb; a += per) {
         unsigned long long cyc = 0, se = 0, ro = 0; u32 mx = 0;
         for (u32 k = a; k < a + per && k < nb; ++k) { cyc += hb2[k].dbg_kcycles; se += hb2[k].dbg_searches; ro += hb2[k].dbg_rows; if (hb2[k].dbg_kcycles > mx) mx = hb2[k].dbg_kcycles; }

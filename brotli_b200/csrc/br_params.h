@@ -27,7 +27,7 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->size_hint = size_hint;
   P->n = n;
   P->nbuckets = 1u << P->bucket_bits;
-  P->cpb_shift = (u32)P->lgblock - BR_CHUNK_BITS;
+  P->chunk_bits = n < BR_SMALL_STREAM ? BR_CHUNK_BITS_SMALL : BR_CHUNK_BITS;
   P->heavy_min = 65536;
   P->step_cap = 4096;
   P->sweep_epoch = 3;    // text / web input settles in 3 launches; what is still dirty then is swept run by run
@@ -43,7 +43,7 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
 // last block carries is_last); otherwise the stream simply stops behind its last block.
 static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u32 ncuts, bool is_final,
                                    std::vector<BrBlockIn>& chunks, std::vector<BrBlk>& blks) {
-  const u32 bs = 1u << P.lgblock, ch = 1u << BR_CHUNK_BITS;
+  const u32 bs = 1u << P.lgblock, ch = 1u << P.chunk_bits;
   u32 ci = 0;
   u64 bstart = 0;
   while (bstart < n) {

@@ -27,7 +27,7 @@ struct BrParams {
   u32 n;            // input bytes
   u32 nblocks;      // number of chunks (speculation units); input blocks are groups of them
   u32 nbuckets;     // 1 << bucket_bits (+1 overflow bucket for the unhashable tail positions)
-  u32 cpb_shift;    // lgblock - BR_CHUNK_BITS: chunks per full input block = 1 << cpb_shift
+  u32 chunk_bits;   // the unit of speculation is a chunk of 1 << chunk_bits bytes (see BR_CHUNK_BITS below)
   u32 sweep_epoch;  // from this launch on: only the HEAD of every run of consecutive dirty chunks is scheduled; its walker
                     // sweeps the run serially, seeing its own fresh stored-bits (Gauss-Seidel inside a run, Jacobi across runs)
   u32 force_epoch;  // from this launch on the first scheduled walker also runs to the end of its input block whatever the
@@ -42,7 +42,11 @@ struct BrParams {
 
 // The unit of speculation is a CHUNK: a slice (1 << BR_CHUNK_BITS bytes) of one of the
 // reference's input blocks.  Per chunk: what the chain hands to the chunk's walker.
+// 2 KiB chunks for streams of a megabyte and more; 512-byte chunks below that: a small stream has few chunks and its
+// latency is the serial walk of ONE chunk per launch, so finer chunks cut it four-fold (a 64 KiB stream: 12.7 -> see DESIGN.md).
 #define BR_CHUNK_BITS 11
+#define BR_CHUNK_BITS_SMALL 9
+#define BR_SMALL_STREAM (1u << 20)
 struct BrBlockIn {
   u32 pos, end;          // nominal slice [pos, end) of the input
   u32 blk_start, blk_end;  // the reference input block (one EncodeData call) that contains it

@@ -93,7 +93,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   if (getenv("BR_SIM_SWEEP_EPOCH")) P.sweep_epoch = (u32)atoi(getenv("BR_SIM_SWEEP_EPOCH"));
   if (getenv("BR_SIM_SWEEP_BLOCKS")) P.sweep_blocks = (u32)atoi(getenv("BR_SIM_SWEEP_BLOCKS"));
   if (getenv("BR_SIM_FORCE_EPOCH")) P.force_epoch = (u32)atoi(getenv("BR_SIM_FORCE_EPOCH"));
-  const u32 ch = 1u << BR_CHUNK_BITS;
+  const u32 ch = 1u << P.chunk_bits;
   std::vector<BrBlockIn> chunks;
   P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
   br_build_blocks(P, n, cuts ? cuts->pos : nullptr, cuts ? cuts->n : 0, cuts ? (cuts->is_final != 0 && !cuts->finish_empty) : true, chunks, m->blks);
