@@ -256,10 +256,24 @@ BR_DEV void br_chain_b(const BrStream& s) {
   u32 dbg_slow = 0;
   bool mb_valid = true;
   const u32 blocksize = 1u << P.lgblock;
-  BrBlk Bnext = s.blk[0];
+  // The recurrence is serial, but its loads need not be: every lane fetches the summary of one of the next BR_WARP
+  // blocks, and the loop takes them out of the lanes' registers with shuffles (the loop-carried state is in registers
+  // only, so a block costs arithmetic latency instead of a memory round trip).
+  BrBlk mine; memset(&mine, 0, sizeof(mine));
   for (u32 bi = 0; bi < nblk; ++bi) {
-    const BrBlk B = Bnext;
-    if (bi + 1 < nblk) Bnext = s.blk[bi + 1];   // software prefetch: the loop-carried state is in registers only
+    if ((bi % BR_WARP) == 0) { const u32 mi = bi + (u32)lane; if (mi < nblk) mine = s.blk[mi]; }
+    BrBlk B;
+    {
+      const int src = (int)(bi % BR_WARP);
+      B.start = br_shfl(mine.start, src); B.end = br_shfl(mine.end, src); B.first_chunk = br_shfl(mine.first_chunk, src);
+      B.nchunks = br_shfl(mine.nchunks, src); B.is_last = br_shfl(mine.is_last, src); B.force_flush = br_shfl(mine.force_flush, src);
+      B.ncmd = br_shfl(mine.ncmd, src); B.nlit_rel = br_shfl(mine.nlit_rel, src); B.has_cmd = br_shfl(mine.has_cmd, src);
+      B.lil_head = br_shfl(mine.lil_head, src); B.lil_tail = br_shfl(mine.lil_tail, src); B.last_cmd_chunk = br_shfl(mine.last_cmd_chunk, src);
+      B.dl = br_shfl(mine.dl, src); B.dm = br_shfl(mine.dm, src); B.ext_len = br_shfl(mine.ext_len, src); B.valid = br_shfl(mine.valid, src);
+      for (int i = 0; i < 4; ++i) B.out_dc[i] = br_shfl(mine.out_dc[i], src);
+      B.lc_copy_len = br_shfl(mine.lc_copy_len, src); B.lc_dist_prefix = br_shfl(mine.lc_dist_prefix, src); B.lc_dist_extra = br_shfl(mine.lc_dist_extra, src);
+      B.changed_epoch = br_shfl(mine.changed_epoch, src); B.state_dirty = br_shfl(mine.state_dirty, src);
+    }
     u32 ext_dist = 0;
     if (num_cmds > 0 && last_insert_len == 0 && have_last) {
       u32 dcode = br_cmd_restore_dcode(lc_dist_prefix, lc_dist_extra);
