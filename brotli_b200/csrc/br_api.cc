@@ -85,8 +85,9 @@ bool supported(Params p) {
   if (p.lgwin > 24 && !p.large_window) p.lgwin = 24;
   if (p.quality != 1 && (p.quality < 5 || p.quality > 9)) return false;
   if (p.quality == 1 ? p.lgwin > 24 : (p.lgwin < 17 || p.lgwin > 24)) return false;
-  if (p.large_window || p.npostfix || p.ndirect || p.stream_offset || p.base64 || p.disable_ctx) return false;
-  if (p.lgblock != 0) return false;
+  if (p.large_window || p.npostfix || p.ndirect || p.stream_offset || p.base64) return false;
+  /* LGBLOCK and DISABLE_LITERAL_CONTEXT_MODELING are honoured at quality 5..9; at quality 1 the reference ignores both
+     (quality.h:79: lgblock = lgwin; no context modeling in the fragment coder) */
   if (p.mode == BROTLI_MODE_FONT) return false;
   return true;
 }
@@ -223,7 +224,10 @@ void put_metadata(BitOut& w, const std::vector<uint8_t>& meta) {
   w.align();
   w.v.insert(w.v.end(), meta.begin(), meta.end());
 }
-int lgblock_of(const Params& p) { return (p.quality >= 9 && p.lgwin > 16) ? (p.lgwin < 18 ? p.lgwin : 18) : 16; }
+int lgblock_of(const Params& p) {   /* quality.h:76 ComputeLgBlock, quality >= 4 */
+  if (p.lgblock != 0) return p.lgblock > 24 ? 24 : p.lgblock < 16 ? 16 : p.lgblock;
+  return (p.quality >= 9 && p.lgwin > 16) ? (p.lgwin < 18 ? p.lgwin : 18) : 16;
+}
 
 // The whole stream for the operations seen so far (quality 5..9): the device compresses the accumulated input cut at the
 // positions of the FLUSH / EMIT_METADATA operations (br_kernels.cu k_assemble_scan pads behind a FLUSH); metadata blocks and
@@ -256,6 +260,7 @@ int build_wire(BrotliEncoderState* s, bool is_final, bool finish_empty, std::vec
   BrCuts c; c.pos = cut_pos.data(); c.kind = cut_kind.data(); c.n = (uint32_t)cut_pos.size();
   c.is_final = (is_final && !cut_at_end) ? 1 : 0; c.with_header = lead ? 0 : 1;
   c.finish_empty = (c.is_final && finish_empty) ? 1 : 0; c.end_bit = end_bit.data();
+  c.lgblock = s->params.lgblock; c.disable_ctx = (int)s->params.disable_ctx;
   if (!c.is_final && !cut_at_end) return 0;   // (callers only build the wire at a cut or at FINISH)
   std::vector<uint8_t> D;
   size_t got = 0;

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(32) k_mb_setup(BrStream s, BrEnt e) {
   if (!mb.compress) return;
   u8* sc = e.scratch + e.scratch_off[i];
   BrMbMem* M = (BrMbMem*)sc;
-  u32 which = br_decide_context_modeling(s, mb.start, mb.end - mb.start, M->sc.rle_syms);
+  u32 which = s.P.disable_ctx ? 1u : br_decide_context_modeling(s, mb.start, mb.end - mb.start, M->sc.rle_syms);
   if (threadIdx.x == 0) {
     BrMbAux a; memset(&a, 0, sizeof(a));
     a.which = which;
@@ -472,8 +472,9 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   BrDeviceTables* T = get_tables();
   if (!T || n == 0) return 0;
   BrStream s; memset(&s, 0, sizeof(s));
-  if (!br_derive_params(quality, lgwin, size_hint, n, &s.P)) return 0;
+  if (!br_derive_params(quality, lgwin, size_hint, n, &s.P, cuts ? cuts->lgblock : 0)) return 0;
   BrParams& P = s.P;
+  P.disable_ctx = cuts && cuts->disable_ctx ? 1u : 0u;
 #ifdef BR_DEBUG_KNOBS   // experiment switches: never in the release build (an environment variable must not change the bytes)
   if (getenv("BR_HEAVY_MIN")) P.heavy_min = (u32)strtoul(getenv("BR_HEAVY_MIN"), 0, 10);
   if (getenv("BR_STEP_CAP")) P.step_cap = (u32)strtoul(getenv("BR_STEP_CAP"), 0, 10);

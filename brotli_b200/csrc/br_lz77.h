@@ -104,7 +104,8 @@ struct BrWalk {
   u32 stale;       // the byte the reference finds just past the block end (see oracle)
   bool warming;    // warm-up (state refinement before the chunk proper): reads the snapshot, records nothing
   u32* own;        // the bits_cur bitmap of this run (parity of the sweep's head chunk)
-  bool fence_due;  // own bits were written since the last fence (see br_own_sync)
+  bool fence_due;  // own bits were written to memory since the last fence (see br_own_sync)
+  u32 acc_wi, acc_own, acc_srch;   // the word of the own / searched bitmaps the parse stands in, gathered in registers
 #ifdef BR_DEBUG_KNOBS
   u32 dbg_searches, dbg_rows, dbg_mlsteps;
 #endif
@@ -119,13 +120,17 @@ BR_DEV u32 br_ld_cur(const u32* p) {
   return *p;
 #endif
 }
+// The walker's writes are gathered per 32-position word: the parse moves forward, so the bits it sets (stored, searched)
+// cluster in the word that holds its position.  `acc_*` is that word -- warp-uniform registers, visible to every lane
+// at once -- and it goes to memory (one atomic OR each) only when the parse leaves the word.  Reads of own bits merge it in.
 BR_DEV int br_own_get(const BrWalk& w, u32 q) {
-  return (br_ld_cur(w.own + (q >> 5)) >> (q & 31)) & 1;
+  u32 v = br_ld_cur(w.own + (q >> 5));
+  if ((q >> 5) == w.acc_wi) v |= w.acc_own;
+  return (v >> (q & 31)) & 1;
 }
-// Writers (lane 0, or one lane per word) and readers (any lane) of the own bits are different threads of the warp:
-// a fence + warp barrier must lie between a write and the next read.  The fence is not paid at the write -- it
-// would wait for the atomic's round trip to L2 on every search -- but right before the next read, several memory
-// round trips later, when the atomic has long been performed.
+// Writers (one lane per word) and readers (any lane) of the own bits in MEMORY are different threads of the warp: a
+// fence + warp barrier must lie between a write and the next read.  The fence is not paid at the write -- it would wait
+// for the atomic's round trip to L2 -- but right before the next read, several memory round trips later.
 BR_DEV void br_own_sync(BrWalk& w) {
   if (w.fence_due) {
 #if BR_GPU
@@ -135,24 +140,44 @@ BR_DEV void br_own_sync(BrWalk& w) {
     br_syncwarp();
   }
 }
+BR_DEV void br_own_flush(BrWalk& w) {
+  if (w.acc_wi != 0xffffffffu) {
+    if (br_lane() == 0) {
+      if (w.acc_own) br_atomic_or(w.own + w.acc_wi, w.acc_own);
+      if (w.acc_srch) br_atomic_or(w.s->srch_cur + w.acc_wi, w.acc_srch);
+    }
+    w.fence_due = true;
+    w.acc_wi = 0xffffffffu; w.acc_own = 0; w.acc_srch = 0;
+  }
+}
+BR_DEV void br_own_word(BrWalk& w, u32 wi) {   // make wi the gathered word
+  if (wi != w.acc_wi) { br_own_flush(w); w.acc_wi = wi; }
+}
 BR_DEV void br_own_set(BrWalk& w, u32 q) {
   BR_W(5, 1);
   if (w.warming) return;   // warm-up: the snapshot is read, nothing is recorded
-  if (br_lane() == 0) br_atomic_or(w.own + (q >> 5), 1u << (q & 31));
-  w.fence_due = true;      // (runs: cur and cur + 1 share a bucket, so the next search may consult this very bit)
+  br_own_word(w, q >> 5);
+  w.acc_own |= 1u << (q & 31);
+}
+BR_DEV void br_srch_set(BrWalk& w, u32 q) {
+  if (w.warming) return;
+  br_own_word(w, q >> 5);
+  w.acc_srch |= 1u << (q & 31);
 }
 BR_DEV void br_own_set_range(BrWalk& w, u32 a, u32 b) {
   BR_W(6, 1);
   if (a >= b) return;
   if (w.warming) return;
-  u32 wa = a >> 5, wb = (b - 1) >> 5;
-  for (u32 x = wa + (u32)br_lane(); x <= wb; x += BR_WARP) {
-    u32 m = 0xffffffffu;
-    if (x == wa) m &= 0xffffffffu << (a & 31);
-    if (x == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
-    br_atomic_or(w.own + x, m);
-  }
+  const u32 wa = a >> 5, wb = (b - 1) >> 5;
+  const u32 ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - ((b - 1) & 31));
+  if (wa == wb) { br_own_word(w, wa); w.acc_own |= ma & mb; return; }
+  // several words: the gathered word may be the first one; the middle goes straight to memory, the last becomes the gathered word
+  if (w.acc_wi == wa) w.acc_own |= ma;
+  else if (br_lane() == 0) br_atomic_or(w.own + wa, ma);
+  for (u32 x = wa + 1 + (u32)br_lane(); x < wb; x += BR_WARP) br_atomic_or(w.own + x, 0xffffffffu);
   w.fence_due = true;
+  br_own_word(w, wb);
+  w.acc_own |= mb;
 }
 BR_DEV int br_is_stored(const BrWalk& w, u32 q) {
   if (q >= w.p0) return br_own_get(w, q);
@@ -406,7 +431,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
       jj = jj > (u32)(G * BR_WARP) ? jj - (u32)(G * BR_WARP) : 0;
     }
     br_own_set(w, cur);  // the insertion at hash_longest_match64_inc.h:268
-    if (!w.warming && br_lane() == 0) br_atomic_or(s.srch_cur + (cur >> 5), 1u << (cur & 31));
+    br_srch_set(w, cur);
   }
   if (min_score == out.score) br_search_static_dict(w, cur, max_length, dict_distance, out);
 }
@@ -444,6 +469,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
   w.min_wrap = 0xffffffffu;
   w.fence_due = false;
+  w.acc_wi = 0xffffffffu; w.acc_own = 0; w.acc_srch = 0;
 #ifdef BR_DEBUG_KNOBS
   w.dbg_searches = w.dbg_rows = w.dbg_mlsteps = 0;
   const long long dbg_t0 = clock64();
@@ -577,6 +603,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     w.dict_l = dict_l0; w.dict_m = dict_m0; w.dl = w.dm = w.gate_checks = w.gate_fail = 0;
     w.min_wrap = 0xffffffffu;
   }
+  br_own_flush(w);
   br_own_sync(w);   // a sweep's next chunk starts with a fresh BrWalk: nothing may stay pending
   if (in.last) {
     insert_length += pos_end - position;

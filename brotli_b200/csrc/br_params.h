@@ -7,13 +7,15 @@
 
 // Returns 0 if the combination is outside what this library implements (the BrotliEncoder*
 // entry points then fail instead of silently doing something else).
-static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n, BrParams* P) {
+// lgblock_user: BROTLI_PARAM_LGBLOCK (0 = let the encoder choose, quality.h:76 ComputeLgBlock).
+static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n, BrParams* P, int lgblock_user = 0) {
   memset(P, 0, sizeof(*P));
   if (quality < 5 || quality > 9) return 0;   // q0-4: other hashers; q10-11: Zopfli path
   if (lgwin < 17 || lgwin > 24) return 0;      // <=16: forgetful-chain hashers; >24: large window
   P->quality = quality; P->lgwin = lgwin;
   P->lgblock = 16;                              // quality.h:86
   if (quality >= 9 && lgwin > 16) P->lgblock = lgwin < 18 ? lgwin : 18;
+  if (lgblock_user != 0) P->lgblock = lgblock_user > 24 ? 24 : lgblock_user < 16 ? 16 : lgblock_user;   // quality.h:88
   P->hash64 = (size_hint >= (1u << 20) && lgwin >= 19) ? 1 : 0;   // quality.h:182
   P->block_bits = quality - 1;
   P->bucket_bits = P->hash64 ? 15 : (quality < 7 ? 14 : 15);
@@ -32,7 +34,7 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->step_cap = 4096;
   P->sweep_epoch = 3;    // text / web input settles in 3 launches; what is still dirty then is swept run by run
   P->force_epoch = 64;
-  P->sweep_blocks = P->lgblock >= 18 ? 8 : 32;   // sweeps are at most 2 MiB of input long
+  P->sweep_blocks = P->lgblock >= 21 ? 1u : (1u << (21 - P->lgblock));   // sweeps are at most 2 MiB of input long
   return 1;
 }
 

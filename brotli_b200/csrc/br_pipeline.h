@@ -16,7 +16,9 @@ struct BrJobStats {
 // stream ends behind the cut at n.  with_header = 0: the window bits were already sent.  end_bit (host, nullable) receives
 // the bit position in the output where the metablock in front of each cut ended.
 // finish_empty: FINISH came without input right behind a full input block (BrParams::finish_empty).
-struct BrCuts { const uint32_t* pos; const uint32_t* kind; uint32_t n; int is_final; int with_header; int finish_empty; uint64_t* end_bit; };
+// lgblock (0 = default) / disable_ctx: BROTLI_PARAM_LGBLOCK / BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING.
+struct BrCuts { const uint32_t* pos; const uint32_t* kind; uint32_t n; int is_final; int with_header; int finish_empty; uint64_t* end_bit;
+                int lgblock; int disable_ctx; };
 extern "C" {
 BrJob* br_job_create(void);
 void br_job_destroy(BrJob*);

@@ -129,7 +129,7 @@ def ref_compress_stream(ref, data, quality, lgwin, chunk, out_buf=1 << 19):
     return bytes(out)
 
 
-def ref_stream_ops(ref, data, quality, lgwin, sizes, ops, out_buf=1 << 16):
+def ref_stream_ops(ref, data, quality, lgwin, sizes, ops, out_buf=1 << 16, params=None):
     """Drives the reference's CompressStream with an explicit list of (size, op) calls, draining the
     output after each call the way encode.h:473 asks (repeat until no input and no more output)."""
     L = ref.lib
@@ -143,6 +143,8 @@ def ref_stream_ops(ref, data, quality, lgwin, sizes, ops, out_buf=1 << 16):
     s = L.BrotliEncoderCreateInstance(None, None, None)
     L.BrotliEncoderSetParameter(s, 1, quality)
     L.BrotliEncoderSetParameter(s, 2, lgwin)
+    for k, v in (params or {}).items():        # further BrotliEncoderParameter ids (3 LGBLOCK, 4 DISABLE_LITERAL_CONTEXT_MODELING ...)
+        assert L.BrotliEncoderSetParameter(s, k, v) == 1
     src = C.create_string_buffer(data, max(1, len(data)))
     dst = C.create_string_buffer(out_buf)
     out = bytearray()

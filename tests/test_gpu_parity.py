@@ -132,6 +132,29 @@ def test_streaming_flush_and_metadata(b200):
     assert ref.decompress(part + rest, len(d)) == d
 
 
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_lgblock_and_context_modeling_parameters(b200):
+    """BROTLI_PARAM_LGBLOCK (encode.h:184, quality.h:76) and BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING (encode.h:191,
+    encode.c:561) through the streaming API, against the reference with the same parameters."""
+    from corpus import synth_web
+    ref = Ref()
+    L = b200.lib()
+    d = synth_web(1500000, 65)
+    for q, w in ((5, 22), (9, 24)):
+        for lgb, dis in ((0, 1), (17, 0), (20, 1), (24, 0)):
+            prm = {}
+            if lgb:
+                prm[3] = lgb
+            if dis:
+                prm[4] = 1
+            want = ref_stream_ops(ref, d, q, w, [700000, len(d) - 700000], [1, 2], params=prm)
+            c = b200.Compressor(quality=q, lgwin=w, lgblock=lgb)
+            if dis:
+                assert L.BrotliEncoderSetParameter(c._s, 4, 1)
+            got = c._stream(d[:700000], 1) + c._stream(d[700000:], 2)
+            assert got == want, (q, w, lgb, dis)
+
+
 def test_custom_allocator(b200):
     """encode.h:295: an instance created with an allocator pair takes its memory (state and buffers) from it."""
     L = b200.lib()

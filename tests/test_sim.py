@@ -137,3 +137,61 @@ def test_sim_fuzz_sample(sim):
             assert _fuzz_check(sim, d, q, w), (i, len(d), q, w)
     for i, d, q, w in dict_cases(20250923, 40, TABLES):
         assert _fuzz_check(sim, d, q, w), ("dict", i, len(d), q, w)
+
+
+def _sim_cuts(sim, d, q, w, hint, cuts, kinds, is_final, finish_empty=0, lgblock=0, disable_ctx=0):
+    sim.sim_compress_cuts.restype = C.c_long
+    sim.sim_compress_cuts.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+    cp = (C.c_uint32 * max(1, len(cuts)))(*cuts)
+    ck = (C.c_uint32 * max(1, len(cuts)))(*kinds)
+    eb = (C.c_uint64 * max(1, len(cuts)))()
+    cap = len(d) + len(d) // 2 + 4096
+    out = C.create_string_buffer(cap)
+    st = np.zeros(8, np.uint32)
+    r = sim.sim_compress_cuts(q, w, hint, d, len(d), cp, ck, len(cuts), is_final, 1, finish_empty, eb, out, cap, st.ctypes.data,
+                              lgblock, disable_ctx)
+    assert r >= 0
+    return out.raw[:r]
+
+
+def test_sim_flush_cuts_and_parameters(sim):
+    """The device code with the input cut by FLUSH operations (encode.c:1356, :1700), with FINISH arriving without input
+    behind a full block (encode.c:520), and with BROTLI_PARAM_LGBLOCK / DISABLE_LITERAL_CONTEXT_MODELING, against the
+    reference's CompressStream driven with the same calls (needs oracle/_ref)."""
+    from brotli_libs import REF_SO, Ref, ref_stream_ops
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    from corpus import synth_binary, synth_text, synth_web
+    ref = Ref()
+    for d in (synth_text(400000, 3), synth_binary(600000, 5)):
+        n = len(d)
+        for q, w in ((5, 22), (9, 24), (7, 19)):
+            bs = 1 << (18 if (q >= 9 and w >= 18) else 16)
+            for sizes, ops in (([100000, 50000, n - 150000], [0, 1, 2]), ([bs, 0, n - bs, 0], [0, 1, 1, 2]), ([100, n - 100, 0], [1, 0, 2])):
+                want = ref_stream_ops(ref, d, q, w, sizes, ops)
+                pos, cuts, acc, fixed, hint = 0, [], 0, False, 0
+                for a, op in zip(sizes, ops):
+                    if not fixed and (op != 0 or acc + a >= bs):   # encode.c:1619: the size hint freezes at the first EncodeData
+                        hint, fixed = acc + a, True
+                    acc += a
+                    pos += a
+                    if op == 1 and pos > 0 and (not cuts or cuts[-1] != pos):
+                        cuts.append(pos)
+                if cuts and cuts[-1] == n:
+                    got = _sim_cuts(sim, d, q, w, hint, cuts, [1] * len(cuts), 0) + b"\x03"
+                else:
+                    got = _sim_cuts(sim, d, q, w, hint, cuts, [1] * len(cuts), 1)
+                assert got == want, (q, w, sizes, ops)
+    d = synth_web(2 * 262144, 9)
+    for q, w in ((5, 22), (9, 24)):
+        want = ref_stream_ops(ref, d, q, w, [len(d), 0], [0, 2])          # FINISH without input behind full blocks
+        assert _sim_cuts(sim, d, q, w, 1 << (18 if q == 9 else 16), [], [], 1, finish_empty=1) == want
+        for lgb, dis in ((0, 1), (17, 0), (20, 1), (24, 0)):
+            prm = {}
+            if lgb:
+                prm[3] = lgb
+            if dis:
+                prm[4] = 1
+            want = ref_stream_ops(ref, d, q, w, [len(d)], [2], params=prm)
+            assert _sim_cuts(sim, d, q, w, len(d), [], [], 1, lgblock=lgb, disable_ctx=dis) == want, (q, w, lgb, dis)
