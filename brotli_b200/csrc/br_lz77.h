@@ -84,6 +84,8 @@ BR_DEV u32 br_hash_key(const BrParams& P, const u8* d, u32 pos) {
   return (br_ld32u(d, pos) * 0x1E35A7BDu) >> (32 - P.bucket_bits);
 }
 
+// tag of a position: 16 bits of a hash of its first four bytes (BrStream::tagS)
+BR_DEV u32 br_tag4(u32 first4) { return (first4 * 0x9E3779B1u) >> 16; }
 // same, from the 8 bytes at the position
 BR_DEV u32 br_hash_key_v(const BrParams& P, u64 v) {
   if (P.hash64) return (u32)((v * (0x1FE35A7BD3579BD3ull << 24)) >> (64 - 15));
@@ -289,13 +291,15 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
     dback[i] = (u32)back_i;
     da0[i] = dvalid[i] ? br_ld64u(d, cur - (u32)back_i) : 0;
   }
-  // first G rows of the bucket ring (consumed by the loop further down)
-  u32 q[G]; bool has[G];
+  // first G rows of the bucket ring (consumed by the loop further down), with their tags
+  const u32 tag_cur = br_tag4((u32)c0);
+  u32 q[G]; bool has[G], tagok[G];
 #pragma unroll
   for (int r = 0; r < G; ++r) {
     const u32 jr = j > (u32)(r * BR_WARP) ? j - (u32)(r * BR_WARP) : 0u;
     has[r] = jr >= lo + 1 + (u32)lane;
     q[r] = has[r] ? br_ldg(s.S + (jr - 1 - (u32)lane)) : 0;
+    tagok[r] = has[r] && (G == 1 || (u32)br_ldg(s.tagS + (jr - 1 - (u32)lane)) == tag_cur);   // (tags: deep rings only, see k_tags)
   }
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
@@ -374,16 +378,25 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
           const u32 jr = jj > (u32)(r * BR_WARP) ? jj - (u32)(r * BR_WARP) : 0u;
           has[r] = jr >= lo + 1 + (u32)lane;
           q[r] = has[r] ? br_ldg(s.S + (jr - 1 - (u32)lane)) : 0;
+          tagok[r] = has[r] && (G == 1 || (u32)br_ldg(s.tagS + (jr - 1 - (u32)lane)) == tag_cur);
         }
       }
 #pragma unroll
       for (int r = 0; r < G; ++r) {
         inwin[r] = has[r] && cur - q[r] <= max_backward;
-        st[r] = inwin[r] && br_is_stored(w, q[r]);
+        // Stored bits.  A row that lies entirely before this walker's own range (its newest entry, lane 0's, does) reads the
+        // S-ordered copy of the snapshot: the row's 32 bits sit in one or two words.  Otherwise every lane reads the bit of
+        // its position (own bitmap or snapshot): 32 scattered sectors.
+        const u32 jr = jj > (u32)(r * BR_WARP) ? jj - (u32)(r * BR_WARP) : 0u;
+        const u32 q0 = br_shfl(q[r], 0);
+        if (q0 < w.p0) {
+          const u32 idx = jr - 1 - (u32)lane;
+          st[r] = inwin[r] && ((br_ldg(s.storedS + (idx >> 5)) >> (idx & 31)) & 1u);
+        } else st[r] = inwin[r] && br_is_stored(w, q[r]);
       }
       if (G > 1 || BR_WALK_SPEC1) {
 #pragma unroll
-        for (int r = 0; r < G; ++r) d0[r] = inwin[r] ? br_ld64u(d, q[r]) : 0;
+        for (int r = 0; r < G; ++r) d0[r] = (inwin[r] && tagok[r]) ? br_ld64u(d, q[r]) : 0;
       }
       // ---- fold, row by row, newest first
 #pragma unroll
@@ -405,7 +418,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
         // full match length of every taken candidate
         // (H6: the first four bytes must agree, then the length counts on; H5: length >= 4.  Same thing.)
         u32 len = 0; int eqmax = 0;
-        if (take) {
+        if (take && tagok[r]) {
           BR_W(9, 1);
           len = (G > 1 || BR_WALK_SPEC1) ? br_match_len_d0(d, q[r], cur, max_length, c0, c1, d0[r]) : br_match_len_c(d, q[r], cur, max_length, c0, c1);
           if (len < 4) len = 0;

@@ -155,6 +155,9 @@ struct BrStream {
   int* changed_epoch;    // [nblocks] last walker launch whose commit changed this chunk's bits (-1: never)
   int* bitdep_epoch;     // [nblocks] last launch that changed a stored-bit this chunk's searches may consult
   const u16* skeys;      // bucket key of S[j]
+  const u16* tagS;       // 16-bit hash of the first four bytes at S[j]: a candidate whose tag differs from the search position's
+                         // cannot match four bytes, so its bytes are never fetched (the reference's H58 / H68 keep 8-bit tags
+                         // for the same reason, hash_longest_match64_simd_inc.h:26)
   u32* epoch_cum;        // [max_epochs + 1] epoch_cum[t] = sum over launches <= t of the largest number of stored-bit flips
                          // any single heavy bucket saw in that launch (bucket counter wrap rule)
   u32 epoch;             // current walker launch number (1-based)

@@ -38,7 +38,7 @@ struct SimStream {
   std::vector<u32> S, rank, seg, bits_latest, bits_cur, bits_prev, srch_latest, srch_cur, storedS, prefS, dirty, changed_bits,
       epoch_cum, ext_total, lil_in, cmd_off, force_unc, counters, hist, block_mb;
   std::vector<int> changed_epoch, bitdep_epoch;
-  std::vector<u16> skeys;
+  std::vector<u16> skeys, tagS;
   std::vector<BrBlockIn> bin, bin_used;
   std::vector<BrBlockOut> bout;
   std::vector<BrCmd> cmd_blocks, cmds_all;
@@ -65,6 +65,9 @@ static void sim_build_sorted(SimStream& m) {
   m.skeys.resize(n + 1);
   for (u32 p = 0; p < n; ++p) { u32 j = cur[key[p]]++; m.S[j] = p; m.rank[p] = j; m.skeys[j] = (u16)key[p]; }
   s.skeys = m.skeys.data();
+  m.tagS.resize(n + 1);
+  for (u32 j = 0; j < n; ++j) m.tagS[j] = (u16)br_tag4(br_ld32u(s.data, m.S[j]));
+  s.tagS = m.tagS.data();
   s.S = m.S.data(); s.rank = m.rank.data(); s.seg = m.seg.data();
 }
 static void sim_build_storedS(SimStream& m) {
