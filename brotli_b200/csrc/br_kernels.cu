@@ -88,6 +88,16 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const u16* __restrict__ k
     __syncwarp();
   }
 }
+// chunk table of one input block (what br_build_blocks would fill on the host): one CTA per block
+__global__ void k_build_chunks(const BrBlk* __restrict__ blk, BrBlockIn* __restrict__ bin, u32 ch) {
+  const BrBlk B = blk[blockIdx.x];
+  for (u32 c = threadIdx.x; c < B.nchunks; c += blockDim.x) {
+    BrBlockIn k; memset(&k, 0, sizeof(k));
+    k.pos = B.start + c * ch; k.end = k.pos + ch < B.end ? k.pos + ch : B.end; k.blk_start = B.start; k.blk_end = B.end;
+    k.first = c == 0; k.last = k.end == B.end; k.is_last = B.is_last; k.force_flush = B.force_flush; k.blk = blockIdx.x;
+    bin[B.first_chunk + c] = k;
+  }
+}
 // tagS[j] = tag of the position S[j] (br_lz77.h br_tag4)
 __global__ void k_tags(const u8* __restrict__ data, const u32* __restrict__ S, u32 n, u16* __restrict__ tagS) {
   u32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,17 +501,18 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 #endif
   const u32 ch = 1u << P.chunk_bits;
   // chunk / block tables: the reference's input blocks (1 << lgblock bytes, shorter where a FLUSH cut the input)
-  std::vector<BrBlockIn> hb; std::vector<BrBlk> hblk;
+  std::vector<BrBlk> hblk;
   const u32 ncuts = cuts ? cuts->n : 0;
   const bool is_final = cuts ? cuts->is_final != 0 : true;
   const int with_header = cuts ? cuts->with_header : 1;
   P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
   if (!is_final && (ncuts == 0 || cuts->pos[ncuts - 1] != n)) return 0;   // an unfinished stream ends at a cut
   if (P.finish_empty && (!is_final || (ncuts && cuts->pos[ncuts - 1] == n))) return 0;
-  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, ncuts, is_final && !P.finish_empty, hb, hblk);
+  u32 nb = 0;
+  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, ncuts, is_final && !P.finish_empty, nullptr, hblk, &nb);   // chunks: k_build_chunks
   std::vector<u32> h_slot(((size_t)n >> P.lgblock) + 2, 0);
   { u32 b = 0; for (size_t i = 0; i < h_slot.size(); ++i) { const u64 p = (u64)i << P.lgblock; while (b + 1 < hblk.size() && hblk[b].end <= p) ++b; h_slot[i] = b; } }
-  const u32 nb = (u32)hb.size(), nblk = (u32)hblk.size();
+  const u32 nblk = (u32)hblk.size();
   P.nblocks = nb;
   cudaStream_t st = job->st;
   memset(&job->stats, 0, sizeof(job->stats));
@@ -569,12 +580,13 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     s.dict_hash_words = (const u16*)p; p += 65536; s.dict_hash_lengths = p; p += 32768; s.ctx_lut = p; }
   s.log2tab = T->log2tab; s.log2tab_n = T->log2tab_n;
 
-  CK(cudaMemcpyAsync(bin, hb.data(), nb * sizeof(BrBlockIn), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_blk, hblk.data(), nblk * sizeof(BrBlk), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(slot_blk, h_slot.data(), h_slot.size() * 4, cudaMemcpyHostToDevice, st));
   if (ncuts) CK(cudaMemcpyAsync(d_cut_kind, cuts->kind, ncuts * 4, cudaMemcpyHostToDevice, st));
   s.slot_blk = slot_blk;
-  CK(cudaStreamSynchronize(st));
+  CK(cudaMemsetAsync(bin, 0, nb * sizeof(BrBlockIn), st));
+  k_build_chunks<<<nblk, 64, 0, st>>>(d_blk, bin, 1u << P.chunk_bits);
+  CK(cudaStreamSynchronize(st));   // (hblk / h_slot are host vectors: their copies must be done before they go out of scope ... and before the arrays below are reused)
   CK(cudaMemsetAsync(bout, 0, nb * sizeof(BrBlockOut), st));
   CK(cudaMemsetAsync(bin_used, 0, nb * sizeof(BrBlockIn), st));
   CK(cudaMemsetAsync(changed_bits, 0, (nb + 16) * 4, st));

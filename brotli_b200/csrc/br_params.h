@@ -43,10 +43,11 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
 // of a CompressStream call: the running block ends there with force_flush set (encode.c:1700) and the next one starts
 // with a full 1 << lgblock budget again (encode.c:1016 UpdateLastProcessedPos).  is_final: FINISH has been seen (the
 // last block carries is_last); otherwise the stream simply stops behind its last block.
+// chunks == nullptr: only the block table (the CUDA pipeline fills the chunk table on the device, k_build_chunks).
 static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u32 ncuts, bool is_final,
-                                   std::vector<BrBlockIn>& chunks, std::vector<BrBlk>& blks) {
+                                   std::vector<BrBlockIn>* chunks, std::vector<BrBlk>& blks, u32* nchunks_total = nullptr) {
   const u32 bs = 1u << P.lgblock, ch = 1u << P.chunk_bits;
-  u32 ci = 0;
+  u32 ci = 0, total = 0;
   u64 bstart = 0;
   while (bstart < n) {
     while (ci < ncuts && cuts[ci] <= bstart) ++ci;
@@ -56,15 +57,18 @@ static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u3
     BrBlk B; memset(&B, 0, sizeof(B));
     B.start = (u32)bstart; B.end = (u32)bend; B.is_last = (is_final && bend == n) ? 1u : 0u;
     B.force_flush = forced && !B.is_last ? 1u : 0u; B.changed_epoch = -1;
-    B.first_chunk = (u32)chunks.size();
-    for (u64 c = bstart; c < bend; c += ch) {
-      BrBlockIn k; memset(&k, 0, sizeof(k));
-      k.pos = (u32)c; k.end = (u32)(c + ch < bend ? c + ch : bend); k.blk_start = (u32)bstart; k.blk_end = (u32)bend;
-      k.first = (c == bstart); k.last = (k.end == bend); k.is_last = B.is_last; k.force_flush = B.force_flush; k.blk = (u32)blks.size();
-      chunks.push_back(k);
-    }
-    B.nchunks = (u32)chunks.size() - B.first_chunk;
+    B.first_chunk = total;
+    B.nchunks = (u32)((bend - bstart + ch - 1) / ch);
+    if (chunks)
+      for (u64 c = bstart; c < bend; c += ch) {
+        BrBlockIn k; memset(&k, 0, sizeof(k));
+        k.pos = (u32)c; k.end = (u32)(c + ch < bend ? c + ch : bend); k.blk_start = (u32)bstart; k.blk_end = (u32)bend;
+        k.first = (c == bstart); k.last = (k.end == bend); k.is_last = B.is_last; k.force_flush = B.force_flush; k.blk = (u32)blks.size();
+        chunks->push_back(k);
+      }
+    total += B.nchunks;
     blks.push_back(B);
     bstart = bend;
   }
+  if (nchunks_total) *nchunks_total = total;
 }

@@ -100,7 +100,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   const u32 ch = 1u << P.chunk_bits;
   std::vector<BrBlockIn> chunks;
   P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
-  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, cuts ? cuts->n : 0, cuts ? (cuts->is_final != 0 && !cuts->finish_empty) : true, chunks, m->blks);
+  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, cuts ? cuts->n : 0, cuts ? (cuts->is_final != 0 && !cuts->finish_empty) : true, &chunks, m->blks);
   m->slot_blk.assign(((size_t)n >> P.lgblock) + 2, 0);
   { u32 bb = 0; for (size_t i = 0; i < m->slot_blk.size(); ++i) { const u64 pp = (u64)i << P.lgblock; while (bb + 1 < m->blks.size() && m->blks[bb].end <= pp) ++bb; m->slot_blk[i] = bb; } }
   s.slot_blk = m->slot_blk.data();
