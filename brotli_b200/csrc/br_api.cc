@@ -81,6 +81,7 @@ struct Params {
 bool supported(Params p) {
   if (p.quality > 11) p.quality = 11;          // quality.h:60 SanitizeParams
   if (p.quality < 0) p.quality = 0;
+  if (p.quality <= 2) p.large_window = 0;      // quality.h:63: no large window with the static entropy codes; lgwin clamps to 24
   if (p.lgwin < 10) p.lgwin = 10;
   if (p.lgwin > 24 && !p.large_window) p.lgwin = 24;
   if (p.quality != 1 && (p.quality < 5 || p.quality > 9)) return false;
@@ -132,7 +133,7 @@ int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t
   if (!br_job_compress_device(tls.job, q, w, size_hint, tls.d_in, (uint32_t)n, &d_out, &sz, cuts)) return 0;
   record_stats();
   if (out_vec) { out_vec->resize(sz); out = out_vec->data(); out_cap = sz; }
-  if (sz > out_cap) return 0;
+  if (sz > out_cap) { *out_n = sz; return 2; }   /* compressed, but the caller's buffer is too small (encode.c:1336: "not finished") */
   if (cudaMemcpyAsync(out, d_out, sz, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 0;
   if (cudaStreamSynchronize(st) != cudaSuccess) return 0;
   *out_n = sz;
@@ -325,15 +326,16 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
     ok = compress_host_q1(p, input_buffer, input_size, nullptr, &tmp);
     got = tmp.size();
     if (ok && got <= max_out_size) {
-      if (got > out_size) { *encoded_size = 0; return BROTLI_FALSE; }
-      memcpy(encoded_buffer, tmp.data(), got);
+      if (got > out_size) ok = 2;
+      else memcpy(encoded_buffer, tmp.data(), got);
     }
   } else {
     ok = compress_host(p, (uint32_t)input_size, input_buffer, input_size, encoded_buffer, out_size, &got, nullptr);
   }
-  if (ok && !(max_out_size && got > max_out_size)) { *encoded_size = got; return BROTLI_TRUE; }
+  if (ok == 1 && !(max_out_size && got > max_out_size)) { *encoded_size = got; return BROTLI_TRUE; }
   *encoded_size = 0;
   if (!ok) return BROTLI_FALSE;   /* GPU path failed: fail loudly, never substitute other bytes */
+  /* ok == 2: the stream did not fit the caller's buffer -- the reference's "not finished" case, same fallback */
   /* encode.c:1345: result larger than BrotliEncoderMaxCompressedSize -> raw stream */
   if (!max_out_size) return BROTLI_FALSE;
   if (out_size >= max_out_size) {
@@ -366,7 +368,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
     /* one device batch: all streams through the same four launches (br_q1.cu) */
     Params p; p.quality = 1; p.lgwin = lgwin;
     if (!supported(p) || !ensure_q1()) { for (size_t i = 0; i < count; ++i) encoded_sizes[i] = 0; return 0; }
-    int w = lgwin < 10 ? 10 : lgwin;
+    int w = lgwin < 10 ? 10 : lgwin > 24 ? 24 : lgwin;   /* quality.h:60-69 (no large window at quality <= 2) */
     std::vector<int> ok(count, 0);
     std::vector<size_t> caps(encoded_sizes, encoded_sizes + count);
     br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, nullptr, outputs, encoded_sizes, ok.data(), threads, 1, 2);

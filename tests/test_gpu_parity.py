@@ -300,6 +300,25 @@ def test_cli_dropin_stdin(b200, tmp_path):
         assert outs[0] == outs[1] and len(outs[0]) > 0, (n, q, w)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_one_shot_wrapper_rules(b200):
+    """encode.c:1296-1353 / quality.h:60: quality 1 with lgwin above 24 is sanitised to 24 (no large window at quality <= 2);
+    an output buffer that is too small fails; an incompressible input still fits BrotliEncoderMaxCompressedSize."""
+    import numpy as np
+    from corpus import synth_text
+    ref = Ref()
+    L = b200.lib()
+    d = synth_text(200000, 66)
+    assert b200.compress_oneshot(d, 1, 27) == ref.compress(d, 1, 27) == ref.compress(d, 1, 24)
+    noise = np.random.RandomState(67).randint(0, 256, 300000, dtype=np.uint8).tobytes()
+    for q, w in ((1, 22), (5, 22), (9, 24)):
+        got = b200.compress_oneshot(noise, q, w)
+        assert got == ref.compress(noise, q, w) and len(got) <= L.BrotliEncoderMaxCompressedSize(len(noise))
+    out = C.create_string_buffer(1000)
+    n = C.c_size_t(1000)
+    assert L.BrotliEncoderCompress(5, 22, 0, len(d), d, C.byref(n), out) == 0 and n.value == 0     # too small: FALSE, size 0
+
+
 def test_q1_oneshot_against_oracle(b200):
     """Quality 1 through BrotliEncoderCompress: every hash-table size / min_match, block and fragment
     boundaries, raw meta-blocks, the raw-stream rule."""
