@@ -86,7 +86,8 @@ bool supported(Params p) {
   if (p.lgwin > 24 && !p.large_window) p.lgwin = 24;
   if (p.quality != 1 && (p.quality < 5 || p.quality > 9)) return false;
   if (p.quality == 1 ? p.lgwin > 24 : (p.lgwin < 17 || p.lgwin > 24)) return false;
-  if (p.large_window || p.npostfix || p.ndirect || p.stream_offset || p.base64) return false;
+  if (p.large_window || p.npostfix || p.ndirect || p.base64) return false;
+  if (p.stream_offset && p.quality == 1) return false;   /* STREAM_OFFSET: quality 5..9 only */
   /* LGBLOCK and DISABLE_LITERAL_CONTEXT_MODELING are honoured at quality 5..9; at quality 1 the reference ignores both
      (quality.h:79: lgblock = lgwin; no context modeling in the fragment coder) */
   if (p.mode == BROTLI_MODE_FONT) return false;
@@ -189,6 +190,7 @@ struct BrotliEncoderStateStruct {
   Params params;
   bool initialized = false, finished = false, compressed = false, hint_fixed = false;
   bool q1_header_done = false;   // quality 1: a FLUSH already delivered the window bits
+  bool flint_done = false;       // STREAM_OFFSET: the cut behind the first two bytes has been recorded
   ByteVec input, output;
   std::vector<size_t> calls;     // quality 1: bytes brought by each CompressStream call (encode.c:1425 cuts fragments per call)
   std::vector<StreamEvent> events;   // quality 5..9: the FLUSH / EMIT_METADATA operations so far
@@ -242,8 +244,9 @@ int build_wire(BrotliEncoderState* s, bool is_final, bool finish_empty, std::vec
   size_t e = 0;
   const std::vector<StreamEvent>& ev = s->events;
   const bool lead = !ev.empty() && ev[0].pos == 0;
+  const bool continued = s->params.stream_offset != 0;   /* encode.c:675: a stream that continues another one has no window bits */
   if (lead || n == 0) {
-    if (lgwin == 17) w.put(7, 1); else w.put(4, (uint64_t)(((lgwin - 17) << 1) | 1));   // encode.c:670 window bits
+    if (!continued) { if (lgwin == 17) w.put(7, 1); else w.put(4, (uint64_t)(((lgwin - 17) << 1) | 1)); }   // encode.c:670 window bits
     for (; e < ev.size() && ev[e].pos == 0; ++e) {
       if (ev[e].kind == 1) { if (w.pb) { w.put(6, 6); w.align(); } }   // encode.c:1356 InjectBytePaddingBlock
       else put_metadata(w, ev[e].meta);
@@ -259,7 +262,8 @@ int build_wire(BrotliEncoderState* s, bool is_final, bool finish_empty, std::vec
   const bool cut_at_end = !cut_pos.empty() && cut_pos.back() == n;
   std::vector<uint64_t> end_bit(cut_pos.size() + 1, 0);
   BrCuts c; c.pos = cut_pos.data(); c.kind = cut_kind.data(); c.n = (uint32_t)cut_pos.size();
-  c.is_final = (is_final && !cut_at_end) ? 1 : 0; c.with_header = lead ? 0 : 1;
+  c.is_final = (is_final && !cut_at_end) ? 1 : 0; c.with_header = (lead || continued) ? 0 : 1;
+  c.stream_offset = s->params.stream_offset;
   c.finish_empty = (c.is_final && finish_empty) ? 1 : 0; c.end_bit = end_bit.data();
   c.lgblock = s->params.lgblock; c.disable_ctx = (int)s->params.disable_ctx;
   if (!c.is_final && !cut_at_end) return 0;   // (callers only build the wire at a cut or at FINISH)
@@ -535,11 +539,19 @@ static BROTLI_BOOL compress_stream_impl(BrotliEncoderState* s, BrotliEncoderOper
     if (!s->hint_fixed) {
       /* encode.c:1619 UpdateSizeHint runs at the first EncodeData: when the first input block (1 << lgblock) is full
          or the operation is not PROCESS. */
-      if (op != BROTLI_OPERATION_PROCESS || s->input.size() >= ((size_t)1 << lgblock_of(s->params))) {
+      if (op != BROTLI_OPERATION_PROCESS || s->input.size() >= ((size_t)1 << lgblock_of(s->params)) ||
+          (s->params.stream_offset && s->input.size() >= 2)) {
         /* (an estimate of zero -- an operation before any input -- is taken again at the next EncodeData) */
         if (s->params.size_hint == 0) s->params.size_hint = (uint32_t)s->input.size();
         s->hint_fixed = s->params.size_hint != 0;
       }
+    }
+    if (s->params.stream_offset && !s->flint_done && s->input.size() >= 2 &&
+        !(s->input.size() == 2 && op == BROTLI_OPERATION_FINISH)) {
+      /* encode.c:1704: with a stream offset the first two bytes are flushed on their own (unless the stream ends there) */
+      StreamEvent e; e.pos = 2; e.kind = 1;
+      s->events.push_back(std::move(e));
+      s->flint_done = true;
     }
     if (op == BROTLI_OPERATION_EMIT_METADATA) {
       StreamEvent e; e.pos = (uint32_t)s->input.size(); e.kind = 2; e.meta.assign(*next_in, *next_in + *available_in);

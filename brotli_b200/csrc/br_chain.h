@@ -207,7 +207,7 @@ BR_DEV void br_chain_a(const BrStream& s, u32 bi) {
       if (to > from) lil_run += to - from;
       flow_pos = to > from ? to : sp; flow_rh = flow_pos + P.spree;
       flow_se = cur.blk_end - cur.blk_start >= P.htl ? cur.blk_end - P.htl + 1 : cur.blk_start;
-      if (c == 0) { fdc[0] = 4; fdc[1] = 11; fdc[2] = 15; fdc[3] = 16; }
+      if (c == 0) { fdc[0] = 4; fdc[1] = 11; fdc[2] = 15; fdc[3] = 16; if (P.stream_offset) fdc[0] = fdc[1] = fdc[2] = fdc[3] = -16; }
     }
   }
   B.ncmd = ncmd; B.nlit_rel = nlit_rel; B.has_cmd = has_cmd; B.lil_head = lil_head; B.lil_tail = lil_run;
@@ -249,6 +249,7 @@ BR_DEV void br_chain_b(const BrStream& s) {
 #endif
   u32 num_cmds = 0, num_lits = 0, last_insert_len = 0;
   int dc[4] = {4, 11, 15, 16}, saved_dc[4] = {4, 11, 15, 16};
+  if (P.stream_offset) for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i] = -16;   // encode.c:656: poisoned distance cache
   u32 last_flush_pos = 0, first_blk = 0, cmd_total = 0, n_mbs = 0;
   u64 dict_l = 0, dict_m = 0;
   bool have_last = false;

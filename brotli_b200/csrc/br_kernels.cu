@@ -490,6 +490,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   if (!br_derive_params(quality, lgwin, size_hint, n, &s.P, cuts ? cuts->lgblock : 0)) return 0;
   BrParams& P = s.P;
   P.disable_ctx = cuts && cuts->disable_ctx ? 1u : 0u;
+  P.stream_offset = cuts ? (cuts->stream_offset < P.max_backward ? cuts->stream_offset : P.max_backward) : 0u;   // encode.c:680
 #ifdef BR_DEBUG_KNOBS   // experiment switches: never in the release build (an environment variable must not change the bytes)
   if (getenv("BR_HEAVY_MIN")) P.heavy_min = (u32)strtoul(getenv("BR_HEAVY_MIN"), 0, 10);
   if (getenv("BR_STEP_CAP")) P.step_cap = (u32)strtoul(getenv("BR_STEP_CAP"), 0, 10);

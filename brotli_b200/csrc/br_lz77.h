@@ -555,8 +555,9 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     for (;;) {
       const u32 sp = position + (have ? 1u : 0u);
       const u32 md = br_min(sp, P.max_backward);
+      const u32 dd = P.stream_offset ? br_min(sp + P.stream_offset, P.max_backward) : md;   // backward_references_inc.h:94 dictionary_start
       BrSR cur; cur.len = 0; cur.delta = 0; cur.distance = 0; cur.score = BR_MIN_SCORE;
-      br_find_longest_match<G>(w, sp, max_length, md, md, cur);
+      br_find_longest_match<G>(w, sp, max_length, md, dd, cur);
       if (!have) {
         sr = cur;
         if (!(sr.score > BR_MIN_SCORE)) break;
@@ -571,7 +572,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     }
     if (have) {
       apply_random_heuristics = position + 2 * sr.len + window;
-      u32 dictionary_start = br_min(position, P.max_backward);
+      u32 dictionary_start = br_min(position + P.stream_offset, P.max_backward);
       u32 dcode = br_compute_distance_code(sr.distance, dictionary_start, w.dc);
       if (sr.distance <= dictionary_start && dcode > 0) {
         w.dc[3] = w.dc[2]; w.dc[2] = w.dc[1]; w.dc[1] = w.dc[0]; w.dc[0] = (int)sr.distance;

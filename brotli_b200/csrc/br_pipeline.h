@@ -16,9 +16,10 @@ struct BrJobStats {
 // stream ends behind the cut at n.  with_header = 0: the window bits were already sent.  end_bit (host, nullable) receives
 // the bit position in the output where the metablock in front of each cut ended.
 // finish_empty: FINISH came without input right behind a full input block (BrParams::finish_empty).
-// lgblock (0 = default) / disable_ctx: BROTLI_PARAM_LGBLOCK / BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING.
+// lgblock (0 = default) / disable_ctx / stream_offset: BROTLI_PARAM_LGBLOCK / DISABLE_LITERAL_CONTEXT_MODELING / STREAM_OFFSET
+// (the caller passes with_header = 0 and the cut behind the first two bytes that a stream offset implies, encode.c:1704).
 struct BrCuts { const uint32_t* pos; const uint32_t* kind; uint32_t n; int is_final; int with_header; int finish_empty; uint64_t* end_bit;
-                int lgblock; int disable_ctx; };
+                int lgblock; int disable_ctx; uint32_t stream_offset; };
 extern "C" {
 BrJob* br_job_create(void);
 void br_job_destroy(BrJob*);

@@ -32,6 +32,8 @@ struct BrParams {
                     // sweeps the run serially, seeing its own fresh stored-bits (Gauss-Seidel inside a run, Jacobi across runs)
   u32 force_epoch;  // from this launch on the first scheduled walker also runs to the end of its input block whatever the
                     // flags say: every launch then finalises at least one block, which bounds the number of launches
+  u32 stream_offset; // BROTLI_PARAM_STREAM_OFFSET (encode.h:231), clamped to the window: the stream continues another one -- no window
+                    // bits, poisoned distance cache (encode.c:656), dictionary distances count from the virtual start
   u32 disable_ctx;  // BROTLI_PARAM_DISABLE_LITERAL_CONTEXT_MODELING: one literal context (encode.c:561)
   u32 finish_empty; // FINISH arrived without input right behind a full input block: that block was encoded as a non-last one
                     // (encode.c:1700), the stream is closed by whatever is still pending or by an empty last metablock

@@ -84,13 +84,14 @@ static void sim_build_storedS(SimStream& m) {
   }
 }
 
-struct SimCuts { const u32* pos; const u32* kind; u32 n; int is_final; int with_header; int finish_empty; u64* end_bit; u32 size_hint; int lgblock; int disable_ctx; };
+struct SimCuts { const u32* pos; const u32* kind; u32 n; int is_final; int with_header; int finish_empty; u64* end_bit; u32 size_hint; int lgblock; int disable_ctx; u32 stream_offset; };
 static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts* cuts = nullptr) {
   SimStream* m = new SimStream();
   BrStream& s = m->s;
   memset(&s, 0, sizeof(s));
   if (!br_derive_params(q, lgwin, cuts ? cuts->size_hint : n, n, &s.P, cuts ? cuts->lgblock : 0)) { delete m; return nullptr; }
   s.P.disable_ctx = cuts && cuts->disable_ctx ? 1u : 0u;
+  s.P.stream_offset = cuts ? (cuts->stream_offset < s.P.max_backward ? cuts->stream_offset : s.P.max_backward) : 0u;
   BrParams& P = s.P;
   if (getenv("BR_SIM_HEAVY_MIN")) P.heavy_min = (u32)atoi(getenv("BR_SIM_HEAVY_MIN"));
   if (getenv("BR_SIM_STEP_CAP")) P.step_cap = (u32)atoi(getenv("BR_SIM_STEP_CAP"));
@@ -389,8 +390,8 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
 }
 extern "C" long sim_compress_cuts(int q, int lgwin, u32 size_hint, const u8* in, u32 n, const u32* cut_pos, const u32* cut_kind, u32 ncuts,
                                   int is_final, int with_header, int finish_empty, u64* end_bit, u8* out, size_t out_cap, u32* stats,
-                                  int lgblock, int disable_ctx) {
-  SimCuts c; c.lgblock = lgblock; c.disable_ctx = disable_ctx; c.pos = cut_pos; c.kind = cut_kind; c.n = ncuts; c.is_final = is_final; c.with_header = with_header; c.finish_empty = finish_empty; c.end_bit = end_bit; c.size_hint = size_hint;
+                                  int lgblock, int disable_ctx, u32 stream_offset) {
+  SimCuts c; c.lgblock = lgblock; c.disable_ctx = disable_ctx; c.stream_offset = stream_offset; c.pos = cut_pos; c.kind = cut_kind; c.n = ncuts; c.is_final = is_final; c.with_header = with_header; c.finish_empty = finish_empty; c.end_bit = end_bit; c.size_hint = size_hint;
   return sim_compress_impl(q, lgwin, in, n, out, out_cap, stats, &c);
 }
 #endif

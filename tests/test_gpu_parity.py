@@ -155,6 +155,33 @@ def test_lgblock_and_context_modeling_parameters(b200):
             assert got == want, (q, w, lgb, dis)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_stream_offset_stitches_shards(b200):
+    """one valid stream out of independently compressed shards -- every shard but the first is compressed with
+    BROTLI_PARAM_STREAM_OFFSET = its start (encode.h:231), every shard but the last ends with FLUSH instead of FINISH.
+    Each shard equals the reference run with the same parameters and calls; the concatenation decodes to the input."""
+    from corpus import synth_web
+    ref = Ref()
+    L = b200.lib()
+    d = synth_web(1800000, 68)
+    cuts = [0, 500000, 1300001, len(d)]
+    for q, w in ((5, 22), (9, 24)):
+        whole = b""
+        for i in range(3):
+            part = d[cuts[i]:cuts[i + 1]]
+            last = i == 2
+            prm = {9: cuts[i]} if i else {}
+            want = ref_stream_ops(ref, part, q, w, [len(part)], [2 if last else 1], params=prm)
+            c = b200.Compressor(quality=q, lgwin=w)
+            if i:
+                # (the Compressor has not been used yet: parameters can still be set)
+                assert L.BrotliEncoderSetParameter(c._s, 9, cuts[i])
+            got = c._stream(part, 2 if last else 1)
+            assert got == want, (q, w, i, len(got), len(want))
+            whole += got
+        assert ref.decompress(whole, len(d)) == d
+
+
 def test_custom_allocator(b200):
     """encode.h:295: an instance created with an allocator pair takes its memory (state and buffers) from it."""
     L = b200.lib()

@@ -139,18 +139,18 @@ def test_sim_fuzz_sample(sim):
         assert _fuzz_check(sim, d, q, w), ("dict", i, len(d), q, w)
 
 
-def _sim_cuts(sim, d, q, w, hint, cuts, kinds, is_final, finish_empty=0, lgblock=0, disable_ctx=0):
+def _sim_cuts(sim, d, q, w, hint, cuts, kinds, is_final, finish_empty=0, lgblock=0, disable_ctx=0, stream_offset=0, with_header=1):
     sim.sim_compress_cuts.restype = C.c_long
     sim.sim_compress_cuts.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
-                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_uint32]
     cp = (C.c_uint32 * max(1, len(cuts)))(*cuts)
     ck = (C.c_uint32 * max(1, len(cuts)))(*kinds)
     eb = (C.c_uint64 * max(1, len(cuts)))()
     cap = len(d) + len(d) // 2 + 4096
     out = C.create_string_buffer(cap)
     st = np.zeros(8, np.uint32)
-    r = sim.sim_compress_cuts(q, w, hint, d, len(d), cp, ck, len(cuts), is_final, 1, finish_empty, eb, out, cap, st.ctypes.data,
-                              lgblock, disable_ctx)
+    r = sim.sim_compress_cuts(q, w, hint, d, len(d), cp, ck, len(cuts), is_final, with_header, finish_empty, eb, out, cap, st.ctypes.data,
+                              lgblock, disable_ctx, stream_offset)
     assert r >= 0
     return out.raw[:r]
 
@@ -195,3 +195,20 @@ def test_sim_flush_cuts_and_parameters(sim):
                 prm[4] = 1
             want = ref_stream_ops(ref, d, q, w, [len(d)], [2], params=prm)
             assert _sim_cuts(sim, d, q, w, len(d), [], [], 1, lgblock=lgb, disable_ctx=dis) == want, (q, w, lgb, dis)
+
+
+def test_sim_stream_offset(sim):
+    """BROTLI_PARAM_STREAM_OFFSET (encode.h:231, the sanctioned way to stitch shards into one stream): no
+    window bits, poisoned distance cache (encode.c:656), dictionary distances counted from the virtual start
+    (backward_references_inc.h:94), and the first two bytes flushed on their own (encode.c:1704) -- against the reference."""
+    from brotli_libs import REF_SO, Ref, ref_stream_ops
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    from corpus import synth_text, synth_web
+    ref = Ref()
+    for d in (synth_text(300000, 4), synth_web(500000, 10)):
+        for q, w in ((5, 22), (9, 24), (6, 18)):
+            for off in (1, 1000, 1 << 20, 1 << 30):
+                want = ref_stream_ops(ref, d, q, w, [len(d)], [2], params={9: off})
+                got = _sim_cuts(sim, d, q, w, len(d), [2], [1], 1, stream_offset=off, with_header=0)
+                assert got == want, (q, w, off, len(got), len(want))
