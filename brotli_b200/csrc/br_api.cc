@@ -141,10 +141,10 @@ int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t
   return 1;
 }
 
-// Quality 1 (two-pass fragment coder, br_q1.cu): one stream = a batch of one.  `calls`: sizes of the
+// Quality 1 (two-pass fragment coder, br_q1.cu): one segment of one stream = a batch of one.  `calls`: sizes of the
 // CompressStream calls that delivered the input (nullptr: a single call).
 int compress_host_q1(const Params& p0, const uint8_t* in, size_t n, const std::vector<size_t>* calls,
-                     std::vector<uint8_t>* out_vec, int with_header = 1, int end_op = 2) {
+                     std::vector<uint8_t>* out_vec, int with_header = 1, int end_op = 2, uint32_t start_bits = 0, uint32_t* end_bit = nullptr) {
   Params p = p0;
   if (p.lgwin < 10) p.lgwin = 10;      // quality.h:60 SanitizeParams
   if (p.lgwin > 24) p.lgwin = 24;
@@ -155,11 +155,73 @@ int compress_host_q1(const Params& p0, const uint8_t* in, size_t n, const std::v
   const uint8_t* ins[1] = {in}; size_t in_n[1] = {n};
   const size_t* cl[1] = {calls ? calls->data() : nullptr}; size_t ncl[1] = {calls ? calls->size() : 0};
   uint8_t* outs[1] = {out_vec->data()}; size_t out_n[1] = {cap}; int ok[1] = {0};
-  if (!br_q1_compress_batch(tls.q1, p.lgwin, 1, ins, in_n, calls ? cl : nullptr, calls ? ncl : nullptr, nullptr, outs, out_n, ok, 1, with_header, end_op))
+  uint32_t sb[1] = {start_bits}, eb[1] = {0};
+  if (!br_q1_compress_batch(tls.q1, p.lgwin, 1, ins, in_n, calls ? cl : nullptr, calls ? ncl : nullptr, nullptr, outs, out_n, ok, 1,
+                            with_header, end_op, sb, eb))
     return 0;
   record_q1_stats();
   out_vec->resize(out_n[0]);
+  if (end_bit) *end_bit = eb[0];
   return 1;
+}
+
+// What a quality-1 stream carries from one device segment to the next (encode.c:1445 last_bytes_ / last_bytes_bits_):
+// the bits of its last, incomplete byte, and whether the window bits went out.
+struct Q1Tail { uint32_t bits = 0; uint8_t byte = 0; bool header_done = false; };
+// One device segment holds at most this much input (bit offsets inside a segment are 32-bit); a stream is any number of them.
+static const size_t kQ1SegmentBytes = (size_t)1 << 27;
+
+template <class Vec>
+int q1_segment(const Params& p, const uint8_t* in, size_t n, const std::vector<size_t>& calls, int end_op, Q1Tail& t, Vec& out) {
+  const int with_header = !t.header_done;
+  if (n == 0) {
+    /* nothing to parse: window bits (encode.c:1006), ISLAST + ISEMPTY (compress_fragment_two_pass.c:641) or the
+       padding block of a FLUSH (encode.c:1356) behind the pending bits */
+    uint32_t acc = t.byte & ((1u << t.bits) - 1u), nb = t.bits;
+    if (with_header) {
+      int lgwin = p.lgwin > 24 ? 24 : p.lgwin;
+      if (lgwin < 18) lgwin = 18;      /* encode.c:673 */
+      acc |= (uint32_t)(((lgwin - 17) << 1) | 1) << nb; nb += 4;
+    }
+    if (end_op == 2) { acc |= 3u << nb; nb = (nb + 2 + 7) & ~7u; }
+    else if (end_op == 1 && (nb & 7)) { acc |= 6u << nb; nb = (nb + 6 + 7) & ~7u; }
+    while (nb >= 8) { out.push_back((uint8_t)acc); acc >>= 8; nb -= 8; }
+    t.bits = nb; t.byte = (uint8_t)acc;
+  } else {
+    std::vector<uint8_t> seg; uint32_t end_bit = 0;
+    if (!compress_host_q1(p, in, n, &calls, &seg, with_header, end_op, t.bits, &end_bit) || seg.empty()) return 0;
+    if (t.bits) seg[0] |= (uint8_t)(t.byte & ((1u << t.bits) - 1u));
+    t.bits = 0; t.byte = 0;
+    if (end_op == 0 && (end_bit & 7)) { t.bits = end_bit & 7; t.byte = seg.back(); seg.pop_back(); }
+    out.insert(out.end(), seg.begin(), seg.end());
+  }
+  t.header_done = true;
+  return 1;
+}
+
+// [in, in+n) as delivered by `calls` (nullptr: one call), through the device in segments of at most kQ1SegmentBytes.  A call
+// that straddles a segment is split at a multiple of the fragment size (1 << lgwin), which leaves the reference's fragments
+// (encode.c:1425) as they were.  Complete bytes are appended to `out`; end_op as in br_q1_host.h.
+template <class Vec>
+int q1_run(const Params& p, const uint8_t* in, size_t n, const size_t* calls, size_t ncalls, int end_op, Q1Tail& t, Vec& out) {
+  int lgwin = p.lgwin < 10 ? 10 : p.lgwin > 24 ? 24 : p.lgwin;
+  const size_t limit = (size_t)1 << lgwin;
+  if (!calls) { calls = &n; ncalls = 1; }
+  size_t ci = 0, rem = ncalls ? calls[0] : 0, pos = 0;
+  for (;;) {
+    std::vector<size_t> sc; size_t seg_n = 0;
+    while (ci < ncalls) {
+      const size_t room = kQ1SegmentBytes - seg_n;
+      if (rem <= room) { sc.push_back(rem); seg_n += rem; ++ci; rem = ci < ncalls ? calls[ci] : 0; continue; }
+      const size_t part = room / limit * limit;
+      if (part) { sc.push_back(part); seg_n += part; rem -= part; }
+      break;
+    }
+    const bool last = ci >= ncalls;
+    if (!q1_segment(p, in + pos, seg_n, sc, last ? end_op : 0, t, out)) return 0;
+    pos += seg_n;
+    if (last) return pos == n;
+  }
 }
 
 }  // namespace
@@ -189,7 +251,7 @@ struct BrotliEncoderStateStruct {
   brotli_alloc_func alloc_func; brotli_free_func free_func; void* opaque;
   Params params;
   bool initialized = false, finished = false, compressed = false, hint_fixed = false;
-  bool q1_header_done = false;   // quality 1: a FLUSH already delivered the window bits
+  Q1Tail q1_tail;                // quality 1: pending bits between device segments, window bits sent
   bool flint_done = false;       // STREAM_OFFSET: the cut behind the first two bytes has been recorded
   ByteVec input, output;
   std::vector<size_t> calls;     // quality 1: bytes brought by each CompressStream call (encode.c:1425 cuts fragments per call)
@@ -326,8 +388,8 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
   size_t got = 0;
   int ok;
   if (quality == 1) {
-    std::vector<uint8_t> tmp;
-    ok = compress_host_q1(p, input_buffer, input_size, nullptr, &tmp);
+    std::vector<uint8_t> tmp; Q1Tail tail;
+    ok = q1_run(p, input_buffer, input_size, nullptr, 0, 2, tail, tmp);
     got = tmp.size();
     if (ok && got <= max_out_size) {
       if (got > out_size) ok = 2;
@@ -375,7 +437,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
     int w = lgwin < 10 ? 10 : lgwin > 24 ? 24 : lgwin;   /* quality.h:60-69 (no large window at quality <= 2) */
     std::vector<int> ok(count, 0);
     std::vector<size_t> caps(encoded_sizes, encoded_sizes + count);
-    br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, nullptr, outputs, encoded_sizes, ok.data(), threads, 1, 2);
+    br_q1_compress_batch(tls.q1, w, count, inputs, input_sizes, nullptr, nullptr, nullptr, outputs, encoded_sizes, ok.data(), threads, 1, 2, nullptr, nullptr);
     record_q1_stats();
     size_t good = 0;
     for (size_t i = 0; i < count; ++i) {
@@ -421,7 +483,7 @@ size_t BrotliB200CompressBatchDevice(int quality, int lgwin, size_t count, const
   pk.out_cap = encoded_capacity; pk.out_off = encoded_offsets;
   std::vector<int> ok(count, 0);
   int w = lgwin < 10 ? 10 : lgwin > 24 ? 24 : lgwin;
-  if (!br_q1_compress_batch(tls.q1, w, count, nullptr, input_sizes, nullptr, nullptr, &pk, nullptr, encoded_sizes, ok.data(), 1, 1, 2)) return 0;
+  if (!br_q1_compress_batch(tls.q1, w, count, nullptr, input_sizes, nullptr, nullptr, &pk, nullptr, encoded_sizes, ok.data(), 1, 1, 2, nullptr, nullptr)) return 0;
   record_q1_stats();
   size_t good = 0;
   for (size_t i = 0; i < count; ++i) {
@@ -507,26 +569,6 @@ static BROTLI_BOOL compress_stream_impl(BrotliEncoderState* s, BrotliEncoderOper
   if (!supported(s->params)) return BROTLI_FALSE;
   if (op == BROTLI_OPERATION_EMIT_METADATA && q1) return BROTLI_FALSE;   /* not built for the fragment coder */
   if (s->compressed && (*available_in != 0 || op == BROTLI_OPERATION_EMIT_METADATA)) return BROTLI_FALSE;   /* input after finish */
-  if (op == BROTLI_OPERATION_FLUSH && q1 && !s->compressed) {
-    /* Quality 1 (encode.c:1425): the fragments of this call are compressed now, then the stream is padded
-       to a byte boundary (encode.c:1356), so everything delivered so far is decodable. */
-    if (*available_in) {
-      s->calls.push_back(*available_in);
-      s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
-      *next_in += *available_in; *available_in = 0;
-    }
-    if (!s->input.empty() || !s->q1_header_done) {
-      std::vector<uint8_t> seg;
-      if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &seg, !s->q1_header_done, 1))
-        return BROTLI_FALSE;
-      s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
-      s->output.insert(s->output.end(), seg.begin(), seg.end());
-      s->q1_header_done = true;
-      s->input.clear(); s->calls.clear();
-    }
-    push_output(s, available_out, next_out, total_out);
-    return BROTLI_TRUE;
-  }
   if (!q1 && !s->compressed) {
     /* ---- quality 5..9 */
     if (op == BROTLI_OPERATION_EMIT_METADATA) {
@@ -580,38 +622,24 @@ static BROTLI_BOOL compress_stream_impl(BrotliEncoderState* s, BrotliEncoderOper
     if (s->compressed && s->out_pos == s->output.size()) s->finished = true;
     return BROTLI_TRUE;
   }
-  /* ---- quality 1, PROCESS / FINISH */
-  if (!s->compressed && (*available_in || op == BROTLI_OPERATION_FINISH)) s->calls.push_back(*available_in);
-  if (*available_in) {
-    if (s->input.size() + *available_in > ((size_t)1 << 28)) return BROTLI_FALSE;   /* bit offsets of a stream are 32-bit */
-    s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
-    *next_in += *available_in; *available_in = 0;
-  }
-  if (op == BROTLI_OPERATION_FINISH && !s->compressed && s->q1_header_done) {
-    /* quality 1 behind a FLUSH: the last segment has no window bits */
-    std::vector<uint8_t> seg;
-    if (s->input.empty()) seg.assign(1, 3);          /* ISLAST + ISEMPTY on a byte boundary */
-    else if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &seg, 0, 2)) return BROTLI_FALSE;
-    s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
-    s->output.insert(s->output.end(), seg.begin(), seg.end());
-    s->compressed = true;
-    ByteVec(s->input.get_allocator()).swap(s->input);
-  }
-  if (op == BROTLI_OPERATION_FINISH && !s->compressed) {
-    std::vector<uint8_t> seg;
-    if (s->input.empty()) {
-      /* encode.c:1006: empty stream = window bits + ISLAST + ISEMPTY */
-      int lgwin = s->params.lgwin > 24 ? 24 : s->params.lgwin;
-      if (lgwin < 18) lgwin = 18;      /* encode.c:673 */
-      uint32_t bits = (uint32_t)(((lgwin - 17) << 1) | 1), nb = 4;
-      bits |= 3u << nb; nb += 2;
-      seg.assign((nb + 7) / 8, 0);
-      for (uint32_t i = 0; i < (nb + 7) / 8; ++i) seg[i] = (uint8_t)(bits >> (8 * i));
-    } else if (!compress_host_q1(s->params, s->input.data(), s->input.size(), &s->calls, &seg)) return BROTLI_FALSE;
-    s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
-    s->output.insert(s->output.end(), seg.begin(), seg.end());
-    s->compressed = true;
-    ByteVec(s->input.get_allocator()).swap(s->input);
+  /* ---- quality 1 (encode.c:1425): the reference compresses the fragments of every call at once.  Here calls are
+     collected (their sizes recorded: they decide the fragments) and run through the device as one segment when the
+     operation is FLUSH / FINISH or kQ1SegmentBytes / 2 of input are waiting, so memory stays bounded and a stream has no
+     size limit; between segments only the pending bits of the last byte are kept (Q1Tail). */
+  if (!s->compressed) {
+    if (*available_in || op == BROTLI_OPERATION_FINISH) s->calls.push_back(*available_in);
+    if (*available_in) {
+      s->input.insert(s->input.end(), *next_in, *next_in + *available_in);
+      *next_in += *available_in; *available_in = 0;
+    }
+    if (op != BROTLI_OPERATION_PROCESS || s->input.size() >= kQ1SegmentBytes / 2) {
+      const int end_op = op == BROTLI_OPERATION_FINISH ? 2 : op == BROTLI_OPERATION_FLUSH ? 1 : 0;
+      s->output.erase(s->output.begin(), s->output.begin() + (long)s->out_pos); s->out_pos = 0;
+      if (!q1_run(s->params, s->input.data(), s->input.size(), s->calls.data(), s->calls.size(), end_op, s->q1_tail, s->output))
+        return BROTLI_FALSE;
+      s->input.clear(); s->calls.clear();
+      if (op == BROTLI_OPERATION_FINISH) { s->compressed = true; ByteVec(s->input.get_allocator()).swap(s->input); }
+    }
   }
   push_output(s, available_out, next_out, total_out);
   if (s->compressed && s->out_pos == s->output.size()) s->finished = true;

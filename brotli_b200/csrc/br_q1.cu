@@ -228,7 +228,8 @@ static void run_threads(int threads, size_t count, const std::function<void(size
 
 extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const uint8_t* const* in, const size_t* in_n,
                                     const size_t* const* calls, const size_t* ncalls, const BrQ1Packed* packed,
-                                    uint8_t* const* out, size_t* out_n, int* ok, int threads, int with_header, int end_op) {
+                                    uint8_t* const* out, size_t* out_n, int* ok, int threads, int with_header, int end_op,
+                                    const uint32_t* start_bits, uint32_t* end_bit) {
   const bool inputs_on_device = packed != nullptr;
   if (!j || lgwin < 10 || lgwin > 24 || count == 0 || count > (1u << 24)) return 0;
   std::vector<BrQ1Stream> streams; std::vector<BrQ1Frag> frags; std::vector<BrQ1Block> blocks;
@@ -237,7 +238,7 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
   u32 max_tb = 8;
   for (size_t s = 0; s < count; ++s) {
     if (in_n[s] > (1u << 28)) return 0;         // bit offsets of a stream are 32-bit
-    br_q1_plan_stream(lgwin, (u32)s, in_off, out_off, in_n[s], calls ? calls[s] : nullptr, calls ? ncalls[s] : 0, streams, frags, blocks, with_header, end_op);
+    br_q1_plan_stream(lgwin, (u32)s, in_off, out_off, in_n[s], calls ? calls[s] : nullptr, calls ? ncalls[s] : 0, streams, frags, blocks, with_header, end_op, start_bits ? start_bits[s] : 0u);
     in_off += (in_n[s] + 15 + 16) & ~(u64)15;   // >= 16 bytes of slack behind every stream (unaligned 8-byte loads)
     out_off += br_q1_stream_bound(frags, streams.back());
   }
@@ -341,6 +342,7 @@ extern "C" int br_q1_compress_batch(BrQ1Job* j, int lgwin, size_t count, const u
     });
     for (size_t s = 0; s < count; ++s) { ok[s] = okv[s]; good += okv[s]; }
   }
+  if (end_bit) for (size_t s = 0; s < count; ++s) end_bit[s] = h_streams[s].end_bit;
   BrQ1Stats& S = j->stats;
   cudaEventElapsedTime(&S.ms_h2d, j->ev[0], j->ev[1]);
   cudaEventElapsedTime(&S.ms_parse, j->ev[1], j->ev[2]);

@@ -36,6 +36,8 @@ struct BrQ1Stream {
   u32 hdr_lgwin;           // encode.c:673: max(lgwin, 18); 0 = no stream header (segment behind a FLUSH)
   u32 out_bytes;           // chain: size of the compressed stream
   u32 flush_end;           // the segment ends with a FLUSH: pad to a byte boundary (encode.c:1356)
+  u32 start_bits;          // 0..7 bits of the stream's previous segment sit in byte 0 (encode.c:1445 last_bytes_); the caller ORs them in
+  u32 end_bit;             // chain: bit length of the segment including start_bits (a segment that neither flushes nor finishes may end mid-byte)
 };
 struct BrQ1Frag {
   u32 stream, start, size; // start: offset in the stream
@@ -555,8 +557,8 @@ BR_DEV void br_q1_prep_block(const BrQ1& q, u32 bi, BrQ1Smem* sm) {
 BR_DEV void br_q1_chain_stream(const BrQ1& q, u32 si) {
   BrQ1Stream& st = q.streams[si];
   u32* out = q.out + (st.out_off >> 2);
-  u32 ix = 0;
-  if (st.hdr_lgwin) {      // encode.c:203 EncodeWindowBits for lgwin >= 18
+  u32 ix = st.start_bits;
+  if (st.hdr_lgwin) {      // encode.c:203 EncodeWindowBits for lgwin >= 18 (a header segment starts at bit 0)
     br_put_bits_at(out, 0, 4, (u64)(((st.hdr_lgwin - 17u) << 1) | 1u));
     ix = 4;
   }
@@ -584,6 +586,7 @@ BR_DEV void br_q1_chain_stream(const BrQ1& q, u32 si) {
     ix = (ix + 6u + 7u) & ~7u;
   }
   st.out_bytes = (ix + 7u) >> 3;
+  st.end_bit = ix;
 }
 
 // ------------------------------------------------------------------ emit

@@ -22,8 +22,10 @@ const BrQ1Stats* br_q1_job_stats(const BrQ1Job*);
 // call.  out_n: capacity in, size out.  ok[s] = 0 when out[s] was too small.  packed (nullable): the
 // device-resident form above (in[] / out[] are then unused, out_n receives the sizes).  with_header / end_op: 1 / 2 for whole streams; a segment of a stream that
 // is cut by FLUSH calls has no header after the first one (0) and ends with byte padding (end_op 1).
-// Returns 1 when every stream was compressed.
+// end_op 0: a segment with more input behind it (may end mid-byte: end_bit[s] = its bit length, byte 0 leaves start_bits[s]
+// low bits free for the previous segment's tail).  Returns 1 when every stream was compressed.
 int br_q1_compress_batch(BrQ1Job* job, int lgwin, size_t count, const uint8_t* const* in, const size_t* in_n,
                          const size_t* const* calls, const size_t* ncalls, const BrQ1Packed* packed,
-                         uint8_t* const* out, size_t* out_n, int* ok, int threads, int with_header, int end_op);
+                         uint8_t* const* out, size_t* out_n, int* ok, int threads, int with_header, int end_op,
+                         const uint32_t* start_bits, uint32_t* end_bit);
 }

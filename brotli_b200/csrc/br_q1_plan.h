@@ -9,15 +9,18 @@
 // fragments of at most 1 << lgwin bytes; FINISH (the last call) closes the stream behind its last
 // fragment, an empty one if that call brought nothing.  calls == nullptr: one call with everything.
 // with_header = 0: a segment that continues a stream behind a FLUSH (byte aligned, no window bits);
-// end_op = 1: the segment ends with a FLUSH instead of FINISH (no ISLAST, byte padding instead).
+// end_op = 1: the segment ends with a FLUSH instead of FINISH (no ISLAST, byte padding instead);
+// end_op = 0: more input follows (no ISLAST, no padding: the segment may end mid-byte, BrQ1Stream::end_bit);
+// start_bits: bits of the previous segment's last, partial byte (the next segment starts behind them).
 static inline void br_q1_plan_stream(int lgwin, u32 si, u64 in_off, u64 out_off, size_t n, const size_t* calls, size_t ncalls,
                         std::vector<BrQ1Stream>& streams, std::vector<BrQ1Frag>& frags, std::vector<BrQ1Block>& blocks,
-                        int with_header = 1, int end_op = 2) {
+                        int with_header = 1, int end_op = 2, u32 start_bits = 0) {
   const size_t limit = (size_t)1 << lgwin;
   BrQ1Stream s; memset(&s, 0, sizeof(s));
   s.in_off = in_off; s.out_off = out_off; s.size = (u32)n; s.first_frag = (u32)frags.size();
   s.hdr_lgwin = with_header ? (u32)(lgwin < 18 ? 18 : lgwin) : 0u;
   s.flush_end = end_op == 1;
+  s.start_bits = with_header ? 0u : (start_bits & 7u);
   size_t one = n;
   if (!calls) { calls = &one; ncalls = 1; }
   size_t pos = 0;

@@ -401,9 +401,9 @@ extern "C" long sim_compress_cuts(int q, int lgwin, u32 size_hint, const u8* in,
 #include "../../brotli_b200/csrc/br_q1_plan.h"
 // One stream through the q1 device code with a one-lane warp and a one-thread CTA.
 extern "C" long sim_q1_compress_seg(int lgwin, const u8* in, u32 n, const size_t* calls, size_t ncalls, u8* out, size_t out_cap,
-                                    int with_header, int end_op) {
+                                    int with_header, int end_op, u32 start_bits, u32* end_bit) {
   std::vector<BrQ1Stream> streams; std::vector<BrQ1Frag> frags; std::vector<BrQ1Block> blocks;
-  br_q1_plan_stream(lgwin, 0, 0, 0, n, calls, ncalls, streams, frags, blocks, with_header, end_op);
+  br_q1_plan_stream(lgwin, 0, 0, 0, n, calls, ncalls, streams, frags, blocks, with_header, end_op, start_bits);
   const size_t bound = br_q1_stream_bound(frags, streams[0]);
   std::vector<u8> din((size_t)n + 64, 0); memcpy(din.data(), in, n);
   std::vector<u32> dout(bound / 4 + 16, 0), cmds((size_t)n + 16), hdr(blocks.size() * BR_Q1_HDR_WORDS + 1, 0), counters(16, 0);
@@ -434,11 +434,12 @@ extern "C" long sim_q1_compress_seg(int lgwin, const u8* in, u32 n, const size_t
   u32 scratch[8];
   for (u32 b = 0; b < q.nblocks; ++b) br_q1_emit_block(q, b, scratch);
   const size_t sz = streams[0].out_bytes;
+  if (end_bit) *end_bit = streams[0].end_bit;
   if (sz > out_cap) return -1;
   memcpy(out, dout.data(), sz);
   return (long)sz;
 }
 extern "C" long sim_q1_compress(int lgwin, const u8* in, u32 n, const size_t* calls, size_t ncalls, u8* out, size_t out_cap) {
-  return sim_q1_compress_seg(lgwin, in, n, calls, ncalls, out, out_cap, 1, 2);
+  return sim_q1_compress_seg(lgwin, in, n, calls, ncalls, out, out_cap, 1, 2, 0, nullptr);
 }
 #endif

@@ -448,6 +448,33 @@ def test_q1_flush(b200):
                 assert out == ref_stream_ops(Ref(), d, 1, w, sizes, ops)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_q1_stream_beyond_one_device_segment(b200):
+    """Quality 1 has no stream-size limit: input above one device segment (128 MiB) runs as several, a segment that
+    neither flushes nor finishes ends mid-byte and the next starts behind its pending bits (br_api.cc q1_run).
+    300 MB in one call (split at multiples of the fragment size) and in 24 MiB + 1 calls (a segment every 64 MiB)."""
+    from corpus import synth_web
+    rng = np.random.default_rng(77)
+    base = np.frombuffer(synth_web(8 << 20, 71), np.uint8)
+    d = np.tile(base, 37)[:300_000_000].copy()
+    idx = rng.integers(0, d.size, d.size // 50)
+    d[idx] = rng.integers(0, 256, idx.size, dtype=np.uint8)
+    d[(1 << 27) - 3_000_000:(1 << 27) + 3_000_000] = rng.integers(0, 256, 6_000_000, dtype=np.uint8)   # raw fragments across a cut
+    d = d.tobytes()
+    ref = Ref()
+    for w in (22, 18):
+        assert b200.compress_oneshot(d, 1, w) == ref.compress(d, 1, w), w
+    step = (24 << 20) + 1
+    sizes = [min(step, len(d) - o) for o in range(0, len(d), step)] + [0]
+    ops = [0] * (len(sizes) - 1) + [2]
+    c = b200.Compressor(quality=1, lgwin=22)
+    out, o = [], 0
+    for a, op in zip(sizes, ops):
+        piece = d[o:o + a]; o += a
+        out.append(c.process(piece) if op == 0 else c._stream(piece, c._FINISH))
+    assert b"".join(out) == ref_stream_ops(ref, d, 1, 22, sizes, ops, out_buf=1 << 24)
+
+
 def test_fuzz_gpu(b200):
     """Structured random inputs (tests/fuzz_cases.py) through the C ABI on the GPU, plus the regression inputs."""
     from fuzz_cases import REGRESSIONS, cases

@@ -28,7 +28,7 @@ def sim():
     L.sim_q1_compress.argtypes = [C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     L.sim_q1_compress_seg.restype = C.c_long
     L.sim_q1_compress_seg.argtypes = [C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                      C.c_int, C.c_int]
+                                      C.c_int, C.c_int, C.c_uint32, C.c_void_p]
     return L
 
 
@@ -96,12 +96,50 @@ def test_sim_q1_flush_segments(sim):
                         arr = (C.c_size_t * max(1, len(seg_calls)))(*seg_calls)
                         cap = 2 * len(piece) + 100000
                         out = C.create_string_buffer(cap)
-                        r = sim.sim_q1_compress_seg(w, piece, len(piece), arr if seg_calls else None, len(seg_calls), out, cap, header, op)
+                        r = sim.sim_q1_compress_seg(w, piece, len(piece), arr if seg_calls else None, len(seg_calls), out, cap, header, op, 0, None)
                         assert r >= 0
                         got += out.raw[:r]
                         header = 0
                     seg_calls, seg_start = [], pos
             assert got == want, (sizes, ops, w)
+
+
+def test_sim_q1_segments_mid_byte(sim):
+    """Bounded-memory streaming at quality 1: the stream is cut into device segments between calls; a segment that
+    neither flushes nor finishes ends mid-byte and the next one starts behind its pending bits (encode.c:1445
+    last_bytes_).  Device code per segment, stitched the way br_api.cc q1_segment does == oracle for the op sequence."""
+    from corpus import synth_web
+    d = synth_web(400000, 7) + bytes(np.random.default_rng(5).integers(0, 256, 70000, dtype=np.uint8))
+    ora = Oracle()
+    cases = [([100000, 200000, 170000], [0, 0, 2]), ([1, 65536, 70000, 334463], [0, 0, 1, 2]),
+             ([300000, 100000, 70000, 0], [0, 0, 0, 2]), ([131072, 131072, 207856], [0, 1, 2]), ([470000], [2])]
+    for sizes, ops in cases:
+        for w in (16, 18, 22):
+            want = ora.compress_q1_stream(d, w, sizes, ops)
+            got, pos, header, bits, byte = bytearray(), 0, 1, 0, 0
+            for a, op in zip(sizes, ops):
+                piece = d[pos:pos + a]
+                pos += a
+                if not piece:
+                    assert op == 2 and not header
+                    acc = (byte & ((1 << bits) - 1)) | (3 << bits)
+                    got += acc.to_bytes((bits + 2 + 7) // 8, "little")
+                    continue
+                arr = (C.c_size_t * 1)(a)
+                cap = 2 * a + 100000
+                out = C.create_string_buffer(cap)
+                eb = C.c_uint32(0)
+                r = sim.sim_q1_compress_seg(w, piece, a, arr, 1, out, cap, header, op, bits, C.byref(eb))
+                assert r >= 0 and (eb.value + 7) // 8 == r
+                seg = bytearray(out.raw[:r])
+                if bits:
+                    assert seg[0] & ((1 << bits) - 1) == 0
+                    seg[0] |= byte & ((1 << bits) - 1)
+                bits, byte, header = 0, 0, 0
+                if op == 0 and eb.value & 7:
+                    bits, byte = eb.value & 7, seg.pop()
+                got += seg
+            assert bytes(got) == want, (sizes, ops, w)
 
 
 def _fuzz_check(sim, d, q, w):
