@@ -20,9 +20,10 @@ struct TlsJob {
   BrJob* job = nullptr;
   BrQ1Job* q1 = nullptr;
   uint8_t* d_in = nullptr; size_t d_in_cap = 0;
+  uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // pinned staging area of the stream batches
   double last[16] = {0};
   double last_q1[12] = {0};
-  ~TlsJob() { if (d_in) cudaFree(d_in); if (job) br_job_destroy(job); if (q1) br_q1_job_destroy(q1); }
+  ~TlsJob() { if (d_in) cudaFree(d_in); if (h_stage) cudaFreeHost(h_stage); if (job) br_job_destroy(job); if (q1) br_q1_job_destroy(q1); }
 };
 thread_local TlsJob tls;
 
@@ -224,6 +225,75 @@ int q1_run(const Params& p, const uint8_t* in, size_t n, const size_t* calls, si
   }
 }
 
+// Quality 5..9, streams shorter than 1 MiB: a group of them is ONE device job (the streams laid end to end, cuts of kind 3
+// in br_pipeline.h), so the launches, the fixpoint's host round trips and the copies are paid once per group instead of
+// once per stream.  idx: the streams of the group; encoded_sizes: capacity in, size out (0 = failed).  What
+// BrotliEncoderCompress adds around the encoder (encode.c:1345 raw-stream rule) is applied per stream.  Returns the
+// number of streams compressed.
+static const size_t kBatchGroupBytes = (size_t)128 << 20;
+template <class F> void batch_threads(int threads, size_t count, F f) {
+  if (threads <= 1 || count < 64) { f(0, count); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) {
+    const size_t a = count * (size_t)t / (size_t)threads, b = count * (size_t)(t + 1) / (size_t)threads;
+    if (a < b) th.emplace_back([=, &f] { f(a, b); });
+  }
+  for (auto& t : th) t.join();
+}
+size_t compress_stream_group(int quality, int lgwin, const std::vector<size_t>& idx, const uint8_t* const* inputs,
+                             const size_t* input_sizes, uint8_t* const* outputs, size_t* encoded_sizes, int threads) {
+  const size_t k = idx.size();
+  auto fail_all = [&]() { for (size_t i : idx) encoded_sizes[i] = 0; return (size_t)0; };
+  if (!ensure_job()) return fail_all();
+  std::vector<uint64_t> off(k + 1, 0);
+  uint32_t hint = 0;
+  for (size_t j = 0; j < k; ++j) { off[j + 1] = off[j] + input_sizes[idx[j]]; if (input_sizes[idx[j]] > hint) hint = (uint32_t)input_sizes[idx[j]]; }
+  const size_t n = off[k];
+  const size_t out_bound = n + (n >> 3) + 4096 + 64 * k;
+  const size_t stage = n > out_bound ? n : out_bound;
+  if (tls.h_stage_cap < stage) {
+    if (tls.h_stage) cudaFreeHost(tls.h_stage);
+    tls.h_stage = nullptr; tls.h_stage_cap = 0;
+    if (cudaMallocHost(&tls.h_stage, stage + 64) != cudaSuccess) { cudaGetLastError(); return fail_all(); }
+    tls.h_stage_cap = stage;
+  }
+  if (tls.d_in_cap < n) {
+    if (tls.d_in) cudaFree(tls.d_in);
+    tls.d_in = nullptr; tls.d_in_cap = 0;
+    if (cudaMalloc(&tls.d_in, n + 64) != cudaSuccess) { cudaGetLastError(); return fail_all(); }
+    tls.d_in_cap = n;
+  }
+  uint8_t* hs = tls.h_stage;
+  batch_threads(threads, k, [&](size_t a, size_t b) { for (size_t j = a; j < b; ++j) memcpy(hs + off[j], inputs[idx[j]], input_sizes[idx[j]]); });
+  cudaStream_t st = (cudaStream_t)br_job_stream(tls.job);
+  if (cudaMemcpyAsync(tls.d_in, hs, n, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail_all();
+  std::vector<uint32_t> pos(k, 0), kind(k, 3);
+  for (size_t j = 0; j + 1 < k; ++j) pos[j] = (uint32_t)off[j + 1];
+  std::vector<uint64_t> ends(k + 1, 0);
+  BrCuts c; memset(&c, 0, sizeof(c));
+  c.pos = pos.data(); c.kind = kind.data(); c.n = (uint32_t)(k - 1); c.is_final = 1; c.with_header = 1; c.stream_end = ends.data();
+  const uint8_t* d_out = nullptr; size_t sz = 0;
+  int w = lgwin > 24 ? 24 : lgwin;
+  if (!br_job_compress_device(tls.job, quality, w, hint, tls.d_in, (uint32_t)n, &d_out, &sz, k > 1 ? &c : nullptr)) return fail_all();
+  record_stats();
+  if (k == 1) ends[0] = sz;
+  if (sz > tls.h_stage_cap || ends[k - 1] != sz) return fail_all();
+  if (cudaMemcpyAsync(hs, d_out, sz, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return fail_all();
+  std::vector<uint8_t> good(k, 0);
+  batch_threads(threads, k, [&](size_t a, size_t b) {
+    for (size_t j = a; j < b; ++j) {
+      const size_t i = idx[j], from = j ? (size_t)ends[j - 1] : 0, got = (size_t)ends[j] - from, cap = encoded_sizes[i];
+      const size_t bound = BrotliEncoderMaxCompressedSize(input_sizes[i]);
+      if (got <= cap && got <= bound) { memcpy(outputs[i], hs + from, got); encoded_sizes[i] = got; good[j] = 1; }
+      else if (cap >= bound) { encoded_sizes[i] = make_uncompressed_stream(inputs[i], input_sizes[i], outputs[i]); good[j] = 1; }   /* encode.c:1345 */
+      else encoded_sizes[i] = 0;
+    }
+  });
+  size_t ok = 0;
+  for (size_t j = 0; j < k; ++j) ok += good[j];
+  return ok;
+}
+
 }  // namespace
 
 // Buffers of an encoder instance come from the caller's allocator pair when one was given (encode.h:295-306).
@@ -327,7 +397,7 @@ int build_wire(BrotliEncoderState* s, bool is_final, bool finish_empty, std::vec
   c.is_final = (is_final && !cut_at_end) ? 1 : 0; c.with_header = (lead || continued) ? 0 : 1;
   c.stream_offset = s->params.stream_offset;
   c.finish_empty = (c.is_final && finish_empty) ? 1 : 0; c.end_bit = end_bit.data();
-  c.lgblock = s->params.lgblock; c.disable_ctx = (int)s->params.disable_ctx;
+  c.lgblock = s->params.lgblock; c.disable_ctx = (int)s->params.disable_ctx; c.stream_end = nullptr;
   if (!c.is_final && !cut_at_end) return 0;   // (callers only build the wire at a cut or at FINISH)
   std::vector<uint8_t> D;
   size_t got = 0;
@@ -455,21 +525,39 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
     }
     return good;
   }
-  if ((size_t)threads > count) threads = (int)count;
+  /* quality 5..9: streams below 1 MiB go through the device in groups (one job per group, compress_stream_group); longer
+     ones one by one, `threads` host workers each with its own CUDA stream */
+  Params p; p.quality = quality; p.lgwin = lgwin;
+  if (lgwin > 24) p.large_window = 1;
+  if (!supported(p)) { for (size_t i = 0; i < count; ++i) encoded_sizes[i] = 0; return 0; }
+  size_t ok = 0;
+  std::vector<size_t> big, group;
+  size_t group_bytes = 0;
+  for (size_t i = 0; i < count; ++i) {
+    if (input_sizes[i] == 0 || input_sizes[i] >= ((size_t)1 << 20)) { big.push_back(i); continue; }
+    if (group_bytes + input_sizes[i] > kBatchGroupBytes && !group.empty()) {
+      ok += compress_stream_group(quality, lgwin, group, inputs, input_sizes, outputs, encoded_sizes, threads);
+      group.clear(); group_bytes = 0;
+    }
+    group.push_back(i); group_bytes += input_sizes[i];
+  }
+  if (!group.empty()) ok += compress_stream_group(quality, lgwin, group, inputs, input_sizes, outputs, encoded_sizes, threads);
+  if (big.empty()) return ok;
+  if ((size_t)threads > big.size()) threads = (int)big.size();
   std::vector<size_t> okc((size_t)threads, 0);
   int dev = 0; cudaGetDevice(&dev);
   std::vector<std::thread> th;
   for (int t = 0; t < threads; ++t)
     th.emplace_back([&, t] {
       cudaSetDevice(dev);
-      for (size_t i = (size_t)t; i < count; i += (size_t)threads) {
+      for (size_t bi = (size_t)t; bi < big.size(); bi += (size_t)threads) {
+        const size_t i = big[bi];
         size_t sz = encoded_sizes[i];
         if (BrotliEncoderCompress(quality, lgwin, BROTLI_MODE_GENERIC, input_sizes[i], inputs[i], &sz, outputs[i])) {
           encoded_sizes[i] = sz; ++okc[(size_t)t];
         } else encoded_sizes[i] = 0;
       }
     });
-  size_t ok = 0;
   for (int t = 0; t < threads; ++t) { th[(size_t)t].join(); ok += okc[(size_t)t]; }
   return ok;
 }

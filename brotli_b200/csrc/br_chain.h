@@ -51,6 +51,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
   }
   const u32* mine = s.bits_cur + (size_t)(s.bout[k].own_par & 1u) * s.bits_words;
   const u32 my_head = s.bout[k].head;
+  const u32 send = s.blk[in.blk].send;   // (batch of streams: nobody behind the end of my stream looks at my positions)
   if (b > a) {
     // stitch positions inside [a, b): the next block(s) starting at or shortly after blk_end
     u32 st_lo = 0, st_hi = 0;   // [st_lo, st_hi) of stitch-stored positions (at most one run here)
@@ -61,7 +62,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
         if (!s.bin[nb].first) continue;
         u32 np = s.bin[nb].blk_start, ne = s.bin[nb].blk_end;
         if (np >= in.blk_end + 3) break;
-        if (ne - np >= s.P.htl - 1 && np >= 3) { st_lo = np - 3; st_hi = np; }
+        if (ne - np >= s.P.htl - 1 && np - s.bin[nb].base >= 3) { st_lo = np - 3; st_hi = np; }
         break;
       }
     }
@@ -117,7 +118,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
               break;
             }
             const u32 pp = s.S[j];
-            if (pp - q > s.P.max_backward) break;
+            if (pp - q > s.P.max_backward || pp >= send) break;
             if ((s.bits_prev[pp >> 5] >> (pp & 31)) & 1) ++cnt;
             if (pp >= a && pp < b) continue;            // my own run is consistent with my own bits
             if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
@@ -274,6 +275,12 @@ BR_DEV void br_chain_b(const BrStream& s) {
       for (int i = 0; i < 4; ++i) B.out_dc[i] = br_shfl(mine.out_dc[i], src);
       B.lc_copy_len = br_shfl(mine.lc_copy_len, src); B.lc_dist_prefix = br_shfl(mine.lc_dist_prefix, src); B.lc_dist_extra = br_shfl(mine.lc_dist_extra, src);
       B.changed_epoch = br_shfl(mine.changed_epoch, src); B.state_dirty = br_shfl(mine.state_dirty, src);
+      B.base = br_shfl(mine.base, src); B.send = br_shfl(mine.send, src);
+    }
+    if (bi > 0 && B.start == B.base) {
+      // a new stream of the batch begins (the block before carried is_last, so nothing is pending): fresh encoder state
+      for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i] = (i == 0 ? 4 : i == 1 ? 11 : i == 2 ? 15 : 16);
+      dict_l = dict_m = 0; last_insert_len = 0; have_last = false;
     }
     u32 ext_dist = 0;
     if (num_cmds > 0 && last_insert_len == 0 && have_last) {
@@ -281,7 +288,7 @@ BR_DEV void br_chain_b(const BrStream& s) {
       int cmd_dist = dc[0];
       if (dcode < 16 || (cmd_dist > 0 && dcode - 15 == (u32)cmd_dist)) {
         u32 lpp = B.start - (lc_copy_len & 0x1FFFFFF);
-        u32 maxd = br_min(lpp, P.max_backward);
+        u32 maxd = br_min(lpp - B.base, P.max_backward);
         if (cmd_dist > 0 && (u32)cmd_dist <= maxd) ext_dist = (u32)cmd_dist;
       }
     }
@@ -352,8 +359,9 @@ BR_DEV void br_chain_b(const BrStream& s) {
       m.first_block = first_blk_chunk; m.last_block = B.first_chunk + B.nchunks - 1;
       m.cmd_off = first_blk_cmd_base; m.ncmd = num_cmds; m.nlit = num_lits;
       m.is_last = (B.is_last || closes_stream) ? 1u : 0u; m.compress = (u32)compress;
-      m.prev_byte = last_flush_pos > 0 ? s.data[last_flush_pos - 1] : 0;
-      m.prev_byte2 = last_flush_pos > 1 ? s.data[last_flush_pos - 2] : 0;
+      m.prev_byte = last_flush_pos > B.base ? s.data[last_flush_pos - 1] : 0;
+      m.prev_byte2 = last_flush_pos > B.base + 1 ? s.data[last_flush_pos - 2] : 0;
+      m.base = B.base;
       m.flushed = (u8)B.force_flush; m.empty_last = empty_last ? 1 : 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
       s.mbs[n_mbs] = m;
     }
@@ -381,7 +389,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
   // blocks inside this block's window (including itself)
   int ovf = B.changed_epoch;
   {
-    const u32 lowpos = B.start > s.P.max_backward ? B.start - s.P.max_backward : 0;
+    const u32 lowpos = B.start - B.base > s.P.max_backward ? B.start - s.P.max_backward : B.base;
     for (u32 j = bi; j-- > 0;) {
       if (s.blk[j].end <= lowpos) break;
       int ce = s.blk[j].changed_epoch;
@@ -480,7 +488,7 @@ BR_DEV void br_chain_d(const BrStream& s, u32 k) {
     // second launch only: a sweep that stops early (its state fell in step again) leaves these chunks unwalked, and
     // they must not wait behind ever new sweeps of the blocks before them.
     const u32 bi = s.bin[k].blk, g0 = bi & ~(s.P.sweep_blocks - 1u);
-    for (u32 j = g0; j < bi; ++j) if (s.blk[j].state_dirty) { d |= BR_DEFER_SWEEP; break; }
+    for (u32 j = g0; j < bi; ++j) if (s.blk[j].state_dirty && s.blk[j].base == s.blk[bi].base) { d |= BR_DEFER_SWEEP; break; }
   }
   s.dirty[k] = d;
   if (!(d & BR_DEFER)) {

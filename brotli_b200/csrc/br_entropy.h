@@ -376,7 +376,8 @@ BR_DEV u32 br_static_ctx_map(int which, u32 ctx) {
                       5, 5, 10, 5, 5, 5, 10, 5, 6, 6, 6, 6, 6, 6, 6, 6};
   return c13[ctx];
 }
-BR_DEV u8 br_data_or_zero(const BrStream& st, u32 pos, u32 back) { return pos >= back ? st.data[pos - back] : 0; }
+// the byte `back` positions in front of pos; zero in front of the stream's first byte (base)
+BR_DEV u8 br_data_or_zero(const BrStream& st, u32 pos, u32 back, u32 base) { return pos - base >= back ? st.data[pos - back] : 0; }
 
 // encode.c:258 EstimateEntropy
 BR_DEV double br_estimate_entropy(const BrStream& st, const u32* pop, u32 size) {

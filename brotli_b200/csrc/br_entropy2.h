@@ -120,7 +120,7 @@ BR_DEV void br_symbol_at(const BrStream& st, const BrEnt& e, const BrMetaBlock& 
   if (cat == 0) {
     u32 p = e.lit_pos[a.lit_base + o];
     *sym = st.data[p];
-    if (a.which != 1) *ctx = br_static_ctx_map((int)a.which, BR_CTX_UTF8(st, br_data_or_zero(st, p, 1), br_data_or_zero(st, p, 2)));
+    if (a.which != 1) *ctx = br_static_ctx_map((int)a.which, BR_CTX_UTF8(st, br_data_or_zero(st, p, 1, mb.base), br_data_or_zero(st, p, 2, mb.base)));
   } else if (cat == 1) {
     *sym = e.cmds[mb.cmd_off + o].cmd_prefix;
   } else {
@@ -397,7 +397,8 @@ BR_DEV u32 br_lit_code(const BrStream& st, const BrEnt& e, u32 o, u32* code, u64
   const u32 b = br_block_of(bi, a.num_blocks[0], orel);
   const u32 p = e.lit_pos[o], lit = st.data[p], type = bi[b].type;
   u32 hix;
-  if (a.cmap_size) hix = M->cmap[(type << 6) + BR_CTX_UTF8(st, br_data_or_zero(st, p, 1), br_data_or_zero(st, p, 2))] * 256 + lit;
+  const u32 base = st.mbs[m].base;
+  if (a.cmap_size) hix = M->cmap[(type << 6) + BR_CTX_UTF8(st, br_data_or_zero(st, p, 1, base), br_data_or_zero(st, p, 2, base))] * 256 + lit;
   else hix = type * 256 + lit;
   if (bi[b].start == orel) { *swn = bi[b].sw_nbits; *sw = bi[b].sw_bits; }
   *code = M->lit_bits[hix];

@@ -17,6 +17,7 @@
 #include "br_chain.h"
 #include "br_entropy.h"
 #include "br_entropy2.h"
+#include "br_assemble.h"
 #include "br_pipeline.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -94,7 +95,7 @@ __global__ void k_build_chunks(const BrBlk* __restrict__ blk, BrBlockIn* __restr
   for (u32 c = threadIdx.x; c < B.nchunks; c += blockDim.x) {
     BrBlockIn k; memset(&k, 0, sizeof(k));
     k.pos = B.start + c * ch; k.end = k.pos + ch < B.end ? k.pos + ch : B.end; k.blk_start = B.start; k.blk_end = B.end;
-    k.first = c == 0; k.last = k.end == B.end; k.is_last = B.is_last; k.force_flush = B.force_flush; k.blk = blockIdx.x;
+    k.first = c == 0; k.last = k.end == B.end; k.is_last = B.is_last; k.force_flush = B.force_flush; k.blk = blockIdx.x; k.base = B.base;
     bin[B.first_chunk + c] = k;
   }
 }
@@ -201,12 +202,12 @@ __global__ void __launch_bounds__(1024) k_build_storedS(BrStream s, u32* __restr
 #ifndef BR_WALK_G_SMALL
 #define BR_WALK_G_SMALL 1   /* rows fetched together for the 16/32-entry rings */
 #endif
-template <int G>
+template <int G, bool M>
 __global__ void __launch_bounds__(128, G <= 2 ? BR_WALK1_MINB : G == 4 ? 5 : 4) k_walk(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.counters[5]) return;
   const u32 b = br_sched_entry(s, t);
-  br_walk_block<G>(s, b, s.forced && b == s.counters[6]);
+  br_walk_block<G, M>(s, b, s.forced && b == s.counters[6]);
 }
 __global__ void k_commit(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -308,60 +309,9 @@ __global__ void k_emit_lit(BrStream s, BrEnt e) {
 }
 
 // ---------------------------------------------------------------------------- stream assembly
-struct BrCopyDesc { u64 dst_bit; u64 src_off; u32 nbits; u32 kind; };  // kind 0: bit copy from outbits, 1: raw bytes from input
-// res[0..1]: total bytes (u64), res[2]: first metablock that needs the late fallback (+1), 0 if none, res[3]: cuts seen.
-// with_header: the stream starts here (window bits); 0 when the caller already sent them (a FLUSH / EMIT_METADATA before any
-// input).  cut_kind[i] says what ended the i-th flushed metablock: 1 = FLUSH (encode.c:1356 InjectBytePaddingBlock: an empty
-// metadata block pads to a byte boundary unless the stream stands on one), 2 = EMIT_METADATA (encode.c:1549: no padding
-// block -- the caller merges its metadata header into the pending bits -- and the next metablock starts on the next byte
-// boundary).  cut_end_bit[i] receives the bit position where that metablock ended (before any padding).
 __global__ void k_assemble_scan(BrStream s, const u64* __restrict__ out_off, u32* out, BrCopyDesc* desc, u32* res,
-                                int with_header, const u32* __restrict__ cut_kind, u64* cut_end_bit) {
-  if (threadIdx.x != 0) return;
-  u64 bit = 0;
-  u32 ncut = 0;
-  const int lgwin = s.P.lgwin;
-  if (with_header) {
-    if (lgwin == 17) { br_put_bits_at(out, 0, 7, 1); bit = 7; }
-    else { br_put_bits_at(out, 0, 4, (u64)(((lgwin - 17) << 1) | 1)); bit = 4; }
-  }
-  u32 nm = s.counters[1], fallback = 0;
-  for (u32 i = 0; i < nm; ++i) {
-    BrMetaBlock mb = s.mbs[i];
-    u32 bytes = mb.end - mb.start;
-    BrCopyDesc d;
-    if (mb.compress) {
-      u64 storage_ix = (bit & 7) + mb.out_bits;
-      if (mb.is_last) storage_ix = (storage_ix + 7) & ~7ull;
-      if ((u64)bytes + 4 < (storage_ix >> 3)) { if (!fallback) fallback = i + 1; }   // encode.c:604
-      d.dst_bit = bit; d.src_off = out_off[i]; d.nbits = mb.out_bits; d.kind = 0;
-      bit += mb.out_bits;
-      if (mb.is_last) bit = (bit + 7) & ~7ull;
-    } else {
-      // brotli_bit_stream.c:1321 BrotliStoreUncompressedMetaBlock
-      u32* w32 = out + (bit >> 5); u32 sh = (u32)(bit & 31);   // write relative to a word base to keep ix in 32 bits
-      u32 ix = sh;
-      br_put_bits_at(w32, ix, 1, 0); ix += 1;
-      { u32 lg = bytes == 1 ? 1 : br_log2floor(bytes - 1) + 1; u32 mn = (lg < 16 ? 16 : (lg + 3)) / 4;
-        br_put_bits_at(w32, ix, 2, mn - 4); ix += 2; br_put_bits_at(w32, ix, mn * 4, bytes - 1); ix += mn * 4; }
-      br_put_bits_at(w32, ix, 1, 1); ix += 1;
-      bit += ix - sh;
-      bit = (bit + 7) & ~7ull;
-      d.dst_bit = bit; d.src_off = mb.start; d.nbits = bytes; d.kind = 1;
-      bit += (u64)bytes * 8;
-      if (mb.is_last) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 2, 3); bit += 2; bit = (bit + 7) & ~7ull; }
-    }
-    desc[i] = d;
-    if (mb.empty_last) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 2, 3); bit += 2; bit = (bit + 7) & ~7ull; }   // encode.c:520
-    if (mb.flushed && !mb.is_last) {
-      cut_end_bit[ncut] = bit;
-      if (cut_kind[ncut] == 1 && (bit & 7)) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 6, 6); bit += 6; }
-      bit = (bit + 7) & ~7ull;
-      ++ncut;
-    }
-  }
-  u64 total = (bit + 7) >> 3;
-  res[0] = (u32)total; res[1] = (u32)(total >> 32); res[2] = fallback; res[3] = ncut;
+                                int with_header, const u32* __restrict__ cut_kind, u64* cut_end_bit, u64* stream_end) {
+  if (threadIdx.x == 0) br_assemble_scan(s, out_off, out, desc, res, with_header, cut_kind, cut_end_bit, stream_end);
 }
 // grid.y = metablock, grid.x strides over its words / bytes
 __global__ void k_assemble_copy(BrStream s, const BrCopyDesc* __restrict__ desc, const u32* __restrict__ outbits, u32* out) {
@@ -500,17 +450,26 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 #else
   const bool trace = false;
 #endif
-  const u32 ch = 1u << P.chunk_bits;
   // chunk / block tables: the reference's input blocks (1 << lgblock bytes, shorter where a FLUSH cut the input)
   std::vector<BrBlk> hblk;
   const u32 ncuts = cuts ? cuts->n : 0;
+  u32 nstreams = 1;
+  for (u32 i = 0; i < ncuts; ++i) if (cuts->kind[i] == 3) ++nstreams;
+  if (nstreams > 1) {
+    // a batch of independent streams (each below BR_SMALL_STREAM, size_hint = the largest): no FLUSH cuts, all finished
+    if (nstreams != ncuts + 1 || !cuts->is_final || !cuts->with_header || cuts->finish_empty || cuts->stream_offset ||
+        cuts->pos[ncuts - 1] >= n || size_hint >= BR_SMALL_STREAM) return 0;
+    P.multi = nstreams;
+    P.chunk_bits = br_batch_chunk_bits(n);
+  }
+  const u32 ch = 1u << P.chunk_bits;
   const bool is_final = cuts ? cuts->is_final != 0 : true;
   const int with_header = cuts ? cuts->with_header : 1;
   P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
   if (!is_final && (ncuts == 0 || cuts->pos[ncuts - 1] != n)) return 0;   // an unfinished stream ends at a cut
   if (P.finish_empty && (!is_final || (ncuts && cuts->pos[ncuts - 1] == n))) return 0;
   u32 nb = 0;
-  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, ncuts, is_final && !P.finish_empty, nullptr, hblk, &nb);   // chunks: k_build_chunks
+  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, ncuts, is_final && !P.finish_empty, nullptr, hblk, &nb, cuts ? cuts->kind : nullptr);   // chunks: k_build_chunks
   std::vector<u32> h_slot(((size_t)n >> P.lgblock) + 2, 0);
   { u32 b = 0; for (size_t i = 0; i < h_slot.size(); ++i) { const u64 p = (u64)i << P.lgblock; while (b + 1 < hblk.size() && hblk[b].end <= p) ++b; h_slot[i] = b; } }
   const u32 nblk = (u32)hblk.size();
@@ -532,7 +491,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
   for (int i = 0; i < 14; ++i) add(nb * 4ull + 64);
   add(nblk * sizeof(BrBlk)); add(nblk * sizeof(BrBlkIn)); add((P.nbuckets + 8) * 4ull);
-  add(h_slot.size() * 4); add((ncuts + 2) * 4ull); add((ncuts + 2) * 8ull);
+  add(h_slot.size() * 4); add((ncuts + 2) * 4ull); add((ncuts + 2) * 8ull); add((nstreams + 2) * 8ull);
   // Launch bound: in forced mode every launch finalises at least one input block (at most two launches per block with
   // the conservative block-level re-marks), and a late uncompressed fallback restarts the count at most once per metablock.
   P.max_epochs = 4 * nb + 4096;
@@ -561,6 +520,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   BrBlk* d_blk = A.take<BrBlk>(nblk); BrBlkIn* d_blkin = A.take<BrBlkIn>(nblk);
   u32* key_flips = A.take<u32>(P.nbuckets + 8);
   u32* slot_blk = A.take<u32>(h_slot.size()); u32* d_cut_kind = A.take<u32>(ncuts + 2); u64* d_cut_end = A.take<u64>(ncuts + 2);
+  u64* d_stream_end = A.take<u64>(nstreams + 2);
   u32* epoch_cum = A.take<u32>((size_t)P.max_epochs + 2);
   BrMetaBlock* mbs = A.take<BrMetaBlock>(nb + 1);
   u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256);
@@ -651,9 +611,12 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
       scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
       cudaEventRecord(ev[6], st);
-      if (P.block_bits >= 8) k_walk<BR_WALK_G_DEEP><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
-      else if (P.block_bits >= 6) k_walk<4><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
-      else k_walk<BR_WALK_G_SMALL><<<(n_sched + 3) / 4, 128, 0, st>>>(s);
+      const u32 wg = (n_sched + 3) / 4;
+      if (P.multi) {
+        if (P.block_bits >= 6) k_walk<BR_WALK_G_DEEP, true><<<wg, 128, 0, st>>>(s);
+        else k_walk<BR_WALK_G_SMALL, true><<<wg, 128, 0, st>>>(s);
+      } else if (P.block_bits >= 6) k_walk<BR_WALK_G_DEEP, false><<<wg, 128, 0, st>>>(s);
+      else k_walk<BR_WALK_G_SMALL, false><<<wg, 128, 0, st>>>(s);
       cudaEventRecord(ev[7], st);
       walk_pending = true; ++job->stats.walk_launches; job->stats.launches += 6;
       job->stats.walk_bytes += (u64)n_sched * ch;
@@ -741,15 +704,12 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     cudaEventRecord(ev[9], st);
     cudaEventRecord(ev[3], st);
     ++job->stats.encode_launches; job->stats.launches += 24;
-    k_assemble_scan<<<1, 32, 0, st>>>(s, d_ooff, out, desc, res, with_header, d_cut_kind, d_cut_end);
+    k_assemble_scan<<<1, 32, 0, st>>>(s, d_ooff, out, desc, res, with_header, d_cut_kind, d_cut_end, d_stream_end);
     CK(cudaMemcpyAsync(hp + 16, res, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (hp[18]) {   // encode.c:604: the coded metablock is larger than the input -> store it raw and
-                    // redo the parse behind it with the restored distance cache
-      u32 idx = hp[18] - 1, one = 1;
-      CK(cudaMemcpyAsync(force_unc + idx, &one, 4, cudaMemcpyHostToDevice, st));
-      CK(cudaStreamSynchronize(st));
-      if (rounds > (int)nblk + 8) return 0;   // (every round stores one more metablock raw)
+    if (hp[18]) {   // encode.c:604: a coded metablock is larger than its input -> it is stored raw (br_assemble_scan marked
+                    // it in force_unc) and the parse behind it is redone with the restored distance cache
+      if (rounds > (int)nblk + 8) return 0;   // (every round stores at least one more metablock raw)
       continue;
     }
     k_assemble_copy<<<dim3(64, n_mbs), 256, 0, st>>>(s, desc, outbits, out);
@@ -769,8 +729,12 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   job->stats.total_cmds = total_cmds; job->stats.launches += 12;
   job->stats.nblocks = nb; job->stats.n_metablocks = n_mbs; job->stats.rounds = (u32)rounds;
   job->stats.out_bytes = final_size; job->stats.in_bytes = n;
-  if (cuts && cuts->end_bit && ncuts) {
+  if (cuts && cuts->end_bit && ncuts && nstreams == 1) {
     CK(cudaMemcpyAsync(cuts->end_bit, d_cut_end, ncuts * 8ull, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  if (cuts && cuts->stream_end && nstreams > 1) {
+    CK(cudaMemcpyAsync(cuts->stream_end, d_stream_end, nstreams * 8ull, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
   *d_out = final_out; *out_size = final_size;

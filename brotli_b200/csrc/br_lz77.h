@@ -99,6 +99,7 @@ struct BrWalk {
   const BrStream* s;
   const u8* d;
   u32 p0, pend;    // p0: first position this walker owns; pend: end of the reference input block
+  u32 base;        // first byte of the stream (BrBlockIn::base): ring-buffer positions and distance limits count from it
   int dc[4];       // distance cache; entries 4..15 of the reference (hash.h:80) are derived on the fly
   u64 dict_l, dict_m;
   u32 dl, dm, gate_checks, gate_fail;
@@ -257,7 +258,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   const u8* d = w.d;
   const int lane = br_lane();
   const u32 rmask = P.rmask;
-  const u32 cur_m = cur & rmask;
+  const u32 cur_m = (cur - w.base) & rmask;
   const u32 min_score = out.score;
   u32 best_score = out.score, best_len = out.len;
   out.len = 0; out.delta = 0;
@@ -315,7 +316,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
     u32 score = 135u * len + BR_SCORE_BASE + 15u;
     if (k != 0) score -= 39u + ((0x1CA10u >> (k & 0xE)) & 0xEu);
     const bool lenok = valid && (len >= 3 || (len == 2 && k < 2));
-    const u32 pm = (cur - back) & rmask;
+    const u32 pm = (cur - back - w.base) & rmask;
     int last = -1;
     for (;;) {
       // candidates are examined in order; everything up to `last` has been decided
@@ -337,9 +338,16 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   {
     const u32 block_size = 1u << P.block_bits;
     u32 V = block_size;
-    if (hi - lo >= P.heavy_min) {
+    if (hi - lo >= P.heavy_min && cur - w.base >= 65536u) {
       // The reference's per-bucket counter is a uint16 (hash_longest_match64_inc.h:52): after
-      // 65536 insertions it wraps and the ring looks empty again.  c = insertions so far.
+      // 65536 insertions it wraps and the ring looks empty again.  c = insertions so far (of this stream: it cannot
+      // reach 65536 before the stream is that long).
+      u32 lo_s = lo;
+      if (w.base) {   // batch of streams: the bucket's slice starts with the positions of the streams in front
+        u32 a = lo, b = j;
+        while (a < b) { const u32 mid = (a + b) >> 1; if (br_ldg(s.S + mid) < w.base) a = mid + 1; else b = mid; }
+        lo_s = a;
+      }
       u32 own_cnt = 0, jj = j, n_own = 0;
       BR_W(2, 1);
       br_own_sync(w);
@@ -356,7 +364,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
         jj -= BR_WARP;
       }
       u32 jb = j - n_own;
-      u32 prev_cnt = br_countS_upto(s, jb) - br_countS_upto(s, lo);
+      u32 prev_cnt = br_countS_upto(s, jb) - br_countS_upto(s, lo_s);
       u32 c = (prev_cnt + own_cnt) & 0xFFFFu;
       if (c < block_size) { V = c; w.min_wrap = 0; }
       else {
@@ -425,7 +433,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
           if (len == max_length) eqmax = (w.stale == (u32)br_ldg(d + q[r] + max_length));
         }
         const u32 score = len ? BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward) : 0;
-        const u32 pm = q[r] & rmask;
+        const u32 pm = (q[r] - w.base) & rmask;
         int last = -1;
         for (;;) {
           if (cur_m + best_len > rmask) { done = true; break; }
@@ -470,7 +478,8 @@ BR_DEV u32 br_compute_distance_code(u32 distance, u32 max_distance, const int* d
 // `head` is the first chunk of the sweep this run belongs to (== b when the walker starts here), `sweep_p0` the
 // first position the sweep owns (0xffffffff on entry for the head, which sets it): a walker that continues into the
 // chunks behind its own keeps writing the head's bitmap and reads its own fresh bits from sweep_p0 on.
-template <int G>
+// M: the job is a batch of streams (BrParams::multi); with M = false the stream base is the constant 0 and folds away.
+template <int G, bool M = false>
 BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOut& o, u32 head, u32& sweep_p0) {
   const BrParams& P = s.P;
   const int lane = br_lane();
@@ -487,7 +496,9 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
   w.dbg_searches = w.dbg_rows = w.dbg_mlsteps = 0;
   const long long dbg_t0 = clock64();
 #endif
-  w.stale = in.blk_end <= P.rmask ? 0u : (u32)s.data[in.blk_end - (P.rmask + 1)];
+  const u32 base = M ? in.base : 0u;
+  w.base = base;
+  w.stale = in.blk_end - base <= P.rmask ? 0u : (u32)s.data[in.blk_end - (P.rmask + 1)];
   for (int i = 0; i < 4; ++i) w.dc[i] = in.dc[i];
   const u32 pos_end = in.blk_end;
   u32 position = in.start_pos;
@@ -554,7 +565,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     int delayed = 0;
     for (;;) {
       const u32 sp = position + (have ? 1u : 0u);
-      const u32 md = br_min(sp, P.max_backward);
+      const u32 md = br_min(sp - base, P.max_backward);
       const u32 dd = P.stream_offset ? br_min(sp + P.stream_offset, P.max_backward) : md;   // backward_references_inc.h:94 dictionary_start
       BrSR cur; cur.len = 0; cur.delta = 0; cur.distance = 0; cur.score = BR_MIN_SCORE;
       br_find_longest_match<G>(w, sp, max_length, md, dd, cur);
@@ -572,7 +583,7 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
     }
     if (have) {
       apply_random_heuristics = position + 2 * sr.len + window;
-      u32 dictionary_start = br_min(position + P.stream_offset, P.max_backward);
+      u32 dictionary_start = br_min(position - base + P.stream_offset, P.max_backward);
       u32 dcode = br_compute_distance_code(sr.distance, dictionary_start, w.dc);
       if (sr.distance <= dictionary_start && dcode > 0) {
         w.dc[3] = w.dc[2]; w.dc[2] = w.dc[1]; w.dc[1] = w.dc[0]; w.dc[0] = (int)sr.distance;
@@ -679,7 +690,7 @@ BR_DEV bool br_predict_next_block(const BrStream& s, u32 b, const BrBlockIn& in,
       const int cmd_dist = o.dc[0];
       if (dcode < 16 || (cmd_dist > 0 && dcode - 15 == (u32)cmd_dist)) {
         const u32 lpp = in.blk_end - (lc.copy_len & 0x1FFFFFF);
-        const u32 maxd = br_min(lpp, P.max_backward);
+        const u32 maxd = br_min(lpp - in.base, P.max_backward);
         if (cmd_dist > 0 && (u32)cmd_dist <= maxd) ext_dist = (u32)cmd_dist;
       }
     }
@@ -700,14 +711,14 @@ BR_DEV bool br_predict_next_block(const BrStream& s, u32 b, const BrBlockIn& in,
 // the sequential parse of that stretch: serial ripples (the position phase of the sparse search running through
 // incompressible data, a distance-cache change flowing through match-free data) cost one launch per input block, not
 // one launch per chunk.
-template <int G>
+template <int G, bool M = false>
 BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
   BrBlockIn in = s.bin[b];
   const u32 head = b;
   u32 sweep_p0 = 0xffffffffu;
   for (;;) {
     BrBlockOut o;
-    br_walk_one<G>(s, b, in, o, head, sweep_p0);
+    br_walk_one<G, M>(s, b, in, o, head, sweep_p0);
     if (br_lane() == 0) br_atomic_max((int*)s.counters + 16, (int)(b - head + 1));   // longest sweep of this launch (diagnostic)
     const u32 nb = b + 1;
     BrBlockIn ni;
@@ -742,7 +753,7 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
       if (same) return;
     }
     ni.dict_l_lo = (u32)dl; ni.dict_l_hi = (u32)(dl >> 32); ni.dict_m_lo = (u32)dm; ni.dict_m_hi = (u32)(dm >> 32);
-    if (in.last && ni.blk_end - ni.blk_start >= s.P.htl - 1 && ni.blk_start >= 3) {
+    if (in.last && ni.blk_end - ni.blk_start >= s.P.htl - 1 && ni.blk_start - ni.base >= 3) {
       // StitchToPreviousBlock (hash_longest_match64_inc.h:127) of the block the sweep enters: the last three positions of
       // the block it leaves.  br_commit_bits adds them for their owner; the sweep reads its own bitmap from sweep_p0 on.
       u32* own = s.bits_cur + (size_t)(head & 1u) * s.bits_words;

@@ -38,24 +38,32 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   return 1;
 }
 
+// Chunk size of a BATCH of streams (BrParams::multi): the fine chunks of a small stream buy latency with extra warm-up
+// work (256 bytes re-parsed in front of every chunk); a batch that fills the GPU anyway takes the 2 KiB chunks.
+static inline u32 br_batch_chunk_bits(u32 n_total) { return n_total < (8u << 20) ? BR_CHUNK_BITS_SMALL : BR_CHUNK_BITS; }
+
 // The reference's input blocks (one EncodeData call each, c/enc/encode.c:1665-1719) and their 2 KiB chunks for a stream
 // of n bytes.  `cuts` (sorted, each in (0, n]) are the positions where a FLUSH / EMIT_METADATA operation ended the input
 // of a CompressStream call: the running block ends there with force_flush set (encode.c:1700) and the next one starts
 // with a full 1 << lgblock budget again (encode.c:1016 UpdateLastProcessedPos).  is_final: FINISH has been seen (the
 // last block carries is_last); otherwise the stream simply stops behind its last block.
+// kinds (nullable) = what each cut is: 1 FLUSH, 2 EMIT_METADATA, 3 = END OF A STREAM (a batch of independent streams laid
+// end to end, BrParams::multi): the block in front of the cut carries is_last, the blocks behind it belong to a new stream.
 // chunks == nullptr: only the block table (the CUDA pipeline fills the chunk table on the device, k_build_chunks).
 static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u32 ncuts, bool is_final,
-                                   std::vector<BrBlockIn>* chunks, std::vector<BrBlk>& blks, u32* nchunks_total = nullptr) {
+                                   std::vector<BrBlockIn>* chunks, std::vector<BrBlk>& blks, u32* nchunks_total = nullptr,
+                                   const u32* kinds = nullptr) {
   const u32 bs = 1u << P.lgblock, ch = 1u << P.chunk_bits;
   u32 ci = 0, total = 0;
-  u64 bstart = 0;
+  u64 bstart = 0, base = 0;
   while (bstart < n) {
     while (ci < ncuts && cuts[ci] <= bstart) ++ci;
     u64 bend = bstart + bs < n ? bstart + bs : n;
-    bool forced = false;
-    if (ci < ncuts && cuts[ci] <= bend) { bend = cuts[ci]; forced = true; }
+    bool forced = false, stream_end = false;
+    if (ci < ncuts && cuts[ci] <= bend) { bend = cuts[ci]; forced = true; stream_end = kinds && kinds[ci] == 3; }
     BrBlk B; memset(&B, 0, sizeof(B));
-    B.start = (u32)bstart; B.end = (u32)bend; B.is_last = (is_final && bend == n) ? 1u : 0u;
+    B.start = (u32)bstart; B.end = (u32)bend; B.is_last = ((is_final && bend == n) || stream_end) ? 1u : 0u;
+    B.base = (u32)base;
     B.force_flush = forced && !B.is_last ? 1u : 0u; B.changed_epoch = -1;
     B.first_chunk = total;
     B.nchunks = (u32)((bend - bstart + ch - 1) / ch);
@@ -64,11 +72,14 @@ static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u3
         BrBlockIn k; memset(&k, 0, sizeof(k));
         k.pos = (u32)c; k.end = (u32)(c + ch < bend ? c + ch : bend); k.blk_start = (u32)bstart; k.blk_end = (u32)bend;
         k.first = (c == bstart); k.last = (k.end == bend); k.is_last = B.is_last; k.force_flush = B.force_flush; k.blk = (u32)blks.size();
+        k.base = B.base;
         chunks->push_back(k);
       }
     total += B.nchunks;
     blks.push_back(B);
     bstart = bend;
+    if (stream_end) base = bend;
   }
+  { u32 send = n; for (size_t i = blks.size(); i-- > 0;) { if (blks[i].is_last) send = blks[i].end; blks[i].send = send; } }
   if (nchunks_total) *nchunks_total = total;
 }

@@ -18,8 +18,12 @@ struct BrJobStats {
 // finish_empty: FINISH came without input right behind a full input block (BrParams::finish_empty).
 // lgblock (0 = default) / disable_ctx / stream_offset: BROTLI_PARAM_LGBLOCK / DISABLE_LITERAL_CONTEXT_MODELING / STREAM_OFFSET
 // (the caller passes with_header = 0 and the cut behind the first two bytes that a stream offset implies, encode.c:1704).
+// kind[i] = 3: the input is a BATCH of independent streams laid end to end and pos[i] is where one ends and the next begins
+// (all cuts are of this kind then; every stream is shorter than 1 MiB and size_hint is the largest of them): each stream is
+// compressed as BrotliEncoderCompress would compress it alone, its bytes start on a byte boundary of the output and
+// stream_end[k] (host, n + 1 entries) receives the byte offset where stream k ends.
 struct BrCuts { const uint32_t* pos; const uint32_t* kind; uint32_t n; int is_final; int with_header; int finish_empty; uint64_t* end_bit;
-                int lgblock; int disable_ctx; uint32_t stream_offset; };
+                int lgblock; int disable_ctx; uint32_t stream_offset; uint64_t* stream_end; };
 extern "C" {
 BrJob* br_job_create(void);
 void br_job_destroy(BrJob*);

@@ -41,6 +41,8 @@ struct BrParams {
   u32 max_epochs;   // size of the per-launch arrays (a bound no input reaches: see br_kernels.cu)
   u32 step_cap;     // successor-walk budget per flipped bit in the dependency marking; beyond it the block-level rule
   u32 heavy_min;    // buckets with at least this many positions take the counter-wrap path (65536; tests lower it)
+  u32 multi;        // != 0: the job is a BATCH of this many independent streams laid end to end in `data` (cuts of kind 3,
+                    // br_params.h): every position-dependent rule counts from the stream's first byte (BrBlk::base)
 };
 
 // The unit of speculation is a CHUNK: a slice (1 << BR_CHUNK_BITS bytes) of one of the
@@ -65,6 +67,7 @@ struct BrBlockIn {
   u32 is_last;           // block flags (copied to all its chunks)
   u32 force_flush;       // BROTLI_OPERATION_FLUSH ended the input here (encode.c:1700)
   u32 warm;              // != 0: the state above is a guess; walk this many bytes before `pos` first to refine it
+  u32 base;              // first byte of the stream the block belongs to (0 unless BrParams::multi)
 };
 #define BR_WARM_BYTES 256
 // What the walker reports back.
@@ -97,6 +100,7 @@ struct BrBlk {
   u32 lc_copy_len, lc_dist_prefix, lc_dist_extra;   // the block's last command
   int changed_epoch;
   u32 state_dirty;   // br_chain_c: the block holds a chunk whose in-state is off (a sweep starts in it)
+  u32 base, send;    // [base, send): the stream the block belongs to ([0, n) unless BrParams::multi)
 };
 // What the block-to-block recurrence derives for an input block (br_chain_b -> br_chain_c).
 struct BrBlkIn {
@@ -118,6 +122,7 @@ struct BrMetaBlock {
   u32 tail_insert;       // insert-only command appended at flush (0 if none)
   u32 out_bits;          // bits produced by the compressed encoder (relative, from bit 0)
   u32 scratch_off;
+  u32 base;              // first byte of the metablock's stream (literal contexts see zeros in front of it)
 };
 
 // BrStream::dirty[] values: 0 clean; reason (1..5) = scheduled for the next walker launch; with a BR_DEFER_* bit the

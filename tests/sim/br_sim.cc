@@ -15,6 +15,7 @@
 #ifdef BR_SIM_ENTROPY
 #include "../../brotli_b200/csrc/br_entropy.h"
 #include "../../brotli_b200/csrc/br_entropy2.h"
+#include "../../brotli_b200/csrc/br_assemble.h"
 #endif
 
 struct SimTables {
@@ -84,7 +85,7 @@ static void sim_build_storedS(SimStream& m) {
   }
 }
 
-struct SimCuts { const u32* pos; const u32* kind; u32 n; int is_final; int with_header; int finish_empty; u64* end_bit; u32 size_hint; int lgblock; int disable_ctx; u32 stream_offset; };
+struct SimCuts { const u32* pos; const u32* kind; u32 n; int is_final; int with_header; int finish_empty; u64* end_bit; u32 size_hint; int lgblock; int disable_ctx; u32 stream_offset; u64* stream_end; };
 static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts* cuts = nullptr) {
   SimStream* m = new SimStream();
   BrStream& s = m->s;
@@ -98,10 +99,12 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   if (getenv("BR_SIM_SWEEP_EPOCH")) P.sweep_epoch = (u32)atoi(getenv("BR_SIM_SWEEP_EPOCH"));
   if (getenv("BR_SIM_SWEEP_BLOCKS")) P.sweep_blocks = (u32)atoi(getenv("BR_SIM_SWEEP_BLOCKS"));
   if (getenv("BR_SIM_FORCE_EPOCH")) P.force_epoch = (u32)atoi(getenv("BR_SIM_FORCE_EPOCH"));
+  { u32 ns = 1; for (u32 i = 0; cuts && i < cuts->n; ++i) if (cuts->kind[i] == 3) ++ns;
+    if (ns > 1) { P.multi = ns; P.chunk_bits = getenv("BR_SIM_BATCH_CHUNK_BITS") ? (u32)atoi(getenv("BR_SIM_BATCH_CHUNK_BITS")) : br_batch_chunk_bits(n); } }   // (as br_job_compress_device)
   const u32 ch = 1u << P.chunk_bits;
   std::vector<BrBlockIn> chunks;
   P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
-  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, cuts ? cuts->n : 0, cuts ? (cuts->is_final != 0 && !cuts->finish_empty) : true, &chunks, m->blks);
+  br_build_blocks(P, n, cuts ? cuts->pos : nullptr, cuts ? cuts->n : 0, cuts ? (cuts->is_final != 0 && !cuts->finish_empty) : true, &chunks, m->blks, nullptr, cuts ? cuts->kind : nullptr);
   m->slot_blk.assign(((size_t)n >> P.lgblock) + 2, 0);
   { u32 bb = 0; for (size_t i = 0; i < m->slot_blk.size(); ++i) { const u64 pp = (u64)i << P.lgblock; while (bb + 1 < m->blks.size() && m->blks[bb].end <= pp) ++bb; m->slot_blk[i] = bb; } }
   s.slot_blk = m->slot_blk.data();
@@ -118,7 +121,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
     for (u32 p = m->bin[k].pos; p < m->bin[k].end && p + P.htl <= m->bin[k].blk_end; ++p) m->bits_latest[p >> 5] |= 1u << (p & 31);
   for (size_t bi = 1; bi < m->blks.size(); ++bi) {   // StitchToPreviousBlock positions
     const BrBlk& B = m->blks[bi];
-    if (B.end - B.start >= P.htl - 1 && B.start >= 3)
+    if (B.end - B.start >= P.htl - 1 && B.start - B.base >= 3)
       for (u32 q = B.start - 3; q < B.start; ++q) m->bits_latest[q >> 5] |= 1u << (q & 31);
   }
   m->storedS.assign(words + 32, 0); m->prefS.assign(n / 1024 + 4, 0);
@@ -180,7 +183,8 @@ static void sim_lz77_fixpoint(SimStream& m) {
     s.counters[4] = 0; s.counters[16] = 0;
     s.forced = s.epoch >= s.P.force_epoch;
     { u32 nd = s.counters[5]; std::vector<u32> dl(nd); for (u32 t = 0; t < nd; ++t) dl[t] = br_sched_entry(s, t); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
-      if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
+      if (s.P.multi) { if (s.P.block_bits >= 6) br_walk_block<4, true>(s, k, f); else br_walk_block<1, true>(s, k, f); }
+      else if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
     m.block_runs += s.counters[4];
 #ifdef BR_SIM_DEBUG
     if (getenv("BR_SIM_TRACE")) { fprintf(stderr, "   work: searches %llu rows %llu groups %llu taken %llu | heavy %llu own-scan rows %llu countS %llu | own_set %llu set_range %llu dict %llu\n",
@@ -328,56 +332,39 @@ static long sim_compress_impl(int q, int lgwin, const u8* in, u32 n, u8* out, si
   if (!m) return -1;
   BrStream& s = m->s;
   std::vector<u8> res;
-  std::vector<u32> smem(4096);
   int rounds = 0;
   for (;;) {
     ++rounds;
     sim_lz77_fixpoint(*m);
     u32 nm = s.counters[1];
-    res.clear();
-    u64 bit = 0;
     SimEnt E;
     sim_entropy2(*m, E);
-    if (!cuts || cuts->with_header) { if (lgwin == 17) put_bits_host(res, bit, 7, 1); else put_bits_host(res, bit, 4, ((lgwin - 17) << 1) | 1); }
-    bool redo = false;
-    u32 ncut = 0;
-    for (u32 i = 0; i < nm && !redo; ++i) {
-      BrMetaBlock mb = s.mbs[i];
-      u32 bytes = mb.end - mb.start;
-      bool compressed = mb.compress != 0;
-      if (compressed) {
-        std::vector<u32> obuf((2 * (size_t)bytes + 503) / 4 + 8, 0);
-        const u32 bits = s.mbs[i].out_bits;
-        memcpy(obuf.data(), E.outbits.data() + E.out_off[i], ((size_t)bits + 31) / 32 * 4);
-        u64 storage_ix = (bit & 7) + bits;
-        if (mb.is_last) storage_ix = (storage_ix + 7) & ~7ull;
-        if ((u64)bytes + 4 < (storage_ix >> 3)) {
-          s.force_unc[i] = 1; redo = true; break;   // encode.c:604 late fallback
+    // stream assembly: the shared scan (br_assemble.h), then the copies of k_assemble_copy
+    std::vector<u32> outw(((size_t)n + ((size_t)n >> 3) + 4096 + 8ull * nm) / 4 + 16, 0);
+    std::vector<BrCopyDesc> desc(nm + 1);
+    std::vector<u64> cut_end((cuts ? cuts->n : 0) + 2, 0), stream_end(s.P.multi + 2, 0);
+    u32 r4[4] = {0, 0, 0, 0};
+    br_assemble_scan(s, E.out_off.data(), outw.data(), desc.data(), r4, (!cuts || cuts->with_header) ? 1 : 0, cuts ? cuts->kind : nullptr,
+                     cut_end.data(), stream_end.data());
+    const bool redo = r4[2] != 0;
+    if (!redo) {
+      for (u32 i = 0; i < nm; ++i) {
+        const BrCopyDesc& d = desc[i];
+        if (d.kind == 0) {
+          const u32* src = E.outbits.data() + d.src_off;
+          for (u32 b = 0; b < d.nbits; ++b) if ((src[b >> 5] >> (b & 31)) & 1) { const u64 db = d.dst_bit + b; outw[db >> 5] |= 1u << (db & 31); }
+        } else {
+          u8* ob = (u8*)outw.data() + (d.dst_bit >> 3);
+          memcpy(ob, in + d.src_off, d.nbits);
         }
-        for (u32 b = 0; b < bits; ++b) put_bits_host(res, bit, 1, (obuf[b >> 5] >> (b & 31)) & 1);
-        if (mb.is_last) bit = (bit + 7) & ~7ull;
-      } else {
-        put_bits_host(res, bit, 1, 0);
-        u32 lg = bytes == 1 ? 1 : (32 - __builtin_clz(bytes - 1));
-        u32 mn = (lg < 16 ? 16 : lg + 3) / 4;
-        put_bits_host(res, bit, 2, mn - 4); put_bits_host(res, bit, mn * 4, bytes - 1);
-        put_bits_host(res, bit, 1, 1);
-        bit = (bit + 7) & ~7ull;
-        res.resize(bit >> 3, 0);
-        res.insert(res.end(), in + mb.start, in + mb.end);
-        bit += (u64)bytes * 8;
-        if (mb.is_last) { put_bits_host(res, bit, 2, 3); bit = (bit + 7) & ~7ull; }
       }
-      if (mb.empty_last) { put_bits_host(res, bit, 2, 3); bit = (bit + 7) & ~7ull; }
-      if (mb.flushed && !mb.is_last) {   // k_assemble_scan's cut handling
-        if (cuts->end_bit) cuts->end_bit[ncut] = bit;
-        if (cuts->kind[ncut] == 1 && (bit & 7)) put_bits_host(res, bit, 6, 6);
-        bit = (bit + 7) & ~7ull;
-        ++ncut;
-      }
+      const u64 total = ((u64)r4[1] << 32) | r4[0];
+      res.assign((u8*)outw.data(), (u8*)outw.data() + total);
+      if (cuts && cuts->end_bit) for (u32 i = 0; i < r4[3]; ++i) cuts->end_bit[i] = cut_end[i];
+      if (cuts && cuts->stream_end) for (u32 i = 0; i < s.P.multi; ++i) cuts->stream_end[i] = stream_end[i];
+      break;
     }
-    if (!redo) { res.resize((bit + 7) >> 3, 0); break; }
-    if (rounds > 64) { delete m; return -4; }
+    if (rounds > 64 + (int)s.P.multi) { delete m; return -4; }
   }
   stats[0] = (u32)m->iterations; stats[1] = (u32)m->block_runs; stats[2] = s.P.nblocks; stats[3] = (u32)rounds; stats[4] = (u32)m->model_cost;
   delete m;
@@ -391,7 +378,7 @@ extern "C" long sim_compress(int q, int lgwin, const u8* in, u32 n, u8* out, siz
 extern "C" long sim_compress_cuts(int q, int lgwin, u32 size_hint, const u8* in, u32 n, const u32* cut_pos, const u32* cut_kind, u32 ncuts,
                                   int is_final, int with_header, int finish_empty, u64* end_bit, u8* out, size_t out_cap, u32* stats,
                                   int lgblock, int disable_ctx, u32 stream_offset) {
-  SimCuts c; c.lgblock = lgblock; c.disable_ctx = disable_ctx; c.stream_offset = stream_offset; c.pos = cut_pos; c.kind = cut_kind; c.n = ncuts; c.is_final = is_final; c.with_header = with_header; c.finish_empty = finish_empty; c.end_bit = end_bit; c.size_hint = size_hint;
+  SimCuts c; c.lgblock = lgblock; c.disable_ctx = disable_ctx; c.stream_offset = stream_offset; c.pos = cut_pos; c.kind = cut_kind; c.n = ncuts; c.is_final = is_final; c.with_header = with_header; c.finish_empty = finish_empty; c.end_bit = end_bit; c.size_hint = size_hint; c.stream_end = nullptr;
   return sim_compress_impl(q, lgwin, in, n, out, out_cap, stats, &c);
 }
 #endif
@@ -441,5 +428,19 @@ extern "C" long sim_q1_compress_seg(int lgwin, const u8* in, u32 n, const size_t
 }
 extern "C" long sim_q1_compress(int lgwin, const u8* in, u32 n, const size_t* calls, size_t ncalls, u8* out, size_t out_cap) {
   return sim_q1_compress_seg(lgwin, in, n, calls, ncalls, out, out_cap, 1, 2, 0, nullptr);
+}
+#endif
+
+#ifdef BR_SIM_ENTROPY
+// A batch of independent streams laid end to end (cuts of kind 3, br_pipeline.h): bounds[k] = end of stream k (bounds[ns-1] = n).
+// stream_end[k] receives the byte offset where stream k ends in `out`.
+extern "C" long sim_compress_multi(int q, int lgwin, const u8* in, u32 n, const u32* bounds, u32 nstreams, u64* stream_end,
+                                   u8* out, size_t out_cap, u32* stats) {
+  std::vector<u32> kind(nstreams, 3);
+  u32 hint = 0;
+  for (u32 k = 0; k < nstreams; ++k) { const u32 sz = bounds[k] - (k ? bounds[k - 1] : 0); if (sz > hint) hint = sz; }
+  SimCuts c; memset(&c, 0, sizeof(c));
+  c.pos = bounds; c.kind = kind.data(); c.n = nstreams - 1; c.is_final = 1; c.with_header = 1; c.size_hint = hint; c.stream_end = stream_end;
+  return sim_compress_impl(q, lgwin, in, n, out, out_cap, stats, &c);
 }
 #endif

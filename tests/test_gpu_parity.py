@@ -245,6 +245,35 @@ def test_device_and_batch_api(b200):
         assert bufs[i].raw[:osz[i]] == ora.compress(ins[i], 5, 22), i
 
 
+def test_batch_of_small_streams(b200):
+    """BrotliB200CompressBatch at quality 5..9: streams below 1 MiB run as ONE device job per group (streams laid end to
+    end, cuts of kind 3 in br_pipeline.h); every stream must equal what BrotliEncoderCompress gives for it alone -- sizes
+    1 byte .. 900 KB, empty streams, streams above 1 MiB in the same call, incompressible ones (raw fallback, raw-stream
+    rule), long zero runs (bucket counter wrap), windows smaller than the stream."""
+    from corpus import synth_binary, synth_text, synth_web
+    ora = Oracle()
+    rnd = np.random.RandomState(17)
+    web = synth_web(3_000_000, 81); txt = synth_text(1_000_000, 82); binr = synth_binary(1_000_000, 83)
+    noise = rnd.randint(0, 256, 200000, dtype=np.uint8).tobytes()
+    pool = web + txt + binr + noise + bytes(200000)
+    streams = [web[:65536], b"", b"a", web[:3], noise[:300], noise[:65536], bytes(150000) + web[:1000] + bytes(100000), web[:900000],
+               web[100000:100000 + 1_200_000], txt[:65537], binr[:262144], (b"abcdefgh" * 9000)[:66000], noise[:70000] * 3]
+    for _ in range(120):
+        n = int(rnd.choice([1, 2, 5, 100, 1000, 4096, 20000, 65536, 65536, 65536, 70000, 150000, 400000]))
+        n = max(1, int(n * rnd.uniform(0.5, 1.0)))
+        o = int(rnd.randint(0, len(pool) - n))
+        streams.append(pool[o:o + n])
+    for q, w in ((5, 22), (9, 24), (6, 17), (7, 18)):
+        got = b200.compress_batch(streams, q, w, threads=4)
+        for k, x in enumerate(streams):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    # a batch that fills the GPU takes the 2 KiB chunks (br_params.h br_batch_chunk_bits): 400 x 64 KiB
+    big = [pool[o:o + 65536] for o in [(i * 104729) % (len(pool) - 65536) for i in range(400)]]
+    got = b200.compress_batch(big, 5, 22, threads=4)
+    for k, x in enumerate(big):
+        assert got[k] == ora.compress(x, 5, 22), k
+
+
 @pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
 def test_full_size_properties(b200):
     """BASELINE.json's full size (100 MB, q5, lgwin 22): equality with the reference run on the

@@ -235,6 +235,72 @@ def test_sim_flush_cuts_and_parameters(sim):
             assert _sim_cuts(sim, d, q, w, len(d), [], [], 1, lgblock=lgb, disable_ctx=dis) == want, (q, w, lgb, dis)
 
 
+def _sim_multi(sim, streams, q, w):
+    """streams through the device code as ONE batch job (cuts of kind 3); returns the list of compressed streams"""
+    sim.sim_compress_multi.restype = C.c_long
+    sim.sim_compress_multi.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p]
+    d = b"".join(streams)
+    bounds = np.cumsum([len(x) for x in streams]).astype(np.uint32)
+    ends = np.zeros(len(streams) + 1, np.uint64)
+    cap = len(d) + len(d) // 2 + 4096 + 64 * len(streams)
+    out = C.create_string_buffer(cap)
+    st = np.zeros(8, np.uint32)
+    r = sim.sim_compress_multi(q, w, d, len(d), bounds.ctypes.data, len(streams), ends.ctypes.data, out, cap, st.ctypes.data)
+    assert r >= 0, r
+    assert int(ends[len(streams) - 1]) == r
+    res, a = [], 0
+    for k in range(len(streams)):
+        res.append(out.raw[a:int(ends[k])])
+        a = int(ends[k])
+    return res
+
+
+def test_sim_batch_of_streams(sim):
+    """Many small streams as one device job (br_pipeline.h, cuts of kind 3): every stream must come out exactly as the
+    reference compresses it alone -- fresh distance cache / dictionary counters / ring positions at every stream start,
+    zero literal contexts in front of it, no match, stitch or merged metablock across a boundary, own window bits."""
+    from corpus import synth_binary, synth_text, synth_web
+    ora = Oracle()
+    rnd = np.random.RandomState(11)
+    web = synth_web(700000, 21); txt = synth_text(300000, 22); binr = synth_binary(300000, 23)
+    noise = rnd.randint(0, 256, 100000, dtype=np.uint8).tobytes()
+    streams = [web[:65536], web[65536:131072], txt[:65536], binr[:65536], noise[:65536], web[131072:131072 + 70000],
+               b"a", b"ab", txt[:3], web[:17], bytes(5000), noise[:300], txt[1000:1000 + 65537], web[200000:200000 + 200000],
+               binr[100000:100000 + 131072], noise[:40000] + web[:40000], (b"abcdefgh" * 9000)[:66000], web[:65536]]
+    for q, w in ((5, 22), (6, 18), (9, 24), (7, 17)):
+        got = _sim_multi(sim, streams, q, w)
+        for k, x in enumerate(streams):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    # streams longer than the ring buffer of a small window (positions wrap relative to the stream start), a bucket with
+    # more than 65536 positions of one stream (the reference's uint16 bucket counter wraps), late raw fallbacks
+    big = [web[:300000], bytes(150000) + web[:1000] + bytes(100000), web[300000:300000 + 600000], noise[:70000] * 3,
+           bytes(rnd.randint(0, 4, 90000, dtype=np.uint8)), web[:100]]
+    for q, w in ((5, 17), (8, 18), (6, 22)):
+        got = _sim_multi(sim, big, q, w)
+        for k, x in enumerate(big):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    # random batches (the last ones with the 2 KiB chunks of a batch that fills the GPU)
+    pool = web + txt + binr + noise + bytes(30000)
+    for it in range(8):
+        if it >= 5:
+            os.environ["BR_SIM_BATCH_CHUNK_BITS"] = "11"
+        k = int(rnd.randint(2, 40))
+        ss = []
+        for _ in range(k):
+            n = int(rnd.choice([1, 2, 5, 100, 1000, 4096, 20000, 65536, 65536, 70000, 150000]))
+            n = max(1, int(n * rnd.uniform(0.5, 1.0)))
+            o = int(rnd.randint(0, len(pool) - n))
+            ss.append(pool[o:o + n])
+        q, w = int(rnd.randint(5, 10)), int(rnd.randint(17, 25))
+        try:
+            got = _sim_multi(sim, ss, q, w)
+        finally:
+            os.environ.pop("BR_SIM_BATCH_CHUNK_BITS", None)
+        for j, x in enumerate(ss):
+            assert got[j] == ora.compress(x, q, w), (it, q, w, j, len(x))
+
+
 def test_sim_stream_offset(sim):
     """BROTLI_PARAM_STREAM_OFFSET (encode.h:231, the sanctioned way to stitch shards into one stream): no
     window bits, poisoned distance cache (encode.c:656), dictionary distances counted from the virtual start
