@@ -41,13 +41,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 C2_BYTES, C3_BYTES, C4_BYTES = 100_000_000, 1 << 30, 200_000_000
 C5_COUNT, C5_SIZE = 10_000, 65536
+C5Q5_COUNT = 2_000
 WORKLOADS = {
     "c2": "100 MB enwik8-shaped synthetic text (tests/corpus.py synth_text, seed 20250922+rank), quality 5, lgwin 22, one stream per GPU",
     "c3": "1 GiB synthetic web mix (synth_web, seed 20250923) cut into N shards of 2^30/N bytes, quality 5, lgwin 22, shard i on GPU i",
     "c4": "200 MB Silesia-shaped binary mix (synth_binary, seed 20250924), quality 9, lgwin 24, one stream per GPU (replicas at N > 1)",
     "c5": "10 000 x 64 KiB streams (slices of the c3 mix at offsets i*104729 mod (2^30-65536)), quality 1, lgwin 22, stream j on GPU j mod N",
+    "c5q5": "the first 2 000 of c5's 64 KiB streams at quality 5, lgwin 22 (many small web payloads; not a BASELINE config), stream j on GPU j mod N",
 }
-QL = {"c2": (5, 22), "c3": (5, 22), "c4": (9, 24), "c5": (1, 22)}
+QL = {"c2": (5, 22), "c3": (5, 22), "c4": (9, 24), "c5": (1, 22), "c5q5": (5, 22)}
 METRIC = "encoder input MB/s (bit-exact)"
 # the headline's config: identical in both arms (the driver compares them)
 HEAD_CONFIG = {"workload": WORKLOADS["c2"], "quality": 5, "lgwin": 22, "input_bytes_per_gpu": C2_BYTES,
@@ -165,13 +167,14 @@ def reference_config(cfg, lib, n_gpus, steps, warmup):
             run_threads(n_gpus, lambda i: lib.compress(shards[i], q, w))
     else:
         web = web_mix()
-        streams = [web[o:o + C5_SIZE] for o in c5_offsets()]
+        count = C5_COUNT if cfg == "c5" else C5Q5_COUNT
+        streams = [web[o:o + C5_SIZE] for o in c5_offsets()[:count]]
         cores = ncpu
-        units = C5_COUNT * C5_SIZE
-        sample = "all 10 000 streams per step, dealt over %d host threads (ctypes releases the GIL)" % cores
+        units = count * C5_SIZE
+        sample = "all %d streams per step, dealt over %d host threads (ctypes releases the GIL)" % (count, cores)
         def step():
             def work(k):
-                for i in range(k, C5_COUNT, cores):
+                for i in range(k, count, cores):
                     lib.compress(streams[i], q, w)
             run_threads(cores, work)
     for _ in range(warmup):
@@ -481,6 +484,72 @@ def bench_c5(ctx, steps, warmup):
     return r
 
 
+def bench_c5q5(ctx, steps, warmup):
+    """2 000 x 64 KiB at quality 5 through BrotliB200CompressBatch (host buffers in and out: the call IS the end-to-end
+    path): the streams of a rank run as one device job (br_api.cc compress_stream_group)."""
+    import brotli_b200
+    from brotli_b200.shard import streams_of_rank
+    L, world, rank = ctx.L, ctx.world, ctx.rank
+    q, w = QL["c5q5"]
+    web = web_mix()
+    offs = c5_offsets()
+    mine = streams_of_rank(C5Q5_COUNT, rank, world)
+    cnt = len(mine)
+    streams = [web[offs[j]:offs[j] + C5_SIZE] for j in mine]
+    bufs = [C.create_string_buffer(x, len(x)) for x in streams]
+    sizes = (C.c_size_t * cnt)(*[len(x) for x in streams])
+    caps = [L.BrotliEncoderMaxCompressedSize(len(x)) + 16 for x in streams]
+    outs = [C.create_string_buffer(c) for c in caps]
+    in_ptrs = (C.c_void_p * cnt)(*[C.addressof(b) for b in bufs])
+    out_ptrs = (C.c_void_p * cnt)(*[C.addressof(b) for b in outs])
+    out_sizes = (C.c_size_t * cnt)()
+    nbytes = cnt * C5_SIZE
+
+    def step():
+        for k in range(cnt):
+            out_sizes[k] = caps[k]
+        good = L.BrotliB200CompressBatch(q, w, cnt, in_ptrs, sizes, out_ptrs, out_sizes, 16)
+        assert good == cnt, "BrotliB200CompressBatch: %d of %d" % (good, cnt)
+        return sum(out_sizes[k] for k in range(cnt))
+
+    for _ in range(warmup):
+        step()
+    dt, o = ctx.timed(step, steps)
+    st = brotli_b200.last_stats()
+    kind, lib = ref_lib()
+    ncpu = max(1, (os.cpu_count() or 1) // world)
+    want = [None] * cnt
+    t1 = time.time()
+    def work(k):
+        for i in range(k, cnt, ncpu):
+            want[i] = lib.compress(streams[i], q, w)
+    run_threads(ncpu, work)
+    t_cpu = time.time() - t1
+    ok = all(outs[k].raw[:out_sizes[k]] == want[k] for k in range(cnt))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    total_in = ctx.sum_over_ranks(nbytes)
+    total_out = ctx.sum_over_ranks(o[-1])
+    v = round(total_in * steps / dt / 1e6, 2)
+    r = {"workload": WORKLOADS["c5q5"], "quality": q, "lgwin": w, "steps": steps, "warmup": warmup, "scaling": "strong",
+         "streams": C5Q5_COUNT, "input_bytes": total_in, "compressed_bytes": total_out, "bit_exact": ok,
+         "value": v, "unit": "MB/s", "ms_per_step": round(1e3 * dt / steps, 2),
+         "value_note": "host buffers in and out (pageable): value == e2e for this call",
+         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": total_in, "d2h_bytes_per_step": total_out,
+                 "path": "BrotliB200CompressBatch(host pointer arrays): concat into pinned memory, H2D, one device job per rank, D2H, split"},
+         "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_index", "ms_lz77", "ms_walk", "ms_entropy", "ms_assemble")},
+         "lz77": {"walk_launches": int(st["walk_launches"]), "walked_over_input": round(st["walk_bytes"] / max(1, nbytes), 3)},
+         "gpu_launches": int(st["launches"]) * steps}
+    if world == 1:
+        r["cpu_baseline"] = {"value": round(nbytes / t_cpu / 1e6, 2), "unit": "MB/s", "cores": ncpu, "kind": kind,
+                             "sample": "all %d streams once, dealt over %d host threads" % (cnt, ncpu)}
+    return r
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -488,7 +557,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--configs", default="c2,c4,c3,c5")
+    ap.add_argument("--configs", default="c2,c4,c3,c5,c5q5")
     args = ap.parse_args()
     args.configs = [c for c in args.configs.split(",") if c in WORKLOADS]
     rank = int(os.environ.get("RANK", "0"))
@@ -549,6 +618,8 @@ def main():
             sub[cfg] = bench_stream(ctx, "c3", 3, 1, extra_warm=False)
         elif cfg == "c5":
             sub[cfg] = bench_c5(ctx, 5, 2)
+        elif cfg == "c5q5":
+            sub[cfg] = bench_c5q5(ctx, 5, 2)
         if cfg in sub:
             log("rank %d: %s done in %.1fs" % (rank, cfg, time.time() - t0))
     if rank == 0:

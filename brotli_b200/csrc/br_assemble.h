@@ -10,7 +10,8 @@ BR_DEV u32 br_put_window_bits(u32* out, u64 bit, int lgwin) {
   br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 4, (u64)(((lgwin - 17) << 1) | 1));
   return 4;
 }
-// res[0..1]: total bytes (u64), res[2]: number of metablocks that need the late fallback (marked in force_unc: the FIRST
+// res[0..1]: total bytes (u64), res[2]: number of metablocks that need the late fallback (marked in force_unc under the
+// number of their first chunk, which is what the chain looks up when it forms the metablock again: the FIRST
 // such metablock of every stream -- storing it raw restores the distance cache behind it, so the rest of that stream is
 // parsed again), res[3]: cuts seen.
 // with_header: the stream starts here (window bits); 0 when the caller already sent them (a FLUSH / EMIT_METADATA before any
@@ -39,7 +40,7 @@ BR_DEV void br_assemble_scan(const BrStream& s, const u64* out_off, u32* out, Br
     if (mb.compress) {
       u64 storage_ix = (bit & 7) + mb.out_bits;
       if (mb.is_last) storage_ix = (storage_ix + 7) & ~7ull;
-      if ((u64)bytes + 4 < (storage_ix >> 3) && !skip) { s.force_unc[i] = 1; ++fallbacks; skip = true; }   // encode.c:604
+      if ((u64)bytes + 4 < (storage_ix >> 3) && !skip) { s.force_unc[mb.first_block] = 1; ++fallbacks; skip = true; }   // encode.c:604
       d.dst_bit = bit; d.src_off = out_off[i]; d.nbits = mb.out_bits; d.kind = 0;
       bit += mb.out_bits;
       if (mb.is_last) bit = (bit + 7) & ~7ull;

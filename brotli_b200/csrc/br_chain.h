@@ -146,11 +146,10 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
 }
 
 // encode.c:457 ShouldCompress
-BR_DEV int br_should_compress(const BrStream& s, u32 start, u32 bytes, u32 num_literals, u32 num_commands) {
+BR_DEV int br_should_compress(const BrStream& s, u32* h, u32 start, u32 bytes, u32 num_literals, u32 num_commands) {
   if (bytes <= 2) return 0;
   if (num_commands < (bytes >> 8) + 2) {
     if ((double)num_literals > br_dmul(0.99, (double)bytes)) {
-      u32* h = s.hist_scratch;
       for (u32 i = (u32)br_lane(); i < 256; i += BR_WARP) h[i] = 0;
       br_syncwarp();
       u32 t = (bytes + 12) / 13;
@@ -224,13 +223,10 @@ BR_DEV void br_chain_a(const BrStream& s, u32 bi) {
   s.blk[bi] = B;
 }
 
-BR_DEV void br_chain_b(const BrStream& s) {
+BR_DEV void br_chain_prologue(const BrStream& s) {
   const BrParams& P = s.P;
-  const u32 nblk = s.nblk, t_now = s.epoch;
+  const u32 t_now = s.epoch;
   const int lane = br_lane();
-#if BR_GPU
-  long long t_begin = clock64();
-#endif
   // counter-wrap rule: per launch, the largest number of stored-bit flips any single (heavy) bucket saw
   {
     u32 mx = 0;
@@ -245,13 +241,19 @@ BR_DEV void br_chain_b(const BrStream& s) {
       for (int i = 8; i < 16; ++i) s.counters[i] = 0;
     }
   }
-#if BR_GPU
-  long long t_phase0 = clock64();
-#endif
+}
+
+// The block-to-block recurrence over the input blocks [bi0, bi1) (a whole stream: every stream of a batch is independent of
+// the others).  Command offsets (BrBlkIn::cmd_base, BrMetaBlock::cmd_off) and metablock numbers (BrBlkIn::mb) count from
+// the first block of the range; metablock records go to mbs_out[0..].  hist: 256 words of scratch (br_should_compress).
+BR_DEV void br_chain_blocks(const BrStream& s, u32 bi0, u32 bi1, BrMetaBlock* mbs_out, u32* hist, u32* n_mbs_out, u32* cmd_total_out,
+                            u32* dbg_slow_out) {
+  const BrParams& P = s.P;
+  const int lane = br_lane();
   u32 num_cmds = 0, num_lits = 0, last_insert_len = 0;
   int dc[4] = {4, 11, 15, 16}, saved_dc[4] = {4, 11, 15, 16};
   if (P.stream_offset) for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i] = -16;   // encode.c:656: poisoned distance cache
-  u32 last_flush_pos = 0, first_blk = 0, cmd_total = 0, n_mbs = 0;
+  u32 last_flush_pos = s.blk[bi0].start, first_blk = bi0, cmd_total = 0, n_mbs = 0;
   u64 dict_l = 0, dict_m = 0;
   bool have_last = false;
   u32 lc_copy_len = 0, lc_dist_prefix = 0, lc_dist_extra = 0, lc_chunk = 0, first_blk_chunk = 0, first_blk_cmd_base = 0;
@@ -262,11 +264,11 @@ BR_DEV void br_chain_b(const BrStream& s) {
   // blocks, and the loop takes them out of the lanes' registers with shuffles (the loop-carried state is in registers
   // only, so a block costs arithmetic latency instead of a memory round trip).
   BrBlk mine; memset(&mine, 0, sizeof(mine));
-  for (u32 bi = 0; bi < nblk; ++bi) {
-    if ((bi % BR_WARP) == 0) { const u32 mi = bi + (u32)lane; if (mi < nblk) mine = s.blk[mi]; }
+  for (u32 bi = bi0; bi < bi1; ++bi) {
+    if (((bi - bi0) % BR_WARP) == 0) { const u32 mi = bi + (u32)lane; if (mi < bi1) mine = s.blk[mi]; }
     BrBlk B;
     {
-      const int src = (int)(bi % BR_WARP);
+      const int src = (int)((bi - bi0) % BR_WARP);
       B.start = br_shfl(mine.start, src); B.end = br_shfl(mine.end, src); B.first_chunk = br_shfl(mine.first_chunk, src);
       B.nchunks = br_shfl(mine.nchunks, src); B.is_last = br_shfl(mine.is_last, src); B.force_flush = br_shfl(mine.force_flush, src);
       B.ncmd = br_shfl(mine.ncmd, src); B.nlit_rel = br_shfl(mine.nlit_rel, src); B.has_cmd = br_shfl(mine.has_cmd, src);
@@ -277,7 +279,7 @@ BR_DEV void br_chain_b(const BrStream& s) {
       B.changed_epoch = br_shfl(mine.changed_epoch, src); B.state_dirty = br_shfl(mine.state_dirty, src);
       B.base = br_shfl(mine.base, src); B.send = br_shfl(mine.send, src);
     }
-    if (bi > 0 && B.start == B.base) {
+    if (bi > bi0 && B.start == B.base) {
       // a new stream of the batch begins (the block before carried is_last, so nothing is pending): fresh encoder state
       for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i] = (i == 0 ? 4 : i == 1 ? 11 : i == 2 ? 15 : 16);
       dict_l = dict_m = 0; last_insert_len = 0; have_last = false;
@@ -342,16 +344,16 @@ BR_DEV void br_chain_b(const BrStream& s) {
       const u32 processed = end - last_flush_pos;
       const bool next_fits = processed + blocksize <= P.max_mb;
       if (!B.is_last && !B.force_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) {
-        if (!(P.finish_empty && bi + 1 == nblk)) continue;
+        if (!(P.finish_empty && bi + 1 == s.nblk)) continue;
         closes_stream = true;    // merged, and the FINISH call that brought nothing flushes it as the last metablock
-      } else if (P.finish_empty && bi + 1 == nblk) empty_last = true;
+      } else if (P.finish_empty && bi + 1 == s.nblk) empty_last = true;
     }
     u32 tail = 0;
     if (last_insert_len > 0) { tail = last_insert_len; ++num_cmds; num_lits += tail; last_insert_len = 0; ++cmd_total; }
     const u32 bytes = end - last_flush_pos;
     // (summaries of chunks that never ran are placeholders: do not sample the input for them)
-    int compress = mb_valid ? br_should_compress(s, last_flush_pos, bytes, num_lits, num_cmds) : 1;
-    if (compress && s.force_unc[n_mbs]) compress = 0;
+    int compress = mb_valid ? br_should_compress(s, hist, last_flush_pos, bytes, num_lits, num_cmds) : 1;
+    if (compress && s.force_unc[first_blk_chunk]) compress = 0;   // (late fallback of an earlier round: br_assemble_scan)
     if (!compress) for (int i = 0; i < 4; ++i) dc[i] = saved_dc[i];
     if (lane == 0) {
       BrMetaBlock m;
@@ -363,20 +365,65 @@ BR_DEV void br_chain_b(const BrStream& s) {
       m.prev_byte2 = last_flush_pos > B.base + 1 ? s.data[last_flush_pos - 2] : 0;
       m.base = B.base;
       m.flushed = (u8)B.force_flush; m.empty_last = empty_last ? 1 : 0; m.tail_insert = tail; m.out_bits = 0; m.scratch_off = 0;
-      s.mbs[n_mbs] = m;
+      mbs_out[n_mbs] = m;
     }
     br_syncwarp();
     ++n_mbs;
     last_flush_pos = end; num_cmds = 0; num_lits = 0; have_last = false; first_blk = bi + 1;
     for (int i = 0; i < 4; ++i) saved_dc[i] = dc[i];
   }
-  if (lane == 0) {
+  *n_mbs_out = n_mbs; *cmd_total_out = cmd_total; *dbg_slow_out = dbg_slow;
+}
+
+// one stream: the whole recurrence in one warp
+BR_DEV void br_chain_b(const BrStream& s) {
+#if BR_GPU
+  long long t_begin = clock64();
+#endif
+  br_chain_prologue(s);
+  br_syncwarp();
+#if BR_GPU
+  long long t_phase0 = clock64();
+#endif
+  u32 n_mbs, cmd_total, dbg_slow;
+  br_chain_blocks(s, 0, s.nblk, s.mbs, s.hist_scratch, &n_mbs, &cmd_total, &dbg_slow);
+  if (br_lane() == 0) {
     s.counters[1] = n_mbs; s.counters[2] = cmd_total;
 #if BR_GPU
     long long t_end = clock64();
     s.counters[20] = (u32)((t_phase0 - t_begin) >> 10); s.counters[21] = (u32)((t_end - t_phase0) >> 10); s.counters[22] = dbg_slow;
 #endif
   }
+}
+// A batch of streams (BrParams::multi): the recurrence runs per stream, a warp each (b1); metablock numbers and command
+// offsets are made global by a scan over the streams' totals (b2) and added to what b1 left (b3, thread per input block).
+BR_DEV void br_chain_b1(const BrStream& s, u32 st) {
+  const u32 fb = s.stream_blk[st], lb = s.stream_blk[st + 1];
+  u32 n_mbs, cmd_total, dbg_slow;
+  br_chain_blocks(s, fb, lb, s.mbs_stage + fb, s.hist_scratch + 256u * st, &n_mbs, &cmd_total, &dbg_slow);
+  if (br_lane() == 0) { s.stream_nmb[st] = n_mbs; s.stream_ncmd[st] = cmd_total; }
+}
+BR_DEV void br_chain_b2(const BrStream& s) {   // one warp
+  br_chain_prologue(s);
+  br_syncwarp();
+  const u32 ns = s.P.multi;
+  u32 mb_run = 0, cmd_run = 0;
+  for (u32 st0 = 0; st0 < ns; st0 += BR_WARP) {
+    const u32 st = st0 + (u32)br_lane();
+    const u32 a = st < ns ? s.stream_nmb[st] : 0u, c = st < ns ? s.stream_ncmd[st] : 0u;
+    u32 ta, tc;
+    const u32 ea = br_warp_excl_scan(a, &ta), ec = br_warp_excl_scan(c, &tc);
+    if (st < ns) { s.stream_nmb[st] = mb_run + ea; s.stream_ncmd[st] = cmd_run + ec; }
+    mb_run += ta; cmd_run += tc;
+  }
+  if (br_lane() == 0) { s.stream_nmb[ns] = mb_run; s.stream_ncmd[ns] = cmd_run; s.counters[1] = mb_run; s.counters[2] = cmd_run; }
+}
+BR_DEV void br_chain_b3(const BrStream& s, u32 bi) {
+  const u32 st = s.blk[bi].stream, fb = s.stream_blk[st];
+  const u32 mb0 = s.stream_nmb[st], c0 = s.stream_ncmd[st];
+  s.blkin[bi].cmd_base += c0; s.blkin[bi].mb += mb0;
+  const u32 j = bi - fb;
+  if (j < s.stream_nmb[st + 1] - mb0) { BrMetaBlock m = s.mbs_stage[bi]; m.cmd_off += c0; s.mbs[mb0 + j] = m; }
 }
 
 BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
@@ -509,7 +556,11 @@ BR_DEV u32 br_sched_entry(const BrStream& s, u32 t) {
 // sequential driver for the CPU sim / single-thread use
 BR_DEV void br_chain(const BrStream& s) {
   for (u32 bi = 0; bi < s.nblk; ++bi) br_chain_a(s, bi);
-  br_chain_b(s);
+  if (s.P.multi) {
+    for (u32 st = 0; st < s.P.multi; ++st) br_chain_b1(s, st);
+    br_chain_b2(s);
+    for (u32 bi = 0; bi < s.nblk; ++bi) br_chain_b3(s, bi);
+  } else br_chain_b(s);
   for (u32 bi = 0; bi < s.nblk; ++bi) br_chain_c(s, bi);
   for (u32 k = 0; k < s.P.nblocks; ++k) br_chain_d(s, k);
 }

@@ -219,6 +219,15 @@ __global__ void k_chain_a(BrStream s) {
   if (bi < s.nblk) br_chain_a(s, bi);
 }
 __global__ void __launch_bounds__(32) k_chain_b(BrStream s) { br_chain_b(s); }
+__global__ void __launch_bounds__(128) k_chain_b1(BrStream s) {   // batch of streams: a warp per stream
+  const u32 st = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (st < s.P.multi) br_chain_b1(s, st);
+}
+__global__ void __launch_bounds__(32) k_chain_b2(BrStream s) { br_chain_b2(s); }
+__global__ void k_chain_b3(BrStream s) {
+  const u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi < s.nblk) br_chain_b3(s, bi);
+}
 __global__ void k_chain_c(BrStream s) {
   u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
   if (bi < s.nblk) br_chain_c(s, bi);
@@ -492,6 +501,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   for (int i = 0; i < 14; ++i) add(nb * 4ull + 64);
   add(nblk * sizeof(BrBlk)); add(nblk * sizeof(BrBlkIn)); add((P.nbuckets + 8) * 4ull);
   add(h_slot.size() * 4); add((ncuts + 2) * 4ull); add((ncuts + 2) * 8ull); add((nstreams + 2) * 8ull);
+  add((nstreams + 2) * 4ull * 3); add(nblk * sizeof(BrMetaBlock)); add(1024ull * nstreams);
   // Launch bound: in forced mode every launch finalises at least one input block (at most two launches per block with
   // the conservative block-level re-marks), and a late uncompressed fallback restarts the count at most once per metablock.
   P.max_epochs = 4 * nb + 4096;
@@ -523,7 +533,9 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   u64* d_stream_end = A.take<u64>(nstreams + 2);
   u32* epoch_cum = A.take<u32>((size_t)P.max_epochs + 2);
   BrMetaBlock* mbs = A.take<BrMetaBlock>(nb + 1);
-  u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256);
+  u32* d_stream_blk = A.take<u32>(nstreams + 2); u32* stream_nmb = A.take<u32>(nstreams + 2); u32* stream_ncmd = A.take<u32>(nstreams + 2);
+  BrMetaBlock* mbs_stage = A.take<BrMetaBlock>(nblk);
+  u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256ull * nstreams);
   if (!hist_scratch) return 0;
 
   CK(cudaMemcpyAsync(data, d_in, n, cudaMemcpyDeviceToDevice, st));
@@ -543,6 +555,10 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 
   CK(cudaMemcpyAsync(d_blk, hblk.data(), nblk * sizeof(BrBlk), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(slot_blk, h_slot.data(), h_slot.size() * 4, cudaMemcpyHostToDevice, st));
+  std::vector<u32> h_stream_blk(nstreams + 1, nblk);
+  for (u32 bi = nblk; bi-- > 0;) h_stream_blk[hblk[bi].stream] = bi;
+  CK(cudaMemcpyAsync(d_stream_blk, h_stream_blk.data(), (nstreams + 1) * 4ull, cudaMemcpyHostToDevice, st));
+  s.stream_blk = d_stream_blk; s.stream_nmb = stream_nmb; s.stream_ncmd = stream_ncmd; s.mbs_stage = mbs_stage;
   if (ncuts) CK(cudaMemcpyAsync(d_cut_kind, cuts->kind, ncuts * 4, cudaMemcpyHostToDevice, st));
   s.slot_blk = slot_blk;
   CK(cudaMemsetAsync(bin, 0, nb * sizeof(BrBlockIn), st));
@@ -588,7 +604,11 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     const u32 round_epoch0 = s.epoch;
     for (;;) {
       k_chain_a<<<(nblk + 31) / 32, 32, 0, st>>>(s);
-      k_chain_b<<<1, 32, 0, st>>>(s);
+      if (P.multi) {
+        k_chain_b1<<<(P.multi + 3) / 4, 128, 0, st>>>(s);
+        k_chain_b2<<<1, 32, 0, st>>>(s);
+        k_chain_b3<<<(nblk + 255) / 256, 256, 0, st>>>(s);
+      } else k_chain_b<<<1, 32, 0, st>>>(s);
       k_chain_c<<<(nblk + 31) / 32, 32, 0, st>>>(s);
       k_chain_d<<<(nb + 255) / 256, 256, 0, st>>>(s);
       CK(cudaMemcpyAsync(hp, counters, 128, cudaMemcpyDeviceToHost, st));

@@ -56,6 +56,7 @@ static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u3
   const u32 bs = 1u << P.lgblock, ch = 1u << P.chunk_bits;
   u32 ci = 0, total = 0;
   u64 bstart = 0, base = 0;
+  u32 stream = 0;
   while (bstart < n) {
     while (ci < ncuts && cuts[ci] <= bstart) ++ci;
     u64 bend = bstart + bs < n ? bstart + bs : n;
@@ -63,7 +64,7 @@ static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u3
     if (ci < ncuts && cuts[ci] <= bend) { bend = cuts[ci]; forced = true; stream_end = kinds && kinds[ci] == 3; }
     BrBlk B; memset(&B, 0, sizeof(B));
     B.start = (u32)bstart; B.end = (u32)bend; B.is_last = ((is_final && bend == n) || stream_end) ? 1u : 0u;
-    B.base = (u32)base;
+    B.base = (u32)base; B.stream = stream;
     B.force_flush = forced && !B.is_last ? 1u : 0u; B.changed_epoch = -1;
     B.first_chunk = total;
     B.nchunks = (u32)((bend - bstart + ch - 1) / ch);
@@ -78,7 +79,7 @@ static inline void br_build_blocks(const BrParams& P, u32 n, const u32* cuts, u3
     total += B.nchunks;
     blks.push_back(B);
     bstart = bend;
-    if (stream_end) base = bend;
+    if (stream_end) { base = bend; ++stream; }
   }
   { u32 send = n; for (size_t i = blks.size(); i-- > 0;) { if (blks[i].is_last) send = blks[i].end; blks[i].send = send; } }
   if (nchunks_total) *nchunks_total = total;

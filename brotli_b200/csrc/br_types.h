@@ -101,6 +101,7 @@ struct BrBlk {
   int changed_epoch;
   u32 state_dirty;   // br_chain_c: the block holds a chunk whose in-state is off (a sweep starts in it)
   u32 base, send;    // [base, send): the stream the block belongs to ([0, n) unless BrParams::multi)
+  u32 stream;        // index of that stream
 };
 // What the block-to-block recurrence derives for an input block (br_chain_b -> br_chain_c).
 struct BrBlkIn {
@@ -184,7 +185,12 @@ struct BrStream {
   BrMetaBlock* mbs;      // [max_mbs]
   u32* force_unc;        // [max_mbs] late fallback: store this metablock uncompressed
   u32* counters;         // [8]: 0 n_dirty, 1 n_mbs, 2 total cmds, 3 error flags, 4 chunks walked this launch, 5 chunks scheduled, 6 first scheduled chunk, 7 last launch entered in epoch_cum (+1), 8.. dirty reasons
-  u32* hist_scratch;     // [256]
+  u32* hist_scratch;     // [256] (batch of streams: 256 per stream)
+  // batch of streams (BrParams::multi): the chain runs per stream (br_chain_b1..b3)
+  const u32* stream_blk; // [multi + 1] first input block of every stream
+  u32* stream_nmb;       // [multi + 1] metablocks of every stream, then (exclusive scan) the number of its first metablock
+  u32* stream_ncmd;      // [multi + 1] likewise for commands
+  BrMetaBlock* mbs_stage;  // [nblk] metablock records of stream k at [stream_blk[k] ..), before they are numbered
   // tables
   const u8* dict;        // RFC 7932 dictionary
   const u32* dict_offsets;  // [32]

@@ -47,7 +47,8 @@ struct SimStream {
   std::vector<BrBlk> blks;
   std::vector<BrBlkIn> blkin;
   std::vector<u32> key_flips;
-  std::vector<u32> dirty_list, ran_list, slot_blk;
+  std::vector<u32> dirty_list, ran_list, slot_blk, stream_blk, stream_nmb, stream_ncmd;
+  std::vector<BrMetaBlock> mbs_stage;
   int iterations = 0;
   u64 block_runs = 0;
   double model_cost = 0;
@@ -129,7 +130,13 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   P.max_epochs = 4 * nb + 4096;
   m->epoch_cum.assign(P.max_epochs + 2, 0);
   m->ext_total.assign(nb, 0); m->lil_in.assign(nb, 0); m->cmd_off.assign(nb, 0); m->force_unc.assign(nb + 1, 0);
-  m->counters.assign(64, 0); m->hist.assign(256, 0); m->mbs.resize(nb + 1);
+  m->counters.assign(64, 0); m->hist.assign(256 * (size_t)(P.multi ? P.multi : 1), 0); m->mbs.resize(nb + 1);
+  if (P.multi) {
+    m->stream_blk.assign(P.multi + 1, (u32)m->blks.size());
+    for (size_t bi = m->blks.size(); bi-- > 0;) m->stream_blk[m->blks[bi].stream] = (u32)bi;
+    m->stream_nmb.assign(P.multi + 1, 0); m->stream_ncmd.assign(P.multi + 1, 0); m->mbs_stage.resize(m->blks.size());
+    s.stream_blk = m->stream_blk.data(); s.stream_nmb = m->stream_nmb.data(); s.stream_ncmd = m->stream_ncmd.data(); s.mbs_stage = m->mbs_stage.data();
+  }
   s.cmd_stride = ch / 2 + 2;
   m->cmd_blocks.resize((size_t)nb * s.cmd_stride);
   s.bits_latest = m->bits_latest.data(); s.bits_cur = m->bits_cur.data(); s.bits_words = (u32)m->bits_latest.size();

@@ -280,6 +280,16 @@ def test_sim_batch_of_streams(sim):
         got = _sim_multi(sim, big, q, w)
         for k, x in enumerate(big):
             assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    # late raw fallbacks (encode.c:604) in many streams of one job: small-alphabet noise passes ShouldCompress and codes
+    # larger than its input; every stream's first such metablock is stored raw in the same round (br_assemble_scan)
+    fb = []
+    for i in range(30):
+        n, k = int(rnd.randint(200, 5000)), int(rnd.choice([3, 8, 40, 200, 256]))
+        fb.append(bytes(rnd.randint(0, k, n, dtype=np.uint8)) + (web[:int(rnd.randint(1, 300))] if i % 3 == 0 else b""))
+    for q, w in ((5, 22), (9, 18)):
+        got = _sim_multi(sim, fb, q, w)
+        for k, x in enumerate(fb):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
     # random batches (the last ones with the 2 KiB chunks of a batch that fills the GPU)
     pool = web + txt + binr + noise + bytes(30000)
     for it in range(8):
