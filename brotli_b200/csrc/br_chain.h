@@ -454,6 +454,15 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     }
     ni.dict_l_lo = (u32)dict_l; ni.dict_l_hi = (u32)(dict_l >> 32);
     ni.dict_m_lo = (u32)dict_m; ni.dict_m_hi = (u32)(dict_m >> 32);
+    if (s.P.multi && !s.bout[k].valid && !(c == 0 && B.start == B.base)) {
+      // Batch of streams, first walk of a chunk that is not the first of its stream: the counters in front of it are not
+      // known yet.  Guess the static-dictionary gate (hash.h:186) CLOSED: it closes within the first kilobytes of a
+      // stream and stays closed, and a walk made with the gate closed is valid for every closed state -- with the gate
+      // guessed open, every chunk that finds a dictionary word has to be walked again once the true (closed) state is
+      // known (44% of the chunks of 64 KiB web payloads).  The chunks where it really is open are chased from the
+      // stream's first chunk (`defer` below).
+      ni.dict_l_lo = 0; ni.dict_l_hi = 1u; ni.dict_m_lo = 0; ni.dict_m_hi = 0;
+    }
     u32 rel = s.lil_in[k];
     u32 lil_true = (rel & 0x7fffffffu) + ((rel & 0x80000000u) ? W.lil_in : 0u);
     ni.last_insert_len = lil_true;
@@ -479,7 +488,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
     // From the third launch on, a chunk whose only problem is the state handed over by a dirty
     // predecessor is not scheduled: the predecessor's walker chases into it (br_walk_block), which
     // resolves a serial ripple in one launch instead of one launch per chunk.
-    bool defer = dirty == 2 && prev_dirty && t_now >= 2;
+    bool defer = (dirty == 2 && prev_dirty && t_now >= 2) || (s.P.multi && dirty == 3 && prev_dirty && t_now >= 1);
     // Sweep mode (from launch sweep_epoch on).  Two kinds of dirt need opposite treatment:
     //  * STATE (reason 2, 3): the parse really arrives here in another state (position phase of the sparse search on
     //    incompressible data, distance cache).  Everything behind it in the input block is suspect, and only a walker
@@ -538,6 +547,7 @@ BR_DEV void br_chain_d(const BrStream& s, u32 k) {
     for (u32 j = g0; j < bi; ++j) if (s.blk[j].state_dirty && s.blk[j].base == s.blk[bi].base) { d |= BR_DEFER_SWEEP; break; }
   }
   s.dirty[k] = d;
+  if (s.P.pilot && t_now == 0 && k != 0) return;   // pilot launch: chunk 0 only (the others stay dirty, unscheduled)
   if (!(d & BR_DEFER)) {
     // Sweep heads (state-dirty chunks) go to the FRONT of the list, the rest is filled from the back: CTAs start in list
     // order, so the long serial sweeps begin with the launch instead of trailing behind thousands of one-chunk walkers.

@@ -468,7 +468,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     // a batch of independent streams (each below BR_SMALL_STREAM, size_hint = the largest): no FLUSH cuts, all finished
     if (nstreams != ncuts + 1 || !cuts->is_final || !cuts->with_header || cuts->finish_empty || cuts->stream_offset ||
         cuts->pos[ncuts - 1] >= n || size_hint >= BR_SMALL_STREAM) return 0;
-    P.multi = nstreams;
+    P.multi = nstreams; P.pilot = 0;
     P.chunk_bits = br_batch_chunk_bits(n);
   }
   const u32 ch = 1u << P.chunk_bits;

@@ -34,6 +34,7 @@ static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n,
   P->step_cap = 4096;
   P->sweep_epoch = 3;    // text / web input settles in 3 launches; what is still dirty then is swept run by run
   P->force_epoch = 64;
+  P->pilot = n >= BR_SMALL_STREAM ? 1u : 0u;   // (a small stream's latency is launches: no extra one)
   P->sweep_blocks = P->lgblock >= 21 ? 1u : (1u << (21 - P->lgblock));   // sweeps are at most 2 MiB of input long
   return 1;
 }

@@ -41,6 +41,9 @@ struct BrParams {
   u32 max_epochs;   // size of the per-launch arrays (a bound no input reaches: see br_kernels.cu)
   u32 step_cap;     // successor-walk budget per flipped bit in the dependency marking; beyond it the block-level rule
   u32 heavy_min;    // buckets with at least this many positions take the counter-wrap path (65536; tests lower it)
+  u32 pilot;        // != 0: the first launch walks only the stream's first chunk: the static-dictionary gate (hash.h:186) nearly
+                    // always closes inside it, and then every other chunk starts with the exact (closed) counters -- no dictionary
+                    // probes in the big launch, no re-walk of chunks that found dictionary words under an open-gate guess
   u32 multi;        // != 0: the job is a BATCH of this many independent streams laid end to end in `data` (cuts of kind 3,
                     // br_params.h): every position-dependent rule counts from the stream's first byte (BrBlk::base)
 };

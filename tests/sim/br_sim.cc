@@ -99,9 +99,10 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   if (getenv("BR_SIM_STEP_CAP")) P.step_cap = (u32)atoi(getenv("BR_SIM_STEP_CAP"));
   if (getenv("BR_SIM_SWEEP_EPOCH")) P.sweep_epoch = (u32)atoi(getenv("BR_SIM_SWEEP_EPOCH"));
   if (getenv("BR_SIM_SWEEP_BLOCKS")) P.sweep_blocks = (u32)atoi(getenv("BR_SIM_SWEEP_BLOCKS"));
+  if (getenv("BR_SIM_PILOT")) P.pilot = (u32)atoi(getenv("BR_SIM_PILOT"));
   if (getenv("BR_SIM_FORCE_EPOCH")) P.force_epoch = (u32)atoi(getenv("BR_SIM_FORCE_EPOCH"));
   { u32 ns = 1; for (u32 i = 0; cuts && i < cuts->n; ++i) if (cuts->kind[i] == 3) ++ns;
-    if (ns > 1) { P.multi = ns; P.chunk_bits = getenv("BR_SIM_BATCH_CHUNK_BITS") ? (u32)atoi(getenv("BR_SIM_BATCH_CHUNK_BITS")) : br_batch_chunk_bits(n); } }   // (as br_job_compress_device)
+    if (ns > 1) { P.pilot = 0; P.multi = ns; P.chunk_bits = getenv("BR_SIM_BATCH_CHUNK_BITS") ? (u32)atoi(getenv("BR_SIM_BATCH_CHUNK_BITS")) : br_batch_chunk_bits(n); } }   // (as br_job_compress_device)
   const u32 ch = 1u << P.chunk_bits;
   std::vector<BrBlockIn> chunks;
   P.finish_empty = cuts && cuts->finish_empty ? 1u : 0u;
@@ -206,6 +207,10 @@ static void sim_lz77_fixpoint(SimStream& m) {
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
     if (s.epoch + 2 >= s.P.max_epochs) { fprintf(stderr, "sim: no fixpoint\n"); break; }
+  }
+  if (getenv("BR_SIM_TRACE")) {   // the static-dictionary gate (hash.h:186) at the fixpoint: chunks that start with it closed
+    u32 closed = 0, hits = 0; for (u32 k = 0; k < nb; ++k) { const u64 l = ((u64)s.bin[k].dict_l_hi << 32) | s.bin[k].dict_l_lo, mm = ((u64)s.bin[k].dict_m_hi << 32) | s.bin[k].dict_m_lo; if (mm < (l >> 7)) ++closed; if (s.bout[k].dm) ++hits; }
+    fprintf(stderr, "dictionary gate: %u of %u chunks start with the gate closed; %u chunks found dictionary matches\n", closed, nb, hits);
   }
   if (getenv("BR_SIM_VERIFY")) {
     // Is the fixpoint self-consistent?  Re-walk every chunk from its final in-state against the final
