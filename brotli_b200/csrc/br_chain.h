@@ -509,6 +509,11 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
       else if (dirty == 2 || dirty == 3) sweeping = true;   // head of a sweep (or chased by the walker of the chunk before it: `defer`)
       else if (sweeping) defer_sweep = BR_DEFER_SWEEP;
     }
+    // Batch of streams, first launch: the walker of a stream's first chunk (the one chunk whose in-state is exact) goes
+    // on through the next BR_BATCH_HEAD_CHUNKS - 1 chunks: the head of a stream is where guesses are worst (the
+    // dictionary gate is still open, the window is empty), and 2 000 long-running warps next to 60 000 one-chunk walkers
+    // cost the launch nothing, while the same chunks chased one launch later cost a whole latency-bound launch.
+    if (s.P.multi && t_now == 0 && dirty == 1 && B.start == B.base && c >= 1 && c < BR_BATCH_HEAD_CHUNKS) defer_sweep = BR_DEFER_FULL;
     if (sweep_mode && !full_sweep && (dirty == 2 || dirty == 3)) blk_state_dirty = 1;
     prev_dirty = dirty != 0;
     s.bin[k] = ni;
@@ -551,7 +556,8 @@ BR_DEV void br_chain_d(const BrStream& s, u32 k) {
   if (!(d & BR_DEFER)) {
     // Sweep heads (state-dirty chunks) go to the FRONT of the list, the rest is filled from the back: CTAs start in list
     // order, so the long serial sweeps begin with the launch instead of trailing behind thousands of one-chunk walkers.
-    if (sweep_mode && (d == 2 || d == 3)) { u32 slot = br_atomic_add(s.counters + 17, 1); s.dirty_list[slot] = k; }
+    const bool stream_head = s.P.multi && t_now == 0 && s.bin[k].first && s.bin[k].blk_start == s.bin[k].base;
+    if ((sweep_mode && (d == 2 || d == 3)) || stream_head) { u32 slot = br_atomic_add(s.counters + 17, 1); s.dirty_list[slot] = k; }
     else { u32 slot = br_atomic_add(s.counters + 18, 1); s.dirty_list[s.P.nblocks - 1u - slot] = k; }
     br_atomic_add(s.counters + 5, 1);
     br_atomic_min(s.counters + 6, k);

@@ -139,6 +139,7 @@ struct BrMetaBlock {
 #define BR_DEFER_SWEEP 0x200u
 #define BR_DEFER_FULL 0x400u
 #define BR_DEFER (BR_DEFER_STATE | BR_DEFER_SWEEP | BR_DEFER_FULL)
+#define BR_BATCH_HEAD_CHUNKS 16u   // batch of streams: chunks the walker of a stream's first chunk covers in the first launch (br_chain_c)
 
 // Device-resident view of one stream (all pointers are device pointers).
 struct BrStream {
