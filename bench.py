@@ -542,7 +542,7 @@ def bench_c5q5(ctx, steps, warmup):
          "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": total_in, "d2h_bytes_per_step": total_out,
                  "path": "BrotliB200CompressBatch(host pointer arrays): concat into pinned memory, H2D, one device job per rank, D2H, split"},
          "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_index", "ms_lz77", "ms_walk", "ms_entropy", "ms_assemble")},
-         "lz77": {"walk_launches": int(st["walk_launches"]), "walked_over_input": round(st["walk_bytes"] / max(1, nbytes), 3)},
+         "lz77": {"walk_launches": int(st["walk_launches"]), "chunk_walks": int(st["block_runs"]), "chunks": int(st["blocks"])},
          "gpu_launches": int(st["launches"]) * steps}
     if world == 1:
         r["cpu_baseline"] = {"value": round(nbytes / t_cpu / 1e6, 2), "unit": "MB/s", "cores": ncpu, "kind": kind,
