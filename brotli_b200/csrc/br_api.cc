@@ -231,6 +231,9 @@ int q1_run(const Params& p, const uint8_t* in, size_t n, const size_t* calls, si
 // BrotliEncoderCompress adds around the encoder (encode.c:1345 raw-stream rule) is applied per stream.  Returns the
 // number of streams compressed.
 static const size_t kBatchGroupBytes = (size_t)128 << 20;
+// ... and at most this many streams: every metablock owns ~1.9 MB of scratch in the entropy stage (histograms for up to 256
+// block types per category, br_entropy.h BrMbMem), and a stream is at least one metablock
+static const size_t kBatchGroupStreams = 8192;
 template <class F> void batch_threads(int threads, size_t count, F f) {
   if (threads <= 1 || count < 64) { f(0, count); return; }
   std::vector<std::thread> th;
@@ -535,7 +538,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
   size_t group_bytes = 0;
   for (size_t i = 0; i < count; ++i) {
     if (input_sizes[i] == 0 || input_sizes[i] >= ((size_t)1 << 20)) { big.push_back(i); continue; }
-    if (group_bytes + input_sizes[i] > kBatchGroupBytes && !group.empty()) {
+    if ((group_bytes + input_sizes[i] > kBatchGroupBytes || group.size() >= kBatchGroupStreams) && !group.empty()) {
       ok += compress_stream_group(quality, lgwin, group, inputs, input_sizes, outputs, encoded_sizes, threads);
       group.clear(); group_bytes = 0;
     }

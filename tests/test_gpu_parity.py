@@ -267,6 +267,15 @@ def test_batch_of_small_streams(b200):
         got = b200.compress_batch(streams, q, w, threads=4)
         for k, x in enumerate(streams):
             assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    # 20 000 tiny streams (1 .. 2 000 bytes): several groups of at most 8 192 streams (br_api.cc kBatchGroupStreams)
+    tiny = []
+    for _ in range(20000):
+        n = int(rnd.choice([1, 2, 3, 7, 30, 200, 700, 2000]))
+        o = int(rnd.randint(0, len(pool) - n))
+        tiny.append(pool[o:o + n])
+    got = b200.compress_batch(tiny, 5, 22, threads=4)
+    for k, x in enumerate(tiny):
+        assert got[k] == ora.compress(x, 5, 22), (k, len(x))
     # a batch that fills the GPU takes the 2 KiB chunks (br_params.h br_batch_chunk_bits): 400 x 64 KiB
     big = [pool[o:o + 65536] for o in [(i * 104729) % (len(pool) - 65536) for i in range(400)]]
     got = b200.compress_batch(big, 5, 22, threads=4)
