@@ -221,6 +221,17 @@ def test_sim_flush_cuts_and_parameters(sim):
                 else:
                     got = _sim_cuts(sim, d, q, w, hint, cuts, [1] * len(cuts), 1)
                 assert got == want, (q, w, sizes, ops)
+    # quality 7..9 above 1 MiB: the pilot launch (BrParams::pilot) with the input cut by FLUSH, incl. a first block of 2 bytes
+    d = synth_web(1_400_000, 3)
+    for q, w in ((9, 24), (7, 18)):
+        for sizes, ops in (([500000, 0, 900000, 0], [1, 1, 0, 2]), ([2, 700000, 699998], [1, 1, 2])):
+            want = ref_stream_ops(ref, d, q, w, sizes, ops)
+            cuts, pos = [], 0
+            for a, op in zip(sizes, ops):
+                pos += a
+                if op == 1 and pos and (not cuts or cuts[-1] != pos):
+                    cuts.append(pos)
+            assert _sim_cuts(sim, d, q, w, sizes[0], cuts, [1] * len(cuts), 1) == want, (q, w, sizes)
     d = synth_web(2 * 262144, 9)
     for q, w in ((5, 22), (9, 24)):
         want = ref_stream_ops(ref, d, q, w, [len(d), 0], [0, 2])          # FINISH without input behind full blocks
