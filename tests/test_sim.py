@@ -322,6 +322,34 @@ def test_sim_batch_of_streams(sim):
             assert got[j] == ora.compress(x, q, w), (it, q, w, j, len(x))
 
 
+def test_sim_batch_fuzz_sample(sim):
+    """The structured fuzz inputs (tests/fuzz_cases.py: periodic, dictionary words, noise, heavy buckets ...) grouped by
+    (quality, lgwin) and compressed a dozen at a time as one batch job, with both chunk sizes."""
+    import collections
+    from fuzz_cases import cases, dict_cases
+    ora = Oracle()
+    groups = collections.defaultdict(list)
+    for src in (cases(4242, 160), dict_cases(4242, 40, TABLES)):
+        for i, d, q, w in src:
+            if 5 <= q <= 9 and 17 <= w <= 24 and 0 < len(d) < (1 << 20):
+                groups[(q, w)].append(d)
+    checked = 0
+    for (q, w), lst in sorted(groups.items()):
+        for a in range(0, len(lst), 12):
+            part = lst[a:a + 12]
+            if len(part) < 2:
+                continue
+            os.environ["BR_SIM_BATCH_CHUNK_BITS"] = "11" if (a // 12) % 2 else "9"
+            try:
+                got = _sim_multi(sim, part, q, w)
+            finally:
+                os.environ.pop("BR_SIM_BATCH_CHUNK_BITS", None)
+            for k, x in enumerate(part):
+                assert got[k] == ora.compress(x, q, w), (q, w, a, k, len(x))
+                checked += 1
+    assert checked > 100
+
+
 def test_sim_stream_offset(sim):
     """BROTLI_PARAM_STREAM_OFFSET (encode.h:231, the sanctioned way to stitch shards into one stream): no
     window bits, poisoned distance cache (encode.c:656), dictionary distances counted from the virtual start
