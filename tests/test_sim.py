@@ -291,6 +291,12 @@ def test_sim_batch_of_streams(sim):
         got = _sim_multi(sim, big, q, w)
         for k, x in enumerate(big):
             assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    # several streams that each wrap the counter of the SAME bucket: the count must start at the stream's own first position
+    zz = [bytes(200000), bytes(180000) + web[:500] + bytes(90000), b"\x01" * 150000, bytes(70000), web[:100000], bytes(300000)]
+    for q, w in ((5, 22), (9, 18)):
+        got = _sim_multi(sim, zz, q, w)
+        for k, x in enumerate(zz):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
     # late raw fallbacks (encode.c:604) in many streams of one job: small-alphabet noise passes ShouldCompress and codes
     # larger than its input; every stream's first such metablock is stored raw in the same round (br_assemble_scan)
     fb = []
