@@ -42,7 +42,7 @@ extern "C" {
 BROTLI_B200_API BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, size_t input_size, const void* d_input, size_t* encoded_size, void* d_encoded);
 /* Many independent streams (one stream per shard / per object).  Inputs and
  * outputs are host pointers; every stream comes out exactly as BrotliEncoderCompress(quality, lgwin, GENERIC) gives it.
- * Quality 5..9: streams shorter than 1 MiB are laid end to end and run as ONE device job per group of <= 128 MiB (one
+ * Quality 5..9: streams shorter than 1 MiB are laid end to end and run as ONE device job per group of <= 128 MiB / 8192 streams (one
  * set of launches, one copy each way; `threads` parallelises the host-side packing); longer streams are spread over
  * `threads` host workers, each with its own CUDA stream.  Quality 1 (compress_fragment_two_pass.c:612, one independent
  * fragment coder per stream): the whole batch is ONE device batch -- four kernel launches, one copy each way.  encoded_sizes[i]: in = capacity of outputs[i], out = bytes written.
