@@ -612,14 +612,19 @@ def main():
     sub = {}
     for cfg in args.configs:
         t0 = time.time()
-        if cfg == "c4":
-            sub[cfg] = bench_stream(ctx, "c4", 1, 1, extra_warm=False)
-        elif cfg == "c3":
-            sub[cfg] = bench_stream(ctx, "c3", 3, 1, extra_warm=False)
-        elif cfg == "c5":
-            sub[cfg] = bench_c5(ctx, 5, 2)
-        elif cfg == "c5q5":
-            sub[cfg] = bench_c5q5(ctx, 5, 2)
+        try:
+            if cfg == "c4":
+                sub[cfg] = bench_stream(ctx, "c4", 1, 1, extra_warm=False)
+            elif cfg == "c3":
+                sub[cfg] = bench_stream(ctx, "c3", 3, 1, extra_warm=False)
+            elif cfg == "c5":
+                sub[cfg] = bench_c5(ctx, 5, 2)
+            elif cfg == "c5q5":
+                sub[cfg] = bench_c5q5(ctx, 5, 2)
+        except Exception as e:      # a sub-result must not take the headline line with it (one rank: the others would hang)
+            if world > 1:
+                raise
+            sub[cfg] = {"workload": WORKLOADS[cfg], "error": repr(e)}
         if cfg in sub:
             log("rank %d: %s done in %.1fs" % (rank, cfg, time.time() - t0))
     if rank == 0:
