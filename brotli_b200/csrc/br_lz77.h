@@ -338,10 +338,13 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   {
     const u32 block_size = 1u << P.block_bits;
     u32 V = block_size;
-    if (hi - lo >= P.heavy_min && cur - w.base >= 65536u) {
+    if (hi - lo >= P.heavy_min) {
       // The reference's per-bucket counter is a uint16 (hash_longest_match64_inc.h:52): after
-      // 65536 insertions it wraps and the ring looks empty again.  c = insertions so far (of this stream: it cannot
-      // reach 65536 before the stream is that long).
+      // 65536 insertions it wraps and the ring looks empty again.  c = insertions so far (of this stream).
+      // (Not skipped while the stream is shorter than 65536 bytes, although c cannot wrap there: the sensitivity this
+      // path records -- min_wrap = 0 while the ring is not full -- also re-walks chunks whose view reached through their
+      // own freshly unstored positions into a range that flipped in the same launch, which the successor count of
+      // br_commit_bits, taken over the previous snapshot, can miss: DESIGN.md section 3, "known gap".)
       u32 lo_s = lo;
       if (w.base) {   // batch of streams: the bucket's slice starts with the positions of the streams in front
         u32 a = lo, b = j;

@@ -39,7 +39,8 @@ def cases(seed, count):
 
 # (seed, index): inputs that exposed real bugs in the speculative parse (stitch-bit ownership when a copy runs
 # to the block end; stale overlapping walker ranges behind ExtendLastCommand)
-REGRESSIONS = [(1, 304), (4, 382), (7, 249), (7, 13), (6, 104), (5, 252), (5, 297)]
+REGRESSIONS = [(1, 304), (4, 382), (7, 249), (7, 13), (6, 104), (5, 252), (5, 297),
+               (35, 22)]   # (35, 22): a view that reaches through the chunk's own unstored positions into a range flipped in the same launch
 
 
 def dict_cases(seed, count, tables_path):

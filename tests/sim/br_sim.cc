@@ -218,6 +218,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     ++s.epoch;
     std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
     std::vector<BrBlockOut> old(s.bout, s.bout + nb);
+    std::vector<BrCmd> old_cmds(m.cmd_blocks);
     s.counters[4] = 0;
     for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; br_walk_one<1>(s, k, s.bin[k], o, k, sp0); }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
@@ -231,6 +232,19 @@ static void sim_lz77_fixpoint(SimStream& m) {
         for (u32 q = s.bin_used[k].start_pos; q < s.bout[k].out_pos && shown < 12; ++q) {
           u32 o = (m.bits_prev[q >> 5] >> (q & 31)) & 1, n2 = (m.bits_latest[q >> 5] >> (q & 31)) & 1;
           if (o != n2) { fprintf(stderr, "  pos %u: fixpoint %u rewalk %u\n", q, o, n2); ++shown; }
+        }
+      }
+      if (!same || memcmp(&old_cmds[(size_t)k * s.cmd_stride], &m.cmd_blocks[(size_t)k * s.cmd_stride], (size_t)std::min(a.ncmd, b.ncmd) * sizeof(BrCmd))) {
+        // first command that differs: where it starts in the input, what it was and what the re-walk says
+        u32 pos = s.bin[k].start_pos;
+        for (u32 i = 0; i < std::min(a.ncmd, b.ncmd); ++i) {
+          const BrCmd& x = old_cmds[(size_t)k * s.cmd_stride + i]; const BrCmd& y = m.cmd_blocks[(size_t)k * s.cmd_stride + i];
+          if (memcmp(&x, &y, sizeof(BrCmd))) {
+            fprintf(stderr, "verify: chunk %u (run of launch %u) command %u at input %u: fixpoint insert %u copy %u dist_prefix %u extra %u | rewalk insert %u copy %u dist_prefix %u extra %u\n", k, a.epoch, i, pos,
+                    x.insert_len, x.copy_len & 0x1FFFFFF, x.dist_prefix, x.dist_extra, y.insert_len, y.copy_len & 0x1FFFFFF, y.dist_prefix, y.dist_extra);
+            break;
+          }
+          pos += x.insert_len + (x.copy_len & 0x1FFFFFF);
         }
       }
       if (s.changed_bits[k] || !same)

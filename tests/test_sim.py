@@ -328,6 +328,25 @@ def test_sim_batch_of_streams(sim):
             assert got[j] == ora.compress(x, q, w), (it, q, w, j, len(x))
 
 
+def test_sim_batch_regression_same_launch_flip(sim):
+    """fuzz case (35, 22) inside a batch (found by batching the fuzz inputs): a search whose view reaches, through positions
+    its own run has just left unstored, into an earlier chunk whose bits flip in the same launch.  The successor count of
+    br_commit_bits (taken over the previous snapshot) does not see that far; the bucket is a heavy one and the
+    counter-wrap sensitivity of the heavy path (br_lz77.h) re-walks the chunk -- in a batch too, from the stream's first byte."""
+    from fuzz_cases import cases
+    ora = Oracle()
+    d = next(x for i, x, q, w in cases(35, 23) if i == 22)
+    other = bytes(np.random.RandomState(1).randint(0, 256, 3000, dtype=np.uint8))
+    for bits in ("9", "11"):
+        os.environ["BR_SIM_BATCH_CHUNK_BITS"] = bits
+        try:
+            for ss in ([other, d], [d, other], [d, d]):
+                got = _sim_multi(sim, ss, 5, 17)
+                assert [got[k] == ora.compress(x, 5, 17) for k, x in enumerate(ss)] == [True] * len(ss), bits
+        finally:
+            os.environ.pop("BR_SIM_BATCH_CHUNK_BITS", None)
+
+
 def test_sim_batch_fuzz_sample(sim):
     """The structured fuzz inputs (tests/fuzz_cases.py: periodic, dictionary words, noise, heavy buckets ...) grouped by
     (quality, lgwin) and compressed a dozen at a time as one batch job, with both chunk sizes."""
