@@ -4,9 +4,11 @@
 #include "br_entropy2.h"
 
 struct BrCopyDesc { u64 dst_bit; u64 src_off; u32 nbits; u32 kind; };  // kind 0: bit copy from outbits, 1: raw bytes from input
-// encode.c:203 EncodeWindowBits (lgwin 17..24)
+// encode.c:185 EncodeWindowBits (lgwin 10..24; no large window)
 BR_DEV u32 br_put_window_bits(u32* out, u64 bit, int lgwin) {
+  if (lgwin == 16) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 1, 0); return 1; }
   if (lgwin == 17) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 7, 1); return 7; }
+  if (lgwin < 17) { br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 7, (u64)(((lgwin - 8) << 4) | 1)); return 7; }
   br_put_bits_at(out + (bit >> 5), (u32)(bit & 31), 4, (u64)(((lgwin - 17) << 1) | 1));
   return 4;
 }

@@ -8,6 +8,7 @@
 // later commit.
 #pragma once
 #include "br_cmd.h"
+#include "br_lz77.h"
 #ifdef BR_SIM_DEBUG
 #include <stdio.h>
 static u32 br_sim_watch = 0xffffffffu;   // tests/sim: report commits that flip this position
@@ -95,6 +96,7 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
         // Who may have consulted a flipped bit?  Position q sits in the bucket ring seen from a later
         // position p of the same key until block_size stored positions lie between them.
         const u32 reach = (1u << s.P.block_bits) + 2;
+        if (s.P.quick) flips = 0;   // qualities 2..4: every run is checked against the committed bits instead (br_verify_run)
         while (flips) {
           const u32 q = (x << 5) + (u32)br_ffs(flips) - 1u;
           flips &= flips - 1;
@@ -143,6 +145,55 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
     s.changed_bits[k] = diff;
     if (diff) s.changed_epoch[k] = (int)s.epoch;
   }
+}
+
+// Qualities 2..4 (BrParams::quick): is the latest run of chunk k consistent with the committed stored-bits?  A slot of the
+// reference's table holds one position, so the run recorded what every search read from each slot (BrStream::saw,
+// br_find_quick): the index in S of the stored position it took, or BR_SAW_ABSENT | the index its backward walk
+// stopped at (everything in front of that index lies outside the window).  The record still holds iff that position is
+// stored and nothing between it and the search position is.  Runs after the commits of every launch, over ALL chunks:
+// a run that read a bit another run flipped -- in this launch or any earlier one -- is walked again (reason 4).  This
+// is an exact check, not a conservative marking: no successor counting, no view mismatch.
+// Warp task; the lanes take the words of the run's range independently and meet in one ballot at the end.
+BR_DEV void br_verify_run(const BrStream& s, u32 k) {
+  const BrParams& P = s.P;
+  const BrBlockOut o = s.bout[k];
+  const u32 a = s.bin_used[k].start_pos, b = o.out_pos;
+  u32 bad = 0;
+  if (o.valid && b > a) {
+    const u32 sweep = 1u << P.qk_sweep_bits, mask = (1u << P.qk_bits) - 1u;
+    const u32 w0 = a >> 5, w1 = (b - 1) >> 5;
+    for (u32 x = w0 + (u32)br_lane(); x <= w1 && !bad; x += BR_WARP) {
+      u32 m = s.srch_latest[x];
+      if (x == w0) m &= 0xffffffffu << (a & 31);
+      if (x == w1) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+      while (m && !bad) {
+        const u32 p = (x << 5) + (u32)br_ffs(m) - 1u;
+        m &= m - 1;
+        const u32 key = br_quick_key_v(P, br_ld64u(s.data, p));
+        const u32* saw = s.saw + ((size_t)p << P.qk_sweep_bits);
+        for (u32 i = 0; i < sweep && !bad; ++i) {
+          const u32 v = saw[i];
+          if (v == BR_SAW_SKIP) continue;
+          const u32 hi = s.seg[((key + (i << 3)) & mask) + 1];
+          u32 j = v & ~BR_SAW_ABSENT;
+          if (j > hi) { bad = 1; break; }
+          if (!(v & BR_SAW_ABSENT)) {
+            if (j >= hi) { bad = 1; break; }
+            const u32 q = s.S[j];
+            if (q >= p || !((s.bits_latest[q >> 5] >> (q & 31)) & 1u)) { bad = 1; break; }
+            ++j;
+          }
+          for (; j < hi; ++j) {
+            const u32 q = s.S[j];
+            if (q >= p) break;
+            if ((s.bits_latest[q >> 5] >> (q & 31)) & 1u) { bad = 1; break; }
+          }
+        }
+      }
+    }
+  }
+  if (br_ballot(bad != 0) != 0 && br_lane() == 0) br_atomic_max(s.bitdep_epoch + k, (int)s.epoch);
 }
 
 // encode.c:457 ShouldCompress
@@ -343,7 +394,9 @@ BR_DEV void br_chain_blocks(const BrStream& s, u32 bi0, u32 bi1, BrMetaBlock* mb
     {
       const u32 processed = end - last_flush_pos;
       const bool next_fits = processed + blocksize <= P.max_mb;
-      if (!B.is_last && !B.force_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) {
+      // (encode.c:1152: without block splitting -- qualities 2, 3 -- at most MAX_NUM_DELAYED_SYMBOLS literals + commands are buffered)
+      const bool should_flush = P.mb_kind != 0 && num_lits + num_cmds >= 0x2FFFu;
+      if (!B.is_last && !B.force_flush && !should_flush && next_fits && num_lits < P.max_mb / 8 && num_cmds < P.max_mb / 8) {
         if (!(P.finish_empty && bi + 1 == s.nblk)) continue;
         closes_stream = true;    // merged, and the FINISH call that brought nothing flushes it as the last metablock
       } else if (P.finish_empty && bi + 1 == s.nblk) empty_last = true;

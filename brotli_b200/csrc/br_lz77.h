@@ -460,6 +460,150 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
   if (min_score == out.score) br_search_static_dict(w, cur, max_length, dict_distance, out);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Qualities 2..4: HashLongestMatchQuickly (hash_longest_match_quickly_inc.h; H2, H3, H4, H54 of hash.h:251-338).
+// The reference's table holds ONE position per slot; a position p is filed in slot (key(p) + (p & SWEEP_MASK)) & MASK
+// (Store, :96) and a search reads the 1 << BUCKET_SWEEP_BITS slots key, key + 8, ... (:231).  Here the index S is sorted by
+// (slot, position), so "the content of slot s at time p" is the latest STORED position in front of p in the slot's
+// segment of S (position 0 when there is none: the table starts zeroed, :76).  Every slot read is recorded in
+// BrStream::saw (index into S of the position read, or BR_SAW_ABSENT | the index the backward walk stopped at), and
+// br_verify_run (br_chain.h) checks the records of every run against the committed stored-bits after each launch.
+// The code below is warp-UNIFORM: every lane executes the same scalar search (the loads are broadcasts); a search is a
+// handful of candidates, and a uniform formulation is what the one-lane CPU sim (tests/sim) validates completely.
+#define BR_SAW_ABSENT 0x80000000u
+// hash_longest_match_quickly_inc.h:27 HashBytes: HASH_LEN bytes, kHashMul64, the top BUCKET_BITS bits
+BR_DEV u32 br_quick_key_v(const BrParams& P, u64 v) {
+  return (u32)(((v << (64 - 8 * P.qk_hash_len)) * 0x1FE35A7BD3579BD3ull) >> (64 - P.qk_bits));
+}
+// the slot position `pos` is filed in (Store, :96)
+BR_DEV u32 br_quick_slot(const BrParams& P, u64 v, u32 pos) {
+  return (br_quick_key_v(P, v) + (pos & (((1u << P.qk_sweep_bits) - 1u) << 3))) & ((1u << P.qk_bits) - 1u);
+}
+// data[cur_ix_masked + off] as the reference reads it (:162, :185): at off == max_length that byte lies just past the
+// input block (w.stale, see the oracle's stale_byte)
+BR_DEV u32 br_cur_byte(const BrWalk& w, u32 cur, u32 off, u32 max_length) {
+  return off < max_length ? (u32)br_ldg(w.d + cur + off) : w.stale;
+}
+// hash.h:179 SearchInStaticDictionary with shallow == TRUE: one probe
+BR_DEV void br_search_static_dict_shallow(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, BrSR& out) {
+  const BrStream& s = *w.s;
+  BR_W(7, 1);
+  ++w.gate_checks;
+  if (w.dict_m < (w.dict_l >> 7)) { ++w.gate_fail; return; }
+  const u32 key = ((br_ld32u(w.d, cur) * 0x1E35A7BDu) >> (32 - 14)) << 1;
+  ++w.dict_l; ++w.dl;
+  const u32 len = br_ldg(s.dict_hash_lengths + key);
+  if (len != 0) {
+    if (br_test_dict_item(w, len, br_ldg(s.dict_hash_words + key), cur, max_length, max_backward, out)) { ++w.dict_m; ++w.dm; }
+  }
+}
+// hash_longest_match_quickly_inc.h:147 FindLongestMatch.  out.len carries best_len_in (backward_references_inc.h:127).
+BR_DEV void br_find_quick(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, u32 dict_distance, BrSR& out) {
+  const BrStream& s = *w.s;
+  const BrParams& P = s.P;
+  const u8* d = w.d;
+  const u32 sweep = 1u << P.qk_sweep_bits, mask = (1u << P.qk_bits) - 1u;
+  const u32 best_len_in = out.len;
+  const u32 min_score = out.score;
+  u32 best_score = out.score, best_len = best_len_in;
+  const u64 c0 = br_ld64u(d, cur), c1 = br_ld64u(d, cur + 8);
+  const u32 key = br_quick_key_v(P, c0);
+  u32 compare_char = br_cur_byte(w, cur, best_len_in, max_length);
+  const bool rec = !w.warming && br_lane() == 0;
+  u32* saw = s.saw + ((size_t)cur << P.qk_sweep_bits);
+  BR_W(0, 1);
+  out.delta = 0;
+  // ---- the slots' index ranges go out first (independent loads), the last-distance candidate is checked meanwhile
+  const u32 i_own = (cur >> 3) & (sweep - 1u);   // the slot `cur` itself is filed in: its predecessors end at rank[cur]
+  u32 lo[4], ja[4], jb[4];
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    lo[i] = ja[i] = jb[i] = 0;
+    if (i < sweep) {
+      const u32 slot = (key + (i << 3)) & mask;
+      lo[i] = br_ldg(s.seg + slot);
+      if (i == i_own) ja[i] = jb[i] = br_ldg(s.rank + cur);
+      else { ja[i] = lo[i]; jb[i] = br_ldg(s.seg + slot + 1); }
+    }
+  }
+  bool early = false;
+  {
+    const int cached = w.dc[0];
+    if (cached > 0 && (u32)cached <= max_backward) {   // (:168: prev_ix < cur_ix && cached_backward <= max_backward)
+      const u32 prev = cur - (u32)cached;
+      if (compare_char == (u32)br_ldg(d + prev + best_len)) {
+        const u32 len = br_match_len_c(d, prev, cur, max_length, c0, c1);
+        if (len >= 4) {
+          const u32 score = 135u * len + BR_SCORE_BASE + 15u;   // BackwardReferenceScoreUsingLastDistance
+          if (best_score < score) {
+            out.len = len; out.distance = (u32)cached; out.score = score;
+            if (sweep == 1) early = true;   // (:178: the slot is overwritten unread)
+            else { best_len = len; best_score = score; compare_char = br_cur_byte(w, cur, len, max_length); }
+          }
+        }
+      }
+    }
+  }
+  if (early) {
+    if (rec) saw[0] = BR_SAW_SKIP;
+    br_own_set(w, cur); br_srch_set(w, cur);
+    return;
+  }
+  // ---- first index of every slot's segment whose position is >= cur (binary searches, interleaved)
+  for (;;) {
+    bool any = false;
+#pragma unroll
+    for (u32 i = 0; i < 4; ++i) {
+      if (i < sweep && ja[i] < jb[i]) {
+        const u32 mid = (ja[i] + jb[i]) >> 1;
+        if (br_ldg(s.S + mid) < cur) ja[i] = mid + 1; else jb[i] = mid;
+        any = true;
+      }
+    }
+    if (!any) break;
+  }
+  br_own_sync(w);
+  bool h2_return = false;
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    if (i >= sweep) break;
+    // the slot's content as this walker sees it: the latest stored position in front of cur, inside the window
+    u32 j = ja[i], cand = 0, rv = 0;
+    bool found = false;
+    while (j > lo[i]) {
+      const u32 q = br_ldg(s.S + (j - 1));
+      if (cur - q > max_backward) break;
+      --j;
+      if (br_is_stored(w, q)) { found = true; cand = q; break; }
+    }
+    rv = found ? j : (BR_SAW_ABSENT | j);
+    if (rec) saw[i] = rv;
+    BR_W(1, 1);
+    // absent: position 0 (the zeroed table) while the window still reaches it; otherwise the slot holds something the
+    // reference rejects (backward > max_backward) whatever its first byte
+    bool valid = found || (j == lo[i] && cur <= max_backward && cur != 0);
+    const u32 prev = found ? cand : 0u;
+    const u32 backward = cur - prev;
+    if (valid && compare_char != (u32)br_ldg(d + prev + best_len)) valid = false;
+    if (valid && (backward == 0 || backward > max_backward)) valid = false;
+    if (!valid) { if (sweep == 1) h2_return = true; continue; }
+    const u32 len = br_match_len_c(d, prev, cur, max_length, c0, c1);
+    if (len >= 4) {
+      const u32 score = BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward);
+      if (best_score < score) {
+        best_len = len; best_score = score;
+        out.len = len; out.distance = backward; out.score = score;
+        compare_char = br_cur_byte(w, cur, len, max_length);
+        if (sweep == 1) h2_return = true;   // (:217)
+      }
+    }
+  }
+  br_own_set(w, cur);   // buckets[key_out] = cur_ix (:208, :265)
+  br_srch_set(w, cur);
+  if (h2_return) return;
+  if (P.qk_dict && min_score == out.score) br_search_static_dict_shallow(w, cur, max_length, dict_distance, out);
+}
+
 // backward_references.c:87 ComputeDistanceCode
 BR_DEV u32 br_compute_distance_code(u32 distance, u32 max_distance, const int* dc) {
   if (distance <= max_distance) {
@@ -571,7 +715,10 @@ BR_DEV void br_walk_one(const BrStream& s, u32 b, const BrBlockIn& in, BrBlockOu
       const u32 md = br_min(sp - base, P.max_backward);
       const u32 dd = P.stream_offset ? br_min(sp + P.stream_offset, P.max_backward) : md;   // backward_references_inc.h:94 dictionary_start
       BrSR cur; cur.len = 0; cur.delta = 0; cur.distance = 0; cur.score = BR_MIN_SCORE;
-      br_find_longest_match<G>(w, sp, max_length, md, dd, cur);
+      if constexpr (G == 0) {   // qualities 2..4 (k_walk<0>): best_len_in of the lazy search, backward_references_inc.h:127
+        if (have) cur.len = br_min(sr.len - 1u, max_length);
+        br_find_quick(w, sp, max_length, md, dd, cur);
+      } else br_find_longest_match<G>(w, sp, max_length, md, dd, cur);
       if (!have) {
         sr = cur;
         if (!(sr.score > BR_MIN_SCORE)) break;

@@ -10,7 +10,33 @@
 // lgblock_user: BROTLI_PARAM_LGBLOCK (0 = let the encoder choose, quality.h:76 ComputeLgBlock).
 static inline int br_derive_params(int quality, int lgwin, u32 size_hint, u32 n, BrParams* P, int lgblock_user = 0) {
   memset(P, 0, sizeof(*P));
-  if (quality < 5 || quality > 9) return 0;   // q0-4: other hashers; q10-11: Zopfli path
+  if (quality >= 2 && quality <= 4) {
+    // Qualities 2..4: the one-position-per-slot hashers (quality.h:172 ChooseHasher, hash.h:251-338), window 10..24 bits.
+    if (lgwin < 10 || lgwin > 24) return 0;
+    P->quality = quality; P->lgwin = lgwin;
+    P->lgblock = quality < 4 ? 14 : 16;          // quality.h:81 (below MIN_QUALITY_FOR_BLOCK_SPLIT the parameter is ignored)
+    if (quality == 4 && lgblock_user != 0) P->lgblock = lgblock_user > 24 ? 24 : lgblock_user < 16 ? 16 : lgblock_user;
+    P->quick = 1; P->qk_hash_len = 5;
+    if (quality == 2) { P->qk_bits = 16; P->qk_sweep_bits = 0; P->qk_dict = 1; }            // H2
+    else if (quality == 3) { P->qk_bits = 16; P->qk_sweep_bits = 1; P->qk_dict = 0; }       // H3
+    else if (size_hint >= (1u << 20)) { P->qk_bits = 20; P->qk_sweep_bits = 2; P->qk_dict = 0; P->qk_hash_len = 7; }   // H54
+    else { P->qk_bits = 17; P->qk_sweep_bits = 2; P->qk_dict = 1; }                         // H4
+    P->mb_kind = quality == 2 ? 2u : quality == 3 ? 1u : 0u;
+    P->htl = 8;                                   // HashTypeLength == StoreLookahead == 8
+    const int rbq = 1 + (lgwin > P->lgblock ? lgwin : P->lgblock);
+    P->rmask = (1u << rbq) - 1;
+    P->max_backward = (1u << lgwin) - 16;
+    P->spree = 64;
+    P->max_mb = 1u << (rbq < 24 ? rbq : 24);
+    P->size_hint = size_hint; P->n = n;
+    P->nbuckets = 1u << P->qk_bits;
+    P->chunk_bits = n < BR_SMALL_STREAM ? BR_CHUNK_BITS_SMALL : BR_CHUNK_BITS;
+    P->heavy_min = 0xffffffffu; P->step_cap = 4096;
+    P->sweep_epoch = 3; P->force_epoch = 64; P->pilot = 0;
+    P->sweep_blocks = P->lgblock >= 21 ? 1u : (1u << (21 - P->lgblock));
+    return 1;
+  }
+  if (quality < 5 || quality > 9) return 0;   // q0: one-pass fragment coder; q10-11: Zopfli path
   if (lgwin < 17 || lgwin > 24) return 0;      // <=16: forgetful-chain hashers; >24: large window
   P->quality = quality; P->lgwin = lgwin;
   P->lgblock = 16;                              // quality.h:86

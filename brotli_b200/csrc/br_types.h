@@ -46,6 +46,15 @@ struct BrParams {
                     // probes in the big launch, no re-walk of chunks that found dictionary words under an open-gate guess
   u32 multi;        // != 0: the job is a BATCH of this many independent streams laid end to end in `data` (cuts of kind 3,
                     // br_params.h): every position-dependent rule counts from the stream's first byte (BrBlk::base)
+  // ---- qualities 2..4: the one-position-per-slot hashers H2 / H3 / H4 / H54 (hash_longest_match_quickly_inc.h, hash.h:251-338)
+  u32 quick;        // != 0: the index is sorted by SLOT (the table entry a position is filed in), searches consult
+                    // 1 << qk_sweep_bits slots and see the latest stored position of each (br_find_quick)
+  u32 qk_bits;      // BUCKET_BITS: 16 (H2, H3), 17 (H4), 20 (H54)
+  u32 qk_sweep_bits;  // BUCKET_SWEEP_BITS: 0 (H2), 1 (H3), 2 (H4, H54)
+  u32 qk_hash_len;  // HASH_LEN: 5, or 7 (H54)
+  u32 qk_dict;      // USE_DICTIONARY (H2, H4): one shallow probe of the static dictionary when nothing else matched
+  u32 mb_kind;      // how a metablock is stored: 0 BrotliStoreMetaBlock after the greedy block split (quality >= 4),
+                    // 1 BrotliStoreMetaBlockTrivial (quality 3), 2 BrotliStoreMetaBlockFast (quality 2) (encode.c:543-556)
 };
 
 // The unit of speculation is a CHUNK: a slice (1 << BR_CHUNK_BITS bytes) of one of the
@@ -139,6 +148,8 @@ struct BrMetaBlock {
 #define BR_DEFER_SWEEP 0x200u
 #define BR_DEFER_FULL 0x400u
 #define BR_DEFER (BR_DEFER_STATE | BR_DEFER_SWEEP | BR_DEFER_FULL)
+#define BR_SAW_NONE 0xffffffffu
+#define BR_SAW_SKIP 0xfffffffeu
 #define BR_BATCH_HEAD_CHUNKS 16u   // batch of streams: chunks the walker of a stream's first chunk covers in the first launch (br_chain_c)
 
 // Device-resident view of one stream (all pointers are device pointers).
@@ -181,6 +192,8 @@ struct BrStream {
   BrBlk* blk;            // [nblk] reference input blocks
   BrBlkIn* blkin;        // [nblk]
   u32* key_flips;        // [nbuckets + 1] stored-bit flips per heavy bucket in the current launch
+  u32* saw;              // BrParams::quick: [n << qk_sweep_bits] what the latest search at a position read from each of its slots
+                         // (index into S of the candidate, BR_SAW_NONE: the slot was empty, BR_SAW_SKIP: not read) -- br_verify_run
   u32 nblk;
   u32* dirty_list;       // [nblocks] chunks scheduled for the next walker launch (counters[5] entries)
   u32* ran_list;         // [nblocks] chunks walked in the current launch (counters[4] entries)

@@ -46,7 +46,7 @@ struct SimStream {
   std::vector<BrMetaBlock> mbs;
   std::vector<BrBlk> blks;
   std::vector<BrBlkIn> blkin;
-  std::vector<u32> key_flips;
+  std::vector<u32> key_flips, saw;
   std::vector<u32> dirty_list, ran_list, slot_blk, stream_blk, stream_nmb, stream_ncmd;
   std::vector<BrMetaBlock> mbs_stage;
   int iterations = 0;
@@ -58,7 +58,7 @@ static void sim_build_sorted(SimStream& m) {
   BrStream& s = m.s; const BrParams& P = s.P; u32 n = P.n;
   std::vector<u32> key(n);
   u32 hashable = n >= P.htl ? n - P.htl + 1 : 0;  // positions with a full hash load
-  for (u32 p = 0; p < n; ++p) key[p] = p < hashable ? br_hash_key(P, s.data, p) : P.nbuckets;
+  for (u32 p = 0; p < n; ++p) key[p] = p >= hashable ? P.nbuckets : P.quick ? br_quick_slot(P, br_ld64u(s.data, p), p) : br_hash_key(P, s.data, p);
   m.seg.assign(P.nbuckets + 2, 0);
   for (u32 p = 0; p < n; ++p) m.seg[key[p] + 1]++;
   for (u32 k = 0; k <= P.nbuckets; ++k) m.seg[k + 1] += m.seg[k];
@@ -153,6 +153,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   s.blk = m->blks.data(); s.nblk = (u32)m->blks.size();
   m->blkin.resize(m->blks.size()); s.blkin = m->blkin.data();
   m->key_flips.assign(P.nbuckets + 2, 0); s.key_flips = m->key_flips.data();
+  if (P.quick) { m->saw.assign(((size_t)n << P.qk_sweep_bits) + 4, 0xdeadbeefu); s.saw = m->saw.data(); }
   m->dirty_list.assign(nb + 1, 0); m->block_mb.assign(nb + 1, 0);
   s.dirty_list = m->dirty_list.data(); s.block_mb = m->block_mb.data();
   m->ran_list.assign(nb + 1, 0); s.ran_list = m->ran_list.data();
@@ -191,7 +192,8 @@ static void sim_lz77_fixpoint(SimStream& m) {
     s.counters[4] = 0; s.counters[16] = 0;
     s.forced = s.epoch >= s.P.force_epoch;
     { u32 nd = s.counters[5]; std::vector<u32> dl(nd); for (u32 t = 0; t < nd; ++t) dl[t] = br_sched_entry(s, t); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
-      if (s.P.multi) { if (s.P.block_bits >= 6) br_walk_block<4, true>(s, k, f); else br_walk_block<1, true>(s, k, f); }
+      if (s.P.quick) br_walk_block<0>(s, k, f);
+      else if (s.P.multi) { if (s.P.block_bits >= 6) br_walk_block<4, true>(s, k, f); else br_walk_block<1, true>(s, k, f); }
       else if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
     m.block_runs += s.counters[4];
 #ifdef BR_SIM_DEBUG
@@ -206,6 +208,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
+    if (s.P.quick) for (u32 k = 0; k < nb; ++k) br_verify_run(s, k);
     if (s.epoch + 2 >= s.P.max_epochs) { fprintf(stderr, "sim: no fixpoint\n"); break; }
   }
   if (getenv("BR_SIM_TRACE")) {   // the static-dictionary gate (hash.h:186) at the fixpoint: chunks that start with it closed
@@ -220,7 +223,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     std::vector<BrBlockOut> old(s.bout, s.bout + nb);
     std::vector<BrCmd> old_cmds(m.cmd_blocks);
     s.counters[4] = 0;
-    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; br_walk_one<1>(s, k, s.bin[k], o, k, sp0); }
+    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; if (s.P.quick) br_walk_one<0>(s, k, s.bin[k], o, k, sp0); else br_walk_one<1>(s, k, s.bin[k], o, k, sp0); }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 k = 0; k < nb; ++k) {
       br_commit_bits(s, k);
