@@ -59,6 +59,19 @@ BR_DEV u8* br_mb2_types(u8* scratch, const BrMbAux& a, int cat, u32 nblk) {
 }
 BR_HD u32 br_mb2_nblk(int cat, u32 nlit, u32 ncmd) { return cat == 0 ? nlit / 512 + 2 : cat == 1 ? ncmd / 1024 + 2 : ncmd / 512 + 2; }
 
+// Qualities 2 and 3 (BrParams::mb_kind != 0): one prefix code per category, no block splits, no contexts
+// (br_entropy_flat.h).  This is the whole per-metablock scratch of such a job.
+struct BrMbFlat {
+  u32 lit_H[256], cmd_H[704], dist_H[64];
+  u8 lit_depth[256], cmd_depth[704], dist_depth[64];
+  u16 lit_bits[256], cmd_bits[704], dist_bits[64];
+  BrHTree tree[2 * 704 + 2];
+  BrTreeSc tsc;
+};
+BR_HD u32 br_mb_scratch_bytes(const BrParams& P, u32 nlit, u32 ncmd) {
+  return P.mb_kind ? br_align8((u32)sizeof(BrMbFlat)) : br_mb2_scratch_bytes(nlit, ncmd);
+}
+
 // stream-wide arrays of the parallel entropy stage
 struct BrEnt {
   const BrCmd* cmds;       // compacted commands of the stream
@@ -391,6 +404,12 @@ BR_DEV u32 br_lit_code(const BrStream& st, const BrEnt& e, u32 o, u32* code, u64
   if (!st.mbs[m].compress) return 0;
   const BrMbAux& a = e.aux[m];
   u8* scratch = e.scratch + e.scratch_off[m];
+  if (st.P.mb_kind) {   // qualities 2, 3: one literal code
+    const BrMbFlat* F = (const BrMbFlat*)scratch;
+    const u32 lit = st.data[e.lit_pos[o]];
+    *code = F->lit_bits[lit];
+    return F->lit_depth[lit];
+  }
   const BrMbMem* M = (const BrMbMem*)scratch;
   const BrBlockInfo* bi = br_mb2_blocks(scratch, a, 0);
   const u32 orel = o - a.lit_base;
@@ -422,6 +441,21 @@ BR_DEV void br_cmd_code(const BrStream& st, const BrEnt& e, u32 i, BrCmdCode* k)
   u8* scratch = e.scratch + e.scratch_off[m];
   const BrMbMem* M = (const BrMbMem*)scratch;
   const BrCmd c = e.cmds[i];
+  if (st.P.mb_kind) {   // qualities 2, 3: one command code, one distance code (brotli_bit_stream.c:1159 StoreDataWithHuffmanCodes)
+    const BrMbFlat* F = (const BrMbFlat*)scratch;
+    k->cn = F->cmd_depth[c.cmd_prefix]; k->csym = F->cmd_bits[c.cmd_prefix];
+    const u32 clc = br_cmd_copy_len_code(c);
+    const u32 ic = br_ins_code(c.insert_len), cc = br_copy_code(clc);
+    const u32 insn = br_ins_extra(ic);
+    const u64 insv = c.insert_len - br_ins_base(ic), copyv = clc - br_copy_base(cc);
+    k->extra = (copyv << insn) | insv; k->en = insn + br_copy_extra(cc);
+    if (br_cmd_copy_len(c) && c.cmd_prefix >= 128) {
+      const u32 ds = c.dist_prefix & 0x3FF;
+      k->dn = F->dist_depth[ds]; k->dsym = F->dist_bits[ds];
+      k->xn = c.dist_prefix >> 10; k->xbits = c.dist_extra;
+    }
+    return;
+  }
   {
     const BrBlockInfo* bi = br_mb2_blocks(scratch, a, 1);
     const u32 orel = i - mb.cmd_off, b = br_block_of(bi, a.num_blocks[1], orel);

@@ -16,6 +16,7 @@
 #include "../../brotli_b200/csrc/br_entropy.h"
 #include "../../brotli_b200/csrc/br_entropy2.h"
 #include "../../brotli_b200/csrc/br_assemble.h"
+#include "../../brotli_b200/csrc/br_entropy_flat.h"
 #endif
 
 struct SimTables {
@@ -315,7 +316,7 @@ static void sim_entropy2(SimStream& m, SimEnt& E) {
     E.scratch_off[i] = st; E.out_off[i] = ot;
     const BrMetaBlock& mb = s.mbs[i];
     for (u32 c = mb.cmd_off; c < mb.cmd_off + mb.ncmd; ++c) E.cmd_mb[c] = i;
-    if (mb.compress) { st += (br_mb2_scratch_bytes(mb.nlit, mb.ncmd) + 255) & ~255u; ot += (2 * (size_t)(mb.end - mb.start) + 503) / 4 + 16; }
+    if (mb.compress) { st += (br_mb_scratch_bytes(s.P, mb.nlit, mb.ncmd) + 255) & ~255u; ot += (2 * (size_t)(mb.end - mb.start) + 503) / 4 + 16; }
   }
   E.scratch.assign(st + 256, 0); E.outbits.assign(ot + 64, 0);
   e.lit_ord = E.lit_ord.data(); e.cmd_pos = E.cmd_pos.data(); e.dist_ord = E.dist_ord.data();
@@ -336,6 +337,7 @@ static void sim_entropy2(SimStream& m, SimEnt& E) {
     a.nsym[0] = mb.nlit; a.nsym[1] = mb.ncmd; a.nsym[2] = E.dist_ord[mb.cmd_off + mb.ncmd] - a.dist_base;
     u32 off = br_align8((u32)sizeof(BrMbMem));
     for (int cat = 0; cat < 3; ++cat) { a.var_off[cat] = off; off += br_mb2_var_bytes(br_mb2_nblk(cat, mb.nlit, mb.ncmd)); }
+    if (s.P.mb_kind) { br_prep_flat(s, e, mb, a, sc, E.outbits.data() + E.out_off[i]); continue; }
     const u32 A[3] = {256, 704, 64}, NC[3] = {a.which, 1, 1}, MB[3] = {512, 1024, 512};
     const double TH[3] = {400.0, 500.0, 100.0};
     u32* H[3] = {M->lit_H, M->cmd_H, M->dist_H};
