@@ -85,10 +85,10 @@ bool supported(Params p) {
   if (p.quality <= 2) p.large_window = 0;      // quality.h:63: no large window with the static entropy codes; lgwin clamps to 24
   if (p.lgwin < 10) p.lgwin = 10;
   if (p.lgwin > 24 && !p.large_window) p.lgwin = 24;
-  if (p.quality != 1 && (p.quality < 5 || p.quality > 9)) return false;
-  if (p.quality == 1 ? p.lgwin > 24 : (p.lgwin < 17 || p.lgwin > 24)) return false;
+  if (p.quality < 1 || p.quality > 9) return false;   /* quality 0: one-pass fragment coder; 10, 11: Zopfli path */
+  if (p.quality <= 4 ? p.lgwin > 24 : (p.lgwin < 17 || p.lgwin > 24)) return false;   /* quality 1..4: any regular window */
   if (p.large_window || p.npostfix || p.ndirect || p.base64) return false;
-  if (p.stream_offset && p.quality == 1) return false;   /* STREAM_OFFSET: quality 5..9 only */
+  if (p.stream_offset && p.quality < 5) return false;   /* STREAM_OFFSET: quality 5..9 only */
   /* LGBLOCK and DISABLE_LITERAL_CONTEXT_MODELING are honoured at quality 5..9; at quality 1 the reference ignores both
      (quality.h:79: lgblock = lgwin; no context modeling in the fragment coder) */
   if (p.mode == BROTLI_MODE_FONT) return false;
@@ -131,7 +131,7 @@ int compress_host(const Params& p, uint32_t size_hint, const uint8_t* in, size_t
   cudaStream_t st = (cudaStream_t)br_job_stream(tls.job);
   if (cudaMemcpyAsync(tls.d_in, in, n, cudaMemcpyHostToDevice, st) != cudaSuccess) return 0;
   const uint8_t* d_out = nullptr; size_t sz = 0;
-  int q = p.quality, w = p.lgwin > 24 ? 24 : p.lgwin;
+  int q = p.quality, w = p.lgwin > 24 ? 24 : p.lgwin < 10 ? 10 : p.lgwin;   /* quality.h:60 SanitizeParams */
   if (!br_job_compress_device(tls.job, q, w, size_hint, tls.d_in, (uint32_t)n, &d_out, &sz, cuts)) return 0;
   record_stats();
   if (out_vec) { out_vec->resize(sz); out = out_vec->data(); out_cap = sz; }
@@ -362,7 +362,8 @@ void put_metadata(BitOut& w, const std::vector<uint8_t>& meta) {
   w.align();
   w.v.insert(w.v.end(), meta.begin(), meta.end());
 }
-int lgblock_of(const Params& p) {   /* quality.h:76 ComputeLgBlock, quality >= 4 */
+int lgblock_of(const Params& p) {   /* quality.h:76 ComputeLgBlock, quality >= 2 */
+  if (p.quality < 4) return 14;
   if (p.lgblock != 0) return p.lgblock > 24 ? 24 : p.lgblock < 16 ? 16 : p.lgblock;
   return (p.quality >= 9 && p.lgwin > 16) ? (p.lgwin < 18 ? p.lgwin : 18) : 16;
 }
@@ -381,7 +382,12 @@ int build_wire(BrotliEncoderState* s, bool is_final, bool finish_empty, std::vec
   const bool lead = !ev.empty() && ev[0].pos == 0;
   const bool continued = s->params.stream_offset != 0;   /* encode.c:675: a stream that continues another one has no window bits */
   if (lead || n == 0) {
-    if (!continued) { if (lgwin == 17) w.put(7, 1); else w.put(4, (uint64_t)(((lgwin - 17) << 1) | 1)); }   // encode.c:670 window bits
+    if (!continued) {   // encode.c:185 EncodeWindowBits
+      if (lgwin == 16) w.put(1, 0);
+      else if (lgwin == 17) w.put(7, 1);
+      else if (lgwin > 17) w.put(4, (uint64_t)(((lgwin - 17) << 1) | 1));
+      else w.put(7, (uint64_t)(((lgwin - 8) << 4) | 1));
+    }
     for (; e < ev.size() && ev[e].pos == 0; ++e) {
       if (ev[e].kind == 1) { if (w.pb) { w.put(6, 6); w.align(); } }   // encode.c:1356 InjectBytePaddingBlock
       else put_metadata(w, ev[e].meta);
@@ -487,8 +493,11 @@ BROTLI_BOOL BrotliEncoderCompress(int quality, int lgwin, BrotliEncoderMode mode
 BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, size_t input_size, const void* d_input,
                                      size_t* encoded_size, void* d_encoded) {
   Params p; p.quality = quality; p.lgwin = lgwin;
+  if (lgwin > 24) p.large_window = 1;   /* as the one-shot wrapper (encode.c:1329): refused unless quality <= 2 drops it again */
   if (!supported(p) || input_size == 0 || input_size > (1u << 30) || !ensure_job()) return BROTLI_FALSE;
   const uint8_t* d_out = nullptr; size_t sz = 0;
+  if (lgwin < 10) lgwin = 10;   /* quality.h:60 SanitizeParams */
+  if (lgwin > 24) lgwin = 24;   /* (only quality <= 2 gets here with more: no large window there, quality.h:63) */
   if (!br_job_compress_device(tls.job, quality, lgwin, (uint32_t)input_size, (const uint8_t*)d_input,
                               (uint32_t)input_size, &d_out, &sz, nullptr)) return BROTLI_FALSE;
   record_stats();
@@ -537,7 +546,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
   std::vector<size_t> big, group;
   size_t group_bytes = 0;
   for (size_t i = 0; i < count; ++i) {
-    if (input_sizes[i] == 0 || input_sizes[i] >= ((size_t)1 << 20)) { big.push_back(i); continue; }
+    if (input_sizes[i] == 0 || input_sizes[i] >= ((size_t)1 << 20) || quality < 5) { big.push_back(i); continue; }   /* (quality 2..4: one job per stream) */
     if ((group_bytes + input_sizes[i] > kBatchGroupBytes || group.size() >= kBatchGroupStreams) && !group.empty()) {
       ok += compress_stream_group(quality, lgwin, group, inputs, input_sizes, outputs, encoded_sizes, threads);
       group.clear(); group_bytes = 0;

@@ -281,6 +281,7 @@ BR_DEV void br_chain_prologue(const BrStream& s) {
   // counter-wrap rule: per launch, the largest number of stored-bit flips any single (heavy) bucket saw
   {
     u32 mx = 0;
+    if (!P.quick)   // (no bucket counters in the one-position-per-slot hashers of quality 2..4, and up to 2^20 slots)
     for (u32 k = (u32)lane; k <= P.nbuckets; k += BR_WARP) { u32 v = s.key_flips[k]; if (v > mx) mx = v; s.key_flips[k] = 0; }
     mx = br_warp_max(mx);
     if (lane == 0) {

@@ -18,6 +18,7 @@
 #include "br_entropy.h"
 #include "br_entropy2.h"
 #include "br_assemble.h"
+#include "br_entropy_flat.h"
 #include "br_pipeline.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -32,10 +33,19 @@ __global__ void k_hash_keys(BrParams P, const u8* __restrict__ data, u16* __rest
   keys[p] = (u16)(p < hashable ? br_hash_key(P, data, p) : P.nbuckets);
 }
 
+// qualities 2..4: the key is the table slot of the one-position-per-slot hashers (br_lz77.h br_quick_slot), up to 20 bits
+// (+ the overflow key of the unhashable tail): 32-bit keys, three radix passes
+__global__ void k_slot_keys(BrParams P, const u8* __restrict__ data, u32* __restrict__ keys) {
+  u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.n) return;
+  u32 hashable = P.n >= P.htl ? P.n - P.htl + 1 : 0;
+  keys[p] = p < hashable ? br_quick_slot(P, br_ld64u(data, p), p) : P.nbuckets;
+}
+
 #define RADIX_TILE 4096
-// digit histogram of one tile -> hist[d * ntiles + tile]
-template <int SHIFT>
-__global__ void __launch_bounds__(256) k_radix_count(const u16* __restrict__ keys, u32 n, u32* __restrict__ hist, u32 ntiles) {
+// digit histogram of one tile -> hist[d * ntiles + tile]   (KT: u16 bucket keys, u32 slot keys)
+template <int SHIFT, class KT = u16>
+__global__ void __launch_bounds__(256) k_radix_count(const KT* __restrict__ keys, u32 n, u32* __restrict__ hist, u32 ntiles) {
   __shared__ u32 cnt[256];
   cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -49,9 +59,9 @@ __global__ void __launch_bounds__(256) k_radix_count(const u16* __restrict__ key
 }
 // stable scatter: warp w of the CTA owns elements [w*512, w*512+512) of the tile, row by row
 // `inv` (nullable): the final pass also writes the inverse permutation inv[position] = index in the sorted order (BrStream::rank)
-template <int SHIFT, bool HAS_VALS>
-__global__ void __launch_bounds__(256) k_radix_scatter(const u16* __restrict__ keys, const u32* __restrict__ vals, u32 n,
-    const u32* __restrict__ hist_scanned, u32 ntiles, u16* __restrict__ out_keys, u32* __restrict__ out_vals, u32* __restrict__ inv) {
+template <int SHIFT, bool HAS_VALS, class KT = u16>
+__global__ void __launch_bounds__(256) k_radix_scatter(const KT* __restrict__ keys, const u32* __restrict__ vals, u32 n,
+    const u32* __restrict__ hist_scanned, u32 ntiles, KT* __restrict__ out_keys, u32* __restrict__ out_vals, u32* __restrict__ inv) {
   __shared__ u32 wcnt[8][256];
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (u32 i = threadIdx.x; i < 8 * 256; i += 256) (&wcnt[0][0])[i] = 0;
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const u16* __restrict__ k
     u32 rank = __popc(m & ((1u << lane) - 1));
     if (j < n) {
       u32 dst = wcnt[warp][d] + rank;
-      out_keys[dst] = (u16)k;
+      out_keys[dst] = (KT)k;
       const u32 v = HAS_VALS ? vals[j] : j;
       out_vals[dst] = v;
       if (inv) inv[v] = dst;
@@ -105,7 +115,8 @@ __global__ void k_tags(const u8* __restrict__ data, const u32* __restrict__ S, u
   if (j < n) tagS[j] = (u16)br_tag4(br_ld32u(data, S[j]));
 }
 // seg[k] = first index in S whose key is >= k, for k in [0, nbuckets + 1]
-__global__ void k_seg(const u16* __restrict__ sorted_keys, u32 n, u32 nbuckets, u32* __restrict__ seg) {
+template <class KT>
+__global__ void k_seg(const KT* __restrict__ sorted_keys, u32 n, u32 nbuckets, u32* __restrict__ seg) {
   u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j > n) return;
   int k0 = j == 0 ? -1 : (int)sorted_keys[j - 1];
@@ -214,6 +225,12 @@ __global__ void k_commit(BrStream s) {
   if (t >= s.counters[4]) return;
   br_commit_bits(s, s.ran_list[t]);
 }
+// qualities 2..4: every run against the committed stored-bits (br_chain.h br_verify_run); warp per chunk
+__global__ void k_verify(BrStream s) {
+  u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= s.P.nblocks) return;
+  br_verify_run(s, t);
+}
 __global__ void k_chain_a(BrStream s) {
   u32 bi = blockIdx.x * blockDim.x + threadIdx.x;
   if (bi < s.nblk) br_chain_a(s, bi);
@@ -297,6 +314,13 @@ __global__ void __launch_bounds__(64) k_prep(BrStream s, BrEnt e) {
   const BrMetaBlock mb = s.mbs[i];
   if (!mb.compress) return;
   br_prep_codes(s, mb, e.aux[i], e.scratch + e.scratch_off[i], e.outbits + e.out_off[i]);
+}
+// qualities 2, 3: histograms + the three codes of a metablock without block splits (br_entropy_flat.h)
+__global__ void __launch_bounds__(64) k_prep_flat(BrStream s, BrEnt e) {
+  const u32 i = blockIdx.x;
+  const BrMetaBlock mb = s.mbs[i];
+  if (!mb.compress) return;
+  br_prep_flat(s, e, mb, e.aux[i], e.scratch + e.scratch_off[i], e.outbits + e.out_off[i]);
 }
 __global__ void k_lit_bits(BrStream s, BrEnt e) {
   u32 o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,9 +492,11 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     // a batch of independent streams (each below BR_SMALL_STREAM, size_hint = the largest): no FLUSH cuts, all finished
     if (nstreams != ncuts + 1 || !cuts->is_final || !cuts->with_header || cuts->finish_empty || cuts->stream_offset ||
         cuts->pos[ncuts - 1] >= n || size_hint >= BR_SMALL_STREAM) return 0;
+    if (P.quick) return 0;   // (qualities 2..4: one job per stream)
     P.multi = nstreams; P.pilot = 0;
     P.chunk_bits = br_batch_chunk_bits(n);
   }
+  if (P.quick && P.stream_offset) return 0;   // (STREAM_OFFSET: quality 5..9)
   const u32 ch = 1u << P.chunk_bits;
   const bool is_final = cuts ? cuts->is_final != 0 : true;
   const int with_header = cuts ? cuts->with_header : 1;
@@ -506,6 +532,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   // the conservative block-level re-marks), and a late uncompressed fallback restarts the count at most once per metablock.
   P.max_epochs = 4 * nb + 4096;
   add(((size_t)P.max_epochs + 2) * 4 + 64); add((nb + 1) * sizeof(BrMetaBlock)); add(4096);
+  if (P.quick) { for (int i = 0; i < 4; ++i) add(4ull * n + 16); add((((size_t)n << P.qk_sweep_bits) + 16) * 4); }   // 32-bit sort keys, slot reads
   need += 1 << 20;
   if (!job->arena.reserve(need)) return 0;
   BrArena& A = job->arena;
@@ -537,6 +564,13 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   BrMetaBlock* mbs_stage = A.take<BrMetaBlock>(nblk);
   u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256ull * nstreams);
   if (!hist_scratch) return 0;
+  u32 *qk_keys = nullptr, *qk_K1 = nullptr, *qk_V1 = nullptr, *qk_V2 = nullptr, *saw = nullptr;
+  if (P.quick) {
+    qk_keys = A.take<u32>((size_t)n + 4); qk_K1 = A.take<u32>((size_t)n + 4); qk_V1 = A.take<u32>((size_t)n + 4); qk_V2 = A.take<u32>((size_t)n + 4);
+    saw = A.take<u32>(((size_t)n << P.qk_sweep_bits) + 16);
+    if (!saw) return 0;
+  }
+  s.saw = saw;
 
   CK(cudaMemcpyAsync(data, d_in, n, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(data + n, 0, 64, st));
@@ -577,6 +611,20 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   CK(cudaMemsetAsync(bits_cur, 0, 2 * (size_t)nwords * 4, st));
 
   // ---- position index: S, rank, seg
+  if (P.quick) {
+    // sorted by (slot, position): three stable 8-bit passes over 32-bit keys (slots have up to 20 bits + the overflow key)
+    k_slot_keys<<<(n + 255) / 256, 256, 0, st>>>(P, data, qk_keys);
+    k_radix_count<0, u32><<<ntiles, 256, 0, st>>>(qk_keys, n, hist, ntiles);
+    scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
+    k_radix_scatter<0, false, u32><<<ntiles, 256, 0, st>>>(qk_keys, nullptr, n, hist, ntiles, qk_K1, qk_V1, nullptr);
+    k_radix_count<8, u32><<<ntiles, 256, 0, st>>>(qk_K1, n, hist, ntiles);
+    scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
+    k_radix_scatter<8, true, u32><<<ntiles, 256, 0, st>>>(qk_K1, qk_V1, n, hist, ntiles, qk_keys, qk_V2, nullptr);
+    k_radix_count<16, u32><<<ntiles, 256, 0, st>>>(qk_keys, n, hist, ntiles);
+    scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
+    k_radix_scatter<16, true, u32><<<ntiles, 256, 0, st>>>(qk_keys, qk_V2, n, hist, ntiles, qk_K1, S, rank);
+    k_seg<u32><<<(n + 1 + 255) / 256, 256, 0, st>>>(qk_K1, n, P.nbuckets, seg);
+  } else {
   k_hash_keys<<<(n + 255) / 256, 256, 0, st>>>(P, data, keys);
   k_radix_count<0><<<ntiles, 256, 0, st>>>(keys, n, hist, ntiles);
   scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
@@ -584,7 +632,8 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   k_radix_count<8><<<ntiles, 256, 0, st>>>(K1, n, hist, ntiles);
   scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
   k_radix_scatter<8, true><<<ntiles, 256, 0, st>>>(K1, V1, n, hist, ntiles, K2, S, rank);
-  k_seg<<<(n + 1 + 255) / 256, 256, 0, st>>>(K2, n, P.nbuckets, seg);
+  k_seg<u16><<<(n + 1 + 255) / 256, 256, 0, st>>>(K2, n, P.nbuckets, seg);
+  }
   // (the 16/32-entry rings of quality 5-6 gain nothing from tags -- measured: C2 58.1 ms with, 56.2 ms without -- so only
   // the deep rings of quality 7-9 use them: config C4 5.46 s -> 3.36 s)
   if (P.block_bits >= 6) k_tags<<<(n + 255) / 256, 256, 0, st>>>(data, S, n, tagS);
@@ -628,11 +677,14 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       CK(cudaMemsetAsync(srch_cur, 0, nwords * 4, st));
       CK(cudaMemsetAsync(counters + 4, 0, 4, st));
       CK(cudaMemsetAsync(counters + 16, 0, 4, st));
-      k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
-      scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
+      if (!P.quick) {   // (the S-ordered copy of the stored bits serves the bucket rings of quality 5..9)
+        k_build_storedS<<<(n + 1023) / 1024, 1024, 0, st>>>(s, storedS, prefS);
+        scan_exclusive(prefS, (n + 1023) / 1024, scan_tmp2, st);
+      }
       cudaEventRecord(ev[6], st);
       const u32 wg = (n_sched + 3) / 4;
-      if (P.multi) {
+      if (P.quick) k_walk<0, false><<<wg, 128, 0, st>>>(s);
+      else if (P.multi) {
         if (P.block_bits >= 6) k_walk<BR_WALK_G_DEEP, true><<<wg, 128, 0, st>>>(s);
         else k_walk<BR_WALK_G_SMALL, true><<<wg, 128, 0, st>>>(s);
       } else if (P.block_bits >= 6) k_walk<BR_WALK_G_DEEP, false><<<wg, 128, 0, st>>>(s);
@@ -642,6 +694,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       job->stats.walk_bytes += (u64)n_sched * ch;
       CK(cudaMemcpyAsync(bits_prev, bits_latest, nwords * 4, cudaMemcpyDeviceToDevice, st));
       k_commit<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s);
+      if (P.quick) k_verify<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s);
     }
     cudaEventRecord(ev[2], st);
 #ifdef BR_DEBUG_KNOBS
@@ -665,7 +718,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     for (u32 i = 0; i < n_mbs; ++i) {
       h_soff[i] = scratch_total; h_ooff[i] = outw_total;
       if (hm[i].compress) {
-        scratch_total += ((size_t)br_mb2_scratch_bytes(hm[i].nlit, hm[i].ncmd) + 255) & ~(size_t)255;
+        scratch_total += ((size_t)br_mb_scratch_bytes(P, hm[i].nlit, hm[i].ncmd) + 255) & ~(size_t)255;
         outw_total += (2 * (size_t)(hm[i].end - hm[i].start) + 503) / 4 + 16;
       }
     }
@@ -709,12 +762,13 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     k_cmd_mb<<<dim3(64, n_mbs), 256, 0, st>>>(s, cmd_mb);
     k_expand<<<(u32)((C + 127) / 128 + 1), 128, 0, st>>>(e);
     k_mb_setup<<<n_mbs, 32, 0, st>>>(s, e);
-    {
+    if (P.mb_kind) k_prep_flat<<<n_mbs, 64, 0, st>>>(s, e);   // qualities 2, 3: no block split, one code per category
+    else {
       const size_t smem_split = br_split_smem_bytes(256, 13) > br_split_smem_bytes(704, 1) ? br_split_smem_bytes(256, 13) : br_split_smem_bytes(704, 1);
       CK(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_split));
       k_split<<<dim3(n_mbs, 3), 256, smem_split, st>>>(s, e);
+      k_prep<<<n_mbs, 64, 0, st>>>(s, e);
     }
-    k_prep<<<n_mbs, 64, 0, st>>>(s, e);
     k_lit_bits<<<(e.total_lits + 1 + 255) / 256, 256, 0, st>>>(s, e);
     k_cmd_bits<<<(u32)((C + 1 + 255) / 256), 256, 0, st>>>(s, e);
     scan_exclusive(lit_len, e.total_lits + 1, stmp, st);
@@ -779,7 +833,7 @@ extern "C" __attribute__((visibility("default"))) int br_debug_sort(int quality,
   k_radix_count<8><<<ntiles, 256>>>(K1, n, hist, ntiles);
   scan_exclusive(hist, 256 * ntiles, tmp, 0);
   k_radix_scatter<8, true><<<ntiles, 256>>>(K1, V1, n, hist, ntiles, K2, S, nullptr);
-  k_seg<<<(n + 1 + 255) / 256, 256>>>(K2, n, P.nbuckets, seg);
+  k_seg<u16><<<(n + 1 + 255) / 256, 256>>>(K2, n, P.nbuckets, seg);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h_S, S, 4ull * n, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(h_seg, seg, (P.nbuckets + 2) * 4ull, cudaMemcpyDeviceToHost));

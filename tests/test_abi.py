@@ -85,9 +85,13 @@ def test_state_api_and_loud_failure(lib):
     assert lib.BrotliEncoderCompress(11, 22, 0, 100, b"x" * 100, C.byref(n), out) == 0
     n = C.c_size_t(4096)
     assert lib.BrotliEncoderCompress(5, 12, 0, 100, b"x" * 100, C.byref(n), out) == 0
-    for q in (0, 2, 3, 4, 10):                            # qualities without a GPU path: refused, never other bytes
+    for q in (0, 10):                                     # qualities without a GPU path: refused, never other bytes
         n = C.c_size_t(4096)
         assert lib.BrotliEncoderCompress(q, 22, 0, 100, b"x" * 100, C.byref(n), out) == 0
+    if not brotli_b200.available():                       # qualities 2..4 have a GPU path and, like the others, no CPU fallback
+        for q in (2, 3, 4):
+            n = C.c_size_t(4096)
+            assert lib.BrotliEncoderCompress(q, 22, 0, 100, b"x" * 100, C.byref(n), out) == 0
 
 
 def test_pkgconfig_dropin_layout(tmp_path):

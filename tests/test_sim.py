@@ -390,3 +390,84 @@ def test_sim_stream_offset(sim):
                 want = ref_stream_ops(ref, d, q, w, [len(d)], [2], params={9: off})
                 got = _sim_cuts(sim, d, q, w, len(d), [2], [1], 1, stream_offset=off, with_header=0)
                 assert got == want, (q, w, off, len(got), len(want))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Qualities 2..4: slot-sorted index + br_find_quick + br_verify_run, flat metablocks at quality 2, 3
+from golden_cases import CASES_ORACLE_ONLY
+
+Q234_SMALL = [c for c in CASES_ORACLE_ONLY if c["n"] <= 1_500_000]
+
+
+@pytest.mark.parametrize("c", Q234_SMALL, ids=lambda c: "%s-%d-q%d-w%d" % (c["kind"], c["n"], c["q"], c["lgwin"]))
+def test_sim_q234_matches_oracle(sim, c):
+    d = make_case(c)
+    want = Oracle().compress(d, c["q"], c["lgwin"])
+    cap = len(d) + len(d) // 2 + 4096
+    out = C.create_string_buffer(cap)
+    st = np.zeros(8, np.uint32)
+    r = sim.sim_compress(c["q"], c["lgwin"], d, len(d), out, cap, st.ctypes.data)
+    assert r >= 0
+    assert out.raw[:r] == want
+
+
+def test_sim_q234_windows_and_shapes(sim):
+    """Small and large windows (lgwin 10..24: window bits of every form, ring smaller than the input block at quality 4),
+    the H4 -> H54 switch at 1 MiB, degenerate inputs (long runs: unstored stretches inside one slot, the slot-0 candidate
+    of the zeroed table), incompressible input (raw metablocks, sparse-search phases)."""
+    from corpus import synth_binary, synth_text, synth_web
+    ora = Oracle()
+    web = synth_web(1_100_000, 41)
+    shapes = [synth_text(180000, 42), synth_binary(250000, 43), web[:(1 << 20) - 1], web[:1 << 20], bytes(300000),
+              bytes(range(256)) * 600, np.random.default_rng(44).integers(0, 256, 120000, dtype=np.uint8).tobytes(),
+              b"abcdefgh" * 20000 + synth_text(50000, 45) + b"abcdefgh" * 20000]
+    for i, d in enumerate(shapes):
+        for q in (2, 3, 4):
+            for w in ((10, 16, 22) if len(d) < 500000 else (17, 24)):
+                assert _fuzz_check(sim, d, q, w), (i, len(d), q, w)
+
+
+def test_sim_q234_fuzz_sample(sim):
+    from fuzz_cases import cases, dict_cases
+    for i, d, q, w in cases(20250925, 90):
+        if d and len(d) <= 120000:
+            q2 = 2 + i % 3
+            assert _fuzz_check(sim, d, q2, w), (i, len(d), q2, w)
+            assert _fuzz_check(sim, d, q2, 10 + i % 8), (i, len(d), q2, 10 + i % 8)
+    for i, d, q, w in dict_cases(20250926, 30, TABLES):     # static-dictionary words: the shallow probe of H2 / H4
+        for q2 in (2, 4):
+            assert _fuzz_check(sim, d, q2, w), ("dict", i, len(d), q2, w)
+
+
+def test_sim_q234_flush_cuts(sim):
+    """Qualities 2..4 with the input cut by FLUSH operations, against the reference's CompressStream driven with the same
+    calls: input blocks of 1 << 14 bytes below quality 4 (quality.h:81), the MAX_NUM_DELAYED_SYMBOLS flush rule
+    (encode.c:1152), FINISH without input behind a full block."""
+    from brotli_libs import REF_SO, Ref, ref_stream_ops
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    from corpus import synth_binary, synth_text
+    ref = Ref()
+    for d in (synth_text(300000, 3), synth_binary(400000, 5)):
+        n = len(d)
+        for q, w in ((2, 22), (3, 18), (4, 22), (4, 12)):
+            bs = 1 << (14 if q < 4 else 16)
+            for sizes, ops in (([100000, 50000, n - 150000], [0, 1, 2]), ([bs, 0, n - bs, 0], [0, 1, 1, 2]), ([100, n - 100, 0], [1, 0, 2])):
+                want = ref_stream_ops(ref, d, q, w, sizes, ops)
+                pos, cuts, acc, fixed, hint = 0, [], 0, False, 0
+                for a, op in zip(sizes, ops):
+                    if not fixed and (op != 0 or acc + a >= bs):   # encode.c:1619: the size hint freezes at the first EncodeData
+                        hint, fixed = acc + a, True
+                    acc += a
+                    pos += a
+                    if op == 1 and pos > 0 and (not cuts or cuts[-1] != pos):
+                        cuts.append(pos)
+                if cuts and cuts[-1] == n:
+                    got = _sim_cuts(sim, d, q, w, hint, cuts, [1] * len(cuts), 0) + b"\x03"
+                else:
+                    got = _sim_cuts(sim, d, q, w, hint, cuts, [1] * len(cuts), 1)
+                assert got == want, (q, w, sizes, ops)
+    d = synth_text(4 * 65536, 9)
+    for q, w in ((2, 22), (3, 22), (4, 22)):
+        want = ref_stream_ops(ref, d, q, w, [len(d), 0], [0, 2])          # FINISH without input behind full blocks
+        assert _sim_cuts(sim, d, q, w, 1 << (14 if q < 4 else 16), [], [], 1, finish_empty=1) == want, (q, w)

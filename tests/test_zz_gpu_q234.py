@@ -1,0 +1,144 @@
+"""GPU suite (-m gpu), last file on purpose: qualities 2..4 (SURVEY.md 8f rank 1 -- the one-position-per-slot hashers
+H2 / H3 / H4 / H54 of c/enc/hash_longest_match_quickly_inc.h, BrotliStoreMetaBlockFast / Trivial of
+c/enc/brotli_bit_stream.c:1196-1317) through the C ABI, against digests of the compiled reference, the oracle and --
+where it travelled -- oracle/_ref itself.  Bit-exact.  The device functions of this path are the ones tests/test_sim.py
+runs on the CPU (test_sim_q234_*); what only these tests cover is the CUDA plumbing around them: the 32-bit three-pass
+radix sort of the slot keys, k_walk<0>, k_verify, k_prep_flat and the host wrapper."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from brotli_libs import REF_SO, Oracle, Ref, ref_stream_ops
+from golden_cases import make_case
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+HERE = os.path.dirname(__file__)
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden_oracle_only.json")))
+FIXDIR = os.path.join(HERE, "golden", "fixtures")
+FIXTURES = json.load(open(os.path.join(HERE, "golden", "fixtures_q234.json")))
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import brotli_b200
+    assert brotli_b200.available(), "no CUDA device"
+    return brotli_b200
+
+
+@pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%s-%d-q%d-w%d" % (g["kind"], g["n"], g["q"], g["lgwin"]))
+def test_q234_golden(b200, g):
+    d = make_case(g)
+    assert hashlib.sha256(d).hexdigest() == g["in_sha256"]
+    out = b200.compress_oneshot(d, g["q"], g["lgwin"])
+    assert len(out) == g["out_len"]
+    assert hashlib.sha256(out).hexdigest() == g["out_sha256"]
+
+
+@pytest.mark.parametrize("g", FIXTURES, ids=lambda g: "%s-q%d-w%d" % (g["label"], g["q"], g["lgwin"]))
+def test_q234_reference_fixtures(b200, g):
+    """The reference's own tests/testdata files at qualities 2..4, against digests of the compiled reference."""
+    d = open(os.path.join(FIXDIR, g["file"]), "rb").read()[:g["n"]]
+    assert hashlib.sha256(d).hexdigest() == g["in_sha256"]
+    out = b200.compress_oneshot(d, g["q"], g["lgwin"])
+    assert len(out) == g["out_len"]
+    assert hashlib.sha256(out).hexdigest() == g["out_sha256"]
+
+
+def test_q234_against_oracle_windows(b200):
+    ora = Oracle()
+    from corpus import synth_binary, synth_text, synth_web
+    d1, d2, d3 = synth_text(700000, 31), synth_web(1300000, 32), synth_binary(900000, 34)
+    for q in (2, 3, 4):
+        for w in (10, 13, 16, 17, 20, 22, 24):
+            for d in (d1, d2, d3):
+                assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (q, w, len(d))
+
+
+def test_q234_edge_sizes(b200):
+    ora = Oracle()
+    from corpus import synth_text
+    base = synth_text(1 << 20, 33) + synth_text(100, 35)
+    for n in (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 63, 64, 65, 511, 512, 4095, 16383, 16384, 16385, 65535, 65536, 65537,
+              131072, 131073, (1 << 20) - 1, 1 << 20, (1 << 20) + 1):
+        for q in (2, 3, 4):
+            assert b200.compress_oneshot(base[:n], q, 22) == ora.compress(base[:n], q, 22), (n, q)
+    for d in (bytes(500000), bytes(range(256)) * 3000, b"ab" * 300000, os.urandom(1) * 7 + bytes(70000)):
+        for q in (2, 3, 4):
+            for w in (12, 22):
+                assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (len(d), q, w)
+
+
+def test_q234_incompressible_and_mixed(b200):
+    """Raw metablocks, the sparse-search phases on noise, the late uncompressed fallback (encode.c:604) at quality 2..4."""
+    ora = Oracle()
+    from corpus import synth_binary, synth_text
+    rnd = np.random.default_rng(77).integers(0, 256, 3_000_000, dtype=np.uint8).tobytes()
+    mix = synth_text(400000, 78) + rnd[:700000] + synth_binary(500000, 79) + rnd[700000:1000000] + synth_text(300000, 80)
+    for q in (2, 3, 4):
+        assert b200.compress_oneshot(rnd, q, 22) == ora.compress(rnd, q, 22), q
+        assert b200.compress_oneshot(mix, q, 20) == ora.compress(mix, q, 20), q
+
+
+def _drive(b200, d, q, w, sizes, ops):
+    c = b200.Compressor(quality=q, lgwin=w)
+    out, pos = b"", 0
+    for a, op in zip(sizes, ops):
+        out += c._stream(d[pos:pos + a], op)
+        pos += a
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_q234_streaming_flush_and_metadata(b200):
+    """PROCESS / FLUSH / EMIT_METADATA / FINISH at quality 2..4 (input blocks of 1 << 14 bytes below quality 4), byte-identical
+    to the reference's CompressStream for the same call sequence."""
+    from corpus import synth_binary, synth_text
+    ref = Ref()
+    for d in (synth_text(500000, 61), synth_binary(600000, 62)):
+        n = len(d)
+        for q, w in ((2, 22), (3, 16), (4, 22), (4, 11)):
+            bs = 1 << (14 if q < 4 else 16)
+            seqs = [
+                ([100000, 50000, 250000, n - 400000], [0, 1, 1, 2]),
+                ([0, 300000, 0, n - 300000, 0], [1, 1, 1, 1, 2]),
+                ([bs, 0, n - bs], [0, 1, 2]),
+                ([4 * bs, 0], [0, 2]),
+                ([7, 200000, 5, n - 200012, 0], [3, 0, 3, 1, 2]),
+                ([0, 100, 0, 0, 11, n - 111], [3, 1, 3, 1, 3, 2]),
+            ]
+            for sizes, ops in seqs:
+                want = ref_stream_ops(ref, d, q, w, sizes, ops)
+                got = _drive(b200, d, q, w, sizes, ops)
+                assert got == want, (q, w, sizes, ops, len(got), len(want))
+
+
+def test_q234_batch_api(b200):
+    """BrotliB200CompressBatch at quality 2..4: one job per stream (host workers), every stream equal to the one-shot call."""
+    ora = Oracle()
+    from corpus import synth_web
+    web = synth_web(3_000_000, 90)
+    rnd = np.random.default_rng(91)
+    streams, off = [], 0
+    for i in range(24):
+        n = int(rnd.choice([1, 100, 5000, 65536, 200000]))
+        streams.append(web[off:off + n]); off += n
+    for q in (2, 3, 4):
+        got = b200.compress_batch(streams, q, 22)
+        assert got == [ora.compress(s, q, 22) for s in streams], q
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_q234_full_size(b200):
+    """100 MB of text (BASELINE config C2's input) at quality 2 and 4, and 64 MiB of the binary mix at quality 3 with a 24-bit
+    window, against the reference itself on the box."""
+    from corpus import synth_binary, synth_text
+    ref = Ref()
+    d = synth_text(100_000_000, 20250922)
+    for q in (2, 4):
+        assert b200.compress_oneshot(d, q, 22) == ref.compress(d, q, 22), q
+    d = synth_binary(64 << 20, 20250924)
+    assert b200.compress_oneshot(d, 3, 24) == ref.compress(d, 3, 24)
