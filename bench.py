@@ -48,8 +48,10 @@ WORKLOADS = {
     "c4": "200 MB Silesia-shaped binary mix (synth_binary, seed 20250924), quality 9, lgwin 24, one stream per GPU (replicas at N > 1)",
     "c5": "10 000 x 64 KiB streams (slices of the c3 mix at offsets i*104729 mod (2^30-65536)), quality 1, lgwin 22, stream j on GPU j mod N",
     "c5q5": "c5's 10 000 x 64 KiB streams at quality 5, lgwin 22 (many small web payloads; not a BASELINE config), stream j on GPU j mod N",
+    "q234": "c2's 100 MB text at quality 2, 3 and 4, lgwin 22 (SURVEY 8f rank 1; not a BASELINE config), N = 1 only, run in a child "
+            "process with a time limit so that this newest path cannot take the headline line with it",
 }
-QL = {"c2": (5, 22), "c3": (5, 22), "c4": (9, 24), "c5": (1, 22), "c5q5": (5, 22)}
+QL = {"c2": (5, 22), "c3": (5, 22), "c4": (9, 24), "c5": (1, 22), "c5q5": (5, 22), "q234": (4, 22)}
 METRIC = "encoder input MB/s (bit-exact)"
 # the headline's config: identical in both arms (the driver compares them)
 HEAD_CONFIG = {"workload": WORKLOADS["c2"], "quality": 5, "lgwin": 22, "input_bytes_per_gpu": C2_BYTES,
@@ -200,6 +202,16 @@ def run_reference(args, rank):
             "host_cores": os.cpu_count(), "sub_results": {}}
     for cfg in args.configs:
         if cfg == "c2":
+            continue
+        if cfg == "q234":
+            d0 = make_stream_input("c2", 0, 1)
+            per = {}
+            for q in (2, 3, 4):
+                t0 = time.time(); lib.compress(d0, q, 22); dt = time.time() - t0
+                per["q%d" % q] = {"value": round(len(d0) / dt / 1e6, 2), "unit": "MB/s", "ms_per_step": round(1e3 * dt, 2), "steps": 1,
+                                  "cpu_baseline": {"value": round(len(d0) / dt / 1e6, 2), "unit": "MB/s", "cores": 1, "kind": kind,
+                                                   "sample": "the whole %d-byte stream once, 1 thread" % len(d0)}}
+            line["sub_results"][cfg] = {"workload": WORKLOADS[cfg], "lgwin": 22, "per_quality": per}
             continue
         v, ms, cores, sample = reference_config(cfg, lib, args.gpus, 1, 0)
         line["sub_results"][cfg] = {"workload": WORKLOADS[cfg], "quality": QL[cfg][0], "lgwin": QL[cfg][1],
@@ -550,14 +562,89 @@ def bench_c5q5(ctx, steps, warmup):
     return r
 
 
+def q234_child():
+    """Child process of the q234 sub-result: C2's input at quality 2, 3, 4 on cuda:0; prints one JSON object."""
+    import torch
+    import brotli_b200
+    from corpus import synth_text
+    L = brotli_b200.lib()
+    torch.cuda.set_device(0)
+    data = synth_text(C2_BYTES, seed=20250922)
+    n = len(data)
+    h_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    d_in = h_in.cuda()
+    cap = L.BrotliEncoderMaxCompressedSize(n) + 64
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    kind, lib = ref_lib()
+    peak, src = hbm_peak()
+    per = {}
+    for q in (2, 3, 4):
+        def dev():
+            sz = C.c_size_t(cap)
+            assert L.BrotliB200CompressDevice(q, 22, n, d_in.data_ptr(), C.byref(sz), d_out.data_ptr()), "BrotliB200CompressDevice failed"
+            return sz.value
+        def e2e():
+            sz = C.c_size_t(cap)
+            assert L.BrotliEncoderCompress(q, 22, 0, n, h_in.data_ptr(), C.byref(sz), h_out.data_ptr()), "BrotliEncoderCompress failed"
+            return sz.value
+        steps = 3
+        dev(); dev(); dev()                       # W = 3 warm-up steps
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(steps):
+            out_size = dev()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        st = brotli_b200.last_stats()
+        e2e()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(steps):
+            assert e2e() == out_size
+        torch.cuda.synchronize(); dt2 = time.perf_counter() - t0
+        got = bytes(h_out[:out_size].numpy().tobytes())
+        t1 = time.time(); want = lib.compress(data, q, 22); t_cpu = time.time() - t1
+        r = {"quality": q, "lgwin": 22, "steps": steps, "warmup": 3, "input_bytes": n, "compressed_bytes": out_size,
+             "bit_exact": got == want, "value": round(n * steps / dt / 1e6, 2), "unit": "MB/s", "ms_per_step": round(1e3 * dt / steps, 2),
+             "e2e": {"value": round(n * steps / dt2 / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": out_size,
+                     "path": "BrotliEncoderCompress(host in, host out), pinned buffers"},
+             "stages_ms": {k: round(st[k], 2) for k in ("ms_total", "ms_index", "ms_lz77", "ms_entropy", "ms_assemble", "ms_walk", "ms_encode")},
+             "lz77": {"walk_launches": int(st["lz77_iterations"]), "chunk_walks": int(st["block_runs"]), "chunks": int(st["blocks"]),
+                      "metablocks": int(st["metablocks"])},
+             "gpu_launches": int(st["launches"]) * steps,
+             "cpu_baseline": {"value": round(n / t_cpu / 1e6, 2), "unit": "MB/s", "cores": 1, "kind": kind,
+                              "sample": "the whole %d-byte stream once, 1 thread" % n}}
+        if st["ms_walk"] > 0:
+            algo = st["walk_bytes"] * (1.0 + out_size / float(n))
+            ach = algo / (st["ms_walk"] / 1e3) / 1e9
+            r["roofline"] = {"bound": "hbm", "kernel": "k_walk<0>", "achieved": round(ach, 3), "peak": peak, "unit": "GB/s",
+                             "frac": round(ach / peak, 6), "traffic": None, "algorithmic_gb": round(algo / 1e9, 4),
+                             "kernel_ms": round(st["ms_walk"], 2), "launches": int(st["walk_launches"]), "peak_source": src}
+        per["q%d" % q] = r
+        log("q234 child: quality %d: %s MB/s, bit_exact %s" % (q, r["value"], r["bit_exact"]))
+    sys.stdout.write(json.dumps({"workload": WORKLOADS["q234"], "lgwin": 22, "per_quality": per}) + "\n")
+    sys.stdout.flush()
+
+
+def bench_q234():
+    """Runs q234_child in a process of its own (time limit 10 minutes): a crash or a hang of the newest path ends the
+    child, not the bench."""
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), "--q234-child"], stdout=subprocess.PIPE, timeout=600)
+    lines = [l for l in p.stdout.decode("utf-8", "replace").splitlines() if l.startswith("{")]
+    if p.returncode != 0 or not lines:
+        raise RuntimeError("q234 child exited with %d" % p.returncode)
+    return json.loads(lines[-1])
+
+
 def main():
+    if "--q234-child" in sys.argv:
+        q234_child()
+        return
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--configs", default="c2,c4,c3,c5,c5q5")
+    ap.add_argument("--configs", default="c2,c4,c3,c5,c5q5,q234")
     args = ap.parse_args()
     args.configs = [c for c in args.configs.split(",") if c in WORKLOADS]
     rank = int(os.environ.get("RANK", "0"))
@@ -621,6 +708,8 @@ def main():
                 sub[cfg] = bench_c5(ctx, 5, 2)
             elif cfg == "c5q5":
                 sub[cfg] = bench_c5q5(ctx, 5, 2)
+            elif cfg == "q234" and world == 1:
+                sub[cfg] = bench_q234()
         except Exception as e:      # a sub-result must not take the headline line with it (one rank: the others would hang)
             if world > 1:
                 raise

@@ -9,7 +9,7 @@
  *
  * The hot path runs on an NVIDIA B200 (sm_100a).  There is NO CPU implementation inside
  * the library: without a CUDA device, or for parameters outside the implemented path
- * (quality 1 and 5..9, no custom dictionary, modes GENERIC/TEXT: limits below), the entry points
+ * (quality 1..9, no custom dictionary, modes GENERIC/TEXT: limits below), the entry points
  * return BROTLI_FALSE / NULL instead of producing different bytes.
  *
  * Plain C: pointers and sizes only, no torch / CUDA types.
@@ -23,12 +23,13 @@
  * reference's own types (no re-definition here, so this header mixes with <brotli/encode.h> and <brotli/decode.h>).
  *
  * Limits of the implemented path (everything else returns BROTLI_FALSE / NULL, never other bytes):
- *   quality 1 (lgwin 10..24) and quality 5..9 (lgwin 17..24), modes GENERIC / TEXT, default NPOSTFIX / NDIRECT, no
- *   dictionaries, no LARGE_WINDOW.  BROTLI_PARAM_LGBLOCK, DISABLE_LITERAL_CONTEXT_MODELING, SIZE_HINT and (quality 5..9)
+ *   quality 1..4 (lgwin 10..24) and quality 5..9 (lgwin 17..24), modes GENERIC / TEXT, default NPOSTFIX / NDIRECT, no
+ *   dictionaries, no LARGE_WINDOW.  (Qualities 2..4 -- hash_longest_match_quickly_inc.h, brotli_bit_stream.c:1196-1317 --
+ *   are the newest path: see DESIGN.md section 3d for what has and has not been run on a GPU.)  BROTLI_PARAM_LGBLOCK, DISABLE_LITERAL_CONTEXT_MODELING, SIZE_HINT and (quality 5..9)
  *   STREAM_OFFSET are honoured.  Quality 1: streams of any size, compressed in device segments of <= 128 MiB as the calls
- *   arrive (bounded memory).  Quality 5..9: one stream <= 1 GiB -- BrotliEncoderCompressStream fails on the PROCESS call
+ *   arrive (bounded memory).  Quality 2..9: one stream <= 1 GiB -- BrotliEncoderCompressStream fails on the PROCESS call
  *   that crosses it; the stream so far is kept in host memory and recompressed at every FLUSH (see csrc/br_api.cc).
- *   FLUSH, FINISH and (quality 5..9) EMIT_METADATA follow encode.h:93-157. */
+ *   FLUSH, FINISH and (quality 2..9) EMIT_METADATA follow encode.h:93-157. */
 #include <brotli/encode.h>
 #ifdef __cplusplus
 extern "C" {
@@ -42,6 +43,7 @@ extern "C" {
 BROTLI_B200_API BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, size_t input_size, const void* d_input, size_t* encoded_size, void* d_encoded);
 /* Many independent streams (one stream per shard / per object).  Inputs and
  * outputs are host pointers; every stream comes out exactly as BrotliEncoderCompress(quality, lgwin, GENERIC) gives it.
+ * Quality 2..4: one device job per stream, on `threads` host workers.
  * Quality 5..9: streams shorter than 1 MiB are laid end to end and run as ONE device job per group of <= 128 MiB / 8192 streams (one
  * set of launches, one copy each way; `threads` parallelises the host-side packing); longer streams are spread over
  * `threads` host workers, each with its own CUDA stream.  Quality 1 (compress_fragment_two_pass.c:612, one independent
