@@ -620,7 +620,55 @@ def q234_child():
                              "kernel_ms": round(st["ms_walk"], 2), "launches": int(st["walk_launches"]), "peak_source": src}
         per["q%d" % q] = r
         log("q234 child: quality %d: %s MB/s, bit_exact %s" % (q, r["value"], r["bit_exact"]))
-    sys.stdout.write(json.dumps({"workload": WORKLOADS["q234"], "lgwin": 22, "per_quality": per}) + "\n")
+    result = {"workload": WORKLOADS["q234"], "lgwin": 22, "per_quality": per}
+    try:      # many small streams at quality 2 and 4: 2 000 x 64 KiB web payloads as device jobs of <= 128 MiB (host buffers in and out)
+        from corpus import synth_web
+        cnt = 2000
+        web = synth_web(cnt * C5_SIZE, 20250923)
+        streams = [web[i * C5_SIZE:(i + 1) * C5_SIZE] for i in range(cnt)]
+        bufs = [C.create_string_buffer(x, len(x)) for x in streams]
+        sizes = (C.c_size_t * cnt)(*[len(x) for x in streams])
+        caps = [L.BrotliEncoderMaxCompressedSize(len(x)) + 16 for x in streams]
+        outs = [C.create_string_buffer(c) for c in caps]
+        in_ptrs = (C.c_void_p * cnt)(*[C.addressof(b) for b in bufs])
+        out_ptrs = (C.c_void_p * cnt)(*[C.addressof(b) for b in outs])
+        caps_arr = (C.c_size_t * cnt)(*caps)
+        out_sizes = (C.c_size_t * cnt)()
+        ncpu = os.cpu_count() or 1
+        batch = {}
+        for q in (2, 4):
+            def step():
+                C.memmove(out_sizes, caps_arr, C.sizeof(caps_arr))
+                good = L.BrotliB200CompressBatch(q, 22, cnt, in_ptrs, sizes, out_ptrs, out_sizes, 16)
+                assert good == cnt, "BrotliB200CompressBatch: %d of %d" % (good, cnt)
+            step(); step(); step()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            st = brotli_b200.last_stats()
+            want = [None] * cnt
+            t1 = time.time()
+            def work(k):
+                for i in range(k, cnt, ncpu):
+                    want[i] = lib.compress(streams[i], q, 22)
+            run_threads(ncpu, work)
+            t_cpu = time.time() - t1
+            v = round(cnt * C5_SIZE * 3 / dt / 1e6, 2)
+            batch["q%d" % q] = {"streams": cnt, "stream_bytes": C5_SIZE, "quality": q, "lgwin": 22, "steps": 3, "warmup": 3,
+                                "bit_exact": all(outs[k].raw[:out_sizes[k]] == want[k] for k in range(cnt)),
+                                "value": v, "unit": "MB/s", "ms_per_step": round(1e3 * dt / 3, 2),
+                                "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": cnt * C5_SIZE,
+                                        "d2h_bytes_per_step": sum(out_sizes[k] for k in range(cnt)),
+                                        "path": "BrotliB200CompressBatch(host pointer arrays): value == e2e for this call"},
+                                "lz77": {"walk_launches": int(st["walk_launches"]), "chunk_walks": int(st["block_runs"]), "chunks": int(st["blocks"])},
+                                "cpu_baseline": {"value": round(cnt * C5_SIZE / t_cpu / 1e6, 2), "unit": "MB/s", "cores": ncpu, "kind": kind,
+                                                 "sample": "all %d streams once, dealt over %d host threads" % (cnt, ncpu)}}
+            log("q234 child: batch quality %d: %s MB/s, bit_exact %s" % (q, v, batch["q%d" % q]["bit_exact"]))
+        result["batch_2000x64KiB"] = batch
+    except Exception as e:
+        result["batch_2000x64KiB"] = {"error": repr(e)}
+    sys.stdout.write(json.dumps(result) + "\n")
     sys.stdout.flush()
 
 

@@ -276,7 +276,7 @@ size_t compress_stream_group(int quality, int lgwin, const std::vector<size_t>& 
   BrCuts c; memset(&c, 0, sizeof(c));
   c.pos = pos.data(); c.kind = kind.data(); c.n = (uint32_t)(k - 1); c.is_final = 1; c.with_header = 1; c.stream_end = ends.data();
   const uint8_t* d_out = nullptr; size_t sz = 0;
-  int w = lgwin > 24 ? 24 : lgwin;
+  int w = lgwin > 24 ? 24 : lgwin < 10 ? 10 : lgwin;   /* quality.h:60 SanitizeParams */
   if (!br_job_compress_device(tls.job, quality, w, hint, tls.d_in, (uint32_t)n, &d_out, &sz, k > 1 ? &c : nullptr)) return fail_all();
   record_stats();
   if (k == 1) ends[0] = sz;
@@ -537,7 +537,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
     }
     return good;
   }
-  /* quality 5..9: streams below 1 MiB go through the device in groups (one job per group, compress_stream_group); longer
+  /* quality 2..9: streams below 1 MiB go through the device in groups (one job per group, compress_stream_group); longer
      ones one by one, `threads` host workers each with its own CUDA stream */
   Params p; p.quality = quality; p.lgwin = lgwin;
   if (lgwin > 24) p.large_window = 1;
@@ -546,7 +546,7 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
   std::vector<size_t> big, group;
   size_t group_bytes = 0;
   for (size_t i = 0; i < count; ++i) {
-    if (input_sizes[i] == 0 || input_sizes[i] >= ((size_t)1 << 20) || quality < 5) { big.push_back(i); continue; }   /* (quality 2..4: one job per stream) */
+    if (input_sizes[i] == 0 || input_sizes[i] >= ((size_t)1 << 20)) { big.push_back(i); continue; }
     if ((group_bytes + input_sizes[i] > kBatchGroupBytes || group.size() >= kBatchGroupStreams) && !group.empty()) {
       ok += compress_stream_group(quality, lgwin, group, inputs, input_sizes, outputs, encoded_sizes, threads);
       group.clear(); group_bytes = 0;

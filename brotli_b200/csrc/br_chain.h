@@ -15,6 +15,13 @@ static u32 br_sim_watch = 0xffffffffu;   // tests/sim: report commits that flip 
 static u64 br_sim_cnt[8];                // tests/sim: marks by source (0 successor, 1 overlap, 2 cap hits, 3 flips, 4 steps)
 #endif
 
+// First byte of the stream that holds position p (0 unless the job is a batch of streams, BrParams::multi).
+BR_DEV u32 br_stream_base_of(const BrStream& s, u32 p) {
+  if (!s.P.multi) return 0u;
+  u32 b = s.slot_blk[p >> s.P.lgblock];
+  while (p >= s.blk[b].end) ++b;
+  return s.blk[b].base;
+}
 // Chunk whose nominal slice holds position p.  Input blocks are at most 1 << lgblock bytes long but need not be aligned
 // (a FLUSH cuts one short): slot_blk gives the block at the aligned position below p, a short scan finds p's block.
 BR_DEV u32 br_chunk_of(const BrStream& s, u32 p) {

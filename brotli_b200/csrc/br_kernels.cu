@@ -35,11 +35,12 @@ __global__ void k_hash_keys(BrParams P, const u8* __restrict__ data, u16* __rest
 
 // qualities 2..4: the key is the table slot of the one-position-per-slot hashers (br_lz77.h br_quick_slot), up to 20 bits
 // (+ the overflow key of the unhashable tail): 32-bit keys, three radix passes
-__global__ void k_slot_keys(BrParams P, const u8* __restrict__ data, u32* __restrict__ keys) {
-  u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P.n) return;
-  u32 hashable = P.n >= P.htl ? P.n - P.htl + 1 : 0;
-  keys[p] = p < hashable ? br_quick_slot(P, br_ld64u(data, p), p) : P.nbuckets;
+// One CTA per input block: the slot depends on the position counted from the first byte of the block's stream (BrBlk::base).
+__global__ void k_slot_keys(BrParams P, const u8* __restrict__ data, const BrBlk* __restrict__ blk, u32* __restrict__ keys) {
+  const BrBlk B = blk[blockIdx.x];
+  const u32 hashable = P.n >= P.htl ? P.n - P.htl + 1 : 0;
+  for (u32 p = B.start + threadIdx.x; p < B.end; p += blockDim.x)
+    keys[p] = p < hashable ? br_quick_slot(P, br_ld64u(data, p), p - B.base) : P.nbuckets;
 }
 
 #define RADIX_TILE 4096
@@ -492,7 +493,6 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     // a batch of independent streams (each below BR_SMALL_STREAM, size_hint = the largest): no FLUSH cuts, all finished
     if (nstreams != ncuts + 1 || !cuts->is_final || !cuts->with_header || cuts->finish_empty || cuts->stream_offset ||
         cuts->pos[ncuts - 1] >= n || size_hint >= BR_SMALL_STREAM) return 0;
-    if (P.quick) return 0;   // (qualities 2..4: one job per stream)
     P.multi = nstreams; P.pilot = 0;
     P.chunk_bits = br_batch_chunk_bits(n);
   }
@@ -613,7 +613,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   // ---- position index: S, rank, seg
   if (P.quick) {
     // sorted by (slot, position): three stable 8-bit passes over 32-bit keys (slots have up to 20 bits + the overflow key)
-    k_slot_keys<<<(n + 255) / 256, 256, 0, st>>>(P, data, qk_keys);
+    k_slot_keys<<<nblk, 256, 0, st>>>(P, data, d_blk, qk_keys);
     k_radix_count<0, u32><<<ntiles, 256, 0, st>>>(qk_keys, n, hist, ntiles);
     scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
     k_radix_scatter<0, false, u32><<<ntiles, 256, 0, st>>>(qk_keys, nullptr, n, hist, ntiles, qk_K1, qk_V1, nullptr);
@@ -683,8 +683,10 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       }
       cudaEventRecord(ev[6], st);
       const u32 wg = (n_sched + 3) / 4;
-      if (P.quick) k_walk<0, false><<<wg, 128, 0, st>>>(s);
-      else if (P.multi) {
+      if (P.quick) {
+        if (P.multi) k_walk<0, true><<<wg, 128, 0, st>>>(s);
+        else k_walk<0, false><<<wg, 128, 0, st>>>(s);
+      } else if (P.multi) {
         if (P.block_bits >= 6) k_walk<BR_WALK_G_DEEP, true><<<wg, 128, 0, st>>>(s);
         else k_walk<BR_WALK_G_SMALL, true><<<wg, 128, 0, st>>>(s);
       } else if (P.block_bits >= 6) k_walk<BR_WALK_G_DEEP, false><<<wg, 128, 0, st>>>(s);

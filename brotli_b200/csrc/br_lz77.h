@@ -475,7 +475,7 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
 BR_DEV u32 br_quick_key_v(const BrParams& P, u64 v) {
   return (u32)(((v << (64 - 8 * P.qk_hash_len)) * 0x1FE35A7BD3579BD3ull) >> (64 - P.qk_bits));
 }
-// the slot position `pos` is filed in (Store, :96)
+// the slot position `pos` (counted from the first byte of its stream) is filed in (Store, :96)
 BR_DEV u32 br_quick_slot(const BrParams& P, u64 v, u32 pos) {
   return (br_quick_key_v(P, v) + (pos & (((1u << P.qk_sweep_bits) - 1u) << 3))) & ((1u << P.qk_bits) - 1u);
 }
@@ -514,7 +514,8 @@ BR_DEV void br_find_quick(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, 
   BR_W(0, 1);
   out.delta = 0;
   // ---- the slots' index ranges go out first (independent loads), the last-distance candidate is checked meanwhile
-  const u32 i_own = (cur >> 3) & (sweep - 1u);   // the slot `cur` itself is filed in: its predecessors end at rank[cur]
+  const u32 base = w.base;   // first byte of the stream (0 unless the job is a batch of streams): the table's positions count from it
+  const u32 i_own = ((cur - base) >> 3) & (sweep - 1u);   // the slot `cur` itself is filed in: its predecessors end at rank[cur]
   u32 lo[4], ja[4], jb[4];
 #pragma unroll
   for (u32 i = 0; i < 4; ++i) {
@@ -570,19 +571,21 @@ BR_DEV void br_find_quick(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, 
     // the slot's content as this walker sees it: the latest stored position in front of cur, inside the window
     u32 j = ja[i], cand = 0, rv = 0;
     bool found = false;
+    bool at_start = true;   // the walk reached the front of the slot's segment (of this stream's part of it)
     while (j > lo[i]) {
       const u32 q = br_ldg(s.S + (j - 1));
-      if (cur - q > max_backward) break;
+      if (q < base) break;                                // (batch of streams: positions of the streams in front)
+      if (cur - q > max_backward) { at_start = false; break; }
       --j;
       if (br_is_stored(w, q)) { found = true; cand = q; break; }
     }
     rv = found ? j : (BR_SAW_ABSENT | j);
     if (rec) saw[i] = rv;
     BR_W(1, 1);
-    // absent: position 0 (the zeroed table) while the window still reaches it; otherwise the slot holds something the
-    // reference rejects (backward > max_backward) whatever its first byte
-    bool valid = found || (j == lo[i] && cur <= max_backward && cur != 0);
-    const u32 prev = found ? cand : 0u;
+    // absent: the stream's first position (the zeroed table holds 0) while the window still reaches it; otherwise the slot
+    // holds something the reference rejects (backward > max_backward) whatever its first byte
+    bool valid = found || (at_start && cur - base <= max_backward && cur != base);
+    const u32 prev = found ? cand : base;
     const u32 backward = cur - prev;
     if (valid && compare_char != (u32)br_ldg(d + prev + best_len)) valid = false;
     if (valid && (backward == 0 || backward > max_backward)) valid = false;

@@ -59,7 +59,7 @@ static void sim_build_sorted(SimStream& m) {
   BrStream& s = m.s; const BrParams& P = s.P; u32 n = P.n;
   std::vector<u32> key(n);
   u32 hashable = n >= P.htl ? n - P.htl + 1 : 0;  // positions with a full hash load
-  for (u32 p = 0; p < n; ++p) key[p] = p >= hashable ? P.nbuckets : P.quick ? br_quick_slot(P, br_ld64u(s.data, p), p) : br_hash_key(P, s.data, p);
+  for (u32 p = 0; p < n; ++p) key[p] = p >= hashable ? P.nbuckets : P.quick ? br_quick_slot(P, br_ld64u(s.data, p), p - br_stream_base_of(s, p)) : br_hash_key(P, s.data, p);
   m.seg.assign(P.nbuckets + 2, 0);
   for (u32 p = 0; p < n; ++p) m.seg[key[p] + 1]++;
   for (u32 k = 0; k <= P.nbuckets; ++k) m.seg[k + 1] += m.seg[k];
@@ -193,7 +193,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     s.counters[4] = 0; s.counters[16] = 0;
     s.forced = s.epoch >= s.P.force_epoch;
     { u32 nd = s.counters[5]; std::vector<u32> dl(nd); for (u32 t = 0; t < nd; ++t) dl[t] = br_sched_entry(s, t); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
-      if (s.P.quick) br_walk_block<0>(s, k, f);
+      if (s.P.quick) { if (s.P.multi) br_walk_block<0, true>(s, k, f); else br_walk_block<0>(s, k, f); }
       else if (s.P.multi) { if (s.P.block_bits >= 6) br_walk_block<4, true>(s, k, f); else br_walk_block<1, true>(s, k, f); }
       else if (s.P.block_bits >= 6) br_walk_block<4>(s, k, f); else br_walk_block<1>(s, k, f); } }
     m.block_runs += s.counters[4];
@@ -224,7 +224,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     std::vector<BrBlockOut> old(s.bout, s.bout + nb);
     std::vector<BrCmd> old_cmds(m.cmd_blocks);
     s.counters[4] = 0;
-    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; if (s.P.quick) br_walk_one<0>(s, k, s.bin[k], o, k, sp0); else br_walk_one<1>(s, k, s.bin[k], o, k, sp0); }
+    for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; if (s.P.quick && s.P.multi) br_walk_one<0, true>(s, k, s.bin[k], o, k, sp0); else if (s.P.quick) br_walk_one<0>(s, k, s.bin[k], o, k, sp0); else br_walk_one<1>(s, k, s.bin[k], o, k, sp0); }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
     for (u32 k = 0; k < nb; ++k) {
       br_commit_bits(s, k);

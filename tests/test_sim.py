@@ -471,3 +471,79 @@ def test_sim_q234_flush_cuts(sim):
     for q, w in ((2, 22), (3, 22), (4, 22)):
         want = ref_stream_ops(ref, d, q, w, [len(d), 0], [0, 2])          # FINISH without input behind full blocks
         assert _sim_cuts(sim, d, q, w, 1 << (14 if q < 4 else 16), [], [], 1, finish_empty=1) == want, (q, w)
+
+
+def test_sim_q234_batch_of_streams(sim):
+    """Qualities 2..4: many small streams as ONE device job (cuts of kind 3).  Slots, window limits and the zeroed-table
+    candidate count from every stream's own first byte; every stream must come out as the reference compresses it alone."""
+    from corpus import synth_binary, synth_text, synth_web
+    ora = Oracle()
+    rnd = np.random.RandomState(12)
+    web = synth_web(700000, 21); txt = synth_text(300000, 22); binr = synth_binary(300000, 23)
+    noise = rnd.randint(0, 256, 100000, dtype=np.uint8).tobytes()
+    streams = [web[:65536], web[65536:131072], txt[:65536], binr[:65536], noise[:65536], web[131072:131072 + 70000],
+               b"a", b"ab", txt[:3], web[:17], bytes(5000), noise[:300], txt[1000:1000 + 65537], web[200000:200000 + 200000],
+               binr[100000:100000 + 131072], noise[:40000] + web[:40000], (b"abcdefgh" * 9000)[:66000], web[:65536]]
+    for q, w in ((2, 22), (3, 18), (4, 24), (4, 12), (2, 10), (3, 16)):
+        got = _sim_multi(sim, streams, q, w)
+        for k, x in enumerate(streams):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    zz = [bytes(200000), bytes(180000) + web[:500] + bytes(90000), b"\x01" * 150000, bytes(70000), web[:100000], bytes(300000),
+          web[:300000], noise[:70000] * 3, bytes(rnd.randint(0, 4, 90000, dtype=np.uint8))]
+    for q, w in ((2, 22), (3, 17), (4, 18)):
+        got = _sim_multi(sim, zz, q, w)
+        for k, x in enumerate(zz):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    fb = []
+    for i in range(30):
+        n, k = int(rnd.randint(200, 5000)), int(rnd.choice([3, 8, 40, 200, 256]))
+        fb.append(bytes(rnd.randint(0, k, n, dtype=np.uint8)) + (web[:int(rnd.randint(1, 300))] if i % 3 == 0 else b""))
+    for q, w in ((2, 22), (3, 22), (4, 18)):
+        got = _sim_multi(sim, fb, q, w)
+        for k, x in enumerate(fb):
+            assert got[k] == ora.compress(x, q, w), (q, w, k, len(x))
+    pool = web + txt + binr + noise + bytes(30000)
+    for it in range(10):
+        if it >= 6:
+            os.environ["BR_SIM_BATCH_CHUNK_BITS"] = "11"
+        k = int(rnd.randint(2, 40))
+        ss = []
+        for _ in range(k):
+            n = int(rnd.choice([1, 2, 5, 100, 1000, 4096, 20000, 65536, 65536, 70000, 150000]))
+            n = max(1, int(n * rnd.uniform(0.5, 1.0)))
+            o = int(rnd.randint(0, len(pool) - n))
+            ss.append(pool[o:o + n])
+        q, w = int(rnd.randint(2, 5)), int(rnd.randint(10, 25))
+        try:
+            got = _sim_multi(sim, ss, q, w)
+        finally:
+            os.environ.pop("BR_SIM_BATCH_CHUNK_BITS", None)
+        for j, x in enumerate(ss):
+            assert got[j] == ora.compress(x, q, w), (it, q, w, j, len(x))
+
+
+def test_sim_q234_batch_fuzz_sample(sim):
+    """The structured fuzz inputs a dozen at a time as one batch job at quality 2..4, with both chunk sizes."""
+    import collections
+    from fuzz_cases import cases, dict_cases
+    ora = Oracle()
+    groups = collections.defaultdict(list)
+    for src in (cases(4243, 150), dict_cases(4243, 40, TABLES)):
+        for i, d, q, w in src:
+            if 0 < len(d) < 300000:
+                groups[(2 + i % 3, 10 + (i * 7) % 15)].append(d)
+    checked = 0
+    for (q, w), lst in sorted(groups.items()):
+        for a in range(0, len(lst), 12):
+            part = lst[a:a + 12]
+            if len(part) < 2:
+                continue
+            os.environ["BR_SIM_BATCH_CHUNK_BITS"] = "11" if (a // 12) % 2 else "9"
+            try:
+                got = _sim_multi(sim, part, q, w)
+            finally:
+                os.environ.pop("BR_SIM_BATCH_CHUNK_BITS", None)
+            for k, x in enumerate(part):
+                assert got[k] == ora.compress(x, q, w), (q, w, a, k, len(x))
+                checked += 1
+    assert checked > 100

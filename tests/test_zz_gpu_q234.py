@@ -117,7 +117,9 @@ def test_q234_streaming_flush_and_metadata(b200):
 
 
 def test_q234_batch_api(b200):
-    """BrotliB200CompressBatch at quality 2..4: one job per stream (host workers), every stream equal to the one-shot call."""
+    """BrotliB200CompressBatch at quality 2..4: streams below 1 MiB run as ONE device job per group (k_walk<0, true>: slots,
+    windows and the zeroed-table candidate count from each stream's first byte), longer ones one by one; every stream equal
+    to the one-shot call."""
     ora = Oracle()
     from corpus import synth_web
     web = synth_web(3_000_000, 90)
@@ -126,9 +128,15 @@ def test_q234_batch_api(b200):
     for i in range(24):
         n = int(rnd.choice([1, 100, 5000, 65536, 200000]))
         streams.append(web[off:off + n]); off += n
-    for q in (2, 3, 4):
-        got = b200.compress_batch(streams, q, 22)
-        assert got == [ora.compress(s, q, 22) for s in streams], q
+    streams.append(web[:1_200_000])          # >= 1 MiB: its own job (H54 at quality 4)
+    streams += [b"", bytes(70000), b"ab" * 40000]
+    for q, w in ((2, 22), (3, 22), (4, 22), (4, 12), (3, 17)):
+        got = b200.compress_batch(streams, q, w)
+        assert got == [ora.compress(s, q, w) if s else b"\x06" for s in streams], (q, w)
+    many = [web[o:o + 65536] for o in range(0, 2_900_000, 31337)][:600]      # a batch that fills the GPU (2 KiB chunks)
+    for q in (2, 4):
+        got = b200.compress_batch(many, q, 22)
+        assert got == [ora.compress(s, q, 22) for s in many], q
 
 
 @pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
