@@ -43,6 +43,14 @@ __global__ void k_slot_keys(BrParams P, const u8* __restrict__ data, const BrBlk
     keys[p] = p < hashable ? br_quick_slot(P, br_ld64u(data, p), p - B.base) : P.nbuckets;
 }
 
+// qualities 2..4: where the search at position p enters each of its slots' segments (br_lz77.h br_quick_pred_fill); one CTA
+// per input block, a thread per position
+__global__ void k_slot_pred(BrStream s, u32* __restrict__ qpred) {
+  const BrBlk B = s.blk[blockIdx.x];
+  for (u32 p = B.start + threadIdx.x; p < B.end; p += blockDim.x)
+    br_quick_pred_fill(s, p, B.base, qpred + ((size_t)p << s.P.qk_sweep_bits));
+}
+
 #define RADIX_TILE 4096
 // digit histogram of one tile -> hist[d * ntiles + tile]   (KT: u16 bucket keys, u32 slot keys)
 template <int SHIFT, class KT = u16>
@@ -532,7 +540,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   // the conservative block-level re-marks), and a late uncompressed fallback restarts the count at most once per metablock.
   P.max_epochs = 4 * nb + 4096;
   add(((size_t)P.max_epochs + 2) * 4 + 64); add((nb + 1) * sizeof(BrMetaBlock)); add(4096);
-  if (P.quick) { for (int i = 0; i < 4; ++i) add(4ull * n + 16); add((((size_t)n << P.qk_sweep_bits) + 16) * 4); }   // 32-bit sort keys, slot reads
+  if (P.quick) { for (int i = 0; i < 4; ++i) add(4ull * n + 16); add((((size_t)n << P.qk_sweep_bits) + 16) * 4); add((((size_t)n << P.qk_sweep_bits) + 16) * 4); }   // 32-bit sort keys, slot entry points, slot reads
   need += 1 << 20;
   if (!job->arena.reserve(need)) return 0;
   BrArena& A = job->arena;
@@ -564,13 +572,14 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   BrMetaBlock* mbs_stage = A.take<BrMetaBlock>(nblk);
   u32* counters = A.take<u32>(64); u32* hist_scratch = A.take<u32>(256ull * nstreams);
   if (!hist_scratch) return 0;
-  u32 *qk_keys = nullptr, *qk_K1 = nullptr, *qk_V1 = nullptr, *qk_V2 = nullptr, *saw = nullptr;
+  u32 *qk_keys = nullptr, *qk_K1 = nullptr, *qk_V1 = nullptr, *qk_V2 = nullptr, *saw = nullptr, *qpred = nullptr;
   if (P.quick) {
     qk_keys = A.take<u32>((size_t)n + 4); qk_K1 = A.take<u32>((size_t)n + 4); qk_V1 = A.take<u32>((size_t)n + 4); qk_V2 = A.take<u32>((size_t)n + 4);
     saw = A.take<u32>(((size_t)n << P.qk_sweep_bits) + 16);
-    if (!saw) return 0;
+    qpred = A.take<u32>(((size_t)n << P.qk_sweep_bits) + 16);
+    if (!qpred) return 0;
   }
-  s.saw = saw;
+  s.saw = saw; s.qpred = qpred;
 
   CK(cudaMemcpyAsync(data, d_in, n, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(data + n, 0, 64, st));
@@ -624,6 +633,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     scan_exclusive(hist, 256 * ntiles, scan_tmp, st);
     k_radix_scatter<16, true, u32><<<ntiles, 256, 0, st>>>(qk_keys, qk_V2, n, hist, ntiles, qk_K1, S, rank);
     k_seg<u32><<<(n + 1 + 255) / 256, 256, 0, st>>>(qk_K1, n, P.nbuckets, seg);
+    k_slot_pred<<<nblk, 256, 0, st>>>(s, qpred);   // (s.S / s.rank / s.seg / s.blk / s.data are set; the kernel reads nothing else)
   } else {
   k_hash_keys<<<(n + 255) / 256, 256, 0, st>>>(P, data, keys);
   k_radix_count<0><<<ntiles, 256, 0, st>>>(keys, n, hist, ntiles);

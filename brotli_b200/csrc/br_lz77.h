@@ -497,7 +497,31 @@ BR_DEV void br_search_static_dict_shallow(BrWalk& w, u32 cur, u32 max_length, u3
     if (br_test_dict_item(w, len, br_ldg(s.dict_hash_words + key), cur, max_length, max_backward, out)) { ++w.dict_m; ++w.dm; }
   }
 }
+// First index of slot `slot`'s segment of S whose position is >= p (p itself is not in that segment): where a search at p
+// starts looking for the slot's content.  Computed once per position and slot by k_slot_pred (BrStream::qpred), outside
+// the fixpoint -- in the walker it would be ~10 dependent memory round trips per foreign slot and search.
+BR_DEV u32 br_quick_lower_bound(const BrStream& s, u32 slot, u32 p) {
+  u32 a = br_ldg(s.seg + slot), b = br_ldg(s.seg + slot + 1);
+  while (a < b) {
+    const u32 mid = (a + b) >> 1;
+    if (br_ldg(s.S + mid) < p) a = mid + 1; else b = mid;
+  }
+  return a;
+}
+// qpred entries of position p (thread task; `base`: first byte of p's stream)
+BR_DEV void br_quick_pred_fill(const BrStream& s, u32 p, u32 base, u32* out) {
+  const BrParams& P = s.P;
+  const u32 sweep = 1u << P.qk_sweep_bits, mask = (1u << P.qk_bits) - 1u;
+  if (p + P.htl > P.n) { for (u32 i = 0; i < sweep; ++i) out[i] = 0; return; }   // (never searched: the parse stops htl bytes before a block end)
+  const u32 key = br_quick_key_v(P, br_ld64u(s.data, p));
+  const u32 i_own = ((p - base) >> 3) & (sweep - 1u);
+  for (u32 i = 0; i < sweep; ++i)
+    out[i] = i == i_own ? br_ldg(s.rank + p) : br_quick_lower_bound(s, (key + (i << 3)) & mask, p);
+}
 // hash_longest_match_quickly_inc.h:147 FindLongestMatch.  out.len carries best_len_in (backward_references_inc.h:127).
+// Load plan (every step = one memory round trip for all slots together): (1) the bytes at cur; (2) segment starts,
+// qpred entries, the last-distance candidate's bytes; (3) the newest entry in front of cur in every slot; (4) their
+// stored bits; (5) the candidates' first bytes and pre-check bytes; then the reference's sequential fold.
 BR_DEV void br_find_quick(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, u32 dict_distance, BrSR& out) {
   const BrStream& s = *w.s;
   const BrParams& P = s.P;
@@ -511,20 +535,16 @@ BR_DEV void br_find_quick(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, 
   u32 compare_char = br_cur_byte(w, cur, best_len_in, max_length);
   const bool rec = !w.warming && br_lane() == 0;
   u32* saw = s.saw + ((size_t)cur << P.qk_sweep_bits);
+  const u32 base = w.base;   // first byte of the stream (0 unless the job is a batch of streams): the table's positions count from it
   BR_W(0, 1);
   out.delta = 0;
-  // ---- the slots' index ranges go out first (independent loads), the last-distance candidate is checked meanwhile
-  const u32 base = w.base;   // first byte of the stream (0 unless the job is a batch of streams): the table's positions count from it
-  const u32 i_own = ((cur - base) >> 3) & (sweep - 1u);   // the slot `cur` itself is filed in: its predecessors end at rank[cur]
-  u32 lo[4], ja[4], jb[4];
+  u32 lo[4], ja[4];
 #pragma unroll
   for (u32 i = 0; i < 4; ++i) {
-    lo[i] = ja[i] = jb[i] = 0;
+    lo[i] = ja[i] = 0;
     if (i < sweep) {
-      const u32 slot = (key + (i << 3)) & mask;
-      lo[i] = br_ldg(s.seg + slot);
-      if (i == i_own) ja[i] = jb[i] = br_ldg(s.rank + cur);
-      else { ja[i] = lo[i]; jb[i] = br_ldg(s.seg + slot + 1); }
+      lo[i] = br_ldg(s.seg + ((key + (i << 3)) & mask));
+      ja[i] = br_ldg(s.qpred + ((size_t)cur << P.qk_sweep_bits) + i);
     }
   }
   bool early = false;
@@ -550,47 +570,63 @@ BR_DEV void br_find_quick(BrWalk& w, u32 cur, u32 max_length, u32 max_backward, 
     br_own_set(w, cur); br_srch_set(w, cur);
     return;
   }
-  // ---- first index of every slot's segment whose position is >= cur (binary searches, interleaved)
-  for (;;) {
-    bool any = false;
+  br_own_sync(w);
+  // ---- (3) the newest entry in front of cur in every slot, (4) its stored bit (own fresh bits inside the walker's range,
+  // the snapshot in front of it), inside the window and the stream
+  u32 q0[4]; bool has0[4], inw[4], st0[4];
 #pragma unroll
-    for (u32 i = 0; i < 4; ++i) {
-      if (i < sweep && ja[i] < jb[i]) {
-        const u32 mid = (ja[i] + jb[i]) >> 1;
-        if (br_ldg(s.S + mid) < cur) ja[i] = mid + 1; else jb[i] = mid;
-        any = true;
+  for (u32 i = 0; i < 4; ++i) { has0[i] = i < sweep && ja[i] > lo[i]; q0[i] = has0[i] ? br_ldg(s.S + (ja[i] - 1)) : 0u; }
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    inw[i] = has0[i] && q0[i] >= base && cur - q0[i] <= max_backward;
+    st0[i] = inw[i] && br_is_stored(w, q0[i]);
+  }
+  // ---- the slot's content as this walker sees it: the latest stored position in front of cur.  Absent: the stream's
+  // first position (the zeroed table holds 0) while the window still reaches it; otherwise the slot holds something the
+  // reference rejects (backward > max_backward) whatever its first byte.
+  u32 prev[4]; bool valid[4]; u64 f8[4]; u32 cb[4];
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    prev[i] = 0; valid[i] = false;
+    if (i >= sweep) continue;
+    u32 j = ja[i];
+    bool found = false, at_start = true;
+    if (st0[i]) { found = true; j = ja[i] - 1; prev[i] = q0[i]; }
+    else if (has0[i] && q0[i] >= base) {
+      if (!inw[i]) at_start = false;
+      else {   // in the window but not stored: walk on (short: most positions are stored)
+        j = ja[i] - 1;
+        while (j > lo[i]) {
+          const u32 q = br_ldg(s.S + (j - 1));
+          if (q < base) break;                                // (batch of streams: positions of the streams in front)
+          if (cur - q > max_backward) { at_start = false; break; }
+          --j;
+          if (br_is_stored(w, q)) { found = true; prev[i] = q; break; }
+        }
       }
     }
-    if (!any) break;
+    if (rec) saw[i] = found ? j : (BR_SAW_ABSENT | j);
+    BR_W(1, 1);
+    if (!found) prev[i] = base;
+    const u32 backward = cur - prev[i];
+    valid[i] = (found || (at_start && cur - base <= max_backward)) && backward != 0 && backward <= max_backward;
   }
-  br_own_sync(w);
+  // ---- (5) first bytes and pre-check byte (data[prev + best_len], :191 / :236) of every candidate
+#pragma unroll
+  for (u32 i = 0; i < 4; ++i) {
+    f8[i] = valid[i] ? br_ld64u(d, prev[i]) : 0ull;
+    cb[i] = valid[i] ? (u32)br_ldg(d + prev[i] + best_len) : 0u;
+  }
+  const u32 bl0 = best_len;
   bool h2_return = false;
 #pragma unroll
   for (u32 i = 0; i < 4; ++i) {
     if (i >= sweep) break;
-    // the slot's content as this walker sees it: the latest stored position in front of cur, inside the window
-    u32 j = ja[i], cand = 0, rv = 0;
-    bool found = false;
-    bool at_start = true;   // the walk reached the front of the slot's segment (of this stream's part of it)
-    while (j > lo[i]) {
-      const u32 q = br_ldg(s.S + (j - 1));
-      if (q < base) break;                                // (batch of streams: positions of the streams in front)
-      if (cur - q > max_backward) { at_start = false; break; }
-      --j;
-      if (br_is_stored(w, q)) { found = true; cand = q; break; }
-    }
-    rv = found ? j : (BR_SAW_ABSENT | j);
-    if (rec) saw[i] = rv;
-    BR_W(1, 1);
-    // absent: the stream's first position (the zeroed table holds 0) while the window still reaches it; otherwise the slot
-    // holds something the reference rejects (backward > max_backward) whatever its first byte
-    bool valid = found || (at_start && cur - base <= max_backward && cur != base);
-    const u32 prev = found ? cand : base;
-    const u32 backward = cur - prev;
-    if (valid && compare_char != (u32)br_ldg(d + prev + best_len)) valid = false;
-    if (valid && (backward == 0 || backward > max_backward)) valid = false;
-    if (!valid) { if (sweep == 1) h2_return = true; continue; }
-    const u32 len = br_match_len_c(d, prev, cur, max_length, c0, c1);
+    if (!valid[i]) { if (sweep == 1) h2_return = true; continue; }   // (:191-196: a rejected candidate ends H2's search)
+    const u32 pc = best_len == bl0 ? cb[i] : (u32)br_ldg(d + prev[i] + best_len);
+    if (compare_char != pc) { if (sweep == 1) h2_return = true; continue; }
+    const u32 backward = cur - prev[i];
+    const u32 len = br_match_len_d0(d, prev[i], cur, max_length, c0, c1, f8[i]);
     if (len >= 4) {
       const u32 score = BR_SCORE_BASE + 135u * len - 30u * br_log2floor(backward);
       if (best_score < score) {

@@ -192,6 +192,8 @@ struct BrStream {
   BrBlk* blk;            // [nblk] reference input blocks
   BrBlkIn* blkin;        // [nblk]
   u32* key_flips;        // [nbuckets + 1] stored-bit flips per heavy bucket in the current launch
+  const u32* qpred;      // BrParams::quick: [n << qk_sweep_bits] for position p and slot i of its search: first index of that slot's
+                         // segment of S whose position is >= p (br_lz77.h br_quick_pred_fill)
   u32* saw;              // BrParams::quick: [n << qk_sweep_bits] what the latest search at a position read from each of its slots
                          // (index into S of the candidate, BR_SAW_NONE: the slot was empty, BR_SAW_SKIP: not read) -- br_verify_run
   u32 nblk;

@@ -47,7 +47,7 @@ struct SimStream {
   std::vector<BrMetaBlock> mbs;
   std::vector<BrBlk> blks;
   std::vector<BrBlkIn> blkin;
-  std::vector<u32> key_flips, saw;
+  std::vector<u32> key_flips, saw, qpred;
   std::vector<u32> dirty_list, ran_list, slot_blk, stream_blk, stream_nmb, stream_ncmd;
   std::vector<BrMetaBlock> mbs_stage;
   int iterations = 0;
@@ -167,6 +167,11 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   s.ctx_lut = p;
   s.log2tab = g_t.log2tab.data(); s.log2tab_n = (u32)g_t.log2tab.size();
   sim_build_sorted(*m);
+  if (P.quick) {   // k_slot_pred
+    m->qpred.assign(((size_t)n << P.qk_sweep_bits) + 4, 0);
+    for (u32 p = 0; p < n; ++p) br_quick_pred_fill(s, p, br_stream_base_of(s, p), m->qpred.data() + ((size_t)p << P.qk_sweep_bits));
+    s.qpred = m->qpred.data();
+  }
   return m;
 }
 
