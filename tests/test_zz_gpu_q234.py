@@ -150,3 +150,20 @@ def test_q234_full_size(b200):
         assert b200.compress_oneshot(d, q, 22) == ref.compress(d, q, 22), q
     d = synth_binary(64 << 20, 20250924)
     assert b200.compress_oneshot(d, 3, 24) == ref.compress(d, 3, 24)
+
+
+def test_q234_fuzz_gpu(b200):
+    """Structured random inputs (tests/fuzz_cases.py: periodic data, dictionary words, noise, long runs ...) at quality 2..4
+    through the C ABI on the GPU, one-shot and a dozen at a time through the batch call."""
+    from brotli_libs import TABLES
+    from fuzz_cases import cases, dict_cases
+    ora = Oracle()
+    todo = [(i, d) for i, d, q, w in cases(31339, 200) if d] + [(1000 + i, d) for i, d, q, w in dict_cases(31340, 40, TABLES) if d]
+    for i, d in todo:
+        q, w = 2 + i % 3, 10 + (i * 7) % 15
+        assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (i, len(d), q, w)
+    small = [d for i, d in todo if len(d) < (1 << 20)]
+    for a in range(0, len(small), 12):
+        part = small[a:a + 12]
+        q, w = 2 + (a // 12) % 3, 10 + (a // 12 * 5) % 15
+        assert b200.compress_batch(part, q, w) == [ora.compress(x, q, w) for x in part], (a, q, w)
