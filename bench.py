@@ -673,9 +673,9 @@ def q234_child():
 
 
 def bench_q234():
-    """Runs q234_child in a process of its own (time limit 10 minutes): a crash or a hang of the newest path ends the
-    child, not the bench."""
-    p = subprocess.run([sys.executable, os.path.abspath(__file__), "--q234-child"], stdout=subprocess.PIPE, timeout=600)
+    """Runs q234_child in a process of its own (time limit 5 minutes; it needs about two): a crash or a hang of the newest
+    path ends the child, not the bench."""
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), "--q234-child"], stdout=subprocess.PIPE, timeout=300)
     lines = [l for l in p.stdout.decode("utf-8", "replace").splitlines() if l.startswith("{")]
     if p.returncode != 0 or not lines:
         raise RuntimeError("q234 child exited with %d" % p.returncode)
