@@ -34,6 +34,18 @@ BR_DEV u32 br_chunk_of(const BrStream& s, u32 p) {
 // walker owns the positions [start_pos, out_pos).  StitchToPreviousBlock of the FOLLOWING input
 // block (hash_longest_match64_inc.h:127) stores the last three positions of a block after its
 // parse; that set is static, so it is added here, by whoever owns those positions.
+// Marks the positions [start_pos, out_pos) of run k in cover_cur (warp task; runs before the commits of the launch).
+BR_DEV void br_cover_run(const BrStream& s, u32 k) {
+  const u32 a = s.bin_used[k].start_pos, b = s.bout[k].out_pos;
+  if (b <= a) return;
+  const u32 w0 = a >> 5, w1 = (b - 1) >> 5;
+  for (u32 x = w0 + (u32)br_lane(); x <= w1; x += BR_WARP) {
+    u32 m = 0xffffffffu;
+    if (x == w0) m &= 0xffffffffu << (a & 31);
+    if (x == w1) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+    br_atomic_or(s.cover_cur + x, m);
+  }
+}
 BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
   const BrBlockIn in = s.bin_used[k];
   const u32 a = in.start_pos, b = s.bout[k].out_pos;
@@ -128,7 +140,16 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
             }
             const u32 pp = s.S[j];
             if (pp - q > s.P.max_backward || pp >= send) break;
-            if ((s.bits_prev[pp >> 5] >> (pp & 31)) & 1) ++cnt;
+            {
+              // A position shields q from pp only if it is stored in EVERY view a dependent run may have had: the snapshot
+              // before this launch and, where a run of this launch covers it, that run's fresh bits (a walker reads its
+              // own bits inside its range: a stretch it has just left unstored lets its searches see further back than
+              // the snapshot count says -- into a range that flips in the same launch; fuzz case (35, 22)).
+              const u32 wi = pp >> 5, sh = pp & 31;
+              const u32 prev = (s.bits_prev[wi] >> sh) & 1u, cov = (s.cover_cur[wi] >> sh) & 1u;
+              const u32 cur = ((s.bits_cur[wi] | s.bits_cur[s.bits_words + wi]) >> sh) & 1u;
+              if (prev && (!cov || cur)) ++cnt;
+            }
             if (pp >= a && pp < b) continue;            // my own run is consistent with my own bits
             if (!(((s.srch_cur[pp >> 5] | s.srch_latest[pp >> 5]) >> (pp & 31)) & 1)) continue;   // never searched there
             u32 c = br_chunk_of(s, pp);

@@ -229,6 +229,12 @@ __global__ void __launch_bounds__(128, G <= 2 ? BR_WALK1_MINB : G == 4 ? 5 : 4) 
   const u32 b = br_sched_entry(s, t);
   br_walk_block<G, M>(s, b, s.forced && b == s.counters[6]);
 }
+// positions covered by the runs of this launch (br_chain.h br_cover_run); before k_commit
+__global__ void k_cover(BrStream s) {
+  u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= s.counters[4]) return;
+  br_cover_run(s, s.ran_list[t]);
+}
 __global__ void k_commit(BrStream s) {
   u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= s.counters[4]) return;
@@ -529,7 +535,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   auto add = [&](size_t bytes) { need += (bytes + 255) & ~(size_t)255; };
   add((size_t)n + 64); add(2ull * n + 4); add(2ull * n + 4); add(4ull * n); add(2ull * n + 4); add(4ull * n); add(4ull * n); add(2ull * n + 4);
   add(256ull * ntiles * 4); add(scan_tmp_words(256ull * ntiles) * 4);
-  add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(2 * nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
+  add((P.nbuckets + 4) * 4ull); add(nwords * 4); add(2 * nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add(nwords * 4); add((nwords + 64) * 4); add(((size_t)n / 1024 + 8) * 4);
   add(scan_tmp_words((size_t)n / 1024 + 8) * 4);
   add(nb * sizeof(BrBlockIn) * 2); add(nb * sizeof(BrBlockOut)); add((size_t)nb * cmd_stride * sizeof(BrCmd));
   for (int i = 0; i < 14; ++i) add(nb * 4ull + 64);
@@ -551,6 +557,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   u32* seg = A.take<u32>(P.nbuckets + 4);
   u32* bits_latest = A.take<u32>(nwords); u32* bits_cur = A.take<u32>(2 * (size_t)nwords);
   u32* srch_latest = A.take<u32>(nwords); u32* srch_cur = A.take<u32>(nwords); u32* bits_prev = A.take<u32>(nwords);
+  u32* cover_cur = A.take<u32>(nwords);
   u32* storedS = A.take<u32>(nwords + 64); u32* prefS = A.take<u32>((size_t)n / 1024 + 8);
   u32* scan_tmp2 = A.take<u32>(scan_tmp_words((size_t)n / 1024 + 8));
   BrBlockIn* bin = A.take<BrBlockIn>(nb); BrBlockIn* bin_used = A.take<BrBlockIn>(nb);
@@ -589,7 +596,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
   s.changed_epoch = changed_epoch; s.epoch_cum = epoch_cum;
   s.ext_total = ext_total; s.cmd_off = cmd_off; s.mbs = mbs; s.force_unc = force_unc;
   s.counters = counters; s.hist_scratch = hist_scratch;
-  s.srch_latest = srch_latest; s.srch_cur = srch_cur; s.bits_prev = bits_prev; s.bitdep_epoch = bitdep_epoch; s.skeys = K2;
+  s.srch_latest = srch_latest; s.srch_cur = srch_cur; s.bits_prev = bits_prev; s.cover_cur = cover_cur; s.bitdep_epoch = bitdep_epoch; s.skeys = K2;
   s.dirty_list = dirty_list; s.block_mb = block_mb; s.ran_list = ran_list; s.lil_in = lil_in; s.blk = d_blk; s.nblk = nblk; s.blkin = d_blkin; s.key_flips = key_flips;
   { const u8* p = T->blob + 8;
     s.dict_size_bits = p; p += 32; s.dict_offsets = (const u32*)p; p += 128; s.dict = p; p += 122784;
@@ -705,6 +712,10 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       walk_pending = true; ++job->stats.walk_launches; job->stats.launches += 6;
       job->stats.walk_bytes += (u64)n_sched * ch;
       CK(cudaMemcpyAsync(bits_prev, bits_latest, nwords * 4, cudaMemcpyDeviceToDevice, st));
+      if (!P.quick) {   // (quality 2..4 check every run instead of marking: br_verify_run)
+        CK(cudaMemsetAsync(cover_cur, 0, nwords * 4, st));
+        k_cover<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s);
+      }
       k_commit<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s);
       if (P.quick) k_verify<<<(nb * 32 + 127) / 128, 128, 0, st>>>(s);
     }

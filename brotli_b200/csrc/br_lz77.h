@@ -344,7 +344,8 @@ BR_DEV void br_find_longest_match(BrWalk& w, u32 cur, u32 max_length, u32 max_ba
       // (Not skipped while the stream is shorter than 65536 bytes, although c cannot wrap there: the sensitivity this
       // path records -- min_wrap = 0 while the ring is not full -- also re-walks chunks whose view reached through their
       // own freshly unstored positions into a range that flipped in the same launch, which the successor count of
-      // br_commit_bits, taken over the previous snapshot, can miss: DESIGN.md section 3, "known gap".)
+      // br_commit_bits, taken over the previous snapshot, could miss before it learnt to count with the runs' own fresh
+      // bits (k_cover): DESIGN.md section 3, "the marking gap".  Kept: it costs nothing and is the net under that rule.)
       u32 lo_s = lo;
       if (w.base) {   // batch of streams: the bucket's slice starts with the positions of the streams in front
         u32 a = lo, b = j;

@@ -166,6 +166,8 @@ struct BrStream {
   const u32* bits_prev;  // copy of bits_latest taken before the commits of this iteration
   u32* srch_latest;      // positions FindLongestMatch was called on (latest run of their owner) ...
   u32* srch_cur;         // ... and in this iteration
+  u32* cover_cur;        // positions covered by a run of this launch (br_cover_run): what br_commit_bits may count as "stored in
+                         // everybody's view" is a position stored before the launch AND, where a run of this launch covers it, after it
   const u32* storedS;    // bits_latest permuted into S order ...
   const u32* prefS;      // ... with exclusive popcount prefix every 1024 bits
   BrBlockIn* bin;        // [nblocks]   chain state handed to walkers

@@ -37,7 +37,7 @@ extern "C" int sim_init(const u8* blob, size_t len, u32 log2n) {
 struct SimStream {
   BrStream s;
   std::vector<u8> data;
-  std::vector<u32> S, rank, seg, bits_latest, bits_cur, bits_prev, srch_latest, srch_cur, storedS, prefS, dirty, changed_bits,
+  std::vector<u32> S, rank, seg, bits_latest, bits_cur, bits_prev, srch_latest, srch_cur, cover_cur, storedS, prefS, dirty, changed_bits,
       epoch_cum, ext_total, lil_in, cmd_off, force_unc, counters, hist, block_mb;
   std::vector<int> changed_epoch, bitdep_epoch;
   std::vector<u16> skeys, tagS;
@@ -118,7 +118,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   m->bin = chunks; m->bin_used.resize(nb); m->bout.resize(nb);
   memset(m->bin_used.data(), 0, nb * sizeof(BrBlockIn));
   memset(m->bout.data(), 0, nb * sizeof(BrBlockOut));
-  m->bits_latest.assign(words, 0); m->bits_cur.assign(2 * words, 0); m->srch_latest.assign(words, 0); m->srch_cur.assign(words, 0);
+  m->bits_latest.assign(words, 0); m->bits_cur.assign(2 * words, 0); m->srch_latest.assign(words, 0); m->srch_cur.assign(words, 0); m->cover_cur.assign(words, 0);
   // initial guess: everything stored except the unsearchable tail of each block
   for (u32 k = 0; k < nb; ++k)
     for (u32 p = m->bin[k].pos; p < m->bin[k].end && p + P.htl <= m->bin[k].blk_end; ++p) m->bits_latest[p >> 5] |= 1u << (p & 31);
@@ -142,7 +142,7 @@ static SimStream* sim_setup(int q, int lgwin, const u8* in, u32 n, const SimCuts
   s.cmd_stride = ch / 2 + 2;
   m->cmd_blocks.resize((size_t)nb * s.cmd_stride);
   s.bits_latest = m->bits_latest.data(); s.bits_cur = m->bits_cur.data(); s.bits_words = (u32)m->bits_latest.size();
-  s.srch_latest = m->srch_latest.data(); s.srch_cur = m->srch_cur.data();
+  s.srch_latest = m->srch_latest.data(); s.srch_cur = m->srch_cur.data(); s.cover_cur = m->cover_cur.data();
   s.storedS = m->storedS.data(); s.prefS = m->prefS.data();
   s.bin = m->bin.data(); s.bin_used = m->bin_used.data(); s.bout = m->bout.data();
   s.cmd_blocks = m->cmd_blocks.data(); s.dirty = m->dirty.data();
@@ -213,6 +213,8 @@ static void sim_lz77_fixpoint(SimStream& m) {
       if (getenv("BR_SIM_TRACE")) fprintf(stderr, "   launch %u: sched %u ran %u longest sweep %u  (model cost %.1f, total %.1f)\n", s.epoch, s.counters[5], s.counters[4], s.counters[16], c, m.model_cost);
     }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
+    std::fill(m.cover_cur.begin(), m.cover_cur.end(), 0);
+    for (u32 i = 0; i < s.counters[4]; ++i) br_cover_run(s, s.ran_list[i]);
     for (u32 i = 0; i < s.counters[4]; ++i) br_commit_bits(s, s.ran_list[i]);
     if (s.P.quick) for (u32 k = 0; k < nb; ++k) br_verify_run(s, k);
     if (s.epoch + 2 >= s.P.max_epochs) { fprintf(stderr, "sim: no fixpoint\n"); break; }
@@ -231,6 +233,8 @@ static void sim_lz77_fixpoint(SimStream& m) {
     s.counters[4] = 0;
     for (u32 k = 0; k < nb; ++k) { BrBlockOut o; u32 sp0 = 0xffffffffu; if (s.P.quick && s.P.multi) br_walk_one<0, true>(s, k, s.bin[k], o, k, sp0); else if (s.P.quick) br_walk_one<0>(s, k, s.bin[k], o, k, sp0); else br_walk_one<1>(s, k, s.bin[k], o, k, sp0); }
     m.bits_prev = m.bits_latest; s.bits_prev = m.bits_prev.data();
+    std::fill(m.cover_cur.begin(), m.cover_cur.end(), 0);
+    for (u32 k = 0; k < nb; ++k) br_cover_run(s, k);
     for (u32 k = 0; k < nb; ++k) {
       br_commit_bits(s, k);
       const BrBlockOut& a = old[k]; const BrBlockOut& b = s.bout[k];
