@@ -281,9 +281,12 @@ __global__ void k_cmd_scan_inputs(const BrCmd* __restrict__ cmds, u32 C, u32* in
   if (i < C) br_cmd_scan_inputs(cmds[i], &a, &b, &d);
   ins[i] = a; span[i] = b; hasd[i] = d;
 }
-__global__ void k_cmd_mb(BrStream s, u32* cmd_mb) {
-  const BrMetaBlock mb = s.mbs[blockIdx.y];
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < mb.ncmd; i += gridDim.x * blockDim.x) cmd_mb[mb.cmd_off + i] = blockIdx.y;
+__global__ void k_cmd_mb(BrStream s, u32* cmd_mb, u32 n_mbs) {
+  // (grid.y is capped at 65535: 16 KiB input blocks of noise at quality 2, 3 make up to 65536 metablocks per GiB)
+  for (u32 m = blockIdx.y; m < n_mbs; m += gridDim.y) {
+    const BrMetaBlock mb = s.mbs[m];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < mb.ncmd; i += gridDim.x * blockDim.x) cmd_mb[mb.cmd_off + i] = m;
+  }
 }
 __global__ void k_expand(BrEnt e) {
   u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -362,8 +365,9 @@ __global__ void k_assemble_scan(BrStream s, const u64* __restrict__ out_off, u32
   if (threadIdx.x == 0) br_assemble_scan(s, out_off, out, desc, res, with_header, cut_kind, cut_end_bit, stream_end);
 }
 // grid.y = metablock, grid.x strides over its words / bytes
-__global__ void k_assemble_copy(BrStream s, const BrCopyDesc* __restrict__ desc, const u32* __restrict__ outbits, u32* out) {
-  const BrCopyDesc d = desc[blockIdx.y];
+__global__ void k_assemble_copy(BrStream s, const BrCopyDesc* __restrict__ desc, const u32* __restrict__ outbits, u32* out, u32 n_mbs) {
+  for (u32 m = blockIdx.y; m < n_mbs; m += gridDim.y) {   // (grid.y is capped at 65535, see k_cmd_mb)
+  const BrCopyDesc d = desc[m];
   if (d.kind == 0) {
     u32 nwords = (d.nbits + 31) / 32;
     const u32* src = outbits + d.src_off;
@@ -390,6 +394,7 @@ __global__ void k_assemble_copy(BrStream s, const BrCopyDesc* __restrict__ desc,
       if (v) atomicOr(out + first_word + i, v);
     }
   }
+}
 }
 
 // ============================================================================ host pipeline
@@ -782,7 +787,8 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
     e.dist_sym = dist_sym; e.lit_len = lit_len; e.cmd_len = cmd_len; e.lit_bit_base = lit_bit_base; e.cmd_mb = cmd_mb;
     e.aux = aux; e.scratch = scratch; e.scratch_off = d_soff; e.outbits = outbits; e.out_off = d_ooff;
     if (e.total_lits > n) return 0;
-    k_cmd_mb<<<dim3(64, n_mbs), 256, 0, st>>>(s, cmd_mb);
+    const u32 grid_mbs = n_mbs < 65535u ? n_mbs : 65535u;
+    k_cmd_mb<<<dim3(64, grid_mbs), 256, 0, st>>>(s, cmd_mb, n_mbs);
     k_expand<<<(u32)((C + 127) / 128 + 1), 128, 0, st>>>(e);
     k_mb_setup<<<n_mbs, 32, 0, st>>>(s, e);
     if (P.mb_kind) k_prep_flat<<<n_mbs, 64, 0, st>>>(s, e);   // qualities 2, 3: no block split, one code per category
@@ -809,7 +815,7 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
       if (rounds > (int)nblk + 8) return 0;   // (every round stores at least one more metablock raw)
       continue;
     }
-    k_assemble_copy<<<dim3(64, n_mbs), 256, 0, st>>>(s, desc, outbits, out);
+    k_assemble_copy<<<dim3(64, grid_mbs), 256, 0, st>>>(s, desc, outbits, out, n_mbs);
     final_out = (const u8*)out; final_size = ((u64)hp[17] << 32) | hp[16];
     break;
   }
