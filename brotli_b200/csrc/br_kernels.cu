@@ -848,6 +848,33 @@ extern "C" int br_job_compress_device(BrJob* job, int quality, int lgwin, u32 si
 extern "C" __attribute__((visibility("default"))) int br_debug_sort(int quality, int lgwin, const u8* h_in, u32 n, u32* h_S, u32* h_seg) {
   BrParams P;
   if (!br_derive_params(quality, lgwin, n, n, &P)) return 0;
+  if (P.quick) {   // qualities 2..4: the slot-sorted index (32-bit keys, three passes), one stream = one block from 0
+    u8* data; u32 *k0, *k1, *v1, *v2, *S, *rank, *hist, *tmp, *seg; BrBlk* blk;
+    const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
+    BrBlk B; memset(&B, 0, sizeof(B)); B.start = 0; B.end = n; B.base = 0; B.send = n;
+    CK(cudaMalloc(&data, (size_t)n + 64)); CK(cudaMemset(data, 0, (size_t)n + 64));
+    CK(cudaMemcpy(data, h_in, n, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&blk, sizeof(BrBlk))); CK(cudaMemcpy(blk, &B, sizeof(BrBlk), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&k0, 4ull * n + 16)); CK(cudaMalloc(&k1, 4ull * n + 16)); CK(cudaMalloc(&v1, 4ull * n + 16)); CK(cudaMalloc(&v2, 4ull * n + 16));
+    CK(cudaMalloc(&S, 4ull * n + 16)); CK(cudaMalloc(&rank, 4ull * n + 16)); CK(cudaMalloc(&hist, 1024ull * ntiles));
+    CK(cudaMalloc(&tmp, scan_tmp_words(256ull * ntiles) * 4)); CK(cudaMalloc(&seg, (P.nbuckets + 4) * 4ull));
+    k_slot_keys<<<1, 256>>>(P, data, blk, k0);
+    k_radix_count<0, u32><<<ntiles, 256>>>(k0, n, hist, ntiles);
+    scan_exclusive(hist, 256 * ntiles, tmp, 0);
+    k_radix_scatter<0, false, u32><<<ntiles, 256>>>(k0, nullptr, n, hist, ntiles, k1, v1, nullptr);
+    k_radix_count<8, u32><<<ntiles, 256>>>(k1, n, hist, ntiles);
+    scan_exclusive(hist, 256 * ntiles, tmp, 0);
+    k_radix_scatter<8, true, u32><<<ntiles, 256>>>(k1, v1, n, hist, ntiles, k0, v2, nullptr);
+    k_radix_count<16, u32><<<ntiles, 256>>>(k0, n, hist, ntiles);
+    scan_exclusive(hist, 256 * ntiles, tmp, 0);
+    k_radix_scatter<16, true, u32><<<ntiles, 256>>>(k0, v2, n, hist, ntiles, k1, S, rank);
+    k_seg<u32><<<(n + 1 + 255) / 256, 256>>>(k1, n, P.nbuckets, seg);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h_S, S, 4ull * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_seg, seg, (P.nbuckets + 2) * 4ull, cudaMemcpyDeviceToHost));
+    cudaFree(data); cudaFree(blk); cudaFree(k0); cudaFree(k1); cudaFree(v1); cudaFree(v2); cudaFree(S); cudaFree(rank); cudaFree(hist); cudaFree(tmp); cudaFree(seg);
+    return 1;
+  }
   u8* data; u16 *keys, *K1, *K2; u32 *V1, *S, *hist, *tmp, *seg;
   const u32 ntiles = (n + RADIX_TILE - 1) / RADIX_TILE;
   CK(cudaMalloc(&data, (size_t)n + 64)); CK(cudaMemset(data, 0, (size_t)n + 64));

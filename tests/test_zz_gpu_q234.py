@@ -29,6 +29,39 @@ def b200():
     return brotli_b200
 
 
+def _same(got, want, ctx):
+    """Byte equality with a useful failure message (this is the path's first run on hardware)."""
+    if got == want:
+        return
+    k = next((i for i in range(min(len(got), len(want))) if got[i] != want[i]), min(len(got), len(want)))
+    raise AssertionError("%r: %d bytes against %d, first difference at byte %d" % (ctx, len(got), len(want), k))
+
+
+def test_q234_index_sorted_by_slot(b200):
+    """The first thing that differs from the measured path: 32-bit slot keys through three radix passes (k_slot_keys,
+    k_radix_*<u32>, k_seg<u32>).  S must be the positions ordered by (slot, position) with the unhashable tail last; seg
+    the segment starts.  Checked against numpy for H2 / H3 (16 bits), H4 (17 bits) and H54 (20 bits, 7-byte hash)."""
+    from corpus import synth_web
+    L = b200.lib()
+    L.br_debug_sort.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    for q, n, bits, sweep_bits, hash_len in ((2, 300000, 16, 0, 5), (3, 300000, 16, 1, 5), (4, 300000, 17, 2, 5), (4, 1 << 20, 20, 2, 7)):
+        d = synth_web(n, 17)
+        S = np.zeros(n, np.uint32); seg = np.zeros((1 << bits) + 2, np.uint32)
+        assert L.br_debug_sort(q, 22, d, n, S.ctypes.data, seg.ctypes.data), q
+        a = np.frombuffer(d + bytes(8), np.uint8)
+        v = np.zeros(n, np.uint64)
+        for k in range(8):
+            v |= a[k:k + n].astype(np.uint64) << np.uint64(8 * k)
+        key = ((v << np.uint64(64 - 8 * hash_len)) * np.uint64(0x1FE35A7BD3579BD3)) >> np.uint64(64 - bits)
+        pos = np.arange(n, dtype=np.uint64)
+        slot = (key + (pos & np.uint64(((1 << sweep_bits) - 1) << 3))) & np.uint64((1 << bits) - 1)
+        slot[n - 7:] = 1 << bits                                   # positions without a full 8-byte load: overflow key
+        want = np.argsort(slot, kind="stable").astype(np.uint32)
+        assert np.array_equal(S, want), (q, n, int(np.argmax(S != want)))
+        want_seg = np.searchsorted(slot[want], np.arange((1 << bits) + 2), side="left").astype(np.uint32)
+        assert np.array_equal(seg, want_seg), (q, n)
+
+
 @pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%s-%d-q%d-w%d" % (g["kind"], g["n"], g["q"], g["lgwin"]))
 def test_q234_golden(b200, g):
     d = make_case(g)
@@ -55,7 +88,7 @@ def test_q234_against_oracle_windows(b200):
     for q in (2, 3, 4):
         for w in (10, 13, 16, 17, 20, 22, 24):
             for d in (d1, d2, d3):
-                assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (q, w, len(d))
+                _same(b200.compress_oneshot(d, q, w), ora.compress(d, q, w), (q, w, len(d)))
 
 
 def test_q234_edge_sizes(b200):
@@ -65,11 +98,11 @@ def test_q234_edge_sizes(b200):
     for n in (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 63, 64, 65, 511, 512, 4095, 16383, 16384, 16385, 65535, 65536, 65537,
               131072, 131073, (1 << 20) - 1, 1 << 20, (1 << 20) + 1):
         for q in (2, 3, 4):
-            assert b200.compress_oneshot(base[:n], q, 22) == ora.compress(base[:n], q, 22), (n, q)
+            _same(b200.compress_oneshot(base[:n], q, 22), ora.compress(base[:n], q, 22), (n, q))
     for d in (bytes(500000), bytes(range(256)) * 3000, b"ab" * 300000, os.urandom(1) * 7 + bytes(70000)):
         for q in (2, 3, 4):
             for w in (12, 22):
-                assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (len(d), q, w)
+                _same(b200.compress_oneshot(d, q, w), ora.compress(d, q, w), (len(d), q, w))
 
 
 def test_q234_incompressible_and_mixed(b200):
@@ -79,8 +112,8 @@ def test_q234_incompressible_and_mixed(b200):
     rnd = np.random.default_rng(77).integers(0, 256, 3_000_000, dtype=np.uint8).tobytes()
     mix = synth_text(400000, 78) + rnd[:700000] + synth_binary(500000, 79) + rnd[700000:1000000] + synth_text(300000, 80)
     for q in (2, 3, 4):
-        assert b200.compress_oneshot(rnd, q, 22) == ora.compress(rnd, q, 22), q
-        assert b200.compress_oneshot(mix, q, 20) == ora.compress(mix, q, 20), q
+        _same(b200.compress_oneshot(rnd, q, 22), ora.compress(rnd, q, 22), q)
+        _same(b200.compress_oneshot(mix, q, 20), ora.compress(mix, q, 20), q)
 
 
 def _drive(b200, d, q, w, sizes, ops):
@@ -147,7 +180,7 @@ def test_q234_full_size(b200):
     ref = Ref()
     d = synth_text(100_000_000, 20250922)
     for q in (2, 4):
-        assert b200.compress_oneshot(d, q, 22) == ref.compress(d, q, 22), q
+        _same(b200.compress_oneshot(d, q, 22), ref.compress(d, q, 22), q)
     d = synth_binary(64 << 20, 20250924)
     assert b200.compress_oneshot(d, 3, 24) == ref.compress(d, 3, 24)
 
@@ -161,7 +194,7 @@ def test_q234_fuzz_gpu(b200):
     todo = [(i, d) for i, d, q, w in cases(31339, 200) if d] + [(1000 + i, d) for i, d, q, w in dict_cases(31340, 40, TABLES) if d]
     for i, d in todo:
         q, w = 2 + i % 3, 10 + (i * 7) % 15
-        assert b200.compress_oneshot(d, q, w) == ora.compress(d, q, w), (i, len(d), q, w)
+        _same(b200.compress_oneshot(d, q, w), ora.compress(d, q, w), (i, len(d), q, w))
     small = [d for i, d in todo if len(d) < (1 << 20)]
     for a in range(0, len(small), 12):
         part = small[a:a + 12]
