@@ -13,6 +13,11 @@ metric, each with its own value / e2e / roofline / cpu_baseline / bit_exact:
       [i * 2^30 / N, (i + 1) * 2^30 / N) as its own stream (strong scaling)
   c5  10 000 x 64 KiB independent streams (slices of the c3 mix), quality 1, lgwin 22, stream j on
       GPU j mod N (strong scaling), one device batch per rank
+  c5q5  c5's streams at quality 5 (many small web payloads as device jobs; not a BASELINE config)
+  q234  the headline's 100 MB text at quality 2, 3 and 4 plus 2 000 x 64 KiB web payloads at quality 2 and 4
+      (not a BASELINE config; N = 1 only).  The path was built after the round's last GPU
+      minute, so it runs LAST and in a CHILD PROCESS with a time limit: whatever it does on its first contact with
+      hardware, the headline line is printed.
 
 Per config:  value = whole-job input MB/s, inputs resident in HBM, shards gathered to rank 0 in the step;
 e2e = the same from HOST buffers: H2D of the inputs and D2H of the compressed bytes inside the timed region
