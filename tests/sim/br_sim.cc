@@ -288,6 +288,16 @@ extern "C" long sim_lz77(int q, int lgwin, const u8* in, u32 n, BrCmd* cmds_out,
   return nm;
 }
 
+// The position index of a one-shot job as the sim builds it (the counterpart of the product's br_debug_sort hook).
+extern "C" int sim_debug_sort(int q, int lgwin, const u8* in, u32 n, u32* S_out, u32* seg_out) {
+  SimStream* m = sim_setup(q, lgwin, in, n);
+  if (!m) return 0;
+  memcpy(S_out, m->S.data(), (size_t)n * 4);
+  memcpy(seg_out, m->seg.data(), (size_t)(m->s.P.nbuckets + 2) * 4);
+  delete m;
+  return 1;
+}
+
 #ifdef BR_SIM_ENTROPY
 static void put_bits_host(std::vector<u8>& o, u64& bit, u32 n, u64 v) {
   for (u32 i = 0; i < n; ++i, ++bit) {

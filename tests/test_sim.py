@@ -547,3 +547,17 @@ def test_sim_q234_batch_fuzz_sample(sim):
                 assert got[k] == ora.compress(x, q, w), (q, w, a, k, len(x))
                 checked += 1
     assert checked > 100
+
+
+def test_sim_q234_index_against_numpy(sim):
+    """tests/slot_index.py (the numpy restatement the GPU test checks the three-pass radix sort against) == the sim's index."""
+    from corpus import synth_web
+    from slot_index import slot_index
+    sim.sim_debug_sort.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    for q, n in ((2, 300000), (3, 300000), (4, 300000), (4, 1 << 20), (4, 5000), (2, 9), (3, 7)):
+        d = synth_web(n, 17)
+        want_S, want_seg, bits = slot_index(d, q)
+        S = np.zeros(n, np.uint32); seg = np.zeros((1 << bits) + 2, np.uint32)
+        assert sim.sim_debug_sort(q, 22, d, n, S.ctypes.data, seg.ctypes.data)
+        assert np.array_equal(S, want_S), (q, n)
+        assert np.array_equal(seg, want_seg), (q, n)

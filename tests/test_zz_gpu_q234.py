@@ -40,25 +40,18 @@ def _same(got, want, ctx):
 def test_q234_index_sorted_by_slot(b200):
     """The first thing that differs from the measured path: 32-bit slot keys through three radix passes (k_slot_keys,
     k_radix_*<u32>, k_seg<u32>).  S must be the positions ordered by (slot, position) with the unhashable tail last; seg
-    the segment starts.  Checked against numpy for H2 / H3 (16 bits), H4 (17 bits) and H54 (20 bits, 7-byte hash)."""
+    the segment starts.  Checked against numpy (tests/slot_index.py, itself checked against the sim's index on the CPU)
+    for H2 / H3 (16 bits), H4 (17 bits) and H54 (20 bits, 7-byte hash)."""
     from corpus import synth_web
+    from slot_index import slot_index
     L = b200.lib()
     L.br_debug_sort.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
-    for q, n, bits, sweep_bits, hash_len in ((2, 300000, 16, 0, 5), (3, 300000, 16, 1, 5), (4, 300000, 17, 2, 5), (4, 1 << 20, 20, 2, 7)):
+    for q, n in ((2, 300000), (3, 300000), (4, 300000), (4, 1 << 20), (4, 5000), (2, 9)):
         d = synth_web(n, 17)
+        want_S, want_seg, bits = slot_index(d, q)
         S = np.zeros(n, np.uint32); seg = np.zeros((1 << bits) + 2, np.uint32)
         assert L.br_debug_sort(q, 22, d, n, S.ctypes.data, seg.ctypes.data), q
-        a = np.frombuffer(d + bytes(8), np.uint8)
-        v = np.zeros(n, np.uint64)
-        for k in range(8):
-            v |= a[k:k + n].astype(np.uint64) << np.uint64(8 * k)
-        key = ((v << np.uint64(64 - 8 * hash_len)) * np.uint64(0x1FE35A7BD3579BD3)) >> np.uint64(64 - bits)
-        pos = np.arange(n, dtype=np.uint64)
-        slot = (key + (pos & np.uint64(((1 << sweep_bits) - 1) << 3))) & np.uint64((1 << bits) - 1)
-        slot[n - 7:] = 1 << bits                                   # positions without a full 8-byte load: overflow key
-        want = np.argsort(slot, kind="stable").astype(np.uint32)
-        assert np.array_equal(S, want), (q, n, int(np.argmax(S != want)))
-        want_seg = np.searchsorted(slot[want], np.arange((1 << bits) + 2), side="left").astype(np.uint32)
+        assert np.array_equal(S, want_S), (q, n, int(np.argmax(S != want_S)))
         assert np.array_equal(seg, want_seg), (q, n)
 
 
