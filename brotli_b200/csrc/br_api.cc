@@ -577,8 +577,73 @@ size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8
 size_t BrotliB200CompressBatchDevice(int quality, int lgwin, size_t count, const void* d_inputs, const uint64_t* input_offsets,
     const size_t* input_sizes, void* d_encoded, size_t encoded_capacity, uint64_t* encoded_offsets, size_t* encoded_sizes) {
   Params p; p.quality = quality; p.lgwin = lgwin;
-  if (quality != 1 || !count || !supported(p) || !ensure_q1()) return 0;   /* quality 5..9: one stream per BrotliB200CompressDevice call */
+  if (lgwin > 24) p.large_window = 1;
+  if (!count || !supported(p)) return 0;
   for (size_t i = 0; i < count; ++i) if (input_sizes[i] == 0) return 0;
+  if (quality != 1) {
+    /* quality 2..9: streams below 1 MiB, consecutive ones grouped into device jobs of <= 128 MiB / 8192 streams (the job
+       of compress_stream_group, without the host staging): a group whose streams lie back to back in d_inputs is read
+       in place, otherwise it is gathered with device copies; the job's output is dense and goes to d_encoded as it is. */
+    for (size_t i = 0; i < count; ++i) if (input_sizes[i] >= ((size_t)1 << 20)) return 0;   /* longer streams: BrotliB200CompressDevice */
+    if (!ensure_job()) return 0;
+    cudaStream_t st = (cudaStream_t)br_job_stream(tls.job);
+    const int w = lgwin > 24 ? 24 : lgwin < 10 ? 10 : lgwin;
+    const uint8_t* din = (const uint8_t*)d_inputs;
+    uint8_t* dout = (uint8_t*)d_encoded;
+    size_t used = 0, good = 0, a = 0;
+    for (size_t i = 0; i < count; ++i) encoded_sizes[i] = 0;
+    bool failed = false;
+    while (a < count && !failed) {
+      size_t b = a, n = 0; uint32_t hint = 0; bool packed = true;
+      while (b < count && b - a < kBatchGroupStreams && n + input_sizes[b] <= kBatchGroupBytes) {
+        if (b > a && input_offsets[b] != input_offsets[b - 1] + input_sizes[b - 1]) packed = false;
+        if (input_sizes[b] > hint) hint = (uint32_t)input_sizes[b];
+        n += input_sizes[b]; ++b;
+      }
+      const size_t k = b - a;
+      const uint8_t* src = din + input_offsets[a];
+      if (!packed) {
+        if (tls.d_in_cap < n) {
+          if (tls.d_in) cudaFree(tls.d_in);
+          tls.d_in = nullptr; tls.d_in_cap = 0;
+          if (cudaMalloc(&tls.d_in, n + 64) != cudaSuccess) { cudaGetLastError(); failed = true; break; }
+          tls.d_in_cap = n;
+        }
+        size_t o = 0;
+        for (size_t j = a; j < b && !failed; ++j) {
+          if (cudaMemcpyAsync(tls.d_in + o, din + input_offsets[j], input_sizes[j], cudaMemcpyDeviceToDevice, st) != cudaSuccess) failed = true;
+          o += input_sizes[j];
+        }
+        if (failed) break;
+        src = tls.d_in;
+      }
+      std::vector<uint32_t> pos(k, 0), kind(k, 3);
+      { size_t o = 0; for (size_t j = 0; j + 1 < k; ++j) { o += input_sizes[a + j]; pos[j] = (uint32_t)o; } }
+      std::vector<uint64_t> ends(k + 1, 0);
+      BrCuts c; memset(&c, 0, sizeof(c));
+      c.pos = pos.data(); c.kind = kind.data(); c.n = (uint32_t)(k - 1); c.is_final = 1; c.with_header = 1; c.stream_end = ends.data();
+      const uint8_t* d_o = nullptr; size_t sz = 0;
+      if (!br_job_compress_device(tls.job, quality, w, hint, src, (uint32_t)n, &d_o, &sz, k > 1 ? &c : nullptr)) { failed = true; break; }
+      record_stats();
+      if (k == 1) ends[0] = sz;
+      if (ends[k - 1] != sz || used + sz > encoded_capacity) { failed = true; break; }
+      if (cudaMemcpyAsync(dout + used, d_o, sz, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { failed = true; break; }
+      for (size_t j = 0; j < k; ++j) {
+        const size_t from = j ? (size_t)ends[j - 1] : 0, got = (size_t)ends[j] - from;
+        encoded_offsets[a + j] = used + from;
+        /* encode.c:1345: above BrotliEncoderMaxCompressedSize the one-shot wrapper substitutes the raw stream, which needs
+           the host copy of the input: such a stream is reported as failed here (size 0), like at quality 1 */
+        if (got <= BrotliEncoderMaxCompressedSize(input_sizes[a + j])) { encoded_sizes[a + j] = got; ++good; }
+      }
+      used += sz;
+      a = b;
+    }
+    for (size_t i = a; i < count; ++i) encoded_offsets[i] = used;   /* (streams behind a failure) */
+    encoded_offsets[count] = used;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 0;
+    return failed ? 0 : good;
+  }
+  if (!ensure_q1()) return 0;
   BrQ1Packed pk; pk.d_in = (const uint8_t*)d_inputs; pk.in_off = input_offsets; pk.d_out = (uint8_t*)d_encoded;
   pk.out_cap = encoded_capacity; pk.out_off = encoded_offsets;
   std::vector<int> ok(count, 0);

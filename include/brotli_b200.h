@@ -50,7 +50,14 @@ BROTLI_B200_API BROTLI_BOOL BrotliB200CompressDevice(int quality, int lgwin, siz
  * fragment coder per stream): the whole batch is ONE device batch -- four kernel launches, one copy each way.  encoded_sizes[i]: in = capacity of outputs[i], out = bytes written.
  * Returns the number of streams compressed successfully. */
 BROTLI_B200_API size_t BrotliB200CompressBatch(int quality, int lgwin, size_t count, const uint8_t* const* inputs, const size_t* input_sizes, uint8_t* const* outputs, size_t* encoded_sizes, int threads);
-/* Quality 1, device resident: `count` non-empty streams sit in ONE device buffer, stream i at d_inputs + input_offsets[i]
+/* Device resident batches.  Quality 2..9: `count` non-empty streams of less than 1 MiB each sit in one device buffer, stream i
+ * at d_inputs + input_offsets[i]; consecutive streams are grouped into device jobs of <= 128 MiB / 8192 streams (a group whose
+ * streams lie back to back is read in place).  The compressed streams are packed DENSELY into d_encoded in input order:
+ * stream i at d_encoded + encoded_offsets[i] (count + 1 entries, last = bytes used), encoded_sizes[i] bytes (0 = above
+ * BrotliEncoderMaxCompressedSize: that stream must go through the host call).  The inputs must be complete before the call (it
+ * runs on the calling thread's own CUDA stream and returns when the outputs are complete).  Returns the number of streams
+ * compressed, 0 if a job failed or d_encoded is too small.
+ * Quality 1, device resident: `count` non-empty streams sit in ONE device buffer, stream i at d_inputs + input_offsets[i]
  * (host array), input_sizes[i] bytes (host array).  The compressed streams are packed into d_encoded (device), stream i at
  * d_encoded + encoded_offsets[i] (host array of count + 1 entries, 16-byte aligned starts, last = bytes used),
  * encoded_sizes[i] bytes (host array; 0 = that stream must go through the host call: it compressed to more than

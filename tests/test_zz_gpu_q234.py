@@ -193,3 +193,49 @@ def test_q234_fuzz_gpu(b200):
         part = small[a:a + 12]
         q, w = 2 + (a // 12) % 3, 10 + (a // 12 * 5) % 15
         assert b200.compress_batch(part, q, w) == [ora.compress(x, q, w) for x in part], (a, q, w)
+
+
+def test_batch_device_resident_quality_2_to_9(b200):
+    """BrotliB200CompressBatchDevice at quality 2..9 (added with the quality 2..4 work): streams resident in one device buffer,
+    back to back (read in place) and with gaps (gathered on the device), compressed streams packed densely into a device
+    buffer; every stream equal to the one-shot call."""
+    import torch
+    ora = Oracle()
+    from corpus import synth_web
+    L = b200.lib()
+    web = synth_web(2_000_000, 95)
+    rnd = np.random.default_rng(96)
+    sizes = [int(x) for x in rnd.choice([1, 7, 300, 5000, 65536, 65536, 150000], 40)]
+    streams, off = [], 0
+    for n in sizes:
+        streams.append(web[off:off + n]); off = (off + n) % 1_800_000
+    cnt = len(streams)
+    for gap in (0, 48):
+        offs, o = [], 0
+        for x in streams:
+            offs.append(o); o += len(x) + gap
+        buf = bytearray(o + 64)
+        for x, p in zip(streams, offs):
+            buf[p:p + len(x)] = x
+        d_in = torch.frombuffer(buf, dtype=torch.uint8).cuda()
+        cap = sum(len(x) for x in streams) * 2 + 4096 * cnt
+        d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        in_off = (C.c_uint64 * cnt)(*offs)
+        in_sz = (C.c_size_t * cnt)(*[len(x) for x in streams])
+        for q, w in ((5, 22), (2, 22), (4, 18), (9, 24), (3, 12)):
+            out_off = (C.c_uint64 * (cnt + 1))()
+            out_sz = (C.c_size_t * cnt)()
+            good = L.BrotliB200CompressBatchDevice(q, w, cnt, d_in.data_ptr(), in_off, in_sz, d_out.data_ptr(), cap, out_off, out_sz)
+            host = d_out.cpu().numpy().tobytes()
+            want = [ora.compress(x, q, w) for x in streams]
+            ok = 0
+            for k in range(cnt):
+                if out_sz[k]:          # (0: above BrotliEncoderMaxCompressedSize, to be sent through the host call)
+                    _same(host[out_off[k]:out_off[k] + out_sz[k]], want[k], (gap, q, w, k, len(streams[k])))
+                    ok += 1
+                else:
+                    assert len(want[k]) > L.BrotliEncoderMaxCompressedSize(len(streams[k])), (gap, q, w, k)
+            assert good == ok and ok >= cnt - 4, (gap, q, w, good, ok)
+            if ok == cnt:
+                assert out_off[cnt] == sum(len(x) for x in want)
