@@ -82,8 +82,9 @@ BR_DEV void br_commit_bits(const BrStream& s, u32 k) {
         if (!s.bin[nb].first) continue;
         u32 np = s.bin[nb].blk_start, ne = s.bin[nb].blk_end;
         if (np >= in.blk_end + 3) break;
-        if (ne - np >= s.P.htl - 1 && np - s.bin[nb].base >= 3) { st_lo = np - 3; st_hi = np; }
-        break;
+        // (a block shorter than HashTypeLength - 1 does not stitch -- a FLUSH one or two bytes behind a block boundary makes
+        // such a block -- but the block behind it may, and its three positions then reach back into this one)
+        if (ne - np >= s.P.htl - 1 && np - s.bin[nb].base >= 3) { st_lo = np - 3; st_hi = np; break; }
       }
     }
     u32 w0 = a >> 5, w1 = (b - 1) >> 5;
@@ -410,7 +411,7 @@ BR_DEV void br_chain_blocks(const BrStream& s, u32 bi0, u32 bi1, BrMetaBlock* mb
           const BrBlockIn u = s.bin_used[B.first_chunk + c];
           const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
           if (ul != dict_l || um != dict_m) {
-            if (!br_dict_gate_valid(dict_l, dict_m, o.dl, o.dm, o.gate_checks, o.gate_fail, &edl, &edm)) { edl = o.dl; edm = o.dm; }
+            if (!br_dict_gate_valid(dict_l, dict_m, o.dl, o.dm, o.gate_checks, o.gate_fail, &edl, &edm, s.P.quick ? 1u : 2u)) { edl = o.dl; edm = o.dm; }
           }
           dict_l += edl; dict_m += edm;
         }
@@ -558,7 +559,7 @@ BR_DEV void br_chain_c(const BrStream& s, u32 bi) {
           u.dc[3] != ni.dc[3]) dirty = 2;
       u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
       if (!dirty && (ul != dict_l || um != dict_m) &&
-          !br_dict_gate_valid(dict_l, dict_m, out.dl, out.dm, out.gate_checks, out.gate_fail, &edl, &edm)) dirty = 3;
+          !br_dict_gate_valid(dict_l, dict_m, out.dl, out.dm, out.gate_checks, out.gate_fail, &edl, &edm, s.P.quick ? 1u : 2u)) dirty = 3;
       if (!dirty && out.out_pos > ni.start_pos) {
         int seen = (int)out.epoch;
         if (s.bitdep_epoch[k] >= seen || ovf >= seen) dirty = 4;

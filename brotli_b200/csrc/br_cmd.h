@@ -118,11 +118,12 @@ BR_DEV double br_bits_entropy(const BrStream& s, const u32* pop, u32 size) {
 }
 
 // Static-dictionary gate (hash.h:186): a search that found nothing probes the dictionary (two
-// lookups) only while matches >= lookups >> 7; once the gate closes it stays closed.  A chunk
+// lookups; ONE for the shallow probe of the quality 2..4 hashers, hash.h:179 -- `per`) only while
+// matches >= lookups >> 7; once the gate closes it stays closed.  A chunk
 // walked from some counters reports its lookups dl, matches dm and how its gate checks went.
 // Given NEW counters (l, m) at its start: is that walk still what the reference would have done,
 // and how many lookups / matches does it really add (*edl, *edm)?  Returns 0 if it must be re-walked.
-BR_DEV int br_dict_gate_valid(u64 l, u64 m, u32 dl, u32 dm, u32 gate_checks, u32 gate_fail, u32* edl, u32* edm) {
+BR_DEV int br_dict_gate_valid(u64 l, u64 m, u32 dl, u32 dm, u32 gate_checks, u32 gate_fail, u32* edl, u32* edm, u32 per = 2) {
   const bool closed = m < (l >> 7);
   *edl = 0; *edm = 0;
   if (gate_checks == 0) return 1;                       // never asked
@@ -133,7 +134,7 @@ BR_DEV int br_dict_gate_valid(u64 l, u64 m, u32 dl, u32 dm, u32 gate_checks, u32
   // no lookup succeeded: the parse is the same; lookups stop once (l >> 7) exceeds m
   const u64 lim = (m + 1) << 7;                          // first l with (l >> 7) > m
   u64 x = lim - l;                                       // > 0 here
-  x = (x + 1) & ~(u64)1;                                 // lookups come in pairs
+  if (per == 2) x = (x + 1) & ~(u64)1;                   // lookups come in pairs (one gate check per search)
   *edl = x < dl ? (u32)x : dl;
   return 1;
 }

@@ -938,7 +938,7 @@ BR_DEV void br_walk_block(const BrStream& s, u32 b, bool to_block_end) {
         const BrBlockOut uo = s.bout[nb];
         const u64 ul = ((u64)u.dict_l_hi << 32) | u.dict_l_lo, um = ((u64)u.dict_m_hi << 32) | u.dict_m_lo;
         u32 edl, edm;
-        if (ul != dl || um != dm) same = br_dict_gate_valid(dl, dm, uo.dl, uo.dm, uo.gate_checks, uo.gate_fail, &edl, &edm) != 0;
+        if (ul != dl || um != dm) same = br_dict_gate_valid(dl, dm, uo.dl, uo.dm, uo.gate_checks, uo.gate_fail, &edl, &edm, s.P.quick ? 1u : 2u) != 0;
       }
       if (same) return;
     }

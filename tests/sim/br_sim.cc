@@ -180,7 +180,9 @@ static void sim_lz77_fixpoint(SimStream& m) {
 #ifdef BR_SIM_DEBUG
   if (getenv("BR_SIM_WATCH")) br_sim_watch = (u32)atoi(getenv("BR_SIM_WATCH"));
 #endif
-  s.epoch = 0;
+  // (the launch counter runs on through the rounds of a late fallback, as in br_job_compress_device: runs are stamped with
+  // it -- BrBlockOut::epoch -- and the marks of br_commit_bits / br_verify_run are compared with those stamps)
+  const u32 round_epoch0 = s.epoch;
   for (;;) {
     br_chain(s);
     if (getenv("BR_SIM_TRACE")) { u32 h[6] = {0}; u32 first = nb; for (u32 k = 0; k < nb; ++k) { h[s.dirty[k] & 7]++; if (s.dirty[k] && first == nb) first = k; }
@@ -196,7 +198,7 @@ static void sim_lz77_fixpoint(SimStream& m) {
     sim_build_storedS(m);
     std::fill(m.bits_cur.begin(), m.bits_cur.end(), 0); std::fill(m.srch_cur.begin(), m.srch_cur.end(), 0);
     s.counters[4] = 0; s.counters[16] = 0;
-    s.forced = s.epoch >= s.P.force_epoch;
+    s.forced = s.epoch - round_epoch0 >= s.P.force_epoch;
     { u32 nd = s.counters[5]; std::vector<u32> dl(nd); for (u32 t = 0; t < nd; ++t) dl[t] = br_sched_entry(s, t); for (u32 k : dl) { const bool f = s.forced && k == s.counters[6];
       if (s.P.quick) { if (s.P.multi) br_walk_block<0, true>(s, k, f); else br_walk_block<0>(s, k, f); }
       else if (s.P.multi) { if (s.P.block_bits >= 6) br_walk_block<4, true>(s, k, f); else br_walk_block<1, true>(s, k, f); }
@@ -389,6 +391,20 @@ static long sim_compress_impl(int q, int lgwin, const u8* in, u32 n, u8* out, si
     u32 nm = s.counters[1];
     SimEnt E;
     sim_entropy2(*m, E);
+    if (getenv("BR_SIM_CHUNKAT")) { const u32 at = (u32)atoi(getenv("BR_SIM_CHUNKAT"));
+      for (u32 k = 0; k < s.P.nblocks; ++k) if (s.bin[k].pos <= at + 3000 && s.bin[k].end + 3000 > at)
+        fprintf(stderr, "CHUNK %u [%u,%u) blk [%u,%u) start %u dc %d %d %d %d rh %u se %u | out_pos %u ncmd %u dc %d %d %d %d valid %u epoch %u\n", k, s.bin[k].pos, s.bin[k].end, s.bin[k].blk_start, s.bin[k].blk_end,
+                s.bin[k].start_pos, s.bin[k].dc[0], s.bin[k].dc[1], s.bin[k].dc[2], s.bin[k].dc[3], s.bin[k].apply_rh, s.bin[k].store_end, s.bout[k].out_pos, s.bout[k].ncmd, s.bout[k].dc[0], s.bout[k].dc[1], s.bout[k].dc[2], s.bout[k].dc[3], s.bout[k].valid, s.bout[k].epoch); }
+    if (getenv("BR_SIM_MBS")) {   // the last metablock's commands (debugging against an instrumented reference)
+      u32 which = nm - 1;
+      if (getenv("BR_DBG_MB")) for (u32 i = 0; i < nm; ++i) if (s.mbs[i].start == (u32)atoi(getenv("BR_DBG_MB"))) which = i;
+      const BrMetaBlock& lm = s.mbs[which]; u32 pos = lm.start;
+      for (u32 i = 0; i < lm.ncmd; ++i) { const BrCmd& c = m->cmds_all[lm.cmd_off + i];
+        fprintf(stderr, "SIMCMD %u ins %u copy %u dprefix %u dextra %u\n", pos, c.insert_len, c.copy_len & 0x1FFFFFF, c.dist_prefix & 0x3FF, c.dist_extra); pos += c.insert_len + (c.copy_len & 0x1FFFFFF); }
+    }
+    if (getenv("BR_SIM_MBS"))   // metablock table (debugging against an instrumented reference)
+      for (u32 i = 0; i < nm; ++i) fprintf(stderr, "SIMMB start %u bytes %u ncmd %u nlit %u last %u compress %u bits %u\n", s.mbs[i].start, s.mbs[i].end - s.mbs[i].start,
+                                           s.mbs[i].ncmd, s.mbs[i].nlit, s.mbs[i].is_last, s.mbs[i].compress, s.mbs[i].out_bits);
     // stream assembly: the shared scan (br_assemble.h), then the copies of k_assemble_copy
     std::vector<u32> outw(((size_t)n + ((size_t)n >> 3) + 4096 + 8ull * nm) / 4 + 16, 0);
     std::vector<BrCopyDesc> desc(nm + 1);

@@ -561,3 +561,26 @@ def test_sim_q234_index_against_numpy(sim):
         assert sim.sim_debug_sort(q, 22, d, n, S.ctypes.data, seg.ctypes.data)
         assert np.array_equal(S, want_S), (q, n)
         assert np.array_equal(seg, want_seg), (q, n)
+
+
+def test_sim_flush_just_behind_a_block_boundary(sim):
+    """A FLUSH one or two bytes (up to HashTypeLength - 2) behind a block boundary leaves an input block too short to stitch
+    (hash_longest_match_quickly_inc.h:119 / hash_longest_match64_inc.h:127: num_bytes >= HashTypeLength - 1); the block behind
+    it stitches instead, and its three positions reach back across the short block into the block in front.  Their owner must
+    still commit them (br_commit_bits; found by a randomized FLUSH campaign: q3, lgwin 12, flush at 14 * 16384 + 2)."""
+    from brotli_libs import REF_SO, Ref, ref_stream_ops
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built")
+    from corpus import synth_text
+    ref = Ref()
+    d = synth_text(200000, 77)
+    n = len(d)
+    for q, w in ((3, 12), (2, 22), (4, 16), (5, 22), (7, 17)):
+        bs = 1 << (14 if q < 4 else 16)
+        for extra in (1, 2, 3, 5, 6):
+            c = 2 * bs + extra
+            want = ref_stream_ops(ref, d, q, w, [c, n - c], [1, 2])
+            assert _sim_cuts(sim, d, q, w, c, [c], [1], 1) == want, (q, w, extra)
+        c1, c2 = bs + 1, bs + 2                                    # two short blocks in a row
+        want = ref_stream_ops(ref, d, q, w, [c1, 1, n - c2], [1, 1, 2])
+        assert _sim_cuts(sim, d, q, w, c1, [c1, c2], [1, 1], 1) == want, (q, w)
