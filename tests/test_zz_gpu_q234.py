@@ -239,3 +239,21 @@ def test_batch_device_resident_quality_2_to_9(b200):
             assert good == ok and ok >= cnt - 4, (gap, q, w, good, ok)
             if ok == cnt:
                 assert out_off[cnt] == sum(len(x) for x in want)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref did not travel")
+def test_flush_just_behind_a_block_boundary(b200):
+    """All qualities: a FLUSH one or two bytes behind a block boundary leaves a block too short to stitch; the positions the
+    block behind it stitches reach back across it (tests/test_sim.py::test_sim_flush_just_behind_a_block_boundary: the case a
+    randomized campaign found in the last session, wrong bytes before the fix of br_commit_bits)."""
+    from corpus import synth_text
+    ref = Ref()
+    d = synth_text(300000, 77)
+    n = len(d)
+    for q, w in ((3, 12), (2, 22), (4, 16), (5, 22), (7, 17), (9, 24)):
+        bs = 1 << (14 if q < 4 else 18 if q >= 9 else 16)
+        for extra in (1, 2, 3, 6):
+            c = bs + extra
+            _same(_drive(b200, d, q, w, [c, n - c], [1, 2]), ref_stream_ops(ref, d, q, w, [c, n - c], [1, 2]), (q, w, extra))
+        c1, c2 = bs + 1, bs + 2
+        _same(_drive(b200, d, q, w, [c1, 1, n - c2], [1, 1, 2]), ref_stream_ops(ref, d, q, w, [c1, 1, n - c2], [1, 1, 2]), (q, w, "two short blocks"))
