@@ -21,6 +21,16 @@ class Ref:
     """The unmodified reference compiled from /root/reference (oracle/Makefile)."""
 
     def __init__(self, path=REF_SO):
+        # The reference reads ring-buffer bytes it never wrote in some call sequences (c/enc/ringbuffer.h:104-116: the first
+        # write of less than a block skips the tail copy, and the buffer is grown by a plain malloc, :70-78; a later block that
+        # runs across the ring's end then compares against tail bytes nobody filled), so its output depends on what malloc
+        # hands out: identical in a fresh process (zero pages), different on a dirty heap (found by tools/sim_campaign.py:
+        # quality 4, lgwin 10, three FLUSHes; MALLOC_PERTURB_ flips it).  Make malloc hand out zeroed memory in this process
+        # -- what a fresh process gets and what the oracle models (stale_byte) -- so that comparisons do not flake.
+        try:
+            C.CDLL(None).mallopt(-6, 255)      # M_PERTURB: allocations are filled with ~255 = 0
+        except Exception:
+            pass
         self.lib = C.CDLL(path, mode=os.RTLD_LOCAL)
         L = self.lib
         L.BrotliEncoderCompress.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p,
