@@ -17,20 +17,24 @@ def _buf(b):
     return (C.c_uint8 * max(1, len(b))).from_buffer_copy(b if len(b) else b"\0")
 
 
+def zeroed_malloc():
+    """The reference reads ring-buffer bytes it never wrote in some call sequences (c/enc/ringbuffer.h:104-116: the first write
+    of less than a block skips the tail copy, and the buffer is grown by a plain malloc, :70-78; a later block that runs across
+    the ring's end then compares against tail bytes nobody filled), so its output depends on what malloc hands out: identical
+    in a fresh process (zero pages), different on a dirty heap (found by tools/sim_campaign.py: quality 4, lgwin 10, three
+    FLUSHes; MALLOC_PERTURB_ flips it).  This makes malloc hand out zeroed memory in the calling process -- what a fresh
+    process gets and what the oracle models (stale_byte) -- so that comparisons do not flake.  Called by tests/conftest.py and
+    the campaign tools only: bench.py must time the reference with the allocator as it is."""
+    try:
+        C.CDLL(None).mallopt(-6, 255)      # M_PERTURB: allocations are filled with ~255 = 0
+    except Exception:
+        pass
+
+
 class Ref:
     """The unmodified reference compiled from /root/reference (oracle/Makefile)."""
 
     def __init__(self, path=REF_SO):
-        # The reference reads ring-buffer bytes it never wrote in some call sequences (c/enc/ringbuffer.h:104-116: the first
-        # write of less than a block skips the tail copy, and the buffer is grown by a plain malloc, :70-78; a later block that
-        # runs across the ring's end then compares against tail bytes nobody filled), so its output depends on what malloc
-        # hands out: identical in a fresh process (zero pages), different on a dirty heap (found by tools/sim_campaign.py:
-        # quality 4, lgwin 10, three FLUSHes; MALLOC_PERTURB_ flips it).  Make malloc hand out zeroed memory in this process
-        # -- what a fresh process gets and what the oracle models (stale_byte) -- so that comparisons do not flake.
-        try:
-            C.CDLL(None).mallopt(-6, 255)      # M_PERTURB: allocations are filled with ~255 = 0
-        except Exception:
-            pass
         self.lib = C.CDLL(path, mode=os.RTLD_LOCAL)
         L = self.lib
         L.BrotliEncoderCompress.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p,

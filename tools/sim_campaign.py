@@ -8,7 +8,8 @@ import sys, os, ctypes as C, time, random
 ROOT_ = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT_, 'tests')); sys.path.insert(0, ROOT_)
 import numpy as np
-from brotli_libs import ROOT, TABLES, Oracle, Ref, ref_stream_ops
+from brotli_libs import ROOT, TABLES, Oracle, Ref, ref_stream_ops, zeroed_malloc
+zeroed_malloc()
 from corpus import synth_text, synth_binary, synth_web
 L = C.CDLL(os.path.join(ROOT, "tests/sim/libbrsim.so"))
 L.sim_init.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
