@@ -585,6 +585,7 @@ def q234_child():
     peak, src = hbm_peak()
     per = {}
     for q in (2, 3, 4):
+      try:
         def dev():
             sz = C.c_size_t(cap)
             assert L.BrotliB200CompressDevice(q, 22, n, d_in.data_ptr(), C.byref(sz), d_out.data_ptr()), "BrotliB200CompressDevice failed"
@@ -625,6 +626,9 @@ def q234_child():
                              "kernel_ms": round(st["ms_walk"], 2), "launches": int(st["walk_launches"]), "peak_source": src}
         per["q%d" % q] = r
         log("q234 child: quality %d: %s MB/s, bit_exact %s" % (q, r["value"], r["bit_exact"]))
+      except Exception as e:      # (one quality failing must not hide the others)
+        per["q%d" % q] = {"quality": q, "error": repr(e)}
+        log("q234 child: quality %d failed: %r" % (q, e))
     result = {"workload": WORKLOADS["q234"], "lgwin": 22, "per_quality": per}
     try:      # many small streams at quality 2 and 4: 2 000 x 64 KiB web payloads as device jobs of <= 128 MiB (host buffers in and out)
         from corpus import synth_web
