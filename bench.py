@@ -214,6 +214,7 @@ def run_reference(args, rank):
             for q in (2, 3, 4):
                 t0 = time.time(); lib.compress(d0, q, 22); dt = time.time() - t0
                 per["q%d" % q] = {"value": round(len(d0) / dt / 1e6, 2), "unit": "MB/s", "ms_per_step": round(1e3 * dt, 2), "steps": 1,
+                                  "e2e": {"value": round(len(d0) / dt / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                                   "cpu_baseline": {"value": round(len(d0) / dt / 1e6, 2), "unit": "MB/s", "cores": 1, "kind": kind,
                                                    "sample": "the whole %d-byte stream once, 1 thread" % len(d0)}}
             line["sub_results"][cfg] = {"workload": WORKLOADS[cfg], "lgwin": 22, "per_quality": per}
